@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""Generates the committed golden vectors under tests/golden/ by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_shim.py) on seeded synthetic inputs.
+
+Only runnable in the build container (needs /root/reference and oracle/_ref/libgridsub_ref.so from
+`make -C oracle ref`).  The .npz files it writes are what travels to the GPU box.
+
+    python tests/golden/make_golden.py
+
+Files:
+  layer_<name>.npz      reference layer modules (layers.py) fwd (train + eval) and autograd grads
+  model_small.npz       PointConvFormer_Segmentation (model_architecture.py) logits + grads, small dims
+  inverse.npz           reference create_inverse_python (test_kernels.py:177-213) on a kNN table
+  grid_subsample.npz    reference C++ grid_subsampling (grid_subsampling.cpp:9-110) via oracle/_ref
+  pconv_linear_seed42.npz  the reference's torch formulation (layers.py:713-719 + Linear) on the
+                        shapes/seed of test_cutlass_vs_cuda_kernel (test_kernels.py:1707-1725)
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim, knn as oknn, grid_subsample as ogs  # noqa: E402
+
+REF = ref_shim.REFERENCE_ROOT
+
+
+def surface_cloud(n, seed, extent=(4.0, 3.0, 2.5)):
+    """Points on the faces of a box room (+ jitter) with face normals: ScanNet-ish geometry."""
+    rng = np.random.default_rng(seed)
+    ex = np.asarray(extent, np.float32)
+    face = rng.integers(0, 5, n)
+    p = rng.random((n, 3)).astype(np.float32) * ex
+    nrm = np.zeros((n, 3), np.float32)
+    for f, (ax, val, sgn) in enumerate([(2, 0.0, 1), (0, 0.0, 1), (0, ex[0], -1), (1, 0.0, 1), (1, ex[1], -1)]):
+        m = face == f
+        p[m, ax] = val
+        nrm[m, ax] = sgn
+    p += rng.normal(0, 0.005, p.shape).astype(np.float32)
+    nrm += rng.normal(0, 0.05, nrm.shape).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    return p.astype(np.float32), nrm.astype(np.float32)
+
+
+def base_cfg(**kw):
+    cfg = ref_shim.EasyDict(USE_VI=True, USE_PE=True, BATCH_NORM=True, USE_CUDA_KERNEL=False, PCONV_OPT=False,
+                            drop_path_rate=0., dropout_rate=0., attention_type='subtraction',
+                            layer_norm_guidance=False)
+    cfg.update(kw)
+    return cfg
+
+
+def randomize_bn(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            with torch.no_grad():
+                m.weight.copy_(1 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
+                m.running_mean.copy_(0.2 * torch.randn(m.bias.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.bias.shape, generator=g))
+
+
+def t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def run_layer(name, ctor, call, n_in_feat, strided, transpose=False, seed=0):
+    """Builds the reference layer, runs train-mode fwd + bwd and eval-mode fwd, saves everything."""
+    L, _, _ = ref_shim.load()
+    torch.manual_seed(seed)
+    layer = ctor(L)
+    randomize_bn(layer, seed + 1)
+    N, M, K = 600, 150, 16
+    xyz, nrm = surface_cloud(N, seed + 2)
+    sub = np.sort(np.random.default_rng(seed + 3).choice(N, M, replace=False))
+    sxyz, snrm = xyz[sub] + 0.01, nrm[sub]
+    rng = np.random.default_rng(seed + 4)
+    out = {}
+    if transpose:           # dense = N points (output), sparse = M points (input features)
+        nei = oknn.knn_numpy(sxyz, xyz, K)
+        feats = rng.standard_normal((M, n_in_feat)).astype(np.float32)
+    elif strided:
+        nei = oknn.knn_numpy(xyz, sxyz, K)
+        feats = rng.standard_normal((N, n_in_feat)).astype(np.float32)
+    else:
+        nei = oknn.knn_numpy(xyz, xyz, K)
+        feats = rng.standard_normal((N, n_in_feat)).astype(np.float32)
+    tens = dict(xyz=t(xyz)[None], nrm=t(nrm)[None], sxyz=t(sxyz)[None], snrm=t(snrm)[None],
+                nei=t(nei)[None], feats=t(feats)[None].requires_grad_(True))
+    layer.train()
+    y, wni = call(layer, tens)
+    gout = torch.from_numpy(np.random.default_rng(seed + 5).standard_normal(tuple(y.shape)).astype(np.float32))
+    (y * gout).sum().backward()
+    out.update(xyz=xyz, nrm=nrm, sxyz=sxyz, snrm=snrm, nei=nei, feats=feats, gout=gout.numpy(),
+               y_train=y.detach().numpy(), g_feats=tens['feats'].grad.numpy())
+    if name in ("pointconv", "pcf_strided", "transpose"):
+        out["wni"] = wni.detach().numpy()
+    for k, p in layer.named_parameters():
+        out["grad." + k] = p.grad.numpy().copy()
+    # state dict as it was *before* the train-mode forward touched the running stats is not
+    # recoverable, so save the post-forward one for eval and the BN buffers are irrelevant in training
+    layer.eval()
+    with torch.no_grad():
+        y_eval, _ = call(layer, tens)
+    out["y_eval"] = y_eval.numpy()
+    for k, v in layer.state_dict().items():
+        out["param." + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "layer_%s.npz" % name), **out)
+    print("layer_%s: y %s  |y|=%.4f" % (name, tuple(y.shape), float(y.abs().mean())))
+
+
+def make_layers():
+    cfg = base_cfg()
+    run_layer("pointconv", lambda L: L.PointConv(6, 32, cfg, [12, 16]),
+              lambda m, a: m(a['xyz'], a['feats'], a['nei'], a['nrm']), 6, False, seed=10)
+    cfg_nope = base_cfg(USE_VI=False, USE_PE=False, BATCH_NORM=False)     # test_configs/pointconv_single.yaml
+    run_layer("pointconv_single", lambda L: L.PointConv(3, 32, cfg_nope, [3, 16]),
+              lambda m, a: m(a['xyz'], a['feats'], a['nei']), 3, False, seed=20)
+    run_layer("stridepe_self", lambda L: L.PointConvStridePE(32, 32, cfg, [12, 16]),
+              lambda m, a: m(a['xyz'], a['feats'], a['nei'], a['nrm']), 32, False, seed=30)
+    run_layer("stridepe_strided", lambda L: L.PointConvStridePE(32, 64, cfg, [12, 16]),
+              lambda m, a: m(a['xyz'], a['feats'], a['nei'], a['nrm'], a['sxyz'], a['snrm']), 32, True, seed=40)
+    run_layer("pcf_self", lambda L: L.PCFLayer(64, 64, cfg, [12, 16], 8),
+              lambda m, a: m(a['xyz'], a['feats'], a['nei'], a['nrm']), 64, False, seed=50)
+    run_layer("pcf_strided", lambda L: L.PCFLayer(32, 64, cfg, [12, 16], 8),
+              lambda m, a: m(a['xyz'], a['feats'], a['nei'], a['nrm'], a['sxyz'], a['snrm']), 32, True, seed=60)
+    run_layer("transpose", lambda L: L.PointConvTransposePE(64, 32, cfg, [12, 1], [32, 32]),
+              lambda m, a: m(a['sxyz'], a['feats'], a['nei'], a['snrm'], a['xyz'], a['nrm'],
+                             torch.from_numpy(np.random.default_rng(7).standard_normal((1, 600, 32)).astype(np.float32))),
+              64, False, transpose=True, seed=70)
+    run_layer("transpose_mid3", lambda L: L.PointConvTransposePE(64, 32, cfg, [12, 3], [32, 32]),
+              lambda m, a: m(a['sxyz'], a['feats'], a['nei'], a['snrm'], a['xyz'], a['nrm']),
+              64, False, transpose=True, seed=80)
+
+
+SMALL_MODEL_CFG = dict(
+    USE_VI=True, USE_PE=True, BATCH_NORM=True, USE_CUDA_KERNEL=False, PCONV_OPT=False, USE_XYZ=True,
+    drop_path_rate=0., dropout_rate=0., dropout_fc=0., attention_type='subtraction', layer_norm_guidance=False,
+    transformer_type='PCF', point_dim=3, num_level=5, base_dim=16, feat_dim=[16, 32, 48, 64, 96],
+    mid_dim=[16, 16, 16, 16, 16], mid_dim_back=1, guided_level=0, num_heads=4, resblocks=[0, 1, 2, 1, 1],
+    resblocks_back=[0, 0, 0, 0, 0], use_level_1=True, num_classes=20,
+    K_self=[16] * 5, K_forward=[16] * 5, K_propagate=[16] * 5, grid_size=[0.1, 0.2, 0.4, 0.8, 1.6])
+
+
+def small_pyramid(seed=100):
+    """Two packed scenes, pyramid built with the oracle's (reference-pinned) grid subsampling."""
+    pcs, nrms, stored = None, None, None
+    per_scene = []
+    for s in range(2):
+        p, n = surface_cloud(2600 + 700 * s, seed + s, extent=(6.0 + s, 5.0, 2.5))
+        keep = np.unique(np.floor(p / 0.1).astype(np.int64), axis=0, return_index=True)[1]
+        keep.sort()
+        per_scene.append(ogs.subsample(p[keep], n[keep], SMALL_MODEL_CFG['grid_size']))
+    L = 5
+    pcs = [np.concatenate([per_scene[s][0][l] for s in range(2)])[None] for l in range(L)]
+    nrms = [np.concatenate([per_scene[s][1][l] for s in range(2)])[None] for l in range(L)]
+    stored = [[per_scene[s][0][l].shape[0] for s in range(2)] for l in range(L)]
+    return pcs, nrms, stored
+
+
+def make_model():
+    _, _, MA = ref_shim.load()
+    cfg = ref_shim.EasyDict(SMALL_MODEL_CFG)
+    cfg = MA.get_default_configs(cfg, cfg.num_level, cfg.base_dim)
+    torch.manual_seed(200)
+    model = MA.PointConvFormer_Segmentation(cfg)
+    randomize_bn(model, 201)
+    pcs, nrms, stored = small_pyramid()
+    es, ef, ep = oknn.compute_knn_packed(pcs, stored, cfg.K_self, cfg.K_forward, cfg.K_propagate)
+    rng = np.random.default_rng(202)
+    feats = rng.random((1, pcs[0].shape[1], 3)).astype(np.float32)
+    target = rng.integers(0, 20, pcs[0].shape[1])
+    tt = lambda lst: [t(x) for x in lst]
+    model.train()
+    logits = model(t(feats), tt(pcs), tt(es), tt(ef), tt(ep), tt(nrms))
+    loss = torch.nn.functional.cross_entropy(logits[0], t(target), label_smoothing=0.2)
+    loss.backward()
+    out = dict(feats=feats, target=target, logits_train=logits.detach().numpy(), loss=np.float32(loss.item()),
+               stored=np.asarray(stored))
+    for l in range(5):
+        out["pc%d" % l] = pcs[l]
+        out["nrm%d" % l] = nrms[l]
+        out["es%d" % l] = es[l]
+    for l in range(4):
+        out["ef%d" % l] = ef[l]
+        out["ep%d" % l] = ep[l]
+    gn = {k: p.grad for k, p in model.named_parameters()}
+    # gradients: keep full tensors for a representative subset, norms for all
+    out["grad_names"] = np.array(sorted(gn.keys()))
+    out["grad_norms"] = np.array([float(gn[k].norm()) for k in sorted(gn.keys())], np.float32)
+    for k in ["pcf_backbone.selfpointconv.linear.c.weight", "pcf_backbone.selfpointconv_res1.linear.c.weight",
+              "pcf_backbone.pointconv.0.linear.c.weight", "pcf_backbone.pointconv_res.1.1.guidance_weight.mlp.0.c.weight",
+              "pcf_backbone.pointconv_res.3.0.weightnet.mlp_convs.0.c.weight", "pointdeconv.3.linear.c.weight",
+              "pointdeconv.0.weightnet.mlp_convs.2.c.weight", "fc2.weight"]:
+        out["grad." + k] = gn[k].numpy()
+    model.eval()
+    with torch.no_grad():
+        out["logits_eval"] = model(t(feats), tt(pcs), tt(es), tt(ef), tt(ep), tt(nrms)).numpy()
+    for k, v in model.state_dict().items():
+        out["param." + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "model_small.npz"), **out)
+    print("model_small: N per level", [p.shape[1] for p in pcs], "loss", loss.item(),
+          "params", sum(p.numel() for p in model.parameters()))
+
+
+def make_inverse():
+    """Executes the reference's own create_inverse_python (test_kernels.py:177-213); the file cannot be
+    imported (pcf_cuda / pykeops / matplotlib at import time) so the function source is extracted
+    with ast and exec'ed with .cuda() patched to a no-op."""
+    path = os.path.join(REF, "cpp_wrappers/cpp_pcf_kernel/test_kernels.py")
+    src = open(path).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "create_inverse_python"][0]
+    ns = {"np": np, "torch": torch}
+    exec(compile(ast.Module([fn], []), path, "exec"), ns)
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        xyz, _ = surface_cloud(700, 300)
+        out = {}
+        for tag, (ref, qry, K) in {"self": (xyz, xyz, 16), "fwd": (xyz, xyz[::4] + 0.01, 16),
+                                  "prop": (xyz[::4] + 0.01, xyz, 8)}.items():
+            nei = oknn.knn_numpy(ref, qry, K)
+            total = ref.shape[0] if tag != "prop" else xyz.shape[0]      # propagate: padded total (common_util.py:303-306)
+            n, k, idx = ns["create_inverse_python"](nei, total)
+            out.update({tag + "_nei": nei, tag + "_total": np.int64(total), tag + "_inv_neighbors": n.numpy(),
+                        tag + "_inv_k": k.numpy(), tag + "_inv_idx": idx.numpy()})
+    finally:
+        torch.Tensor.cuda = orig
+    np.savez_compressed(os.path.join(HERE, "inverse.npz"), **out)
+    print("inverse: ok")
+
+
+def make_grid_subsample():
+    assert ogs.reference_available(), "run `make -C oracle ref` first"
+    out = {}
+    for i, (n, dl, seed) in enumerate([(5000, 0.2, 400), (5000, 0.4, 401), (900, 1.6, 402)]):
+        p, nrm = surface_cloud(n, seed, extent=(7.3, 5.1, 2.6))
+        p -= np.array([1.7, -0.4, 0.3], np.float32)          # negative coordinates exercise floor()
+        rp, rf = ogs.grid_subsample_reference(p, nrm, dl)
+        o = np.lexsort(rp.T[::-1])
+        out.update({"in_p%d" % i: p, "in_f%d" % i: nrm, "dl%d" % i: np.float32(dl), "out_p%d" % i: rp[o], "out_f%d" % i: rf[o]})
+    np.savez_compressed(os.path.join(HERE, "grid_subsample.npz"), **out)
+    print("grid_subsample: ok")
+
+
+def make_pconv_linear():
+    torch.manual_seed(42)
+    B, M, Nout, K, C_in, C_add, C_mid, C_out = 2, 512, 256, 16, 8, 4, 8, 16
+    inp = torch.rand(B, M, C_in)
+    nei = torch.randint(0, M, (B, Nout, K), dtype=torch.int64)
+    add = torch.rand(B, Nout, K, C_add)
+    w = torch.rand(B, Nout, K, C_mid)
+    lw = torch.rand(C_out, (C_in + C_add) * C_mid)
+    lb = torch.rand(C_out)
+    for x in (inp, add, w, lw, lb):
+        x.requires_grad_()
+    _, LU, _ = ref_shim.load()
+    g = torch.cat([LU.index_points(inp, nei), add], dim=-1)
+    pc = torch.matmul(g.permute(0, 1, 3, 2), w).view(B, Nout, -1)         # layers.py:713-716
+    out = torch.nn.functional.linear(pc, lw, lb)
+    go = torch.rand(out.shape)
+    (out * go).sum().backward()
+    np.savez_compressed(os.path.join(HERE, "pconv_linear_seed42.npz"), input=inp.detach().numpy(), nei=nei.numpy(),
+                        additional=add.detach().numpy(), weights=w.detach().numpy(), lin_w=lw.detach().numpy(),
+                        lin_b=lb.detach().numpy(), out=out.detach().numpy(), pconv_out=pc.detach().numpy(), grad_out=go.numpy(),
+                        g_input=inp.grad.numpy(), g_additional=add.grad.numpy(), g_weights=w.grad.numpy(),
+                        g_lin_w=lw.grad.numpy(), g_lin_b=lb.grad.numpy())
+    print("pconv_linear_seed42: ok")
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    make_pconv_linear()
+    make_inverse()
+    make_grid_subsample()
+    make_layers()
+    make_model()
