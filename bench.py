@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the PointConvFormer hot path on B200 (contract: see the task's bench.py section).
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): one PCF_Normal
+`configPCF_Opt_10cm` TRAINING STEP per GPU on a synthetic ScanNet-shaped scene of ~100k level-0 points:
+    compute_knn_packed + prepare (13 edge sets) -> compute_knn_inverse (13 inverse maps) -> model forward ->
+    cross-entropy (label_smoothing 0.2) -> backward -> [DDP gradient all-reduce] -> grad-clip -> AdamW step
+which is the reference's hot loop (train_ScanNet_DDP_WarmUP.py:379-427).  metric = level-0 points / s,
+whole job.  `value` is measured with the pyramid resident in HBM; `e2e` includes, every step, the H2D copy
+of the pyramid (points, normals, colours, labels) from pinned host memory and the D2H read of the loss.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points P]
+
+--impl reference times the CPU path (oracle port of the reference's PyTorch path + C kNN) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "points_per_sec_fwd_bwd_PCF_Normal_10cm"
+UNIT = "points/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=100000, help="level-0 points per scene")
+    ap.add_argument("--scenes", type=int, default=1, help="scenes per GPU (packed)")
+    ap.add_argument("--cpu-points", type=int, default=6000, help="level-0 points of the bounded CPU sample")
+    ap.add_argument("--no-sync-bn", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--variant", type=int, default=0, help="fused forward variant (0 auto, 1 SIMT, 2 tcgen05)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic workload (host side)
+# ---------------------------------------------------------------------------------------------------
+def host_pyramid(seed, n_points, grid_size, n_scenes=1):
+    """Level-0 clouds from the synthetic room generator; coarser levels by the oracle-free numpy voxel
+    barycentre below (host data preparation, like the reference's DataLoader workers)."""
+    from pcf_b200 import synthetic
+    pts, nrm, col, lab = [[] for _ in grid_size], [[] for _ in grid_size], [], []
+    stored = [[] for _ in grid_size]
+    rng = np.random.default_rng(seed + 999)
+    for s in range(n_scenes):
+        xyz, n, c = synthetic.make_scene(seed * 100 + s, n_points, voxel=grid_size[0])
+        p_l, n_l = xyz, n
+        for l, g in enumerate(grid_size):
+            if l > 0:
+                p_l, n_l = voxel_barycentre(p_l, n_l, g)
+            pts[l].append(p_l); nrm[l].append(n_l); stored[l].append(len(p_l))
+        col.append(c)
+        lab.append(rng.integers(0, 20, len(xyz)))
+    cat = lambda lst: np.ascontiguousarray(np.concatenate(lst))
+    return dict(points=[cat(p) for p in pts], normals=[cat(n) for n in nrm], colors=cat(col),
+                labels=cat(lab).astype(np.int64), stored=stored)
+
+
+def voxel_barycentre(p, f, dl):
+    key = np.floor((p - p.min(0)) / np.float32(dl)).astype(np.int64)
+    mx = key.max(0) + 1
+    flat = (key[:, 2] * mx[1] + key[:, 1]) * mx[0] + key[:, 0]
+    order = np.argsort(flat, kind="stable")
+    uniq, start, cnt = np.unique(flat[order], return_index=True, return_counts=True)
+    sp = np.add.reduceat(p[order], start) / cnt[:, None]
+    sf = np.add.reduceat(f[order], start) / cnt[:, None]
+    return sp.astype(np.float32), sf.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvml)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_sm = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:  # nvml unavailable: report that instead of failing the bench
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import pcf_b200  # noqa: F401
+    from pcf_b200 import _lib, pcf_cuda, configs, sharding
+    from pcf_b200 import model_architecture as MA, knn_post_dataloader_utils as KU, common_util as CU
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pcf_cuda.FORWARD_VARIANT = args.variant
+
+    cfgd = configs.CONFIG_PCF_OPT_10CM
+    cfg = configs.make_cfg(cfgd)
+    torch.manual_seed(1)                                            # same init on every rank (DDP broadcast equivalent)
+    model = MA.PointConvFormer_Segmentation(cfg).to(dev)
+    sync_bn = world > 1 and cfgd["sync_bn"] and not args.no_sync_bn
+    if sync_bn:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=cfgd["adamw_decay"], fused=True)
+    params = [p for p in model.parameters()]
+
+    host = host_pyramid(1 + rank, args.points, cfgd["grid_size"], args.scenes)
+    L = cfgd["num_level"]
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_pts = [pin(p) for p in host["points"]]
+    h_nrm = [pin(p) for p in host["normals"]]
+    h_col, h_lab = pin(host["colors"]), pin(host["labels"])
+    stored = host["stored"]
+    n0 = h_pts[0].shape[0]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in h_pts + h_nrm + [h_col, h_lab])
+
+    def upload():
+        pts = [t.to(dev, non_blocking=True) for t in h_pts]
+        nrm = [t.to(dev, non_blocking=True) for t in h_nrm]
+        return pts, nrm, h_col.to(dev, non_blocking=True), h_lab.to(dev, non_blocking=True)
+
+    def step(pts, nrm, col, lab):
+        pcs = [p.unsqueeze(0) for p in pts]
+        nrms = [p.unsqueeze(0) for p in nrm]
+        es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, stored, cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"]))
+        inv_s, inv_f, inv_p = CU.compute_knn_inverse(pcs, es, ef, ep)
+        logits = model(col.unsqueeze(0), pcs, es, ef, ep, nrms, inv_s, inv_f, inv_p)
+        loss = torch.nn.functional.cross_entropy(logits[0], lab, ignore_index=cfgd["ignore_label"],
+                                                 label_smoothing=cfgd["label_smoothing"])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            sharding.allreduce_gradients(params, world)
+        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        opt.step()
+        return loss
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+
+    def timed(e2e, steps):
+        """-> total ms over `steps` steps (sum of per-step CUDA-event times on the launching stream)."""
+        evs = []
+        resident = upload()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for _ in range(steps):
+            flush.zero_()                                                # L2 flush, outside the timed span
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if e2e:
+                loss = step(*upload())
+                _ = loss.item()                                          # D2H read of the step's result
+            else:
+                loss = step(*resident)
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    timed(False, args.warmup)                                            # W untimed warm-up steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ms_dev = timed(False, args.steps)
+    launches = _lib.launch_count() - l0
+    ms_e2e = timed(True, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms_dev, ms_e2e = max_over_ranks(ms_dev), max_over_ranks(ms_e2e)
+    total_points = sum_over_ranks(float(n0))
+    total_scenes = world * args.scenes
+    value = total_points * args.steps / (ms_dev / 1e3)
+    e2e_value = total_points * args.steps / (ms_e2e / 1e3)
+
+    roof, extra = (None, {})
+    if rank == 0:
+        roof, extra = kernel_rooflines(dev, host, cfgd, args)
+    out = None
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step (kNN x13 + inverse maps x13 + fwd + CE + bwd "
+                                   "+ grad-clip + AdamW), %d synthetic scene(s) of ~%d level-0 points per GPU, K=16" % (args.scenes, args.points),
+                       "points_per_gpu": int(n0), "levels": [int(t.shape[0]) for t in h_pts], "parallelism": "dp%d" % world,
+                       "sync_bn": bool(sync_bn), "forward_variant": {0: "auto(tcgen05)", 1: "simt_fp32", 2: "tcgen05"}[args.variant],
+                       "l2": "256 MiB buffer written between timed steps; per-step working set >> 126 MB L2"},
+            "scenes_per_s": total_scenes * args.steps / (ms_dev / 1e3),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.result(),
+            "roofline": roof,
+        }
+        out.update(extra)
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def kernel_rooflines(dev, host, cfgd, args):
+    """Live CUDA-event timing of the hot kernels on this rank's data (each timed alone, L2 flushed before every
+    launch): the fused forward at the level-0 StridePE shape (HBM-bound, reported as `roofline`), plus kNN,
+    the fused backward and the inverse map as extra entries."""
+    from pcf_b200 import pcf_cuda
+    peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = dict(json.load(open(pk)), src="measured")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def time_op(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    xyz = torch.from_numpy(host["points"][0]).to(dev)
+    n = xyz.shape[0]
+    counts = host["stored"][0]
+    K, C_in, C_add, C_mid, C_out = 16, 16, 16, 16, 32
+    g = torch.Generator(device="cpu").manual_seed(0)
+    nei = pcf_cuda.knn_packed(xyz, counts, xyz, counts, K)
+    feats = torch.randn(1, n, C_in, generator=g).to(dev)
+    w = torch.rand(1, n, K, C_mid, generator=g).to(dev)
+    add = torch.rand(1, n, K, C_add, generator=g).to(dev)
+    W = (torch.randn(C_out, (C_in + C_add) * C_mid, generator=g) * 0.05).to(dev)
+    b = torch.randn(C_out, generator=g).to(dev)
+    go = torch.randn(1, n, C_out, generator=g).to(dev)
+    inv = pcf_cuda.compute_knn_inverse(nei[None], n)
+    KK = (C_in + C_add) * C_mid
+
+    res = {}
+    fwd_bytes_pt = 8 * K + 4 * C_in + 4 * K * C_mid + 4 * K * C_add + 4 * C_out
+    for name, variant, save_p in (("fused_fwd", args.variant if args.variant else 2, False), ("fused_fwd_saveP", args.variant if args.variant else 2, True),
+                                  ("fused_fwd_simt", 1, False)):
+        try:
+            ms = time_op(lambda: pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, None, W, b, want_p=save_p, variant=variant))
+        except RuntimeError as e:
+            res[name] = {"error": str(e)[:80]}
+            continue
+        byts = n * (fwd_bytes_pt + (4 * KK if save_p else 0))
+        flops = n * (2 * K * (C_in + C_add) * C_mid + 2 * KK * C_out)
+        res[name] = {"ms": ms, "alg_bytes": byts, "GBps": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"],
+                     "TFLOPs": flops / ms / 1e9}
+    y, p = pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, None, W, b, want_p=True)
+    ms = time_op(lambda: pcf_cuda.pconv_fused_backward(go, None, feats, inv, nei[None], w, add, None, W, p, (True,) * 6))
+    bwd_bytes = n * (8 * K + 4 * C_out + 4 * C_in + 2 * 4 * K * C_mid + 2 * 4 * K * C_add + 5 * K + 4 + 4 * C_in + 4 * KK)
+    res["fused_bwd"] = {"ms": ms, "alg_bytes": bwd_bytes, "GBps": bwd_bytes / ms / 1e6, "frac_hbm": bwd_bytes / ms / 1e6 / peaks["hbm_gbs"]}
+    ms = time_op(lambda: pcf_cuda.knn_packed(xyz, counts, xyz, counts, K))
+    pairs = float(sum(c * c for c in counts))
+    res["knn_self_level0"] = {"ms": ms, "Mqueries_per_s": n / ms / 1e3, "Gpairs_per_s": pairs / ms / 1e6,
+                              "alg_bytes": n * (24 + 8 * K), "GBps": n * (24 + 8 * K) / ms / 1e6,
+                              "frac_fp32_issue": pairs * 9 / ms / 1e3 / (148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6) }
+    ms = time_op(lambda: pcf_cuda.compute_knn_inverse(nei[None], n))
+    inv_bytes = n * K * (8 + 4 + 1) + 4 * (n + 1)
+    res["knn_inverse_level0"] = {"ms": ms, "alg_bytes": inv_bytes, "GBps": inv_bytes / ms / 1e6, "frac_hbm": inv_bytes / ms / 1e6 / peaks["hbm_gbs"]}
+
+    key = "fused_fwd_saveP" if "ms" in res.get("fused_fwd_saveP", {}) else "fused_fwd_simt"
+    r = res[key]
+    roof = {"kernel": "pconv_fwd_umma_kernel<16,16>" if key != "fused_fwd_simt" else "pconv_fwd_simt_kernel<16>",
+            "shape": "level-0 PointConvStridePE contraction: N=%d K=16 C_in=16 C_add=16 C_mid=16 C_out=32, P saved" % n,
+            "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["frac_hbm"],
+            "traffic": None, "peak_source": peaks["src"], "ms": r["ms"], "alg_bytes_per_launch": r["alg_bytes"]}
+    return roof, {"kernels": res, "knn_mpts_per_s": res["knn_self_level0"]["Mqueries_per_s"]}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's PyTorch path + C kNN, on a bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_step_factory(args):
+    import pcf_b200  # noqa: F401
+    from pcf_b200 import configs, model_architecture as MA
+    from oracle import knn as OK, inverse as OI, layers as OL
+    cfgd = configs.CONFIG_PCF_OPT_10CM
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    host = host_pyramid(1, args.cpu_points, cfgd["grid_size"], 1)
+    cfg = configs.make_cfg(dict(cfgd, PCONV_OPT=False, USE_CUDA_KERNEL=False))
+    torch.manual_seed(1)
+    params = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "num_batches" not in k)
+              for k, v in MA.PointConvFormer_Segmentation(cfg).state_dict().items()}
+    ocfg = dict(USE_VI=True, USE_PE=True, USE_XYZ=True, use_level_1=True, num_level=5, guided_level=0,
+                resblocks=cfgd["resblocks"], resblocks_back=cfgd["resblocks_back"])
+    pcs = [torch.from_numpy(p)[None] for p in host["points"]]
+    nrm = [torch.from_numpy(p)[None] for p in host["normals"]]
+    col, lab = torch.from_numpy(host["colors"])[None], torch.from_numpy(host["labels"])
+    leaves = [p for p in params.values() if p.requires_grad]
+    opt = torch.optim.AdamW(leaves, lr=1e-3, weight_decay=cfgd["adamw_decay"])
+
+    def step():
+        es, ef, ep = OK.compute_knn_packed([p.numpy() for p in pcs], host["stored"], cfgd["K_self"], cfgd["K_forward"],
+                                           cfgd["K_propagate"], use_c=True)
+        OI.compute_knn_inverse([p.numpy() for p in pcs], es, ef, ep)
+        t = lambda lst: [torch.from_numpy(x) for x in lst]
+        logits = OL.segmentation_model(params, ocfg, col, pcs, t(es), t(ef), t(ep), nrm, training=True)
+        loss = torch.nn.functional.cross_entropy(logits[0], lab, label_smoothing=0.2)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(leaves, 10.0)
+        opt.step()
+        return float(loss)
+
+    n0 = pcs[0].shape[1]
+    sample = ("1 synthetic scene of %d level-0 points (same generator, same PCF_Normal configPCF_Opt_10cm training step: C kNN x13 "
+              "+ inverse maps + torch-CPU fwd/bwd of the oracle port + AdamW); fp32, %d threads" % (n0, cores))
+    return step, n0, cores, sample
+
+
+def cpu_baseline(args, steps, warmup):
+    step, n0, cores, sample = cpu_step_factory(args)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": n0 * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "s_per_step": dt / steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return None
+    base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1))
+    return {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": base["s_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step on the host CPU (bounded sample)",
+                       "points_per_step": base["sample"]},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    args = parse()
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+/* pcf_b200.h -- C ABI of libpcf_b200.so: the B200 (sm_100a) hot path of PointConvFormer.
+ *
+ * Drop-in boundary for the reference's native extension `pcf_cuda`
+ * (/root/reference/cpp_wrappers/cpp_pcf_kernel/pcf_cuda.cpp:9-19, signatures include/pcf.h:38-250) and
+ * for the third-party kNN it calls (/root/reference/knn_post_dataloader_utils.py:22-41) and its CPU
+ * grid subsampling (/root/reference/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:9-110).
+ *
+ * Conventions (all entry points):
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless named h_*;
+ *   - the caller owns all memory (outputs and workspaces are caller-allocated); nothing is allocated,
+ *     freed or synchronised inside; all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - tensors are dense row-major ("contiguous"), batch dimension folded by the caller (B == 1 packed
+ *     representation, layers.py:216); indices are int64 like the reference's (datasetCommon.py:178-180);
+ *   - return value 0 = success, otherwise an error code; pcfb_last_error() gives the message of the
+ *     last failure on the calling thread.  The reference raises RuntimeError through TORCH_CHECK
+ *     (include/pcf.h:14-24); the Python host mirror re-raises RuntimeError from these codes;
+ *   - neighbour entries outside [0, n_in) (e.g. the -1 padding preserved by listToBatch,
+ *     knn_post_dataloader_utils.py:131-148) contribute zero / are skipped, as the reference's opt
+ *     kernels bounds-check (pconv_ops.cu:453,494; knn.cu:38,75).
+ *   - pconv_out / "P" channel layout is c*C_mid + j (layers.py:713-716, pconv_ops.cu:89-90); gradients
+ *     follow autograd through that layout (NOT the reference CUDA backward's mid*(C)+c indexing, which
+ *     is inconsistent with its own forward -- SURVEY.md trap T1).
+ */
+#ifndef PCF_B200_H
+#define PCF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    PCFB_OK = 0,
+    PCFB_ERR_ARG = 1,        /* bad shape / null pointer / unsupported size */
+    PCFB_ERR_CUDA = 2,       /* a CUDA runtime call failed (launch error etc.) */
+    PCFB_ERR_WORKSPACE = 3,  /* workspace too small */
+    PCFB_ERR_UNSUPPORTED = 4 /* shape not supported by the requested kernel variant */
+};
+
+const char *pcfb_last_error(void);
+/* ABI / build info: "pcf_b200 <abi> sm_100a" */
+const char *pcfb_version(void);
+/* Number of kernel launches enqueued by this library since load (for bench.py's gpu_launches). */
+uint64_t pcfb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * kNN on packed scenes.  Replaces knn_keops (knn_post_dataloader_utils.py:22-41) + the per-scene loop
+ * of compute_knn_packed (171-223) + the offsetting of listToBatch/prepare (113-167) for ONE edge set.
+ *
+ * ref_xyz [n_ref,3], qry_xyz [n_qry,3] fp32 packed over `n_seg` scenes; ref_off / qry_off are
+ * int32[n_seg+1] exclusive prefix sums of the per-scene counts.  For every query q of scene s:
+ *   out[q, 0..K) = ref_off[s] + the K references r of scene s with the smallest (d, r), ascending,
+ *   d = ((qx-rx)^2 + (qy-ry)^2) + (qz-rz)^2 evaluated in fp32 with no FMA contraction.
+ * If a scene has n < K references the n found neighbours are repeated cyclically (the reference draws
+ * random indices there, knn_post_dataloader_utils.py:58-66 -- not reproducible).
+ * 1 <= K <= 255 (inv_k is uint8 downstream, knn.cu:114).  Brute force, exact.
+ * ------------------------------------------------------------------------------------------- */
+int pcfb_knn_packed(const float *ref_xyz, const int32_t *ref_off, const float *qry_xyz,
+                    const int32_t *qry_off, int n_seg, int n_ref, int n_qry, int K,
+                    int64_t *out_idx, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * kNN inverse map (CSR transpose).  Replaces pcf_cuda.compute_knn_inverse
+ * (include/pcf.h:183-186 -> src/knn.cu:104-168).
+ * nei [n_out,K] int64; outputs inv_neighbors int32[n_out*K], inv_k uint8[n_out*K], inv_idx
+ * int32[total+1].  Segment p = [inv_idx[p], inv_idx[p+1]) lists the (n, k) with nei[n,k] == p in
+ * ascending (n, k) order (deterministic; the reference's order inside a segment is atomic-claim
+ * order).  Unused tail entries are zero.  Workspace: pcfb_knn_inverse_workspace(n_out, K, total).
+ * ------------------------------------------------------------------------------------------- */
+size_t pcfb_knn_inverse_workspace(int n_out, int K, int total);
+int pcfb_knn_inverse(const int64_t *nei, int n_out, int K, int total, int32_t *inv_neighbors,
+                     uint8_t *inv_k, int32_t *inv_idx, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Neighbour gather family (index_points, layer_utils.py:13-30, and the strided max-pool shortcut
+ * layers.py:403-408,728-733).
+ * ------------------------------------------------------------------------------------------- */
+/* out[m,k,:] = feats[nei[m,k],:]   feats [n_in,C] -> out [n_out,K,C] */
+int pcfb_gather(const float *feats, const int64_t *nei, int n_in, int n_out, int K, int C, float *out,
+                void *stream);
+/* grad_feats[p,:] = sum over (n,k) in inverse segment p of grad_out[n,k,:]   (no atomics) */
+int pcfb_gather_backward(const float *grad_out, const int32_t *inv_neighbors, const uint8_t *inv_k,
+                         const int32_t *inv_idx, int n_in, int n_out, int K, int C, float *grad_feats,
+                         void *stream);
+/* out[m,c] = max_k feats[nei[m,k],c]; arg[m,c] = the k attaining it (first on ties) */
+int pcfb_gather_max(const float *feats, const int64_t *nei, int n_in, int n_out, int K, int C, float *out,
+                    uint8_t *arg, void *stream);
+int pcfb_gather_max_backward(const float *grad_out, const uint8_t *arg, const int32_t *inv_neighbors,
+                             const uint8_t *inv_k, const int32_t *inv_idx, int n_in, int n_out, int K,
+                             int C, float *grad_feats, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Edge geometry: localized xyz and the 12-d viewpoint-invariant features
+ * (VI_coordinate_transform, layer_utils.py:176-231; prologue layers.py:337-353,660-682,846-863,1024-1037).
+ * xyz_in/nrm_in [n_in,3] are the gathered cloud, xyz_out/nrm_out [n_out,3] the centres.
+ * out_r [n_out,K,3] (may be NULL), out_vi [n_out,K,12] (may be NULL; needs the normals).
+ * ------------------------------------------------------------------------------------------- */
+int pcfb_edge_geometry(const float *xyz_in, const float *nrm_in, const float *xyz_out, const float *nrm_out,
+                       const int64_t *nei, int n_in, int n_out, int K, float *out_r, float *out_vi,
+                       void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused PointConv / PointConvFormer contraction (+ Linear).
+ *   G[m,k,c]  = c <  C_in : feats[nei[m,k],c] * (guidance ? guidance[m,k,c % H] : 1)
+ *               c >= C_in : additional[m,k,c-C_in]
+ *   P[m,c*C_mid+j] = sum_k G[m,k,c] * weights[m,k,j]                       (C_cat = C_in + C_add)
+ *   Y[m,o]   = sum_kk P[m,kk] * lin_w[o,kk] + lin_b[o]
+ * Replaces pconv_linear_cutlass_forward (pcf.h:243-250 -> pconv_ops.cu:969-1269), pconv_linear_forward
+ * (pcf.h:131-138), pconv_forward (pcf.h:81-86; lin_w == NULL -> only P) and pcf_forward (pcf.h:38-43;
+ * guidance != NULL).  out_y [n_out,C_out] (NULL iff lin_w NULL), out_p [n_out,C_cat*C_mid] (may be NULL
+ * when lin_w given).  `variant`: 0 = auto, 1 = exact fp32 SIMT, 2 = tcgen05 (3xTF32 split Linear).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n_in, n_out, K, C_in, C_add, C_mid, C_out, H; /* H = guidance heads (0 if none) */
+} pcfb_pconv_shape;
+
+size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int variant);
+int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei,
+                       const float *weights, const float *additional, const float *guidance,
+                       const float *lin_w, const float *lin_b, float *out_y, float *out_p,
+                       void *workspace, size_t workspace_bytes, int variant, void *stream);
+
+/* Backward of the above (autograd semantics).  Replaces pconv_linear_opt_backward (pcf.h:213-224 ->
+ * pconv_ops.cu:863-948), pconv_linear_backward, pconv_backward, pcf_backward (pcf.h:60-66).
+ * grad_y [n_out,C_out] when lin_w != NULL, else grad_p [n_out,C_cat*C_mid] is the incoming gradient.
+ * pconv_out: the P saved by the forward (the reference saves it, layer_utils.py:52-54); may be NULL,
+ * then P is recomputed into the workspace when grad_lin_w / grad_lin_b are requested.
+ * Outputs (any may be NULL to skip): grad_feats [n_in,C_in] (needs the inverse map; summed per input
+ * point over its inverse segment, no atomics), grad_weights [n_out,K,C_mid], grad_additional
+ * [n_out,K,C_add], grad_guidance [n_out,K,H], grad_lin_w [C_out,C_cat*C_mid], grad_lin_b [C_out].
+ * ------------------------------------------------------------------------------------------- */
+size_t pcfb_pconv_backward_workspace(const pcfb_pconv_shape *s, int variant);
+int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_y, const float *grad_p,
+                        const float *feats, const int64_t *nei, const int32_t *inv_neighbors,
+                        const uint8_t *inv_k, const int32_t *inv_idx, const float *weights,
+                        const float *additional, const float *guidance, const float *lin_w,
+                        const float *pconv_out, float *grad_feats, float *grad_weights, float *grad_additional,
+                        float *grad_guidance, float *grad_lin_w, float *grad_lin_b, void *workspace,
+                        size_t workspace_bytes, int variant, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid (voxel) subsampling with barycentres on packed scenes.  Replaces grid_subsampling()
+ * (grid_subsampling.cpp:9-110) as called per level by subsample() (datasetCommon.py:384-420).
+ * Three phases because the grid extent and the output size are data dependent (the host reads two
+ * small arrays in between):
+ *   pcfb_gridsub_bounds : per scene, origin = floor(min*(1/dl))*dl (float[n_seg*3]) and grid dims
+ *                         N = floor((max-origin)/dl)+1 (int32[n_seg*3]), the reference's fp32
+ *                         arithmetic (grid_subsampling.cpp:28-36).  workspace >= n_seg*24 bytes.
+ *   pcfb_gridsub_count  : bins every point into the dense cell cell_off[s] + iX + NX*iY + NX*NY*iZ
+ *                         (cell_off int32[n_seg+1] = host prefix sum of NX*NY*NZ, total_cells its
+ *                         last entry), builds the cell->points CSR and writes the number of occupied
+ *                         cells per scene to out_counts int32[n_seg].
+ *   pcfb_gridsub_emit   : writes barycentres (sum * float(1.0/count)) and feature means (sum/count)
+ *                         in ascending (scene, voxel key) order; sums accumulate sequentially in
+ *                         input order, so results are bit-identical to the reference's running
+ *                         sums (its own output ORDER is unordered_map iteration order, which is not
+ *                         reproducible; ascending key is the canonical order here).
+ * count and emit share the same workspace (pcfb_gridsub_workspace) which must stay untouched between.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcfb_gridsub_workspace(int n_seg, int n_pts, int64_t total_cells);
+int pcfb_gridsub_bounds(const float *xyz, const int32_t *seg_off, int n_seg, int n_pts, float dl,
+                        float *out_origin, int32_t *out_dims, void *workspace, size_t workspace_bytes,
+                        void *stream);
+int pcfb_gridsub_count(const float *xyz, const int32_t *seg_off, int n_seg, int n_pts, float dl,
+                       const float *origin, const int32_t *dims, const int32_t *cell_off,
+                       int64_t total_cells, int32_t *out_counts, void *workspace, size_t workspace_bytes,
+                       void *stream);
+int pcfb_gridsub_emit(const float *xyz, const float *feats, int n_seg, int n_pts, int F,
+                      int64_t total_cells, float *out_xyz, float *out_feats, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hardware self-test of the tcgen05 (UMMA) operand / accumulator conventions used by the fused
+ * forward: D = A[M x K] * B[N x K]^T on one CTA (M in {64,128}, N % 8 == 0, K % 8 == 0, K <= 64).
+ * h_params is a HOST array of 11 uint32: fill (lbo_a, sbo_a, lbo_b, sbo_b) = where element (r,k) is
+ * written, byte offset (k/4)*lbo + (r/8)*sbo + (r%8)*16 + (k%4)*4; desc (lbo_a, sbo_a, lbo_b, sbo_b) =
+ * what the shared-memory descriptors claim; (kstep_a, kstep_b) = start-address advance per K=8 step;
+ * idesc.  raw receives the accumulator as stored in TMEM: [128 lanes][N columns].  status (device
+ * int) is set to 1 if the MMA never completed.  No reference counterpart (test infrastructure of
+ * the product kernel, exercised by tests/test_umma_selftest.py).
+ * ------------------------------------------------------------------------------------------- */
+int pcfb_selftest_umma(const float *A, const float *B, float *raw, int M, int N, int K,
+                       const uint32_t *h_params, uint64_t desc_or, int split, int *status, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCF_B200_H */

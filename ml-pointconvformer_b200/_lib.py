@@ -1,0 +1,98 @@
+"""ctypes binding of libpcf_b200.so (the C ABI declared in include/pcf_b200.h).
+
+This is the only place the shared library is touched.  There is NO fallback: if the library is
+missing, or a tensor is not a contiguous CUDA tensor, the call raises (the reference raises
+RuntimeError through TORCH_CHECK, cpp_wrappers/cpp_pcf_kernel/include/pcf.h:14-24).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcf_b200.so")
+
+c_void_p, c_int, c_size_t, c_float, c_int64, c_uint64 = (ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t,
+                                                         ctypes.c_float, ctypes.c_int64, ctypes.c_uint64)
+
+
+class PconvShape(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("n_in", "n_out", "K", "C_in", "C_add", "C_mid", "C_out", "H")]
+
+
+_P = c_void_p
+# name -> (restype, argtypes); mirrors include/pcf_b200.h one to one
+SIGNATURES = {
+    "pcfb_last_error": (ctypes.c_char_p, []),
+    "pcfb_version": (ctypes.c_char_p, []),
+    "pcfb_launch_count": (c_uint64, []),
+    "pcfb_knn_packed": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pcfb_knn_inverse_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "pcfb_knn_inverse": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "pcfb_gather": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pcfb_gather_backward": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pcfb_gather_max": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
+    "pcfb_gather_max_backward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pcfb_edge_geometry": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "pcfb_pconv_forward_workspace": (c_size_t, [ctypes.POINTER(PconvShape), c_int]),
+    "pcfb_pconv_forward": (c_int, [ctypes.POINTER(PconvShape), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
+    "pcfb_pconv_backward_workspace": (c_size_t, [ctypes.POINTER(PconvShape), c_int]),
+    "pcfb_pconv_backward": (c_int, [ctypes.POINTER(PconvShape)] + [_P] * 19 + [c_size_t, c_int, _P]),
+    "pcfb_gridsub_workspace": (c_size_t, [c_int, c_int, c_int64]),
+    "pcfb_gridsub_bounds": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
+    "pcfb_gridsub_count": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "pcfb_gridsub_emit": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P, _P, _P, c_size_t, _P]),
+    "pcfb_selftest_umma": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, c_uint64, c_int, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(or make -C ml-pointconvformer_b200/csrc).  There is no CPU fallback." % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().pcfb_last_error().decode("utf-8", "replace")
+        raise RuntimeError("pcf_b200 %s failed (code %d): %s" % (what, rc, msg))
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def require(t, dtype, name):
+    """The reference's CHECK_INPUT (pcf.h:22-24): CUDA + contiguous, plus the dtype."""
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError("%s must be a tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (pcf_b200 has no CPU path)" % name)
+    if not t.is_contiguous():
+        raise RuntimeError("%s must be contiguous" % name)
+    if t.dtype != dtype:
+        raise RuntimeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def launch_count():
+    return int(lib().pcfb_launch_count())

@@ -1,0 +1,349 @@
+"""PointConv / PointConvFormer layer modules with the reference's constructor and forward signatures
+(/root/reference/layers.py): PointConv (744-906), PointConvStridePE (542-741), PCFLayer (194-416),
+PointConvTransposePE (909-1105), WeightNet (127-191), MultiHeadGuidance (23-68).  Parameter / sub-module
+names are the reference's (both PCONV_OPT spellings), so its checkpoints load.
+
+What differs is where the work happens: the gathers of xyz / normals, the localisation and the 12-d VI
+transform are one kernel (layer_utils.edge_geometry); gather -> (guidance) -> K-contraction -> Linear is
+one kernel (layer_utils.FusedPConvFunction, tcgen05 on B200) whose backward scatters through the kNN
+inverse map without atomics; the strided shortcut is a fused max-gather.  The switches keep their
+meaning: cfg.USE_CUDA_KERNEL selects the fused contraction, cfg.PCONV_OPT additionally fuses the
+Linear and changes the parameter spelling.  With USE_CUDA_KERNEL False the contraction is the
+reference's unfused formulation (gather kernel + batched matmul).  CUDA tensors only.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+from .layer_utils import (FusedPConvFunction, PConvLinearOpt, Linear_BN, UnaryBlock, edge_geometry, gather_max,
+                          index_points, resolve_inverse)
+
+
+def _drop_path(cfg):
+    rate = getattr(cfg, "drop_path_rate", 0.)
+    if rate > 0.:
+        try:
+            from timm.models.layers import DropPath
+            return DropPath(rate)
+        except ImportError:
+            return _DropPath(rate)
+    return nn.Identity()
+
+
+class _DropPath(nn.Module):
+    """Stochastic depth per sample (timm.models.layers.DropPath semantics; timm is optional here)."""
+
+    def __init__(self, p):
+        super().__init__()
+        self.p = p
+
+    def forward(self, x):
+        if not self.training or self.p == 0.:
+            return x
+        keep = 1 - self.p
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask / keep
+
+
+def _inv_tuple(nei_inds, n_in, inv_neighbors, inv_k, inv_idx, needed):
+    if not needed:
+        return None
+    return resolve_inverse(nei_inds, n_in, inv_neighbors, inv_k, inv_idx)
+
+
+def _contract(cfg, feats, nei_inds, inv, weights, additional, guidance, lin_w, lin_b):
+    """gather -> (x guidance) -> concat additional -> sum_k (.) w -> (Linear).  Fused kernel when
+    cfg.USE_CUDA_KERNEL, else the reference's unfused torch formulation on our gather."""
+    if cfg.USE_CUDA_KERNEL:
+        return FusedPConvFunction.apply(feats.contiguous(), nei_inds, inv, weights.contiguous(),
+                                        None if additional is None else additional.contiguous(),
+                                        None if guidance is None else guidance.contiguous(), lin_w, lin_b)
+    g = index_points(feats, nei_inds, inv)
+    if guidance is not None:
+        g = g * guidance.repeat(1, 1, 1, g.shape[-1] // guidance.shape[-1])
+    if additional is not None:
+        g = torch.cat([g, additional], dim=-1)
+    p = torch.matmul(g.permute(0, 1, 3, 2), weights).reshape(g.shape[0], g.shape[1], -1)
+    return p if lin_w is None else F.linear(p, lin_w, lin_b)
+
+
+class MultiHeadGuidance(nn.Module):
+    """sigmoid(MLP_{dim -> 8 -> heads}(query - key)) (layers.py:23-68; sigmoid, not softmax: SURVEY D1)."""
+
+    def __init__(self, cfg, num_heads, num_hiddens):
+        super().__init__()
+        self.cfg, self.dim, self.num_heads = cfg, num_hiddens, num_heads
+        self.layer_norm_q = nn.LayerNorm(num_hiddens) if cfg.layer_norm_guidance else nn.Identity()
+        self.layer_norm_k = nn.LayerNorm(num_hiddens) if cfg.layer_norm_guidance else nn.Identity()
+        self.mlp = nn.ModuleList()
+        self.mlp_bns = nn.ModuleList()
+        dims = [num_hiddens, 8, num_heads]
+        for cin, cout in zip(dims[:-1], dims[1:]):
+            self.mlp.append(Linear_BN(cin, cout) if cfg.BATCH_NORM else nn.Linear(cin, cout))
+
+    def forward(self, guidance_query, guidance_key):
+        s = self.layer_norm_q(guidance_query) - self.layer_norm_k(guidance_key)
+        last = len(self.mlp) - 1
+        for i, layer in enumerate(self.mlp):
+            s = layer(s)
+            s = torch.sigmoid(s) if i == last else F.relu(s)
+        return s
+
+
+class MultiHeadGuidanceQK(nn.Module):
+    """QK-style guidance with sigmoid activation (layers.py:77-114)."""
+
+    def __init__(self, cfg, num_heads, num_hiddens, key_dim):
+        super().__init__()
+        assert num_hiddens % num_heads == 0
+        self.cfg, self.dim, self.num_heads, self.key_dim = cfg, num_hiddens, num_heads, key_dim
+        self.scale = key_dim ** -0.5
+        self.qk_linear = Linear_BN(num_hiddens, key_dim * num_heads)
+
+    def forward(self, q, k):
+        B, N, K, _ = q.shape
+        qh = self.qk_linear(q).view(B, N, K, self.num_heads, -1)
+        kh = self.qk_linear(k).view(B, N, K, self.num_heads, -1)[:, :, :1]
+        return torch.sigmoid((qh * kh).sum(-1) * self.scale)
+
+
+class WeightNet(nn.Module):
+    """Per-edge MLP in -> hidden... -> out with ReLU after every Linear_BN, the last included
+    (layers.py:127-171).  `efficient` (gradient checkpointing, 173-191) is accepted and ignored: it only
+    trades memory for recompute and the maths is identical."""
+
+    def __init__(self, in_channel, out_channel, hidden_unit=[8, 8], efficient=False):
+        super().__init__()
+        self.efficient = efficient
+        self.mlp_convs = nn.ModuleList()
+        dims = [in_channel] + list(hidden_unit or []) + [out_channel]
+        for cin, cout in zip(dims[:-1], dims[1:]):
+            self.mlp_convs.append(Linear_BN(cin, cout))
+
+    def forward(self, localized_xyz):
+        w = localized_xyz
+        for conv in self.mlp_convs:
+            w = F.relu(conv(w))
+        return w
+
+
+class _PointLayerBase(nn.Module):
+    def _geometry(self, xyz_in, nrm_in, nei_inds, xyz_out, nrm_out, vi_features, use_vi):
+        """-> (localized_xyz or None, weightNetInput)."""
+        if use_vi and vi_features is not None:
+            need_r = getattr(self, "_needs_r", False)
+            if not need_r:
+                return None, vi_features
+            return vi_features[..., 9:12], vi_features        # the last 3 VI channels ARE localized_xyz
+        r, vi = edge_geometry(xyz_in, nrm_in, nei_inds, xyz_out, nrm_out, use_vi)
+        return r, (vi if use_vi else r)
+
+
+class PCFLayer(_PointLayerBase):
+    """PointConvFormer layer (layers.py:194-416)."""
+
+    def __init__(self, in_channel, out_channel, cfg, weightnet=[9, 16], num_heads=4, guidance_feat_len=32):
+        super().__init__()
+        self.cfg, self.in_channel, self.out_channel, self.num_heads = cfg, in_channel, out_channel, num_heads
+        self.drop_path = _drop_path(cfg)
+        self.mlp_conv = Linear_BN(12, guidance_feat_len) if cfg.BATCH_NORM else nn.Linear(12, guidance_feat_len)
+        self.unary1 = UnaryBlock(in_channel, out_channel // 4, use_bn=True, bn_momentum=0.1) \
+            if in_channel != out_channel // 4 else nn.Identity()
+        self.guidance_unary = UnaryBlock(out_channel // 4, guidance_feat_len, use_bn=True, bn_momentum=0.1, no_relu=True)
+        assert (out_channel // 2) % num_heads == 0
+        if cfg.attention_type == 'subtraction':
+            self.guidance_weight = MultiHeadGuidance(cfg, num_heads, 2 * guidance_feat_len)
+        else:
+            self.guidance_weight = MultiHeadGuidanceQK(cfg, num_heads, 2 * guidance_feat_len, key_dim=16)
+        self.weightnet = WeightNet(weightnet[0], weightnet[1], efficient=True)
+        lin_in = out_channel // 4 * weightnet[-1]
+        self.linear = Linear_BN(lin_in, out_channel // 2, bn_ver='1d') if cfg.BATCH_NORM else nn.Linear(lin_in, out_channel // 2)
+        self.dropout = nn.Dropout(p=cfg.dropout_rate) if cfg.dropout_rate > 0. else nn.Identity()
+        self.unary2 = UnaryBlock(out_channel // 2, out_channel, use_bn=True, bn_momentum=0.1, no_relu=True)
+        self.unary_shortcut = UnaryBlock(in_channel, out_channel, use_bn=True, bn_momentum=0.1, no_relu=True) \
+            if in_channel != out_channel else nn.Identity()
+        self.leaky_relu = nn.LeakyReLU(0.1)
+
+    def forward(self, dense_xyz, dense_feats, nei_inds, dense_xyz_norm, sparse_xyz=None, sparse_xyz_norm=None,
+                vi_features=None, inv_neighbors=None, inv_k=None, inv_idx=None):
+        N = dense_xyz.shape[1]
+        strided = sparse_xyz is not None
+        c_xyz, c_nrm = (sparse_xyz, sparse_xyz_norm) if strided else (dense_xyz, dense_xyz_norm)
+        M, K = c_xyz.shape[1], nei_inds.shape[2]
+        nei_inds = nei_inds.contiguous()
+        inv = _inv_tuple(nei_inds, N, inv_neighbors, inv_k, inv_idx, torch.is_grad_enabled() and dense_feats.requires_grad)
+
+        feats_x = self.unary1(dense_feats)
+        _, weightNetInput = self._geometry(dense_xyz, dense_xyz_norm, nei_inds, c_xyz, c_nrm, vi_features, self.cfg.USE_VI is True)
+        feat_pe = F.relu(self.mlp_conv(weightNetInput))
+        guidance_x = self.guidance_unary(feats_x)
+        guidance_feature = torch.cat([index_points(guidance_x, nei_inds, inv), feat_pe], dim=-1)
+        if M == N:
+            guidance_key = guidance_feature[:, :, :1, :]           # column 0 is the centre itself (T6)
+        else:
+            guidance_key = guidance_feature.max(dim=2, keepdim=True)[0]
+        guidance_score = self.guidance_weight(guidance_feature, guidance_key.expand_as(guidance_feature)
+                                              if self.cfg.attention_type != 'subtraction' else guidance_key)
+        weights = self.weightnet(weightNetInput)
+
+        if isinstance(self.linear, Linear_BN):
+            lin, post_bn = self.linear.c, self.linear
+        else:
+            lin, post_bn = self.linear, None
+        new_feat = _contract(self.cfg, feats_x, nei_inds, inv, weights, None, guidance_score, lin.weight, lin.bias)
+        if post_bn is not None:
+            new_feat = _apply_bn(post_bn.bn, new_feat)
+        new_feat = self.dropout(F.relu(new_feat))
+        new_feat = self.unary2(new_feat)
+        sparse_feats = gather_max(dense_feats, nei_inds, inv) if strided else dense_feats
+        shortcut = self.unary_shortcut(sparse_feats)
+        return self.leaky_relu(self.drop_path(new_feat) + shortcut), weightNetInput
+
+
+def _apply_bn(bn, x):
+    """BatchNorm over the last dim of [B,N,C] with a BatchNorm1d-like module `bn` (batch statistics over all
+    points of the packed batch when training, layer_utils.py:276-277)."""
+    shape = x.shape
+    if isinstance(bn, nn.SyncBatchNorm):
+        return bn(x.reshape(-1, shape[-1])).reshape(shape)
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return F.batch_norm(x.reshape(-1, shape[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                        bn.training or not bn.track_running_stats, 0.0 if bn.momentum is None else bn.momentum,
+                        bn.eps).reshape(shape)
+
+
+class _PConvLinearMixin:
+    """The Linear(+BN) after the contraction in both parameter spellings:
+    PCONV_OPT True  -> self.pconv_linear_opt.linear + self.bn ; False -> self.linear (Linear_BN or Linear)."""
+
+    def _build_linear(self, cfg, lin_in, lin_out):
+        if cfg.PCONV_OPT:
+            self.pconv_linear_opt = PConvLinearOpt(lin_in, lin_out)
+            if cfg.BATCH_NORM:
+                self.bn = nn.BatchNorm1d(lin_out, momentum=0.1)
+        else:
+            self.linear = Linear_BN(lin_in, lin_out, bn_ver='1d') if cfg.BATCH_NORM else nn.Linear(lin_in, lin_out)
+
+    def _contract_linear(self, feats, nei_inds, inv, weights, additional):
+        cfg = self.cfg
+        if cfg.PCONV_OPT:
+            lin, bn = self.pconv_linear_opt.linear, (self.bn if cfg.BATCH_NORM else None)
+        elif isinstance(self.linear, Linear_BN):
+            lin, bn = self.linear.c, self.linear.bn
+        else:
+            lin, bn = self.linear, None
+        y = _contract(cfg, feats, nei_inds, inv, weights, additional, None, lin.weight, lin.bias)
+        return y if bn is None else _apply_bn(bn, y)
+
+
+class PointConvStridePE(_PointLayerBase, _PConvLinearMixin):
+    """PointConv bottleneck block with positional-encoding features (layers.py:542-741)."""
+    _needs_r = True
+
+    def __init__(self, in_channel, out_channel, cfg, weightnet=[9, 16]):
+        super().__init__()
+        self.cfg, self.in_channel, self.out_channel = cfg, in_channel, out_channel
+        self.drop_path = _drop_path(cfg)
+        last_ch = min(out_channel // 4, 32)
+        self.pe_convs = WeightNet(3, last_ch, hidden_unit=[out_channel // 4], efficient=True)
+        self.unary1 = UnaryBlock(in_channel, out_channel // 4, use_bn=True, bn_momentum=0.1) \
+            if in_channel != out_channel // 4 else nn.Identity()
+        self.weightnet = WeightNet(weightnet[0], weightnet[1], efficient=True)
+        self._build_linear(cfg, (out_channel // 4 + last_ch) * weightnet[-1], out_channel // 2)
+        self.dropout = nn.Dropout(p=cfg.dropout_rate) if cfg.dropout_rate > 0. else nn.Identity()
+        self.unary2 = UnaryBlock(out_channel // 2, out_channel, use_bn=True, bn_momentum=0.1, no_relu=True)
+        self.unary_shortcut = UnaryBlock(in_channel, out_channel, use_bn=True, bn_momentum=0.1, no_relu=True) \
+            if in_channel != out_channel else nn.Identity()
+        self.leaky_relu = nn.LeakyReLU(0.1)
+
+    def forward(self, dense_xyz, dense_feats, nei_inds, dense_xyz_norm, sparse_xyz=None, sparse_xyz_norm=None,
+                vi_features=None, inv_neighbors=None, inv_k=None, inv_idx=None):
+        N = dense_xyz.shape[1]
+        strided = sparse_xyz is not None
+        c_xyz, c_nrm = (sparse_xyz, sparse_xyz_norm) if strided else (dense_xyz, dense_xyz_norm)
+        nei_inds = nei_inds.contiguous()
+        inv = _inv_tuple(nei_inds, N, inv_neighbors, inv_k, inv_idx, torch.is_grad_enabled() and dense_feats.requires_grad)
+
+        feats_x = self.unary1(dense_feats)
+        localized_xyz, weightNetInput = self._geometry(dense_xyz, dense_xyz_norm, nei_inds, c_xyz, c_nrm, vi_features,
+                                                       self.cfg.USE_VI is True)
+        feat_pe = self.pe_convs(localized_xyz)
+        weights = self.weightnet(weightNetInput)
+        new_feat = self._contract_linear(feats_x, nei_inds, inv, weights, feat_pe)
+        new_feat = self.dropout(F.relu(new_feat))
+        new_feat = self.unary2(new_feat)
+        sparse_feats = gather_max(dense_feats, nei_inds, inv) if strided else dense_feats
+        shortcut = self.unary_shortcut(sparse_feats)
+        return self.leaky_relu(self.drop_path(new_feat) + shortcut), weightNetInput
+
+
+class PointConv(_PointLayerBase, _PConvLinearMixin):
+    """VI_PointConv / PointConv without bottleneck, used for the first layer (layers.py:744-906)."""
+
+    def __init__(self, in_channel, out_channel, cfg, weightnet=[9, 16], USE_VI=None):
+        super().__init__()
+        self.cfg, self.in_channel, self.out_channel = cfg, in_channel, out_channel
+        self.USE_VI = cfg.USE_VI if USE_VI is None else USE_VI
+        last_ch = in_channel + ((12 if self.USE_VI else 3) if cfg.USE_PE else 0)
+        self.weightnet = WeightNet(weightnet[0], weightnet[1], efficient=True)
+        self._build_linear(cfg, last_ch * weightnet[-1], out_channel)
+        self.dropout = nn.Dropout(p=cfg.dropout_rate) if cfg.dropout_rate > 0. else nn.Identity()
+
+    def forward(self, dense_xyz, dense_feats, nei_inds, dense_xyz_norm=None, sparse_xyz=None, sparse_xyz_norm=None,
+                inv_neighbors=None, inv_k=None, inv_idx=None):
+        N = dense_xyz.shape[1]
+        c_xyz, c_nrm = (sparse_xyz, sparse_xyz_norm) if sparse_xyz is not None else (dense_xyz, dense_xyz_norm)
+        nei_inds = nei_inds.contiguous()
+        inv = _inv_tuple(nei_inds, N, inv_neighbors, inv_k, inv_idx, torch.is_grad_enabled() and dense_feats.requires_grad)
+        _, weightNetInput = self._geometry(dense_xyz, dense_xyz_norm, nei_inds, c_xyz, c_nrm, None, self.USE_VI is True)
+        additional = weightNetInput if self.cfg.USE_PE else None
+        weights = self.weightnet(weightNetInput)
+        new_feat = self._contract_linear(dense_feats, nei_inds, inv, weights, additional)
+        return self.dropout(F.relu(new_feat)), weightNetInput
+
+
+class PointConvTransposePE(_PointLayerBase, _PConvLinearMixin):
+    """Upsampling PointConv: features of the sparse cloud are pulled to the dense points
+    (layers.py:909-1105)."""
+    _needs_r = True
+
+    def __init__(self, in_channel, out_channel, cfg, weightnet=[9, 16], mlp2=None):
+        super().__init__()
+        self.cfg, self.in_channel, self.out_channel = cfg, in_channel, out_channel
+        self.drop_path = _drop_path(cfg)
+        if cfg.USE_PE:
+            last_ch = min(out_channel // 4, 32)
+            self.pe_convs = WeightNet(3, last_ch, hidden_unit=[out_channel // 4], efficient=True)
+        else:
+            last_ch = 0
+            self.pe_convs = nn.ModuleList()
+        self.weightnet = WeightNet(weightnet[0], weightnet[1], efficient=True)
+        self._build_linear(cfg, (last_ch + in_channel) * weightnet[-1], out_channel)
+        self.dropout = nn.Dropout(p=cfg.dropout_rate) if cfg.dropout_rate > 0. else nn.Identity()
+        self.mlp2_convs = nn.ModuleList()
+        self.mlp2_bns = nn.ModuleList()
+        if mlp2 is not None:
+            for i in range(1, len(mlp2)):
+                self.mlp2_convs.append(Linear_BN(mlp2[i - 1], mlp2[i], bn_ver='1d') if cfg.BATCH_NORM
+                                       else nn.Linear(mlp2[i - 1], mlp2[i]))
+
+    def forward(self, sparse_xyz, sparse_feats, nei_inds, sparse_xyz_norm, dense_xyz, dense_xyz_norm,
+                dense_feats=None, vi_features=None, inv_neighbors=None, inv_k=None, inv_idx=None):
+        n_in = sparse_xyz.shape[1]
+        nei_inds = nei_inds.contiguous()
+        inv = _inv_tuple(nei_inds, n_in, inv_neighbors, inv_k, inv_idx, torch.is_grad_enabled() and sparse_feats.requires_grad)
+        if inv is not None and inv[2].shape[1] != n_in + 1:
+            # compute_knn_inverse pads propagate maps to the dense level's size (common_util.py:303-306)
+            inv = (inv[0], inv[1], inv[2][:, :n_in + 1].contiguous())
+        localized_xyz, weightNetInput = self._geometry(sparse_xyz, sparse_xyz_norm, nei_inds, dense_xyz, dense_xyz_norm,
+                                                       vi_features, self.cfg.USE_VI is True)
+        feat_pe = self.pe_convs(localized_xyz) if self.cfg.USE_PE else None
+        weights = self.weightnet(weightNetInput)
+        new_feat = F.relu(self._contract_linear(sparse_feats, nei_inds, inv, weights, feat_pe))
+        if dense_feats is not None:
+            new_feat = new_feat + dense_feats
+        new_feat = self.dropout(new_feat)
+        for conv in self.mlp2_convs:
+            new_feat = F.relu(conv(new_feat))
+        return new_feat, weightNetInput

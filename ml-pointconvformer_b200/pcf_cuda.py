@@ -1,0 +1,337 @@
+"""Op-level API with the names and argument order of the reference's `pcf_cuda` extension
+(/root/reference/cpp_wrappers/cpp_pcf_kernel/pcf_cuda.cpp:9-19; signatures include/pcf.h:38-250), every
+function a thin torch-tensor wrapper over the C ABI (include/pcf_b200.h).  Outputs are freshly
+allocated torch tensors on the current stream like the reference's (pconv_ops.cu:666,707,891-895);
+inputs must be contiguous CUDA tensors or RuntimeError is raised (pcf.h:14-24).
+
+Extra ops that have no `pcf_cuda` counterpart (the reference gets them from pykeops / torch / its
+CPU extension) are exposed with plain names: knn_packed, gather, gather_max, edge_geometry,
+grid_subsample.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import PconvShape, check, lib, ptr, require, stream_ptr, workspace
+
+F32, I64, I32, U8 = torch.float32, torch.int64, torch.int32, torch.uint8
+
+# 0 = auto (tcgen05 when the shape allows it), 1 = exact-fp32 SIMT, 2 = force tcgen05
+FORWARD_VARIANT = 0
+
+
+def _shape(n_in, n_out, K, C_in, C_add, C_mid, C_out, H):
+    return PconvShape(int(n_in), int(n_out), int(K), int(C_in), int(C_add), int(C_mid), int(C_out), int(H))
+
+
+def _batched(t):
+    """All reference ops carry a leading batch dim (always 1 in the packed representation)."""
+    return t.shape[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# fused PConv(+guidance)(+Linear) core
+# ------------------------------------------------------------------------------------------------
+def _pconv_fwd(inp, nei, weights, additional, guidance, lin_w, lin_b, want_p, variant=None):
+    require(inp, F32, "input"); require(nei, I64, "neighbor_inds"); require(weights, F32, "weights")
+    B, N_in, C_in = inp.shape
+    _, M, K = nei.shape
+    C_mid = weights.shape[3]
+    C_add = 0 if additional is None else additional.shape[3]
+    H = 0 if guidance is None else guidance.shape[3]
+    if C_add:
+        require(additional, F32, "additional_features")
+    if H:
+        require(guidance, F32, "guidance")
+    C_out = 0
+    if lin_w is not None:
+        require(lin_w, F32, "linear_weights")
+        C_out = lin_w.shape[0]
+        if lin_w.shape[1] != (C_in + C_add) * C_mid:
+            raise RuntimeError("linear_weights must be [C_out, C_mid*(C_in+C_add)] = [*, %d], got %s"
+                               % ((C_in + C_add) * C_mid, tuple(lin_w.shape)))
+        if lin_b is not None:
+            require(lin_b, F32, "linear_bias")
+    if weights.shape[:3] != (B, M, K) or (C_add and additional.shape[:3] != (B, M, K)):
+        raise RuntimeError("weights / additional_features must be [B, N_out, K, *]")
+    dev = inp.device
+    KK = (C_in + C_add) * C_mid
+    out_y = torch.empty(B, M, C_out, device=dev, dtype=F32) if lin_w is not None else None
+    out_p = torch.empty(B, M, KK, device=dev, dtype=F32) if (want_p or lin_w is None) else None
+    v = FORWARD_VARIANT if variant is None else variant
+    sh = _shape(N_in, M, K, C_in, C_add, C_mid, C_out, H)
+    ws_bytes = lib().pcfb_pconv_forward_workspace(ctypes.byref(sh), v)
+    ws = workspace(ws_bytes, dev) if ws_bytes else None
+    for b in range(B):
+        check(lib().pcfb_pconv_forward(
+            ctypes.byref(sh), ptr(inp[b]), ptr(nei[b]), ptr(weights[b]),
+            ptr(additional[b]) if C_add else 0, ptr(guidance[b]) if H else 0,
+            ptr(lin_w), ptr(lin_b), ptr(out_y[b]) if out_y is not None else 0,
+            ptr(out_p[b]) if out_p is not None else 0, ptr(ws), ws_bytes, v, stream_ptr()), "pconv_forward")
+    return out_y, out_p
+
+
+def _pconv_bwd(grad_y, grad_p, inp, inv, nei, weights, additional, guidance, lin_w, pconv_out,
+               need=(True, True, True, True, True, True)):
+    """-> (g_input, g_weights, g_additional, g_guidance, g_lin_w, g_lin_b); entries not needed are None."""
+    B, N_in, C_in = inp.shape
+    _, M, K = nei.shape
+    C_mid = weights.shape[3]
+    C_add = 0 if additional is None else additional.shape[3]
+    H = 0 if guidance is None else guidance.shape[3]
+    C_out = 0 if lin_w is None else lin_w.shape[0]
+    dev = inp.device
+    n_in, n_w, n_add, n_gd, n_lw, n_lb = need
+    n_add = n_add and C_add > 0
+    n_gd = n_gd and H > 0
+    n_lw = n_lw and lin_w is not None
+    n_lb = n_lb and lin_w is not None
+    if grad_y is not None:
+        require(grad_y, F32, "grad_output")
+    if grad_p is not None:
+        require(grad_p, F32, "grad_output")
+    g_in = torch.empty_like(inp) if n_in else None
+    g_w = torch.empty_like(weights) if n_w else None
+    g_add = torch.empty_like(additional) if n_add else None
+    g_gd = torch.empty_like(guidance) if n_gd else None
+    sh = _shape(N_in, M, K, C_in, C_add, C_mid, C_out, H)
+    ws_bytes = lib().pcfb_pconv_backward_workspace(ctypes.byref(sh), 0)
+    ws = workspace(ws_bytes, dev)
+    g_lw_acc, g_lb_acc = None, None
+    for b in range(B):
+        g_lw = torch.empty_like(lin_w) if n_lw else None
+        g_lb = torch.empty(C_out, device=dev, dtype=F32) if n_lb else None
+        inv_n, inv_k, inv_idx = (None, None, None) if inv is None else (inv[0][b], inv[1][b], inv[2][b])
+        check(lib().pcfb_pconv_backward(
+            ctypes.byref(sh), ptr(grad_y[b]) if grad_y is not None else 0, ptr(grad_p[b]) if grad_p is not None else 0,
+            ptr(inp[b]), ptr(nei[b]), ptr(inv_n), ptr(inv_k), ptr(inv_idx), ptr(weights[b]),
+            ptr(additional[b]) if C_add else 0, ptr(guidance[b]) if H else 0, ptr(lin_w),
+            ptr(pconv_out[b]) if pconv_out is not None else 0,
+            ptr(g_in[b]) if n_in else 0, ptr(g_w[b]) if n_w else 0, ptr(g_add[b]) if n_add else 0,
+            ptr(g_gd[b]) if n_gd else 0, ptr(g_lw), ptr(g_lb), ptr(ws), ws_bytes, 0, stream_ptr()), "pconv_backward")
+        if n_lw:
+            g_lw_acc = g_lw if g_lw_acc is None else g_lw_acc + g_lw
+        if n_lb:
+            g_lb_acc = g_lb if g_lb_acc is None else g_lb_acc + g_lb
+    return g_in, g_w, g_add, g_gd, g_lw_acc, g_lb_acc
+
+
+def _empty_add(additional):
+    return None if additional is None or additional.shape[-1] == 0 else additional
+
+
+def _inverse_for(inp, nei, inverse_neighbors, inverse_k, inverse_idx):
+    """The reference's opt backward needs the inverse map handed in (layer_utils.py:60-68); when it is
+    missing (eval drivers never build it) it is built here on the fly."""
+    if inverse_neighbors is None:
+        return compute_knn_inverse(nei, inp.shape[1])
+    return (require(inverse_neighbors, I32, "inverse_neighbor"), require(inverse_k, U8, "inverse_neighbor_k"),
+            require(inverse_idx, I32, "inverse_neighbor_idx"))
+
+
+# ------------------------------------------------------------------------------------------------
+# the nine pcf_cuda entry points
+# ------------------------------------------------------------------------------------------------
+def pconv_linear_cutlass_forward(input, neighbor_inds, weights, additional_features, linear_weights, linear_bias):
+    """pcf.h:243-250 -> (output [B,N,C_out], pconv_output [B,N,C_mid*(C_in+C_add)])."""
+    y, p = _pconv_fwd(input, neighbor_inds, weights, _empty_add(additional_features), None,
+                      linear_weights, linear_bias, want_p=True)
+    return y, p
+
+
+def pconv_linear_forward(input, neighbor_inds, weights, additional_features, linear_weights, linear_bias):
+    """pcf.h:131-138 (the reference's SIMT fused kernel): same contract; served by the exact-fp32 variant."""
+    y, p = _pconv_fwd(input, neighbor_inds, weights, _empty_add(additional_features), None,
+                      linear_weights, linear_bias, want_p=True, variant=1)
+    return y, p
+
+
+def pconv_linear_opt_backward(grad_output, input, inverse_neighbor, inverse_neighbor_k, inverse_neighbor_idx,
+                              neighbor_inds, weights, additional_features, linear_weights, pconv_output):
+    """pcf.h:213-224 -> [grad_input, grad_weights, grad_additional, grad_linear_weights, grad_linear_bias]."""
+    inv = _inverse_for(input, neighbor_inds, inverse_neighbor, inverse_neighbor_k, inverse_neighbor_idx)
+    add = _empty_add(additional_features)
+    g_in, g_w, g_add, _, g_lw, g_lb = _pconv_bwd(grad_output, None, input, inv, neighbor_inds, weights, add, None,
+                                                 linear_weights, pconv_output)
+    if g_add is None:
+        g_add = torch.zeros_like(additional_features) if additional_features is not None else None
+    return [g_in, g_w, g_add, g_lw, g_lb]
+
+
+def pconv_linear_backward(grad_output, input, neighbor_inds, weights, additional_features, linear_weights, pconv_output):
+    """pcf.h:162-170: as above without a caller-supplied inverse map."""
+    return pconv_linear_opt_backward(grad_output, input, None, None, None, neighbor_inds, weights,
+                                     additional_features, linear_weights, pconv_output)
+
+
+def pconv_forward(input, neighbor_inds, weights, additional_features):
+    """pcf.h:81-86 -> [B,N,C_mid*(C_in+C_add)]."""
+    _, p = _pconv_fwd(input, neighbor_inds, weights, _empty_add(additional_features), None, None, None, want_p=True)
+    return p
+
+
+def pconv_backward(grad_output, input, neighbor_inds, weights, additional_features):
+    """pcf.h:106-112 -> [grad_input, grad_weights, grad_additional]."""
+    inv = compute_knn_inverse(neighbor_inds, input.shape[1])
+    add = _empty_add(additional_features)
+    g_in, g_w, g_add, _, _, _ = _pconv_bwd(None, grad_output, input, inv, neighbor_inds, weights, add, None, None, None)
+    if g_add is None:
+        g_add = torch.zeros_like(additional_features) if additional_features is not None else None
+    return [g_in, g_w, g_add]
+
+
+def pcf_forward(input, neighbor_inds, guidance, weights):
+    """pcf.h:38-43 -> [B,N,C_mid*C_in]; head of channel c is c % H."""
+    _, p = _pconv_fwd(input, neighbor_inds, weights, None, require(guidance, F32, "guidance"), None, None, want_p=True)
+    return p
+
+
+def pcf_backward(grad_output, input, neighbor_inds, guidance, weights):
+    """pcf.h:60-66 -> [grad_input, grad_guidance, grad_weights]."""
+    inv = compute_knn_inverse(neighbor_inds, input.shape[1])
+    g_in, g_w, _, g_gd, _, _ = _pconv_bwd(None, grad_output, input, inv, neighbor_inds, weights, None, guidance, None, None)
+    return [g_in, g_gd, g_w]
+
+
+def compute_knn_inverse(neighbor_inds, total_points):
+    """pcf.h:183-186 -> (inv_neighbors int32 [B,N*K], inv_k uint8 [B,N*K], inv_idx int32 [B,total+1])."""
+    require(neighbor_inds, I64, "neighbor_inds")
+    B, N, K = neighbor_inds.shape
+    total = int(total_points)
+    dev = neighbor_inds.device
+    inv_n = torch.empty(B, N * K, device=dev, dtype=I32)
+    inv_k = torch.empty(B, N * K, device=dev, dtype=U8)
+    inv_idx = torch.empty(B, total + 1, device=dev, dtype=I32)
+    ws_bytes = lib().pcfb_knn_inverse_workspace(N, K, total)
+    ws = workspace(ws_bytes, dev)
+    for b in range(B):
+        check(lib().pcfb_knn_inverse(ptr(neighbor_inds[b]), N, K, total, ptr(inv_n[b]), ptr(inv_k[b]), ptr(inv_idx[b]),
+                                     ptr(ws), ws_bytes, stream_ptr()), "compute_knn_inverse")
+    return inv_n, inv_k, inv_idx
+
+
+# ------------------------------------------------------------------------------------------------
+# fused-layer entry used by layers.py: contraction (+guidance) + Linear in one call
+# ------------------------------------------------------------------------------------------------
+def pconv_fused_forward(input, neighbor_inds, weights, additional_features, guidance, linear_weights, linear_bias,
+                        want_p=True, variant=None):
+    return _pconv_fwd(input, neighbor_inds, weights, _empty_add(additional_features), guidance,
+                      linear_weights, linear_bias, want_p, variant)
+
+
+def pconv_fused_backward(grad_y, grad_p, input, inv, neighbor_inds, weights, additional_features, guidance,
+                         linear_weights, pconv_output, need):
+    return _pconv_bwd(grad_y, grad_p, input, inv, neighbor_inds, weights, _empty_add(additional_features), guidance,
+                      linear_weights, pconv_output, need)
+
+
+# ------------------------------------------------------------------------------------------------
+# ops without a pcf_cuda counterpart
+# ------------------------------------------------------------------------------------------------
+def knn_packed(ref_xyz, ref_counts, qry_xyz, qry_counts, K, out=None):
+    """Exact kNN inside each scene of a packed cloud.  ref_xyz [N_ref,3], qry_xyz [N_qry,3] fp32 CUDA;
+    ref_counts / qry_counts: per-scene point counts (python ints).  -> int64 [N_qry,K], values index the
+    packed reference cloud (scene offset already added, as prepare() does)."""
+    require(ref_xyz, F32, "ref_xyz"); require(qry_xyz, F32, "qry_xyz")
+    dev = ref_xyz.device
+    n_seg = len(ref_counts)
+    assert len(qry_counts) == n_seg
+    ro = torch.tensor([0] + list(ref_counts), dtype=torch.int64).cumsum(0).to(torch.int32)
+    qo = torch.tensor([0] + list(qry_counts), dtype=torch.int64).cumsum(0).to(torch.int32)
+    if int(ro[-1]) != ref_xyz.shape[0] or int(qo[-1]) != qry_xyz.shape[0]:
+        raise RuntimeError("scene counts do not add up to the packed cloud sizes")
+    ro_d, qo_d = ro.to(dev, non_blocking=True), qo.to(dev, non_blocking=True)
+    if out is None:
+        out = torch.empty(qry_xyz.shape[0], K, device=dev, dtype=I64)
+    check(lib().pcfb_knn_packed(ptr(ref_xyz), ptr(ro_d), ptr(qry_xyz), ptr(qo_d), n_seg, ref_xyz.shape[0],
+                                qry_xyz.shape[0], int(K), ptr(out), stream_ptr()), "knn_packed")
+    return out
+
+
+def gather(feats, nei):
+    """index_points for B folded: feats [N,C], nei [M,K] -> [M,K,C]."""
+    require(feats, F32, "feats"); require(nei, I64, "nei")
+    M, K = nei.shape
+    out = torch.empty(M, K, feats.shape[1], device=feats.device, dtype=F32)
+    check(lib().pcfb_gather(ptr(feats), ptr(nei), feats.shape[0], M, K, feats.shape[1], ptr(out), stream_ptr()), "gather")
+    return out
+
+
+def gather_backward(grad_out, inv, n_in):
+    require(grad_out, F32, "grad_out")
+    M, K, C = grad_out.shape
+    g = torch.empty(n_in, C, device=grad_out.device, dtype=F32)
+    check(lib().pcfb_gather_backward(ptr(grad_out), ptr(inv[0]), ptr(inv[1]), ptr(inv[2]), n_in, M, K, C, ptr(g),
+                                     stream_ptr()), "gather_backward")
+    return g
+
+
+def gather_max(feats, nei):
+    require(feats, F32, "feats"); require(nei, I64, "nei")
+    M, K = nei.shape
+    C = feats.shape[1]
+    out = torch.empty(M, C, device=feats.device, dtype=F32)
+    arg = torch.empty(M, C, device=feats.device, dtype=U8)
+    check(lib().pcfb_gather_max(ptr(feats), ptr(nei), feats.shape[0], M, K, C, ptr(out), ptr(arg), stream_ptr()), "gather_max")
+    return out, arg
+
+
+def gather_max_backward(grad_out, arg, inv, n_in, K):
+    require(grad_out, F32, "grad_out")
+    M, C = grad_out.shape
+    g = torch.empty(n_in, C, device=grad_out.device, dtype=F32)
+    check(lib().pcfb_gather_max_backward(ptr(grad_out), ptr(arg), ptr(inv[0]), ptr(inv[1]), ptr(inv[2]), n_in, M, K, C,
+                                         ptr(g), stream_ptr()), "gather_max_backward")
+    return g
+
+
+def edge_geometry(xyz_in, nrm_in, xyz_out, nrm_out, nei, want_r=True, want_vi=True):
+    """-> (localized_xyz [M,K,3] or None, vi_features [M,K,12] or None)."""
+    require(xyz_in, F32, "xyz_in"); require(xyz_out, F32, "xyz_out"); require(nei, I64, "nei")
+    M, K = nei.shape
+    dev = xyz_in.device
+    r = torch.empty(M, K, 3, device=dev, dtype=F32) if want_r else None
+    vi = None
+    if want_vi:
+        require(nrm_in, F32, "nrm_in"); require(nrm_out, F32, "nrm_out")
+        vi = torch.empty(M, K, 12, device=dev, dtype=F32)
+    check(lib().pcfb_edge_geometry(ptr(xyz_in), ptr(nrm_in), ptr(xyz_out), ptr(nrm_out), ptr(nei), xyz_in.shape[0], M, K,
+                                   ptr(r), ptr(vi), stream_ptr()), "edge_geometry")
+    return r, vi
+
+
+def grid_subsample(xyz, feats, counts, dl):
+    """Packed grid subsampling: xyz [N,3], feats [N,F] or None, counts = per-scene sizes.
+    -> (sub_xyz [M,3], sub_feats [M,F] or None, sub_counts list)."""
+    require(xyz, F32, "xyz")
+    dev = xyz.device
+    n_seg, n_pts = len(counts), xyz.shape[0]
+    F = 0 if feats is None else feats.shape[1]
+    if F:
+        require(feats, F32, "feats")
+    off = torch.tensor([0] + list(counts), dtype=torch.int64).cumsum(0).to(torch.int32).to(dev)
+    origin = torch.empty(n_seg, 3, device=dev, dtype=F32)
+    dims = torch.empty(n_seg, 3, device=dev, dtype=I32)
+    ws0 = workspace(n_seg * 24 + 64, dev)
+    check(lib().pcfb_gridsub_bounds(ptr(xyz), ptr(off), n_seg, n_pts, float(dl), ptr(origin), ptr(dims), ptr(ws0),
+                                    ws0.numel(), stream_ptr()), "gridsub_bounds")
+    dims_h = dims.cpu().to(torch.int64)                                  # host sync #1 (grid extent)
+    cells = (dims_h[:, 0] * dims_h[:, 1] * dims_h[:, 2])
+    cell_off_h = torch.cat([torch.zeros(1, dtype=torch.int64), cells.cumsum(0)])
+    total_cells = int(cell_off_h[-1])
+    if total_cells >= (1 << 30):
+        raise RuntimeError("grid_subsample: %d cells is too many for dense binning" % total_cells)
+    cell_off = cell_off_h.to(torch.int32).to(dev)
+    ws_bytes = lib().pcfb_gridsub_workspace(n_seg, n_pts, total_cells)
+    ws = workspace(ws_bytes, dev)
+    out_counts = torch.empty(n_seg, device=dev, dtype=I32)
+    check(lib().pcfb_gridsub_count(ptr(xyz), ptr(off), n_seg, n_pts, float(dl), ptr(origin), ptr(dims), ptr(cell_off),
+                                   total_cells, ptr(out_counts), ptr(ws), ws_bytes, stream_ptr()), "gridsub_count")
+    sub_counts = out_counts.cpu().tolist()                               # host sync #2 (output size)
+    m = int(sum(sub_counts))
+    out_xyz = torch.empty(m, 3, device=dev, dtype=F32)
+    out_f = torch.empty(m, F, device=dev, dtype=F32) if F else None
+    check(lib().pcfb_gridsub_emit(ptr(xyz), ptr(feats), n_seg, n_pts, F, total_cells, ptr(out_xyz), ptr(out_f), ptr(ws),
+                                  ws_bytes, stream_ptr()), "gridsub_emit")
+    return out_xyz, out_f, sub_counts

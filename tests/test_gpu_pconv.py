@@ -1,0 +1,216 @@
+"""GPU parity: the fused PConv(+guidance)+Linear forward (both variants) and backward, the gather family and
+the edge-geometry / VI kernel, against the CPU oracle (oracle/layers.py evaluated in float64).
+
+Tolerance: the reference's own rtol = atol = 1e-4 (test_kernels.py:1756-1764) for the op-level outputs; the
+fp32 SIMT variant and the 3xTF32 tcgen05 variant must both meet it."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import layers as OL, inverse as OI
+from gpu_util import cuda, rel_err, max_err_scaled, surface_cloud
+
+pytestmark = pytest.mark.gpu
+TOL = dict(rtol=1e-4, atol=1e-4)
+
+
+def _pc():
+    from pcf_b200 import pcf_cuda
+    return pcf_cuda
+
+
+def make_case(seed, n_in, n_out, K, C_in, C_add, C_mid, C_out, H, pad=False):
+    g = torch.Generator().manual_seed(seed)
+    d = dict(
+        x=torch.randn(1, n_in, C_in, generator=g),
+        nei=torch.randint(0, n_in, (1, n_out, K), generator=g),
+        w=torch.relu(torch.randn(1, n_out, K, C_mid, generator=g)),
+        add=torch.randn(1, n_out, K, C_add, generator=g) if C_add else None,
+        gd=torch.sigmoid(torch.randn(1, n_out, K, H, generator=g)) if H else None,
+        W=torch.randn(C_out, (C_in + C_add) * C_mid, generator=g) / ((C_in + C_add) * C_mid) ** 0.5 if C_out else None,
+        b=torch.randn(C_out, generator=g) if C_out else None,
+    )
+    if pad:
+        d["nei"][0, ::7, -1] = -1                                      # listToBatch keeps -1 padding
+    return d
+
+
+def oracle_eval(d, grad_out=None):
+    """float64 CPU evaluation (+ autograd) of P and Y; -1 neighbours contribute zero (pconv_ops.cu:453,494)."""
+    t = {k: (v.double().clone().requires_grad_(v.is_floating_point()) if v is not None else None) for k, v in d.items() if k != "nei"}
+    nei = d["nei"]
+    mask = (nei >= 0).unsqueeze(-1).double()
+    g = OL.gather(t["x"], nei.clamp(min=0)) * mask
+    if t["gd"] is not None:
+        g = g * t["gd"].repeat(1, 1, 1, g.shape[-1] // t["gd"].shape[-1])
+    if t["add"] is not None:
+        g = torch.cat([g, t["add"]], -1)
+    P = torch.einsum("bmkc,bmkj->bmcj", g, t["w"]).reshape(1, nei.shape[1], -1)
+    Y = torch.nn.functional.linear(P, t["W"], t["b"]) if t["W"] is not None else None
+    grads = None
+    if grad_out is not None:
+        out = Y if Y is not None else P
+        (out * grad_out.double()).sum().backward()
+        grads = {k: (v.grad if v is not None else None) for k, v in t.items()}
+    return P.detach(), (Y.detach() if Y is not None else None), grads
+
+
+SHAPES = {  # name: (n_in, n_out, K, C_in, C_add, C_mid, C_out, H)
+    "level0_pointconv": (3000, 3000, 16, 6, 12, 16, 64, 0),
+    "level0_stridepe": (3000, 3000, 16, 16, 16, 16, 32, 0),
+    "level1_pcf": (3000, 777, 16, 32, 0, 16, 64, 8),
+    "level2_pcf": (900, 900, 16, 48, 0, 16, 96, 8),
+    "level4_pcf": (300, 300, 16, 96, 0, 16, 192, 8),
+    "decoder_transpose": (300, 1200, 16, 384, 32, 1, 256, 0),
+    "decoder_last": (700, 2900, 16, 128, 16, 1, 64, 0),
+    "lite_mid4": (2000, 501, 16, 32, 16, 4, 64, 4),
+    "mid8_k32": (1000, 333, 32, 24, 8, 8, 40, 0),
+    "ref_test_k64": (2000, 2000, 64, 16, 16, 16, 64, 0),          # test_kernels.py:1086-1120 channel sizes
+}
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("name", sorted(SHAPES))
+def test_forward_matches_oracle(name, variant):
+    d = make_case(hash(name) % 1000, *SHAPES[name], pad=(name == "level1_pcf"))
+    P, Y, _ = oracle_eval(d)
+    dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
+    y, p = _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], dc["gd"], dc["W"], dc["b"], want_p=True, variant=variant)
+    torch.testing.assert_close(p.cpu().double(), P, **TOL)
+    torch.testing.assert_close(y.cpu().double(), Y, **TOL)
+    assert rel_err(y, Y) < 2e-5
+
+
+def test_forward_mid3_falls_back_to_simt():
+    """configPCF_2cm_PTF2 uses mid_dim_back = 3, which the tcgen05 variant does not cover: auto must still work."""
+    d = make_case(3, 500, 900, 16, 64, 16, 3, 32, 0)
+    P, Y, _ = oracle_eval(d)
+    dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
+    y, p = _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], None, dc["W"], dc["b"], want_p=True, variant=0)
+    torch.testing.assert_close(y.cpu().double(), Y, **TOL)
+    with pytest.raises(RuntimeError):
+        _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], None, dc["W"], dc["b"], want_p=True, variant=2)
+
+
+@pytest.mark.parametrize("name", sorted(SHAPES))
+def test_backward_matches_autograd(name):
+    shp = SHAPES[name]
+    d = make_case(hash(name) % 1000 + 1, *shp, pad=(name == "level1_pcf"))
+    go = torch.randn(1, shp[1], shp[6], generator=torch.Generator().manual_seed(9))
+    P, Y, G = oracle_eval(d, go)
+    dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
+    inv = _pc().compute_knn_inverse(dc["nei"], shp[0])
+    y, p = _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], dc["gd"], dc["W"], dc["b"], want_p=True, variant=1)
+    g_in, g_w, g_add, g_gd, g_lw, g_lb = _pc().pconv_fused_backward(
+        cuda(go).contiguous(), None, dc["x"], inv, dc["nei"], dc["w"], dc["add"], dc["gd"], dc["W"], p, (True,) * 6)
+    for got, key in ((g_in, "x"), (g_w, "w"), (g_add, "add"), (g_gd, "gd"), (g_lw, "W"), (g_lb, "b")):
+        if G[key] is None:
+            assert got is None
+            continue
+        assert max_err_scaled(got, G[key]) < 1e-4, key
+    # P recomputed inside the backward (pconv_out = NULL) gives the same dW
+    g2 = _pc().pconv_fused_backward(cuda(go).contiguous(), None, dc["x"], inv, dc["nei"], dc["w"], dc["add"], dc["gd"], dc["W"], None,
+                                    (False, False, False, False, True, True))
+    assert max_err_scaled(g2[4], G["W"]) < 1e-4 and max_err_scaled(g2[5], G["b"]) < 1e-4
+
+
+def test_backward_without_linear():
+    """pconv_backward / pcf_backward contracts (pcf.h:60-66,106-112): incoming gradient is dP."""
+    for name in ("level1_pcf", "lite_mid4"):
+        shp = list(SHAPES[name]); shp[6] = 0
+        d = make_case(77, *shp)
+        KK = (shp[3] + shp[4]) * shp[5]
+        go = torch.randn(1, shp[1], KK, generator=torch.Generator().manual_seed(3))
+        P, _, G = oracle_eval(d, go)
+        dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
+        if d["add"] is None:
+            out = _pc().pcf_forward(dc["x"], dc["nei"], dc["gd"], dc["w"])
+            torch.testing.assert_close(out.cpu().double(), P, **TOL)
+            g_in, g_gd, g_w = _pc().pcf_backward(cuda(go), dc["x"], dc["nei"], dc["gd"], dc["w"])
+            assert max_err_scaled(g_in, G["x"]) < 1e-4 and max_err_scaled(g_gd, G["gd"]) < 1e-4 and max_err_scaled(g_w, G["w"]) < 1e-4
+        else:
+            inv = _pc().compute_knn_inverse(dc["nei"], shp[0])
+            g = _pc().pconv_fused_backward(None, cuda(go), dc["x"], inv, dc["nei"], dc["w"], dc["add"], dc["gd"], None, None, (True,) * 6)
+            assert max_err_scaled(g[0], G["x"]) < 1e-4 and max_err_scaled(g[2], G["add"]) < 1e-4 and max_err_scaled(g[3], G["gd"]) < 1e-4
+
+
+def test_reference_op_contract_seed42(golden_dir):
+    """The reference's only asserting kernel test (test_cutlass_vs_cuda_kernel, test_kernels.py:1707-1769):
+    B=2, M=512, Nout=256, K=16, C_in=8, C_add=4, C_mid=8, C_out=16, seed 42 -- through the pcf_cuda-named entry
+    points, forward (both reference function names) and the opt backward."""
+    g = np.load(os.path.join(golden_dir, "pconv_linear_seed42.npz"))
+    a = {k: cuda(g[k]) for k in g.files}
+    for fn in (_pc().pconv_linear_cutlass_forward, _pc().pconv_linear_forward):
+        out, pc = fn(a["input"], a["nei"], a["weights"], a["additional"], a["lin_w"], a["lin_b"])
+        torch.testing.assert_close(out, a["out"], **TOL)
+        torch.testing.assert_close(pc, a["pconv_out"], **TOL)
+    inv_n, inv_k, inv_idx = _pc().compute_knn_inverse(a["nei"], 512)
+    grads = _pc().pconv_linear_opt_backward(a["grad_out"], a["input"], inv_n, inv_k, inv_idx, a["nei"], a["weights"],
+                                            a["additional"], a["lin_w"], pc)
+    for got, key in zip(grads, ("g_input", "g_weights", "g_additional", "g_lin_w", "g_lin_b")):
+        torch.testing.assert_close(got, a[key], rtol=1e-4, atol=2e-4)
+
+
+def test_errors_like_the_reference():
+    """CHECK_INPUT semantics (pcf.h:14-24): CPU or non-contiguous tensors raise RuntimeError."""
+    d = make_case(1, 100, 50, 16, 8, 0, 4, 16, 0)
+    with pytest.raises(RuntimeError):
+        _pc().pconv_linear_cutlass_forward(d["x"], d["nei"], d["w"], None, d["W"], d["b"])          # CPU tensors
+    dc = {k: (cuda(v) if v is not None else None) for k, v in d.items()}
+    with pytest.raises(RuntimeError):
+        _pc().pconv_linear_cutlass_forward(dc["x"].transpose(1, 2), dc["nei"], dc["w"], None, dc["W"], dc["b"])
+    with pytest.raises(RuntimeError):
+        _pc().pconv_linear_cutlass_forward(dc["x"], dc["nei"], dc["w"], None, dc["W"][:, :-1].contiguous(), dc["b"])
+
+
+def test_gather_family():
+    rng = np.random.default_rng(4)
+    for C in (3, 16, 33):
+        feats = torch.randn(500, C)
+        nei = torch.from_numpy(rng.integers(0, 500, (200, 16)))
+        got = _pc().gather(cuda(feats), cuda(nei))
+        assert torch.equal(got.cpu(), feats[nei])
+        go = torch.randn(200, 16, C)
+        inv = tuple(cuda(x) for x in OI.knn_inverse(nei.numpy(), 500))
+        gb = _pc().gather_backward(cuda(go), inv, 500)
+        want = torch.zeros(500, C, dtype=torch.float64).index_put_((nei.reshape(-1),), go.reshape(-1, C).double(), accumulate=True)
+        assert max_err_scaled(gb, want) < 1e-6
+        mx, arg = _pc().gather_max(cuda(feats), cuda(nei))
+        wmx, warg = feats[nei].max(dim=1)
+        assert torch.equal(mx.cpu(), wmx) and torch.equal(arg.cpu().long(), warg)
+        gm = _pc().gather_max_backward(cuda(go[:, 0].contiguous()), arg, inv, 500, 16)
+        fc = feats.clone().double().requires_grad_(True)
+        (fc[nei].max(dim=1)[0] * go[:, 0].double()).sum().backward()
+        assert max_err_scaled(gm, fc.grad) < 1e-6
+
+
+def test_edge_geometry_vi(golden_dir):
+    """VI features against the reference's own output stored in the golden layer files."""
+    for fname, centre in (("layer_pointconv.npz", "self"), ("layer_pcf_strided.npz", "strided"), ("layer_transpose.npz", "transpose")):
+        g = np.load(os.path.join(golden_dir, fname))
+        xyz, nrm, sxyz, snrm, nei = (cuda(g[k]) for k in ("xyz", "nrm", "sxyz", "snrm", "nei"))
+        if centre == "self":
+            r, vi = _pc().edge_geometry(xyz, nrm, xyz, nrm, nei)
+        elif centre == "strided":
+            r, vi = _pc().edge_geometry(xyz, nrm, sxyz, snrm, nei)
+        else:
+            r, vi = _pc().edge_geometry(sxyz, snrm, xyz, nrm, nei)
+        torch.testing.assert_close(vi.cpu(), torch.from_numpy(g["wni"])[0], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(r.cpu(), torch.from_numpy(g["wni"])[0][..., 9:], rtol=0, atol=0)
+
+
+def test_full_size_linearity():
+    """BASELINE-size op (100k points, level-0 StridePE shape): linearity in the features and agreement of the
+    two variants -- properties that need no oracle at this size."""
+    d = make_case(5, 100000, 100000, 16, 16, 16, 16, 32, 0)
+    dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
+    f = lambda x, v: _pc().pconv_fused_forward(x, dc["nei"], dc["w"], dc["add"], None, dc["W"], None, want_p=False, variant=v)[0]
+    y1, y2 = f(dc["x"], 1), f(dc["x"], 2)
+    assert rel_err(y2, y1) < 2e-5
+    x2 = torch.randn_like(dc["x"])
+    ya, yb, yab = f(dc["x"], 2), f(x2, 2), f(dc["x"] + x2, 2)
+    # Y is affine in x (additional features contribute a constant): Y(x1+x2) + Y(0) = Y(x1) + Y(x2)
+    y0 = f(torch.zeros_like(x2), 2)
+    assert rel_err(yab + y0, ya + yb) < 2e-5

@@ -1,0 +1,127 @@
+"""CPU tests of the host-side logic (no CUDA calls): config defaults, state-dict layout, listToBatch/prepare
+offset logic, scene sharding, loud failure without CUDA."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pcf_b200  # noqa: F401
+from oracle import knn as OK
+
+
+def test_default_configs_fix_the_reference_traps():
+    from pcf_b200 import model_architecture as MA
+    cfg = MA.get_default_configs(MA.EasyDict(), 5, 64)
+    assert cfg.PCONV_OPT is False and cfg.USE_CUDA_KERNEL is False
+    assert cfg.feat_dim == [64, 128, 192, 256, 320, 384]
+    with pytest.raises(AttributeError):
+        cfg.not_a_key
+    for preset, n_params in ((MA.PCF_Tiny, None), (MA.PCF_Normal, 4180960)):
+        model, c = preset(0.1)
+        if n_params:
+            assert sum(p.numel() for p in model.parameters()) == n_params
+
+
+def test_state_dict_layout_matches_reference_golden(golden_dir):
+    """Keys and shapes of the small segmentation model equal the reference's (stored in the golden file)."""
+    from pcf_b200 import model_architecture as MA
+    g = np.load(os.path.join(golden_dir, "model_small.npz"))
+    cfg = MA.EasyDict(USE_VI=True, USE_PE=True, BATCH_NORM=True, USE_CUDA_KERNEL=True, PCONV_OPT=False, feat_dim=[16, 32, 48, 64, 96],
+                      mid_dim=[16] * 5, mid_dim_back=1, guided_level=0, num_heads=4, resblocks=[0, 1, 2, 1, 1],
+                      resblocks_back=[0] * 5, num_classes=20)
+    cfg = MA.get_default_configs(cfg, 5, 16)
+    sd = MA.PointConvFormer_Segmentation(cfg).state_dict()
+    ref = {k[6:]: g[k].shape for k in g.files if k.startswith("param.")}
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v) for k, v in ref.items()}
+    cfg.PCONV_OPT = True                                                     # the other spelling (T5)
+    keys = MA.PointConvFormer_Segmentation(cfg).state_dict().keys()
+    assert "pcf_backbone.selfpointconv.pconv_linear_opt.linear.weight" in keys
+    assert "pcf_backbone.selfpointconv.bn.running_mean" in keys
+    assert "pointdeconv.0.pconv_linear_opt.linear.bias" in keys
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only in the build container")
+@pytest.mark.parametrize("opt", [False, True])
+def test_state_dict_matches_live_reference(opt):
+    import yaml
+    from oracle import ref_shim
+    from pcf_b200 import model_architecture as MA
+    _, _, RMA = ref_shim.load()
+    raw = yaml.safe_load(open("/root/reference/configs/configPCF_Opt_10cm.yaml"))
+    c1 = RMA.get_default_configs(ref_shim.EasyDict(raw), raw["num_level"], raw["base_dim"]); c1.PCONV_OPT = opt
+    c2 = MA.get_default_configs(MA.EasyDict(raw), raw["num_level"], raw["base_dim"]); c2.PCONV_OPT = opt
+    r, m = RMA.PointConvFormer_Segmentation(c1), MA.PointConvFormer_Segmentation(c2)
+    assert {k: tuple(v.shape) for k, v in r.state_dict().items()} == {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict(), strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 5414944
+
+
+def test_list_to_batch_offsets():
+    """listToBatch / prepare (knn_post_dataloader_utils.py:113-167) on genuinely per-scene tables: running
+    offsets per level (forward: dense level, propagate: sparse level), -1 preserved."""
+    from pcf_b200 import knn_post_dataloader_utils as KU
+    stored = [[50, 30], [20, 12], [8, 6]]
+    rng = np.random.default_rng(0)
+    per_scene = []
+    for s in range(2):
+        pts = [rng.standard_normal((stored[l][s], 3)).astype(np.float32) for l in range(3)]
+        es = [torch.from_numpy(OK.knn_numpy(pts[l], pts[l], 4)) for l in range(3)]
+        ef = [torch.from_numpy(OK.knn_numpy(pts[l], pts[l + 1], 4)) for l in range(2)]
+        ep = [torch.from_numpy(OK.knn_numpy(pts[l + 1], pts[l], 4)) for l in range(2)]
+        es[0][0, -1] = -1
+        per_scene.append((pts, es, ef, ep))
+    out = KU.prepare([p[1] for p in per_scene], [p[2] for p in per_scene], [p[3] for p in per_scene])
+    es, ef, ep = out
+    assert tuple(es[0].shape) == (1, 80, 4) and tuple(ef[0].shape) == (1, 32, 4) and tuple(ep[1].shape) == (1, 32, 4)
+    assert es[0][0, 0, -1] == -1
+    assert torch.equal(es[1][0, 20:], per_scene[1][1][1] + 20)
+    assert torch.equal(ef[0][0, 20:], per_scene[1][2][0] + 50)          # forward indexes the dense level
+    assert torch.equal(ep[0][0, 50:], per_scene[1][3][0] + 20)          # propagate indexes the sparse level
+    pcs = [np.concatenate([per_scene[s][0][l] for s in range(2)])[None] for l in range(3)]
+    oes, oef, oep = OK.compute_knn_packed(pcs, stored, [4] * 3, [4] * 3, [4] * 3)
+    assert np.array_equal(ef[1][0].numpy(), oef[1][0]) and np.array_equal(ep[0][0].numpy(), oep[0][0])
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA tensors."""
+    from pcf_b200 import pcf_cuda, layer_utils
+    x = torch.randn(1, 10, 4)
+    nei = torch.zeros(1, 5, 3, dtype=torch.int64)
+    with pytest.raises(RuntimeError):
+        pcf_cuda.compute_knn_inverse(nei, 10)
+    with pytest.raises(RuntimeError):
+        layer_utils.index_points(x, nei)
+    with pytest.raises(RuntimeError):
+        pcf_cuda.pconv_forward(x, nei, torch.randn(1, 5, 3, 2), None)
+    if not torch.cuda.is_available():
+        from pcf_b200 import knn_post_dataloader_utils as KU
+        with pytest.raises(RuntimeError):
+            KU.compute_knn(torch.randn(20, 3), torch.randn(5, 3), 4)
+
+
+def test_product_never_imports_the_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ml-pointconvformer_b200")
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("oracle's", ""), fn
+
+
+def test_synthetic_scene_generator():
+    from pcf_b200 import synthetic
+    xyz, nrm, col = synthetic.make_scene(1, 20000)
+    assert abs(len(xyz) - 20000) < 1500 and xyz.dtype == np.float32
+    assert np.allclose(np.linalg.norm(nrm, axis=1), 1, atol=1e-4)
+    key = np.floor(xyz / np.float32(0.1)).astype(np.int64)
+    assert len(np.unique(key, axis=0)) == len(xyz)                       # one point per 10 cm voxel
+
+
+def test_scene_sharding_balanced():
+    from pcf_b200 import sharding
+    sizes = [100, 90, 80, 20, 20, 10, 5, 5]
+    parts = sharding.shard_scenes(sizes, 3)
+    assert sorted(i for p in parts for i in p) == list(range(8))
+    loads = [sum(sizes[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= 20
+    assert sharding.shard_scenes([7], 4) == [[0], [], [], []]
