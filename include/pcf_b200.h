@@ -117,6 +117,9 @@ typedef struct {
     int n_in, n_out, K, C_in, C_add, C_mid, C_out, H; /* H = guidance heads (0 if none) */
 } pcfb_pconv_shape;
 
+/* 1 if `variant` can run this shape (the tcgen05 variant needs C_mid in {1,4,8,16}, C_out % 8 == 0, a Linear,
+ * C_cat*C_mid % 4 == 0 and a tile that fits in shared memory), else 0. */
+int pcfb_pconv_forward_supported(const pcfb_pconv_shape *s, int variant);
 size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int variant);
 int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei,
                        const float *weights, const float *additional, const float *guidance,

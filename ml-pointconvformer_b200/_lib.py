@@ -34,6 +34,7 @@ SIGNATURES = {
     "pcfb_gather_max": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P, _P]),
     "pcfb_gather_max_backward": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "pcfb_edge_geometry": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "pcfb_pconv_forward_supported": (c_int, [ctypes.POINTER(PconvShape), c_int]),
     "pcfb_pconv_forward_workspace": (c_size_t, [ctypes.POINTER(PconvShape), c_int]),
     "pcfb_pconv_forward": (c_int, [ctypes.POINTER(PconvShape), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
     "pcfb_pconv_backward_workspace": (c_size_t, [ctypes.POINTER(PconvShape), c_int]),

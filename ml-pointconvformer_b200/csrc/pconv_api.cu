@@ -21,6 +21,13 @@ int pconv_forward_umma(const pcfb_pconv_shape *s, const float *feats, const int6
                        float *out_y, float *out_p, void *workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace pcfb
 
+extern "C" int pcfb_pconv_forward_supported(const pcfb_pconv_shape *s, int variant)
+{
+    if (!s) return 0;
+    if (variant == 2) return pcfb::pconv_forward_umma_supported(s, s->C_out > 0) ? 1 : 0;
+    return 1;
+}
+
 extern "C" size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int variant)
 {
     if (!s) return 0;

@@ -77,7 +77,7 @@ __host__ __device__ inline SmemPlan plan_smem(const pcfb_pconv_shape &s, int CC,
 }
 
 static int choose_cc(const pcfb_pconv_shape &s, bool backward) {
-    for (int cc = 32; cc >= 8; cc >>= 1)
+    for (int cc = 32; cc >= 1; cc >>= 1)
         if (plan_smem(s, cc, backward).total <= SMEM_BUDGET) return cc;
     return 0;
 }

@@ -25,6 +25,11 @@ def _shape(n_in, n_out, K, C_in, C_add, C_mid, C_out, H):
     return PconvShape(int(n_in), int(n_out), int(K), int(C_in), int(C_add), int(C_mid), int(C_out), int(H))
 
 
+def forward_variant_supported(n_in, n_out, K, C_in, C_add, C_mid, C_out, H, variant):
+    sh = _shape(n_in, n_out, K, C_in, C_add, C_mid, C_out, H)
+    return bool(lib().pcfb_pconv_forward_supported(ctypes.byref(sh), int(variant)))
+
+
 def _batched(t):
     """All reference ops carry a leading batch dim (always 1 in the packed representation)."""
     return t.shape[0]

@@ -74,7 +74,10 @@ SHAPES = {  # name: (n_in, n_out, K, C_in, C_add, C_mid, C_out, H)
 @pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("name", sorted(SHAPES))
 def test_forward_matches_oracle(name, variant):
-    d = make_case(hash(name) % 1000, *SHAPES[name], pad=(name == "level1_pcf"))
+    if not _pc().forward_variant_supported(*SHAPES[name], variant):
+        assert variant == 2 and name == "ref_test_k64"            # the only shape the tcgen05 tile cannot hold
+        pytest.skip("shape not covered by the tcgen05 variant (K*C_mid tile exceeds shared memory)")
+    d = make_case(sum(map(ord, name)), *SHAPES[name], pad=(name == "level1_pcf"))
     P, Y, _ = oracle_eval(d)
     dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
     y, p = _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], dc["gd"], dc["W"], dc["b"], want_p=True, variant=variant)
@@ -97,7 +100,7 @@ def test_forward_mid3_falls_back_to_simt():
 @pytest.mark.parametrize("name", sorted(SHAPES))
 def test_backward_matches_autograd(name):
     shp = SHAPES[name]
-    d = make_case(hash(name) % 1000 + 1, *shp, pad=(name == "level1_pcf"))
+    d = make_case(sum(map(ord, name)) + 1, *shp, pad=(name == "level1_pcf"))
     go = torch.randn(1, shp[1], shp[6], generator=torch.Generator().manual_seed(9))
     P, Y, G = oracle_eval(d, go)
     dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
