@@ -112,6 +112,22 @@ def run_layer(name, ctor, call, n_in_feat, strided, transpose=False, seed=0):
     out["y_eval"] = y_eval.numpy()
     for k, v in layer.state_dict().items():
         out["param." + k] = v.numpy()
+    # the same reference module evaluated in float64 (stored as float32): the noise-free target for the
+    # GPU tests -- an fp32 evaluation can flip a ReLU whose pre-activation is ~1e-7 and move gradients by %
+    sd32 = {k: v.clone() for k, v in layer.state_dict().items()}
+    torch.manual_seed(seed)
+    layer64 = ctor(L)
+    layer64.load_state_dict(sd32)
+    # running stats were touched by the fp32 train pass; irrelevant in train mode
+    layer64 = layer64.double().train()
+    t64 = {k: (v.detach().double() if v.is_floating_point() else v) for k, v in tens.items()}
+    t64['feats'].requires_grad_(True)
+    y64, _ = call(layer64, t64)
+    (y64 * gout.double()).sum().backward()
+    out["y_train64"] = y64.detach().float().numpy()
+    out["g_feats64"] = t64['feats'].grad.float().numpy()
+    for k, p in layer64.named_parameters():
+        out["grad64." + k] = p.grad.float().numpy().copy()
     np.savez_compressed(os.path.join(HERE, "layer_%s.npz" % name), **out)
     print("layer_%s: y %s  |y|=%.4f" % (name, tuple(y.shape), float(y.abs().mean())))
 

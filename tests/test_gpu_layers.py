@@ -57,16 +57,19 @@ def test_layer_matches_reference_golden(golden_dir, name, use_kernel):
     a["feats"].requires_grad_(True)
     layer.train()
     y, wni = call(layer, a)
+    # targets: the reference module evaluated in float64 (y_train64 / g_feats64 / grad64.*).  The reference's
+    # own fp32 evaluation is NOT a usable gradient target: e.g. in layer_pointconv.npz one ReLU pre-activation
+    # is ~1e-7, flips in fp32 and moves g_feats by 4% of its max, while fp64 and this GPU path agree.
+    torch.testing.assert_close(y.cpu(), torch.from_numpy(g["y_train64"]), rtol=2e-4, atol=2e-4)
     torch.testing.assert_close(y.cpu(), torch.from_numpy(g["y_train"]), rtol=2e-4, atol=2e-4)
     (y * cuda(g["gout"])).sum().backward()
-    assert max_err_scaled(a["feats"].grad, torch.from_numpy(g["g_feats"])) < 2e-3
+    assert max_err_scaled(a["feats"].grad, torch.from_numpy(g["g_feats64"])) < 2e-3
     for k in g.files:
-        if k.startswith("grad."):
-            got = dict(layer.named_parameters())[k[5:]].grad
+        if k.startswith("grad64."):
+            got = dict(layer.named_parameters())[k[7:]].grad
             ref = torch.from_numpy(g[k])
-            # a bias feeding a train-mode BatchNorm has zero true gradient (only cancellation noise); weight
-            # gradients behind BatchNorm chains are fp32-ill-conditioned (see tests/test_oracle_golden.py)
-            tol = 2e-2 if k.endswith(".c.bias") else 5e-3 * max(1.0, float(ref.abs().max()))
+            # a bias feeding a train-mode BatchNorm has zero true gradient (only cancellation noise)
+            tol = 2e-2 if k.endswith(".c.bias") else 2e-3 * max(1.0, float(ref.abs().max()))
             assert float((got.cpu() - ref).abs().max()) <= tol, k
     layer.load_state_dict(sd, strict=True)
     layer.eval()
