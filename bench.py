@@ -159,7 +159,8 @@ def run_ours(args):
     def step(pts, nrm, col, lab):
         pcs = [p.unsqueeze(0) for p in pts]
         nrms = [p.unsqueeze(0) for p in nrm]
-        es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, stored, cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"]))
+        es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, stored, cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"],
+                                                       grid_size=cfgd["grid_size"]))
         inv_s, inv_f, inv_p = CU.compute_knn_inverse(pcs, es, ef, ep)
         logits = model(col.unsqueeze(0), pcs, es, ef, ep, nrms, inv_s, inv_f, inv_p)
         loss = torch.nn.functional.cross_entropy(logits[0], lab, ignore_index=cfgd["ignore_label"],
@@ -318,7 +319,9 @@ def kernel_rooflines(dev, host, cfgd, args):
     pairs = float(sum(c * c for c in counts))
     res["knn_self_level0"] = {"ms": ms, "Mqueries_per_s": n / ms / 1e3, "Gpairs_per_s": pairs / ms / 1e6,
                               "alg_bytes": n * (24 + 8 * K), "GBps": n * (24 + 8 * K) / ms / 1e6,
-                              "frac_fp32_issue": pairs * 9 / ms / 1e3 / (148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6) }
+                              "frac_fp32_issue": pairs * 9 / (ms * 1e-3) / (148 * 128 * peaks.get("sm_max_mhz", 1965.0) * 1e6)}
+    ms = time_op(lambda: pcf_cuda.KnnGrid(xyz, counts, 2.5 * cfgd["grid_size"][0]).query(xyz, counts, K))
+    res["knn_grid_self_level0"] = {"ms": ms, "Mqueries_per_s": n / ms / 1e3, "note": "grid build + query, exact, same table as brute force"}
     ms = time_op(lambda: pcf_cuda.compute_knn_inverse(nei[None], n))
     inv_bytes = n * K * (8 + 4 + 1) + 4 * (n + 1)
     res["knn_inverse_level0"] = {"ms": ms, "alg_bytes": inv_bytes, "GBps": inv_bytes / ms / 1e6, "frac_hbm": inv_bytes / ms / 1e6 / peaks["hbm_gbs"]}
@@ -329,7 +332,8 @@ def kernel_rooflines(dev, host, cfgd, args):
             "shape": "level-0 PointConvStridePE contraction: N=%d K=16 C_in=16 C_add=16 C_mid=16 C_out=32, P saved" % n,
             "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["frac_hbm"],
             "traffic": None, "peak_source": peaks["src"], "ms": r["ms"], "alg_bytes_per_launch": r["alg_bytes"]}
-    return roof, {"kernels": res, "knn_mpts_per_s": res["knn_self_level0"]["Mqueries_per_s"]}
+    return roof, {"kernels": res, "knn_mpts_per_s": res["knn_grid_self_level0"]["Mqueries_per_s"],
+                  "knn_bruteforce_mpts_per_s": res["knn_self_level0"]["Mqueries_per_s"]}
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -61,6 +61,18 @@ int pcfb_knn_packed(const float *ref_xyz, const int32_t *ref_off, const float *q
                     const int32_t *qry_off, int n_seg, int n_ref, int n_qry, int K,
                     int64_t *out_idx, void *stream);
 
+/* Same results, bit for bit, through a uniform grid over the reference cloud (exact
+ * grid-accelerated kNN).  pcfb_knn_grid_build bins the references of every scene (cell edge = cell_hint,
+ * enlarged on the device until each scene's dense grid has <= 2*n+64 cells; cell_hint <= 0 = automatic) into
+ * the workspace; pcfb_knn_grid_query answers any number of query sets against it (1 <= K <= 64).  The grid
+ * of one level serves its self-, forward- and propagate- edge sets. */
+size_t pcfb_knn_grid_workspace(int n_seg, int n_ref);
+int pcfb_knn_grid_build(const float *ref_xyz, const int32_t *ref_off, int n_seg, int n_ref, float cell_hint,
+                        void *workspace, size_t workspace_bytes, void *stream);
+int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, const float *qry_xyz, const int32_t *qry_off,
+                        int n_qry, int K, int64_t *out_idx, const void *workspace, size_t workspace_bytes,
+                        void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * kNN inverse map (CSR transpose).  Replaces pcf_cuda.compute_knn_inverse
  * (include/pcf.h:183-186 -> src/knn.cu:104-168).

@@ -1,0 +1,290 @@
+// Exact kNN on packed scenes through a uniform grid (sm_100a) -- same results, bit for bit, as the
+// brute-force kernel in knn.cu (and therefore as the oracle), at O(N * candidates) instead of O(N^2).
+//
+// "a grid-hash-accelerated exact kNN (same results)".  Distances are evaluated with
+// exactly the same fp32 arithmetic (no FMA contraction) and the K best are kept in (distance, index)
+// lexicographic order, so the result does not depend on the order candidates are visited in.
+//
+// build : per scene bounding box -> cell edge h (caller hint, enlarged on the device until the dense grid
+//         fits the caller's cell budget; no host round trip) -> dense cell id per reference -> cell->refs CSR
+//         (the inverse-map kernels with K = 1).
+// query : one thread per query walks Chebyshev shells R = 0,1,2,... of cells around its own cell.  Every
+//         reference NOT yet visited after shell R differs from the query by more than R*h along some axis
+//         (up to the fp32 rounding of the cell index, bounded explicitly in the kernel), so once the current
+//         K-th best squared distance is below ((R - margin)*h)^2 no unvisited reference can enter: exact.
+#include "common.cuh"
+
+namespace pcfb {
+
+struct GridPlan {          // one per scene, lives in the workspace
+    float ox, oy, oz, h;
+    int nx, ny, nz, cell_off;
+    int ref_lo, ref_hi;    // reference range of the scene
+};
+
+__device__ __forceinline__ int g_float_to_ordered(float f) {
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float g_ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ int g_find_seg(const int32_t *__restrict__ off, int n_seg, int i) {
+    int lo = 0, hi = n_seg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__global__ void kg_init_kernel(int *__restrict__ mm, int n_seg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_seg * 6) mm[i] = (i % 6 < 3) ? 0x7fffffff : (int)0x80000000;
+}
+
+__global__ void kg_bounds_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ off, int n_seg, int n,
+                                 int *__restrict__ mm)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int s = g_find_seg(off, n_seg, i);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int o = g_float_to_ordered(xyz[3 * (size_t)i + d]);
+            atomicMin(&mm[s * 6 + d], o);
+            atomicMax(&mm[s * 6 + 3 + d], o);
+        }
+    }
+}
+
+// single thread: per-scene grid geometry; h grows by 2^(1/3) until the scene's dense grid fits its budget
+__global__ void kg_plan_kernel(const int *__restrict__ mm, const int32_t *__restrict__ off, int n_seg, float cell_hint,
+                               GridPlan *__restrict__ plans)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int cell_off = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        GridPlan p;
+        p.ref_lo = off[s]; p.ref_hi = off[s + 1];
+        const int n = p.ref_hi - p.ref_lo;
+        const long long budget = 2ll * n + 64;
+        if (n <= 0) {
+            p.ox = p.oy = p.oz = 0.f; p.h = 1.f; p.nx = p.ny = p.nz = 1;
+        } else {
+            const float mnx = g_ordered_to_float(mm[s * 6 + 0]), mny = g_ordered_to_float(mm[s * 6 + 1]), mnz = g_ordered_to_float(mm[s * 6 + 2]);
+            const float ex = g_ordered_to_float(mm[s * 6 + 3]) - mnx, ey = g_ordered_to_float(mm[s * 6 + 4]) - mny, ez = g_ordered_to_float(mm[s * 6 + 5]) - mnz;
+            float h = cell_hint;
+            if (!(h > 0.f)) h = fmaxf(fmaxf(ex, ey), ez) * (1.0f / 1024.0f);
+            if (!(h > 1e-20f)) h = 1.f;                 // degenerate cloud (all points equal)
+            while (true) {
+                const long long nx = (long long)floorf(ex / h) + 1, ny = (long long)floorf(ey / h) + 1, nz = (long long)floorf(ez / h) + 1;
+                if (nx * ny * nz <= budget) { p.nx = (int)nx; p.ny = (int)ny; p.nz = (int)nz; break; }
+                h *= 1.2599211f;
+            }
+            p.ox = mnx; p.oy = mny; p.oz = mnz; p.h = h;
+        }
+        p.cell_off = cell_off;
+        cell_off += p.nx * p.ny * p.nz;
+        plans[s] = p;
+    }
+}
+
+__device__ __forceinline__ int cell_coord(float x, float o, float h, int n) {
+    const int c = (int)floorf(__fdiv_rn(__fsub_rn(x, o), h));
+    return min(max(c, 0), n - 1);
+}
+
+__global__ void kg_cell_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ off, int n_seg, int n,
+                               const GridPlan *__restrict__ plans, int64_t *__restrict__ cell)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const GridPlan p = plans[g_find_seg(off, n_seg, i)];
+        const int cx = cell_coord(xyz[3 * (size_t)i], p.ox, p.h, p.nx);
+        const int cy = cell_coord(xyz[3 * (size_t)i + 1], p.oy, p.h, p.ny);
+        const int cz = cell_coord(xyz[3 * (size_t)i + 2], p.oz, p.h, p.nz);
+        cell[i] = (int64_t)p.cell_off + cx + (int64_t)p.nx * (cy + (int64_t)p.ny * cz);
+    }
+}
+
+template <int KP>
+struct TopKLex {
+    float d[KP];
+    int id[KP];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < KP; ++i) { d[i] = __int_as_float(0x7f800000); id[i] = 0x7fffffff; }
+    }
+    __device__ __forceinline__ bool accepts(float dist, int idx) const {
+        return dist < d[KP - 1] || (dist == d[KP - 1] && idx < id[KP - 1]);
+    }
+    __device__ __forceinline__ void insert(float dist, int idx) {
+        d[KP - 1] = dist; id[KP - 1] = idx;
+#pragma unroll
+        for (int i = KP - 1; i > 0; --i) {
+            const bool sw = d[i] < d[i - 1] || (d[i] == d[i - 1] && id[i] < id[i - 1]);
+            const float dl = sw ? d[i] : d[i - 1], dh = sw ? d[i - 1] : d[i];
+            const int il = sw ? id[i] : id[i - 1], ih = sw ? id[i - 1] : id[i];
+            d[i - 1] = dl; d[i] = dh; id[i - 1] = il; id[i] = ih;
+        }
+    }
+    __device__ __forceinline__ float kth(int K) const {         // d[K-1] without dynamic register indexing
+        float r = d[KP - 1];
+#pragma unroll
+        for (int i = 0; i < KP; ++i) if (i == K - 1) r = d[i];
+        return r;
+    }
+};
+
+template <int KP>
+__global__ void __launch_bounds__(128)
+knn_grid_query_kernel(const float *__restrict__ ref, const GridPlan *__restrict__ plans,
+                      const int32_t *__restrict__ cell_ptr, const int32_t *__restrict__ cell_pts,
+                      const float *__restrict__ qry, const int32_t *__restrict__ qry_off, int n_seg, int n_qry, int K,
+                      int64_t *__restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_qry) return;
+    const GridPlan p = plans[g_find_seg(qry_off, n_seg, q)];
+    const float qx = qry[3 * (size_t)q], qy = qry[3 * (size_t)q + 1], qz = qry[3 * (size_t)q + 2];
+    TopKLex<KP> best;
+    best.init();
+    const int n_ref = p.ref_hi - p.ref_lo;
+    if (n_ref > 0) {
+        const int cx = cell_coord(qx, p.ox, p.h, p.nx), cy = cell_coord(qy, p.oy, p.h, p.ny), cz = cell_coord(qz, p.oz, p.h, p.nz);
+        for (int R = 0;; ++R) {
+            const int z0 = max(cz - R, 0), z1 = min(cz + R, p.nz - 1);
+            const int y0 = max(cy - R, 0), y1 = min(cy + R, p.ny - 1);
+            const int x0 = max(cx - R, 0), x1 = min(cx + R, p.nx - 1);
+            for (int z = z0; z <= z1; ++z) {
+                const bool zface = (z == cz - R) || (z == cz + R);
+                for (int y = y0; y <= y1; ++y) {
+                    const bool full_row = zface || (y == cy - R) || (y == cy + R);
+                    // on the shell: whole x-row if the row lies on a z/y face, otherwise only its two end cells
+                    const int step = full_row ? 1 : max(2 * R, 1);
+                    for (int x = full_row ? x0 : cx - R; x <= (full_row ? x1 : cx + R); x += step) {
+                        if (x < 0 || x >= p.nx) continue;
+                        const int c = p.cell_off + x + p.nx * (y + p.ny * z);
+                        const int e1 = cell_ptr[c + 1];
+                        for (int e = cell_ptr[c]; e < e1; ++e) {
+                            const int idx = cell_pts[e];
+                            const float rx = ref[3 * (size_t)idx], ry = ref[3 * (size_t)idx + 1], rz = ref[3 * (size_t)idx + 2];
+                            const float dx = __fsub_rn(qx, rx), dy = __fsub_rn(qy, ry), dz = __fsub_rn(qz, rz);
+                            const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            if (best.accepts(dist, idx)) best.insert(dist, idx);
+                        }
+                    }
+                }
+            }
+            const bool all = (cx - R <= 0) && (cy - R <= 0) && (cz - R <= 0) && (cx + R >= p.nx - 1) && (cy + R >= p.ny - 1) && (cz + R >= p.nz - 1);
+            if (all) break;
+            // unvisited references differ from the query by more than (R - rounding of the cell index) * h
+            const float errc = 3e-7f * (float)max(max(p.nx, p.ny), p.nz);
+            const float reach = ((float)R - 2.f * errc - 1e-4f) * p.h;
+            if (reach > 0.f && best.kth(K) < reach * reach) break;
+        }
+    }
+    const int found = min(n_ref, K);
+    int64_t *o = out + (size_t)q * K;
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+        if (i < K) {
+            int v = best.id[i];
+            if (i >= found) {
+                v = -1;
+                if (found > 0) {
+                    const int src = i % found;
+#pragma unroll
+                    for (int t = 0; t < KP; ++t) if (t == src) v = best.id[t];
+                }
+            }
+            o[i] = (int64_t)v;
+        }
+    }
+}
+
+struct KgWorkspace {
+    int *mm;
+    GridPlan *plans;
+    int64_t *cell;
+    int32_t *cell_ptr, *cell_pts;
+    uint8_t *zero_k;
+    void *inv_ws;
+    size_t inv_ws_bytes, bytes;
+    int max_cells;
+};
+
+static KgWorkspace carve_kg(void *ws, int n_seg, int n_ref) {
+    Carver c(ws);
+    KgWorkspace w{};
+    w.max_cells = 2 * n_ref + 64 * n_seg;
+    w.mm = c.take<int>((size_t)n_seg * 6 + 1);
+    w.plans = c.take<GridPlan>((size_t)n_seg);
+    w.cell = c.take<int64_t>((size_t)n_ref + 1);
+    w.cell_ptr = c.take<int32_t>((size_t)w.max_cells + 2);
+    w.cell_pts = c.take<int32_t>((size_t)n_ref + 1);
+    w.zero_k = c.take<uint8_t>((size_t)n_ref + 1);
+    w.inv_ws_bytes = pcfb_knn_inverse_workspace(n_ref, 1, w.max_cells);
+    w.inv_ws = c.take<char>(w.inv_ws_bytes);
+    w.bytes = align_up(c.off, 256);
+    return w;
+}
+
+static inline int kg_blocks(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace pcfb
+
+extern "C" size_t pcfb_knn_grid_workspace(int n_seg, int n_ref)
+{
+    return pcfb::carve_kg(nullptr, n_seg, n_ref).bytes;
+}
+
+extern "C" int pcfb_knn_grid_build(const float *ref_xyz, const int32_t *ref_off, int n_seg, int n_ref, float cell_hint,
+                                   void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace pcfb;
+    PCFB_REQUIRE(n_seg >= 1 && n_ref >= 0, "pcfb_knn_grid_build: bad sizes");
+    PCFB_REQUIRE((int64_t)2 * n_ref + 64ll * n_seg < (1ll << 30), "pcfb_knn_grid_build: cloud too large");
+    PCFB_REQUIRE(ref_off && workspace && (n_ref == 0 || ref_xyz), "pcfb_knn_grid_build: null pointer");
+    KgWorkspace w = carve_kg(workspace, n_seg, n_ref);
+    if (workspace_bytes < w.bytes) { set_error("pcfb_knn_grid_build: workspace %zu < %zu", workspace_bytes, w.bytes); return PCFB_ERR_WORKSPACE; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    kg_init_kernel<<<ceil_div(n_seg * 6, 256), 256, 0, st>>>(w.mm, n_seg);
+    if ((rc = check_launch("kg_init_kernel"))) return rc;
+    if (n_ref > 0) {
+        kg_bounds_kernel<<<kg_blocks(n_ref), 256, 0, st>>>(ref_xyz, ref_off, n_seg, n_ref, w.mm);
+        if ((rc = check_launch("kg_bounds_kernel"))) return rc;
+    }
+    kg_plan_kernel<<<1, 32, 0, st>>>(w.mm, ref_off, n_seg, cell_hint, w.plans);
+    if ((rc = check_launch("kg_plan_kernel"))) return rc;
+    if (n_ref > 0) {
+        kg_cell_kernel<<<kg_blocks(n_ref), 256, 0, st>>>(ref_xyz, ref_off, n_seg, n_ref, w.plans, w.cell);
+        if ((rc = check_launch("kg_cell_kernel"))) return rc;
+    }
+    return pcfb_knn_inverse(w.cell, n_ref, 1, w.max_cells, w.cell_pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream);
+}
+
+extern "C" int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, const float *qry_xyz, const int32_t *qry_off,
+                                   int n_qry, int K, int64_t *out_idx, const void *workspace, size_t workspace_bytes,
+                                   void *stream)
+{
+    using namespace pcfb;
+    PCFB_REQUIRE(K >= 1 && K <= 64, "pcfb_knn_grid_query: K=%d outside [1,64] (use pcfb_knn_packed for larger K)", K);
+    PCFB_REQUIRE(n_seg >= 1 && n_ref >= 0 && n_qry >= 0, "pcfb_knn_grid_query: bad sizes");
+    if (n_qry == 0) return PCFB_OK;
+    PCFB_REQUIRE(qry_xyz && qry_off && out_idx && workspace && (n_ref == 0 || ref_xyz), "pcfb_knn_grid_query: null pointer");
+    KgWorkspace w = carve_kg(const_cast<void *>(workspace), n_seg, n_ref);
+    if (workspace_bytes < w.bytes) { set_error("pcfb_knn_grid_query: workspace %zu < %zu", workspace_bytes, w.bytes); return PCFB_ERR_WORKSPACE; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = ceil_div(n_qry, 128);
+    if (K <= 16)
+        knn_grid_query_kernel<16><<<grid, 128, 0, st>>>(ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+    else if (K <= 32)
+        knn_grid_query_kernel<32><<<grid, 128, 0, st>>>(ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+    else
+        knn_grid_query_kernel<64><<<grid, 128, 0, st>>>(ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+    return check_launch("knn_grid_query_kernel");
+}

@@ -34,22 +34,40 @@ def compute_knn(ref_points, query_points, K, dilated_rate=1, method='keops'):
                                   "(knn_post_dataloader_utils.py:81-86)")
     ref = _as_cuda_xyz(ref_points)
     qry = _as_cuda_xyz(query_points)
+    if KNN_METHOD == "grid" and K <= 64 and method != "brute":
+        return pcf_cuda.KnnGrid(ref, [ref.shape[0]]).query(qry, [qry.shape[0]], K)
     return pcf_cuda.knn_packed(ref, [ref.shape[0]], qry, [qry.shape[0]], K)
 
 
-def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagate):
+# 'grid' (default): exact uniform-grid search; 'brute': the shared-memory tiled brute-force kernel.  Both return
+# identical tables (tests/test_gpu_knn.py); brute force is O(N^2) per scene.
+KNN_METHOD = "grid"
+
+
+def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagate, grid_size=None, method=None):
     """compute_knn_packed (171-223).  pointclouds: list over levels of [1, sum N_l, 3]; points_stored: list
     over levels of per-scene counts.  Returns (nei_self_list, nei_forward_list, nei_propagate_list) in the
-    reference's nesting [scene][level]; here a single pseudo-scene carries the packed, offset tables."""
+    reference's nesting [scene][level]; here a single pseudo-scene carries the packed, offset tables.
+    grid_size (optional, cfg.grid_size): per-level voxel size, used as a cell-size hint by the grid search."""
+    method = method or KNN_METHOD
     L = len(pointclouds)
     pcs = [_as_cuda_xyz(p.reshape(-1, 3) if isinstance(p, np.ndarray) else p.reshape(-1, 3)) for p in pointclouds]
     counts = [list(map(int, ps)) for ps in points_stored]
+    kmax = max(list(K_self) + list(K_forward) + list(K_propagate))
     e_self, e_fwd, e_prop = [], [], []
+    if method == "brute" or kmax > 64:
+        for j in range(L):
+            e_self.append(pcf_cuda.knn_packed(pcs[j], counts[j], pcs[j], counts[j], K_self[j]))
+            if j >= 1:
+                e_fwd.append(pcf_cuda.knn_packed(pcs[j - 1], counts[j - 1], pcs[j], counts[j], K_forward[j]))
+                e_prop.append(pcf_cuda.knn_packed(pcs[j], counts[j], pcs[j - 1], counts[j - 1], K_propagate[j]))
+        return [e_self], [e_fwd], [e_prop]
+    grids = [pcf_cuda.KnnGrid(pcs[j], counts[j], 2.5 * float(grid_size[j]) if grid_size is not None else 0.0) for j in range(L)]
     for j in range(L):
-        e_self.append(pcf_cuda.knn_packed(pcs[j], counts[j], pcs[j], counts[j], K_self[j]))
+        e_self.append(grids[j].query(pcs[j], counts[j], K_self[j]))
         if j >= 1:
-            e_fwd.append(pcf_cuda.knn_packed(pcs[j - 1], counts[j - 1], pcs[j], counts[j], K_forward[j]))
-            e_prop.append(pcf_cuda.knn_packed(pcs[j], counts[j], pcs[j - 1], counts[j - 1], K_propagate[j]))
+            e_fwd.append(grids[j - 1].query(pcs[j], counts[j], K_forward[j]))
+            e_prop.append(grids[j].query(pcs[j - 1], counts[j - 1], K_propagate[j]))
     return [e_self], [e_fwd], [e_prop]
 
 

@@ -254,6 +254,37 @@ def knn_packed(ref_xyz, ref_counts, qry_xyz, qry_counts, K, out=None):
     return out
 
 
+def _offsets(counts, dev):
+    return torch.tensor([0] + list(counts), dtype=torch.int64).cumsum(0).to(torch.int32).to(dev, non_blocking=True)
+
+
+class KnnGrid:
+    """Uniform grid over a packed reference cloud (pcfb_knn_grid_build); query() returns exactly what
+    knn_packed() returns.  cell_hint: cell edge (about 2.5x the point spacing works best; <= 0 = automatic)."""
+
+    def __init__(self, ref_xyz, ref_counts, cell_hint=0.0):
+        require(ref_xyz, F32, "ref_xyz")
+        self.ref, self.counts, self.n_seg = ref_xyz, list(map(int, ref_counts)), len(ref_counts)
+        if sum(self.counts) != ref_xyz.shape[0]:
+            raise RuntimeError("scene counts do not add up to the packed cloud size")
+        dev = ref_xyz.device
+        self.ref_off = _offsets(self.counts, dev)
+        self.ws_bytes = lib().pcfb_knn_grid_workspace(self.n_seg, ref_xyz.shape[0])
+        self.ws = workspace(self.ws_bytes, dev)
+        check(lib().pcfb_knn_grid_build(ptr(ref_xyz), ptr(self.ref_off), self.n_seg, ref_xyz.shape[0], float(cell_hint),
+                                        ptr(self.ws), self.ws_bytes, stream_ptr()), "knn_grid_build")
+
+    def query(self, qry_xyz, qry_counts, K):
+        require(qry_xyz, F32, "qry_xyz")
+        if len(qry_counts) != self.n_seg or sum(map(int, qry_counts)) != qry_xyz.shape[0]:
+            raise RuntimeError("query scene counts do not match")
+        qo = _offsets(qry_counts, qry_xyz.device)
+        out = torch.empty(qry_xyz.shape[0], K, device=qry_xyz.device, dtype=I64)
+        check(lib().pcfb_knn_grid_query(ptr(self.ref), self.n_seg, self.ref.shape[0], ptr(qry_xyz), ptr(qo), qry_xyz.shape[0],
+                                        int(K), ptr(out), ptr(self.ws), self.ws_bytes, stream_ptr()), "knn_grid_query")
+        return out
+
+
 def gather(feats, nei):
     """index_points for B folded: feats [N,C], nei [M,K] -> [M,K,C]."""
     require(feats, F32, "feats"); require(nei, I64, "nei")

@@ -24,7 +24,7 @@ def main():
     def step():
         pcs = [p.unsqueeze(0) for p in pts]; nrms = [p.unsqueeze(0) for p in nrm]
         with torch.profiler.record_function("edges_knn"):
-            es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, host["stored"], cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"]))
+            es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, host["stored"], cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"], grid_size=cfgd["grid_size"]))
         with torch.profiler.record_function("edges_inverse"):
             inv = CU.compute_knn_inverse(pcs, es, ef, ep)
         with torch.profiler.record_function("forward"):

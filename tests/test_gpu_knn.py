@@ -96,6 +96,51 @@ def test_knn_full_size_properties():
     assert np.array_equal(got[sub], OK.knn_c(xyz, xyz[sub], 16))
 
 
+def _grid(ref, qry, ref_counts, qry_counts, K, hint=0.0):
+    return _pc().KnnGrid(cuda(ref), ref_counts, hint).query(cuda(qry), qry_counts, K).cpu().numpy()
+
+
+@pytest.mark.parametrize("hint", [0.0, 0.05, 0.3, 5.0])
+def test_grid_knn_equals_brute_force_and_oracle(hint):
+    """The grid search must return exactly the brute-force table whatever the cell size: random cloud,
+    surface clouds, tie-heavy grid with duplicates, ragged packed scenes with a scene smaller than K."""
+    rng = np.random.default_rng(3)
+    ref = rng.standard_normal((4000, 3)).astype(np.float32)
+    qry = rng.standard_normal((900, 3)).astype(np.float32) * 1.5            # some queries outside the ref bbox
+    for K in (1, 16, 33, 64):
+        assert np.array_equal(_grid(ref, qry, [4000], [900], K, hint), OK.compute_knn(ref, qry, K))
+    g = np.stack(np.meshgrid(*[np.arange(13)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float32) * 0.1
+    cloud = np.concatenate([g, g[:300]])
+    assert np.array_equal(_grid(cloud, cloud, [len(cloud)], [len(cloud)], 16, hint), _knn_gpu(cloud, cloud, [len(cloud)], [len(cloud)], 16))
+    ref_counts, qry_counts = [700, 5, 1300, 129, 40], [200, 9, 310, 33, 64]
+    ref = np.concatenate([surface_cloud(n, 10 + i)[0] + i for i, n in enumerate(ref_counts)])
+    qry = np.concatenate([surface_cloud(n, 20 + i)[0] + i for i, n in enumerate(qry_counts)])
+    assert np.array_equal(_grid(ref, qry, ref_counts, qry_counts, 16, hint), _knn_oracle_packed(ref, qry, ref_counts, qry_counts, 16))
+    assert np.array_equal(_grid(qry, ref, qry_counts, ref_counts, 8, hint), _knn_oracle_packed(qry, ref, qry_counts, ref_counts, 8))
+
+
+def test_grid_knn_degenerate_clouds():
+    line = np.zeros((3000, 3), np.float32); line[:, 0] = np.linspace(0, 300, 3000)     # 1-D cloud: very elongated grid
+    assert np.array_equal(_grid(line, line, [3000], [3000], 16), _knn_gpu(line, line, [3000], [3000], 16))
+    same = np.ones((500, 3), np.float32)                                               # all points identical
+    assert np.array_equal(_grid(same, same, [500], [500], 16), _knn_gpu(same, same, [500], [500], 16))
+
+
+def test_grid_knn_full_size_equals_brute_force():
+    """BASELINE size: the whole 13-edge-set pyramid of a 100k-point scene, grid vs brute force, exact."""
+    from pcf_b200 import synthetic, knn_post_dataloader_utils as KU, grid_subsampling as GS
+    xyz, nrm, _ = synthetic.make_scene(4, 100000)
+    gs = [0.1, 0.2, 0.4, 0.8, 1.6]
+    pts, _ = GS.subsample(xyz, nrm, gs)
+    pcs = [p[None] for p in pts]
+    stored = [[p.shape[0]] for p in pts]
+    a = KU.prepare(*KU.compute_knn_packed(pcs, stored, [16] * 5, [16] * 5, [16] * 5, grid_size=gs, method="grid"))
+    b = KU.prepare(*KU.compute_knn_packed(pcs, stored, [16] * 5, [16] * 5, [16] * 5, method="brute"))
+    c = KU.prepare(*KU.compute_knn_packed(pcs, stored, [16] * 5, [16] * 5, [16] * 5, method="grid"))     # automatic cell size
+    for x, y, z in zip(a[0] + a[1] + a[2], b[0] + b[1] + b[2], c[0] + c[1] + c[2]):
+        assert torch.equal(x, y) and torch.equal(z, y)
+
+
 # ---------------------------------------------------------------------------------------------------
 def _inv_gpu(nei, total):
     n, k, idx = _pc().compute_knn_inverse(cuda(nei)[None], total)
