@@ -123,7 +123,8 @@ int pcfb_edge_geometry(const float *xyz_in, const float *nrm_in, const float *xy
  * Replaces pconv_linear_cutlass_forward (pcf.h:243-250 -> pconv_ops.cu:969-1269), pconv_linear_forward
  * (pcf.h:131-138), pconv_forward (pcf.h:81-86; lin_w == NULL -> only P) and pcf_forward (pcf.h:38-43;
  * guidance != NULL).  out_y [n_out,C_out] (NULL iff lin_w NULL), out_p [n_out,C_cat*C_mid] (may be NULL
- * when lin_w given).  `variant`: 0 = auto, 1 = exact fp32 SIMT, 2 = tcgen05 (3xTF32 split Linear).
+ * when lin_w given).  `variant`: 0 = auto, 1 = exact fp32 SIMT, 2 = tcgen05 (3xTF32 split Linear; pipelined
+ * kernel when the tile fits in shared memory, else the simple one), 3 = tcgen05 simple kernel (bisecting).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int n_in, n_out, K, C_in, C_add, C_mid, C_out, H; /* H = guidance heads (0 if none) */

@@ -19,12 +19,19 @@ size_t pconv_forward_umma_workspace(const pcfb_pconv_shape *s);
 int pconv_forward_umma(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
                        const float *additional, const float *guidance, const float *lin_w, const float *lin_b,
                        float *out_y, float *out_p, void *workspace, size_t workspace_bytes, cudaStream_t st);
+// pconv_umma2.cu (pipelined tcgen05 forward)
+bool pconv_forward_umma2_supported(const pcfb_pconv_shape *s, bool has_lin);
+size_t pconv_forward_umma2_workspace(const pcfb_pconv_shape *s);
+int pconv_forward_umma2(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
+                        const float *additional, const float *guidance, const float *lin_w, const float *lin_b,
+                        float *out_y, float *out_p, void *workspace, size_t workspace_bytes, cudaStream_t st);
 }  // namespace pcfb
 
 extern "C" int pcfb_pconv_forward_supported(const pcfb_pconv_shape *s, int variant)
 {
     if (!s) return 0;
-    if (variant == 2) return pcfb::pconv_forward_umma_supported(s, s->C_out > 0) ? 1 : 0;
+    if (variant == 2 || variant == 3)
+        return (pcfb::pconv_forward_umma_supported(s, s->C_out > 0) || pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) ? 1 : 0;
     return 1;
 }
 
@@ -32,6 +39,7 @@ extern "C" size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int va
 {
     if (!s) return 0;
     if (variant == 1) return 0;
+    if (variant != 3 && pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) return pcfb::pconv_forward_umma2_workspace(s);
     return pcfb::pconv_forward_umma_supported(s, s->C_out > 0) ? pcfb::pconv_forward_umma_workspace(s) : 0;
 }
 
@@ -46,14 +54,20 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
     PCFB_REQUIRE(s->C_add == 0 || additional, "pcfb_pconv_forward: C_add=%d but additional is NULL", s->C_add);
     PCFB_REQUIRE((s->H > 0) == (guidance != nullptr), "pcfb_pconv_forward: H and guidance disagree");
     PCFB_REQUIRE(lin_w ? out_y != nullptr : out_p != nullptr, "pcfb_pconv_forward: no output requested");
-    PCFB_REQUIRE(variant >= 0 && variant <= 2, "pcfb_pconv_forward: unknown variant %d", variant);
+    PCFB_REQUIRE(variant >= 0 && variant <= 3, "pcfb_pconv_forward: unknown variant %d", variant);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool umma_ok = lin_w && pconv_forward_umma_supported(s, true);
-    if (variant == 2 && !umma_ok) {
+    // variants: 0 auto, 1 exact-fp32 SIMT, 2 tcgen05 (pipelined kernel when the tile fits, else the simple one),
+    // 3 tcgen05 simple kernel only (kept for bisecting)
+    const bool u1_ok = lin_w && pconv_forward_umma_supported(s, true);
+    const bool u2_ok = lin_w && variant != 3 && pconv_forward_umma2_supported(s, true);
+    if ((variant == 2 || variant == 3) && !u1_ok && !u2_ok) {
         set_error("pcfb_pconv_forward: tcgen05 variant does not support this shape");
         return PCFB_ERR_UNSUPPORTED;
     }
-    if (variant == 2 || (variant == 0 && umma_ok))
+    if (variant != 1 && u2_ok)
+        return pconv_forward_umma2(s, feats, nei, weights, additional, guidance, lin_w, lin_b, out_y, out_p,
+                                   workspace, workspace_bytes, st);
+    if (variant != 1 && u1_ok)
         return pconv_forward_umma(s, feats, nei, weights, additional, guidance, lin_w, lin_b, out_y, out_p,
                                   workspace, workspace_bytes, st);
     return pconv_forward_simt(s, feats, nei, weights, additional, guidance, lin_w, lin_b, out_y, out_p, st);
