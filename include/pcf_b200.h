@@ -147,6 +147,8 @@ int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats, const int6
  * Outputs (any may be NULL to skip): grad_feats [n_in,C_in] (needs the inverse map; summed per input
  * point over its inverse segment, no atomics), grad_weights [n_out,K,C_mid], grad_additional
  * [n_out,K,C_add], grad_guidance [n_out,K,H], grad_lin_w [C_out,C_cat*C_mid], grad_lin_b [C_out].
+ * variant 0/2: dP = dY W and dW = dY^T P run as 3xTF32 tcgen05 GEMMs, the per-point part as a CUDA-core kernel on
+ * dP; variant 1: one fused exact-fp32 CUDA-core kernel (bisecting reference).
  * ------------------------------------------------------------------------------------------- */
 size_t pcfb_pconv_backward_workspace(const pcfb_pconv_shape *s, int variant);
 int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_y, const float *grad_p,
@@ -156,6 +158,22 @@ int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_y, const fl
                         const float *pconv_out, float *grad_feats, float *grad_weights, float *grad_additional,
                         float *grad_guidance, float *grad_lin_w, float *grad_lin_b, void *workspace,
                         size_t workspace_bytes, int variant, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32-accurate dense products on tcgen05 (3xTF32 operand split, TMEM accumulators) for the Linear layers
+ * around the contraction (Linear_BN / UnaryBlock, layer_utils.py:241-319; torch runs them as SIMT sgemm) and
+ * for the two dense products of the fused backward (dP = dY W, dW = dY^T P; pconv_ops.cu:434-440,516-533).
+ *   pcfb_gemm_nt : C[M,N] = act(A[M,K] * Wt + bias);  W is [N,K] (w_is_kn = 0, y = x W^T) or [K,N]
+ *                  (w_is_kn = 1, dx = dy W); 1 <= N <= 256; act 0 none / 1 ReLU / 2 LeakyReLU(0.1).
+ *   pcfb_gemm_tn : C[N1,N2] = A[M,N1]^T * B[M,N2], optionally rowsum[N1] = sum_m A[m,:] (bias gradient);
+ *                  1 <= N1 <= 256; reduction over M split across CTAs, partials summed in fixed order.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcfb_gemm_nt_workspace(int N, int K);
+int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,
+                 int M, int N, int K, int act, void *workspace, size_t workspace_bytes, void *stream);
+size_t pcfb_gemm_tn_workspace(int M, int N1, int N2, int with_rowsum);
+int pcfb_gemm_tn(const float *A, int lda, const float *B, int ldb, float *C, int ldc, float *rowsum,
+                 int M, int N1, int N2, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Grid (voxel) subsampling with barycentres on packed scenes.  Replaces grid_subsampling()
@@ -191,10 +209,11 @@ int pcfb_gridsub_emit(const float *xyz, const float *feats, int n_seg, int n_pts
 /* ---------------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05 (UMMA) operand / accumulator conventions used by the fused
  * forward: D = A[M x K] * B[N x K]^T on one CTA (M in {64,128}, N % 8 == 0, K % 8 == 0, K <= 64).
- * h_params is a HOST array of 11 uint32: fill (lbo_a, sbo_a, lbo_b, sbo_b) = where element (r,k) is
- * written, byte offset (k/4)*lbo + (r/8)*sbo + (r%8)*16 + (k%4)*4; desc (lbo_a, sbo_a, lbo_b, sbo_b) =
+ * h_params is a HOST array of 12 uint32: fill (lbo_a, sbo_a, lbo_b, sbo_b) = where element (r,k) is
+ * written, byte offset (k/4)*lbo + (r/8)*sbo + (r%8)*16 + (k%4)*4 for a K-major operand and
+ * (r%4)*4 + (r/4)*sbo + (k%8)*16 + (k/8)*lbo for an MN-major one; desc (lbo_a, sbo_a, lbo_b, sbo_b) =
  * what the shared-memory descriptors claim; (kstep_a, kstep_b) = start-address advance per K=8 step;
- * idesc.  raw receives the accumulator as stored in TMEM: [128 lanes][N columns].  status (device
+ * idesc; mn_flags (bit 0: A is MN-major, bit 1: B is MN-major).  raw receives the accumulator as stored in TMEM: [128 lanes][N columns].  status (device
  * int) is set to 1 if the MMA never completed.  No reference counterpart (test infrastructure of
  * the product kernel, exercised by tests/test_umma_selftest.py).
  * ------------------------------------------------------------------------------------------- */

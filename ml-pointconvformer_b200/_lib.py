@@ -42,6 +42,10 @@ SIGNATURES = {
     "pcfb_pconv_forward": (c_int, [ctypes.POINTER(PconvShape), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, c_int, _P]),
     "pcfb_pconv_backward_workspace": (c_size_t, [ctypes.POINTER(PconvShape), c_int]),
     "pcfb_pconv_backward": (c_int, [ctypes.POINTER(PconvShape)] + [_P] * 19 + [c_size_t, c_int, _P]),
+    "pcfb_gemm_nt_workspace": (c_size_t, [c_int, c_int]),
+    "pcfb_gemm_nt": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "pcfb_gemm_tn_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pcfb_gemm_tn": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "pcfb_gridsub_workspace": (c_size_t, [c_int, c_int, c_int64]),
     "pcfb_gridsub_bounds": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "pcfb_gridsub_count": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_int64, _P, _P, c_size_t, _P]),

@@ -1,0 +1,567 @@
+// fp32-accurate GEMMs on the Blackwell tensor cores (sm_100a): 3xTF32 operand splitting on tcgen05.mma with
+// TMEM accumulators.  These serve the dense per-point / per-edge Linear layers around the fused contraction
+// (Linear_BN / UnaryBlock, /root/reference/layer_utils.py:241-319) and the two dense products
+// of the fused backward (row a12: dP = dY W and dW = dY^T P, /root/reference/.../pconv_ops.cu:434-440,516-533).
+// torch's fp32 path for the same products is a SIMT sgemm (cutlass_80_simt_sgemm); single-pass TF32 misses the
+// 1e-4 parity bar, hence the split: x = hi + lo, D += A_lo B_hi + A_hi B_lo + A_hi B_hi.
+//
+//   gemm_nt : C[M x N] = A[M x K] * Bt (+ bias), A row-major (lda), Bt given as the weight matrix either
+//             [N x K] (y = x W^T) or [K x N] (dx = dy W); the small B is split and laid out in the UMMA
+//             K-major core-matrix order once by a prep kernel and streamed with cp.async.  Tile = 128 rows
+//             (UMMA M = 128: TMEM lane == row), N <= 256 per launch column block.
+//   gemm_tn : C[N1 x N2] = A[M x N1]^T * B[M x N2] (+ optional column of row sums = bias gradient), the
+//             reduction runs over the M rows: split over CTAs, fp32 partials reduced in fixed order
+//             (deterministic).  Operands are transposed in registers while staging (4x4 blocks), so both are
+//             ordinary K-major descriptors.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace pcfb {
+
+constexpr int GT_M = 128;      // rows per tile (gemm_nt)
+constexpr int GT_KC = 32;      // K floats per chunk
+constexpr int G_NT = 256;      // threads
+
+__device__ __forceinline__ void g_cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(umma::smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void g_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+// ---- B preparation: weight matrix -> (hi, lo) tf32, K-major core-matrix order, zero padded ----
+// out[chunk][hi|lo][q = k/4 within chunk][n][4];  src element (n, k) = trans ? W[k*ldw + n] : W[n*ldw + k]
+__global__ void gemm_prep_b_kernel(const float *__restrict__ W, int ldw, int trans, int N, int Npad, int K, int n_chunks,
+                                   float *__restrict__ out)
+{
+    const int units = GT_KC / 4;
+    const int64_t total = (int64_t)n_chunks * units * Npad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % Npad);
+        const int q = (int)((i / Npad) % units);
+        const int ch = (int)(i / ((int64_t)Npad * units));
+        const int k0 = ch * GT_KC + q * 4;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + e;
+            v[e] = (n < N && k < K) ? (trans ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k]) : 0.f;
+        }
+        float4 hi, lo;
+        umma::split_tf32(v[0], hi.x, lo.x); umma::split_tf32(v[1], hi.y, lo.y);
+        umma::split_tf32(v[2], hi.z, lo.z); umma::split_tf32(v[3], hi.w, lo.w);
+        const size_t blk = (size_t)Npad * GT_KC;
+        const size_t off = (size_t)q * Npad * 4 + (size_t)n * 4;
+        *reinterpret_cast<float4 *>(out + ((size_t)ch * 2 + 0) * blk + off) = hi;
+        *reinterpret_cast<float4 *>(out + ((size_t)ch * 2 + 1) * blk + off) = lo;
+    }
+}
+
+struct GemmNtArgs {
+    const float *A;          // [M][lda]
+    const float *b_prep;     // prepared B
+    const float *bias;       // [N] or null
+    float *C;                // [M][ldc]
+    int M, N, Npad, K, lda, ldc, n_chunks, tmem_cols;
+    int b_resident;          // whole prepared B lives in shared memory
+    int vec_a;               // 16-byte loads of A rows allowed
+    int act;                 // 0 none, 1 relu, 2 leaky relu 0.1
+};
+
+struct GemmNtPlan { uint32_t a_bytes, b_bytes; int b_slots; size_t off_A, off_B, off_bar, total; };
+
+__host__ __device__ inline GemmNtPlan gemm_nt_plan(int Npad, int n_chunks, bool resident) {
+    GemmNtPlan pl;
+    pl.a_bytes = GT_M * GT_KC * 4;                       // 16 KB per (hi | lo)
+    pl.b_bytes = (uint32_t)Npad * GT_KC * 4;
+    pl.b_slots = resident ? n_chunks : 3;
+    size_t o = 0;
+    pl.off_A = o; o += 4 * (size_t)pl.a_bytes;           // [2 bufs][hi|lo]
+    pl.off_B = o; o += (size_t)pl.b_slots * 2 * pl.b_bytes;
+    o = align_up(o, 16);
+    pl.off_bar = o; o += 64;
+    pl.total = o;
+    return pl;
+}
+
+__global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const GemmNtPlan pl = gemm_nt_plan(a.Npad, a.n_chunks, a.b_resident != 0);
+    unsigned char *A_base = smem_raw + pl.off_A;
+    unsigned char *B_base = smem_raw + pl.off_B;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + pl.off_bar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + pl.off_bar + 32);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int M = a.M, N = a.N, Npad = a.Npad, K = a.K, n_chunks = a.n_chunks;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                     :: "r"(umma::smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        umma::mbar_init(&bars[0], 1);
+        umma::mbar_init(&bars[1], 1);
+        umma::fence_mbar_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t idesc = umma::make_idesc_tf32(GT_M, Npad);
+    const uint32_t lbo_a = GT_M * 16, lbo_b = (uint32_t)Npad * 16, sbo = 128;
+    uint32_t uses0 = 0, uses1 = 0;
+
+    auto issue_b = [&](int chunk, int slot) {
+        unsigned char *dst = B_base + (size_t)slot * 2 * pl.b_bytes;
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.b_prep) + (size_t)chunk * 2 * pl.b_bytes;
+        for (uint32_t i = tid * 16; i < 2 * pl.b_bytes; i += G_NT * 16) g_cp_async16(dst + i, src + i);
+    };
+    if (a.b_resident) {
+        for (int c = 0; c < n_chunks; ++c) issue_b(c, c);
+        g_cp_commit();
+        g_cp_wait<0>();
+        umma::fence_proxy_async();
+        __syncthreads();
+    }
+
+    // this thread's share of an A chunk: 4 float4 = (row, q) pairs, rows consecutive across threads
+    float4 areg[4];
+    auto load_a = [&](int m0, int chunk) {
+        const int k0 = chunk * GT_KC;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + G_NT * i;
+            const int row = idx & (GT_M - 1), q = idx >> 7;
+            const int m = m0 + row, k = k0 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && k < K) {
+                const float *src = a.A + (size_t)m * a.lda + k;
+                if (a.vec_a && k + 3 < K) {
+                    v = *reinterpret_cast<const float4 *>(src);
+                } else {
+                    v.x = src[0];
+                    if (k + 1 < K) v.y = src[1];
+                    if (k + 2 < K) v.z = src[2];
+                    if (k + 3 < K) v.w = src[3];
+                }
+            }
+            areg[i] = v;
+        }
+    };
+    auto store_a = [&](int buf) {
+        unsigned char *Ah = A_base + (size_t)(buf * 2 + 0) * pl.a_bytes;
+        unsigned char *Al = A_base + (size_t)(buf * 2 + 1) * pl.a_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + G_NT * i;
+            const int row = idx & (GT_M - 1), q = idx >> 7;
+            float4 hi, lo;
+            umma::split_tf32(areg[i].x, hi.x, lo.x); umma::split_tf32(areg[i].y, hi.y, lo.y);
+            umma::split_tf32(areg[i].z, hi.z, lo.z); umma::split_tf32(areg[i].w, hi.w, lo.w);
+            *reinterpret_cast<float4 *>(Ah + (size_t)q * lbo_a + row * 16) = hi;
+            *reinterpret_cast<float4 *>(Al + (size_t)q * lbo_a + row * 16) = lo;
+        }
+    };
+
+    int it = 0;                                   // global chunk counter (A double buffering across tiles)
+    for (int m0 = blockIdx.x * GT_M; m0 < M; m0 += gridDim.x * GT_M) {
+        if (!a.b_resident) {
+            issue_b(0, 0); g_cp_commit();
+            if (n_chunks > 1) issue_b(1, 1);
+            g_cp_commit();
+        }
+        load_a(m0, 0);
+        for (int chunk = 0; chunk < n_chunks; ++chunk, ++it) {
+            const int buf = it & 1;
+            {   // A buffer free? (MMA that read it two chunks ago)
+                const uint32_t u = buf ? uses1 : uses0;
+                if (u > 0 && !umma::mbar_wait(&bars[buf], (u - 1) & 1)) __trap();
+            }
+            store_a(buf);
+            if (chunk + 1 < n_chunks) load_a(m0, chunk + 1);        // next chunk's global loads in flight during the MMA
+            if (!a.b_resident) g_cp_wait<1>();
+            umma::fence_proxy_async();
+            umma::fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                const int slot = a.b_resident ? chunk : (chunk % 3);
+                const uint32_t ah = umma::smem_u32(A_base + (size_t)(buf * 2 + 0) * pl.a_bytes);
+                const uint32_t al = umma::smem_u32(A_base + (size_t)(buf * 2 + 1) * pl.a_bytes);
+                const uint32_t bh = umma::smem_u32(B_base + (size_t)(slot * 2 + 0) * pl.b_bytes);
+                const uint32_t bl = umma::smem_u32(B_base + (size_t)(slot * 2 + 1) * pl.b_bytes);
+#pragma unroll
+                for (int ks = 0; ks < GT_KC / 8; ++ks) {
+                    const uint32_t ao = ks * 2 * lbo_a, bo = ks * 2 * lbo_b;
+                    const uint64_t dah = umma::make_smem_desc(ah + ao, lbo_a, sbo);
+                    const uint64_t dal = umma::make_smem_desc(al + ao, lbo_a, sbo);
+                    const uint64_t dbh = umma::make_smem_desc(bh + bo, lbo_b, sbo);
+                    const uint64_t dbl = umma::make_smem_desc(bl + bo, lbo_b, sbo);
+                    umma::mma_tf32_ss(tmem_d, dal, dbh, idesc, (chunk > 0 || ks > 0) ? 1u : 0u);
+                    umma::mma_tf32_ss(tmem_d, dah, dbl, idesc, 1u);
+                    umma::mma_tf32_ss(tmem_d, dah, dbh, idesc, 1u);
+                }
+                umma::commit(&bars[buf]);
+            }
+            if (buf) ++uses1; else ++uses0;
+            if (!a.b_resident) {
+                if (chunk + 2 < n_chunks) {
+                    if (chunk >= 1) {                    // slot (chunk+2)%3 was read by MMA(chunk-1)
+                        const int pb = (it - 1) & 1;
+                        const uint32_t u = pb ? uses1 : uses0;
+                        if (!umma::mbar_wait(&bars[pb], (u - 1) & 1)) __trap();
+                    }
+                    issue_b(chunk + 2, (chunk + 2) % 3);
+                }
+                g_cp_commit();
+            }
+        }
+        // ---- epilogue: all 8 warps; warp w reads TMEM lanes 32*(w%4).., columns split between w<4 and w>=4 ----
+        {
+            const int lastbuf = (it - 1) & 1;
+            const uint32_t u = lastbuf ? uses1 : uses0;
+            if (!umma::mbar_wait(&bars[lastbuf], (u - 1) & 1)) __trap();
+        }
+        umma::fence_after_sync();
+        {
+            const int row = (warp & 3) * 32 + lane;
+            const int m = m0 + row;
+            const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+            const int half = Npad / 2 >= 8 ? ((Npad / 2 + 7) & ~7) : Npad;     // columns handled by warps 0-3
+            const int c_begin = (warp < 4) ? 0 : half, c_end = (warp < 4) ? half : Npad;
+            for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+                float v[8];
+                umma::tmem_ld8(taddr + c0, v);
+                if (m < M) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int c = c0 + j;
+                        if (c < N) {
+                            float x = v[j] + (a.bias ? __ldg(a.bias + c) : 0.f);
+                            if (a.act == 1) x = fmaxf(x, 0.f);
+                            else if (a.act == 2) x = x > 0.f ? x : 0.1f * x;
+                            v[j] = x;
+                        }
+                    }
+                    float *dst = a.C + (size_t)m * a.ldc + c0;
+                    if (c0 + 8 <= N && ((a.ldc & 3) == 0)) {
+                        reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                        reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (c0 + j < N) dst[j] = v[j];
+                    }
+                }
+            }
+        }
+        umma::fence_before_sync();
+        if (!a.b_resident) g_cp_wait<0>();
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(a.tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gemm_tn: C[N1 x N2] (+ column N2 = row sums of A^T, i.e. sum_m A[m][n1]) = A^T B, reduction over rows m
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TN_RC = 32;          // rows (reduction depth) per chunk
+
+struct GemmTnArgs {
+    const float *A, *B;            // A [M][lda] (N1 used columns), B [M][ldb] (N2 used columns)
+    float *partial;                // [slices][N1][ldp], ldp = N2 + (ones ? 1 : 0)
+    int M, N1, N1pad, N2, lda, ldb, ldp, ones, slice_rows, n2_tile, tmem_cols;
+};
+
+struct GemmTnPlan { uint32_t a_bytes, b_bytes; size_t off_A, off_B, off_bar, total; };
+
+__host__ __device__ inline GemmTnPlan gemm_tn_plan(int N1pad, int n2_tile) {
+    GemmTnPlan pl;
+    pl.a_bytes = (uint32_t)N1pad * TN_RC * 4;
+    pl.b_bytes = (uint32_t)n2_tile * TN_RC * 4;
+    size_t o = 0;
+    pl.off_A = o; o += 4 * (size_t)pl.a_bytes;
+    pl.off_B = o; o += 4 * (size_t)pl.b_bytes;
+    o = align_up(o, 16);
+    pl.off_bar = o; o += 64;
+    pl.total = o;
+    return pl;
+}
+
+// stage a [TN_RC rows x ncols] block of a row-major matrix as the K-major operand of the transposed matrix:
+// element (col, row) -> (row/4)*(ncols_pad*16) + col*16 + (row%4)*4.  Each work item = 4 rows x 4 cols.
+__device__ __forceinline__ void tn_stage(const float *__restrict__ src, int ld, int m0, int m_end, int col0, int ncols,
+                                         int ncols_pad, int ones_col, unsigned char *dst_hi, unsigned char *dst_lo, int tid)
+{
+    const int cgroups = ncols_pad / 4;
+    for (int item = tid; item < cgroups * (TN_RC / 4); item += G_NT) {
+        const int cgp = item % cgroups, rg = item / cgroups;
+        const int c = cgp * 4, r = rg * 4;
+        float v[4][4];                                   // [row][col]
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int m = m0 + r + rr;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int col = c + cc;
+                float x = 0.f;
+                if (m < m_end) {
+                    if (col < ncols) x = src[(size_t)m * ld + col0 + col];
+                    else if (col0 + col == ones_col) x = 1.f;
+                }
+                v[rr][cc] = x;
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float4 hi, lo;
+            umma::split_tf32(v[0][cc], hi.x, lo.x); umma::split_tf32(v[1][cc], hi.y, lo.y);
+            umma::split_tf32(v[2][cc], hi.z, lo.z); umma::split_tf32(v[3][cc], hi.w, lo.w);
+            const size_t off = (size_t)rg * ncols_pad * 16 + (size_t)(c + cc) * 16;
+            *reinterpret_cast<float4 *>(dst_hi + off) = hi;
+            *reinterpret_cast<float4 *>(dst_lo + off) = lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const GemmTnPlan pl = gemm_tn_plan(a.N1pad, a.n2_tile);
+    unsigned char *A_base = smem_raw + pl.off_A;
+    unsigned char *B_base = smem_raw + pl.off_B;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + pl.off_bar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + pl.off_bar + 32);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                     :: "r"(umma::smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        umma::mbar_init(&bars[0], 1);
+        umma::mbar_init(&bars[1], 1);
+        umma::fence_mbar_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_d = *tmem_slot;
+
+    const int n2_0 = blockIdx.x * a.n2_tile;                       // first B column of this CTA
+    const int n2_cols = min(a.n2_tile, a.ldp - n2_0);              // incl. the ones column in the last tile
+    const int slice = blockIdx.y;
+    const int m_begin = slice * a.slice_rows, m_end = min(a.M, m_begin + a.slice_rows);
+    const int n_mblk = a.N1pad / 128 > 0 ? a.N1pad / 128 : 1;      // MMA row blocks of 128 (or one of 64)
+    const int mma_m = a.N1pad >= 128 ? 128 : 64;
+    const uint32_t idesc = umma::make_idesc_tf32(mma_m, a.n2_tile);
+    const uint32_t lbo_a = (uint32_t)a.N1pad * 16, lbo_b = (uint32_t)a.n2_tile * 16, sbo = 128;
+    const int ones_col = a.ones ? a.N2 : -1;
+    uint32_t uses0 = 0, uses1 = 0;
+
+    int chunk = 0;
+    for (int m0 = m_begin; m0 < m_end; m0 += TN_RC, ++chunk) {
+        const int buf = chunk & 1;
+        {
+            const uint32_t u = buf ? uses1 : uses0;
+            if (u > 0 && !umma::mbar_wait(&bars[buf], (u - 1) & 1)) __trap();
+        }
+        tn_stage(a.A, a.lda, m0, m_end, 0, a.N1, a.N1pad, -1, A_base + (size_t)(buf * 2) * pl.a_bytes,
+                 A_base + (size_t)(buf * 2 + 1) * pl.a_bytes, tid);
+        tn_stage(a.B, a.ldb, m0, m_end, n2_0, min(a.n2_tile, a.N2 - n2_0), a.n2_tile, ones_col,
+                 B_base + (size_t)(buf * 2) * pl.b_bytes, B_base + (size_t)(buf * 2 + 1) * pl.b_bytes, tid);
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            const uint32_t ah = umma::smem_u32(A_base + (size_t)(buf * 2 + 0) * pl.a_bytes);
+            const uint32_t al = umma::smem_u32(A_base + (size_t)(buf * 2 + 1) * pl.a_bytes);
+            const uint32_t bh = umma::smem_u32(B_base + (size_t)(buf * 2 + 0) * pl.b_bytes);
+            const uint32_t bl = umma::smem_u32(B_base + (size_t)(buf * 2 + 1) * pl.b_bytes);
+            for (int mb = 0; mb < n_mblk; ++mb) {
+                const uint32_t d = tmem_d + mb * a.n2_tile;
+                const uint32_t arow = mb * 128 * 16;               // rows of this block inside each 16-byte column
+#pragma unroll
+                for (int ks = 0; ks < TN_RC / 8; ++ks) {
+                    const uint32_t ao = ks * 2 * lbo_a + arow, bo = ks * 2 * lbo_b;
+                    const uint64_t dah = umma::make_smem_desc(ah + ao, lbo_a, sbo);
+                    const uint64_t dal = umma::make_smem_desc(al + ao, lbo_a, sbo);
+                    const uint64_t dbh = umma::make_smem_desc(bh + bo, lbo_b, sbo);
+                    const uint64_t dbl = umma::make_smem_desc(bl + bo, lbo_b, sbo);
+                    umma::mma_tf32_ss(d, dal, dbh, idesc, (chunk > 0 || ks > 0) ? 1u : 0u);
+                    umma::mma_tf32_ss(d, dah, dbl, idesc, 1u);
+                    umma::mma_tf32_ss(d, dah, dbh, idesc, 1u);
+                }
+            }
+            umma::commit(&bars[buf]);
+        }
+        if (buf) ++uses1; else ++uses0;
+    }
+    // ---- epilogue: partial[slice][n1][n2_0 + c] ----
+    if (chunk > 0) {
+        const int lastbuf = (chunk - 1) & 1;
+        const uint32_t u = lastbuf ? uses1 : uses0;
+        if (!umma::mbar_wait(&bars[lastbuf], (u - 1) & 1)) __trap();
+    }
+    umma::fence_after_sync();
+    if (warp < 4) {
+        for (int mb = 0; mb < n_mblk; ++mb) {
+            int n1;
+            bool lane_ok = true;
+            if (mma_m == 128) n1 = mb * 128 + warp * 32 + lane;
+            else { n1 = warp * 16 + lane; lane_ok = lane < 16; }   // M = 64: row r <-> lane (r%16) + 32*(r/16)
+            const uint32_t taddr = tmem_d + mb * a.n2_tile + ((uint32_t)(warp * 32) << 16);
+            for (int c0 = 0; c0 < a.n2_tile; c0 += 8) {
+                float v[8];
+                if (chunk > 0) umma::tmem_ld8(taddr + c0, v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                }
+                if (lane_ok && n1 < a.N1) {
+                    float *dst = a.partial + ((size_t)slice * a.N1 + n1) * a.ldp + n2_0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (c0 + j < n2_cols) dst[j] = v[j];
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(a.tmem_cols) : "memory");
+}
+
+__global__ void gemm_tn_reduce_kernel(const float *__restrict__ partial, int S, int N1, int N2, int ldp,
+                                      float *__restrict__ C, int ldc, float *__restrict__ rowsum)
+{
+    const int total = N1 * ldp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < S; ++z) s += partial[(size_t)z * total + i];          // fixed order: deterministic
+        const int n1 = i / ldp, c = i - n1 * ldp;
+        if (c < N2) { if (C) C[(size_t)n1 * ldc + c] = s; }
+        else if (rowsum) rowsum[n1] = s;
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct NtSetup { int Npad, n_chunks, resident; size_t prep_bytes; GemmNtPlan plan; };
+
+static NtSetup nt_setup(int N, int K) {
+    NtSetup s;
+    s.Npad = round_up(N < 16 ? 16 : N, 16);
+    s.n_chunks = ceil_div(K, GT_KC);
+    s.prep_bytes = align_up((size_t)s.n_chunks * 2 * s.Npad * GT_KC * sizeof(float), 256);
+    s.resident = (s.prep_bytes <= 128 * 1024) ? 1 : 0;
+    s.plan = gemm_nt_plan(s.Npad, s.n_chunks, s.resident != 0);
+    if (s.plan.total > 225 * 1024) { s.resident = 0; s.plan = gemm_nt_plan(s.Npad, s.n_chunks, false); }
+    return s;
+}
+
+}  // namespace pcfb
+
+extern "C" size_t pcfb_gemm_nt_workspace(int N, int K)
+{
+    return pcfb::nt_setup(N, K).prep_bytes;
+}
+
+extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,
+                            int M, int N, int K, int act, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace pcfb;
+    PCFB_REQUIRE(M >= 0 && N >= 1 && N <= 256 && K >= 1, "pcfb_gemm_nt: need 1 <= N <= 256, K >= 1 (N=%d K=%d)", N, K);
+    PCFB_REQUIRE(A && W && C && workspace, "pcfb_gemm_nt: null pointer");
+    PCFB_REQUIRE(lda >= K && ldc >= N, "pcfb_gemm_nt: bad leading dimensions");
+    NtSetup s = nt_setup(N, K);
+    PCFB_REQUIRE(s.plan.total <= 225 * 1024, "pcfb_gemm_nt: tile does not fit in shared memory (N=%d)", N);
+    if (workspace_bytes < s.prep_bytes) { set_error("pcfb_gemm_nt: workspace %zu < %zu", workspace_bytes, s.prep_bytes); return PCFB_ERR_WORKSPACE; }
+    if (M == 0) return PCFB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    {
+        const int64_t total = (int64_t)s.n_chunks * (GT_KC / 4) * s.Npad;
+        const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
+        gemm_prep_b_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(W, ldw, w_is_kn, N, s.Npad, K, s.n_chunks, static_cast<float *>(workspace));
+        if ((rc = check_launch("gemm_prep_b_kernel"))) return rc;
+    }
+    GemmNtArgs a{};
+    a.A = A; a.b_prep = static_cast<const float *>(workspace); a.bias = bias; a.C = C;
+    a.M = M; a.N = N; a.Npad = s.Npad; a.K = K; a.lda = lda; a.ldc = ldc; a.n_chunks = s.n_chunks;
+    a.b_resident = s.resident; a.act = act;
+    a.vec_a = ((lda & 3) == 0) && ((uintptr_t)A % 16 == 0);
+    int cols = 32;
+    while (cols < s.Npad) cols <<= 1;
+    a.tmem_cols = cols;
+    static bool attr = false;
+    if (!attr) { PCFB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr = true; }
+    const int tiles = ceil_div(M, GT_M);
+    const int per_sm = (s.plan.total + 1024 <= 113 * 1024) ? 2 : 1;
+    const int grid = tiles < kNumSMs * per_sm ? tiles : kNumSMs * per_sm;
+    gemm_nt_kernel<<<grid, G_NT, s.plan.total, st>>>(a);
+    return check_launch("gemm_nt_kernel");
+}
+
+namespace pcfb {
+struct TnSetup { int N1pad, n2_tile, n2_tiles, S, slice_rows, ldp; size_t ws_bytes; GemmTnPlan plan; };
+static TnSetup tn_setup(int M, int N1, int N2, int ones) {
+    TnSetup s;
+    s.N1pad = N1 <= 64 ? 64 : round_up(N1, 128);
+    s.ldp = N2 + (ones ? 1 : 0);
+    const int max_tile = s.N1pad > 128 ? 128 : 256;               // TMEM columns: n_mblk * n2_tile <= 512; smem
+    s.n2_tile = round_up(s.ldp < max_tile ? s.ldp : max_tile, 16);
+    if (s.n2_tile < 16) s.n2_tile = 16;
+    s.n2_tiles = ceil_div(s.ldp, s.n2_tile);
+    int S = ceil_div(2 * kNumSMs, s.n2_tiles);
+    const int maxS = ceil_div(M > 0 ? M : 1, 8 * TN_RC);
+    if (S > maxS) S = maxS;
+    if (S < 1) S = 1;
+    s.slice_rows = round_up(ceil_div(M > 0 ? M : 1, S), TN_RC);
+    s.S = ceil_div(M > 0 ? M : 1, s.slice_rows);
+    s.ws_bytes = align_up((size_t)s.S * N1 * s.ldp * sizeof(float), 256);
+    s.plan = gemm_tn_plan(s.N1pad, s.n2_tile);
+    return s;
+}
+}  // namespace pcfb
+
+extern "C" size_t pcfb_gemm_tn_workspace(int M, int N1, int N2, int with_rowsum)
+{
+    return pcfb::tn_setup(M, N1, N2, with_rowsum).ws_bytes;
+}
+
+extern "C" int pcfb_gemm_tn(const float *A, int lda, const float *B, int ldb, float *C, int ldc, float *rowsum,
+                            int M, int N1, int N2, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace pcfb;
+    PCFB_REQUIRE(M >= 0 && N1 >= 1 && N1 <= 256 && N2 >= 1, "pcfb_gemm_tn: need 1 <= N1 <= 256, N2 >= 1 (N1=%d N2=%d)", N1, N2);
+    PCFB_REQUIRE(A && B && workspace && (C || rowsum), "pcfb_gemm_tn: null pointer");
+    PCFB_REQUIRE(lda >= N1 && ldb >= N2, "pcfb_gemm_tn: bad leading dimensions");
+    TnSetup s = tn_setup(M, N1, N2, rowsum != nullptr);
+    PCFB_REQUIRE(s.plan.total <= 225 * 1024, "pcfb_gemm_tn: tile does not fit in shared memory");
+    if (workspace_bytes < s.ws_bytes) { set_error("pcfb_gemm_tn: workspace %zu < %zu", workspace_bytes, s.ws_bytes); return PCFB_ERR_WORKSPACE; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GemmTnArgs a{};
+    a.A = A; a.B = B; a.partial = static_cast<float *>(workspace);
+    a.M = M; a.N1 = N1; a.N1pad = s.N1pad; a.N2 = N2; a.lda = lda; a.ldb = ldb; a.ldp = s.ldp; a.ones = rowsum != nullptr;
+    a.slice_rows = s.slice_rows; a.n2_tile = s.n2_tile;
+    int cols = 32;
+    const int need_cols = (s.N1pad >= 128 ? s.N1pad / 128 : 1) * s.n2_tile;
+    while (cols < need_cols) cols <<= 1;
+    a.tmem_cols = cols;
+    static bool attr = false;
+    if (!attr) { PCFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr = true; }
+    int rc;
+    dim3 grid(s.n2_tiles, s.S);
+    gemm_tn_kernel<<<grid, G_NT, s.plan.total, st>>>(a);
+    if ((rc = check_launch("gemm_tn_kernel"))) return rc;
+    const int total = N1 * s.ldp;
+    gemm_tn_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(a.partial, s.S, N1, N2, s.ldp, C, ldc, rowsum);
+    return check_launch("gemm_tn_reduce_kernel");
+}

@@ -73,10 +73,40 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
     return pconv_forward_simt(s, feats, nei, weights, additional, guidance, lin_w, lin_b, out_y, out_p, st);
 }
 
+// ---- backward: variant 0/2 = tensor-core composition, variant 1 = single fused SIMT kernel ----------------
+// With a Linear, the two dense products run on tcgen05 (3xTF32): dP = dY W (pcfb_gemm_nt, column blocks of 128)
+// and dW = dY^T P, db = column sums of dY (pcfb_gemm_tn, deterministic split over points); the per-point part
+// (dw, dadd, dguidance, per-edge dE) then runs as the SIMT contraction-backward kernel on dP, and dx is the CSR
+// segment sum over the inverse map.  Without a Linear the incoming gradient already is dP.
+namespace pcfb {
+struct BwdCompose { float *dP; void *nt_ws; size_t nt_bytes; void *tn_ws; size_t tn_bytes; float *p_re; void *simt_ws; size_t simt_bytes, bytes; };
+static BwdCompose carve_compose(void *ws, const pcfb_pconv_shape &s, bool need_w, bool need_p) {
+    Carver c(ws);
+    BwdCompose w{};
+    const int KK = (s.C_in + s.C_add) * s.C_mid;
+    w.dP = c.take<float>((size_t)s.n_out * KK);
+    w.nt_bytes = pcfb_gemm_nt_workspace(128, s.C_out);
+    w.nt_ws = c.take<char>(w.nt_bytes);
+    if (need_w) {
+        w.tn_bytes = pcfb_gemm_tn_workspace(s.n_out, s.C_out, KK, 1);
+        w.tn_ws = c.take<char>(w.tn_bytes);
+        if (need_p) w.p_re = c.take<float>((size_t)s.n_out * KK);
+    }
+    pcfb_pconv_shape nolin = s; nolin.C_out = 0;
+    w.simt_bytes = pconv_backward_simt_workspace(&nolin);
+    w.simt_ws = c.take<char>(w.simt_bytes);
+    w.bytes = align_up(c.off, 256);
+    return w;
+}
+}  // namespace pcfb
+
 extern "C" size_t pcfb_pconv_backward_workspace(const pcfb_pconv_shape *s, int variant)
 {
-    (void)variant;
-    return s ? pcfb::pconv_backward_simt_workspace(s) : 0;
+    if (!s) return 0;
+    const size_t fused = pcfb::pconv_backward_simt_workspace(s);
+    if (variant == 1 || s->C_out <= 0 || s->C_out > 256) return fused;
+    const size_t comp = pcfb::carve_compose(nullptr, *s, true, true).bytes;
+    return comp > fused ? comp : fused;
 }
 
 extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_y, const float *grad_p,
@@ -94,7 +124,37 @@ extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_
     PCFB_REQUIRE(s->C_add == 0 || additional, "pcfb_pconv_backward: C_add=%d but additional is NULL", s->C_add);
     PCFB_REQUIRE((s->H > 0) == (guidance != nullptr), "pcfb_pconv_backward: H and guidance disagree");
     PCFB_REQUIRE(variant >= 0 && variant <= 2, "pcfb_pconv_backward: unknown variant %d", variant);
-    return pconv_backward_simt(s, grad_y, grad_p, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional,
-                               guidance, lin_w, pconv_out, grad_feats, grad_weights, grad_additional, grad_guidance,
-                               grad_lin_w, grad_lin_b, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (variant == 1 || !lin_w || s->C_out > 256 || s->n_out == 0)
+        return pconv_backward_simt(s, grad_y, grad_p, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional,
+                                   guidance, lin_w, pconv_out, grad_feats, grad_weights, grad_additional, grad_guidance,
+                                   grad_lin_w, grad_lin_b, workspace, workspace_bytes, st);
+    PCFB_REQUIRE(grad_y != nullptr, "pcfb_pconv_backward: missing incoming gradient");
+    const bool need_w = grad_lin_w || grad_lin_b;
+    const bool need_p = need_w && !pconv_out;
+    BwdCompose w = carve_compose(workspace, *s, need_w, need_p);
+    if (!workspace || workspace_bytes < w.bytes) {
+        set_error("pcfb_pconv_backward: workspace %zu < %zu", workspace_bytes, w.bytes);
+        return PCFB_ERR_WORKSPACE;
+    }
+    const int KK = (s->C_in + s->C_add) * s->C_mid;
+    int rc;
+    for (int n0 = 0; n0 < KK; n0 += 128) {                    // dP[:, n0:n0+128] = dY * W[:, n0:n0+128]
+        const int nb = KK - n0 < 128 ? KK - n0 : 128;
+        if ((rc = pcfb_gemm_nt(grad_y, s->C_out, lin_w + n0, KK, 1, nullptr, w.dP + n0, KK, s->n_out, nb, s->C_out, 0,
+                               w.nt_ws, w.nt_bytes, stream))) return rc;
+    }
+    if (need_w) {
+        const float *P = pconv_out;
+        if (need_p) {
+            if ((rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, w.p_re, st))) return rc;
+            P = w.p_re;
+        }
+        if ((rc = pcfb_gemm_tn(grad_y, s->C_out, P, KK, grad_lin_w, KK, grad_lin_b, s->n_out, s->C_out, KK, w.tn_ws, w.tn_bytes, stream))) return rc;
+    }
+    pcfb_pconv_shape nolin = *s;
+    nolin.C_out = 0;
+    return pconv_backward_simt(&nolin, nullptr, w.dP, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional, guidance,
+                               nullptr, nullptr, grad_feats, grad_weights, grad_additional, grad_guidance, nullptr, nullptr,
+                               w.simt_ws, w.simt_bytes, st);
 }

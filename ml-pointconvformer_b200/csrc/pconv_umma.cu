@@ -325,6 +325,7 @@ struct SelftestArgs {
     uint32_t idesc;
     uint64_t desc_or;                                             // extra descriptor bits
     int split;                                                    // 1: 3xTF32
+    uint32_t mn_flags;                                            // bit0: A is MN-major, bit1: B is MN-major
     int *status;
 };
 
@@ -343,7 +344,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelftestArgs t)
         float hi, lo;
         const float x = t.A[i];
         if (t.split) umma::split_tf32(x, hi, lo); else { hi = x; lo = 0.f; }
-        const uint32_t off = (k / 4) * t.fill_lbo_a + (r / 8) * t.fill_sbo_a + (r % 8) * 16 + (k % 4) * 4;
+        const uint32_t off = (t.mn_flags & 1)
+            ? (r % 4) * 4 + (r / 4) * t.fill_sbo_a + (k % 8) * 16 + (k / 8) * t.fill_lbo_a       // MN-major: 4 rows contiguous
+            : (k / 4) * t.fill_lbo_a + (r / 8) * t.fill_sbo_a + (r % 8) * 16 + (k % 4) * 4;
         *reinterpret_cast<float *>(Ah + off) = hi;
         *reinterpret_cast<float *>(Al + off) = lo;
     }
@@ -352,7 +355,9 @@ __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelftestArgs t)
         float hi, lo;
         const float x = t.B[i];
         if (t.split) umma::split_tf32(x, hi, lo); else { hi = x; lo = 0.f; }
-        const uint32_t off = (k / 4) * t.fill_lbo_b + (r / 8) * t.fill_sbo_b + (r % 8) * 16 + (k % 4) * 4;
+        const uint32_t off = (t.mn_flags & 2)
+            ? (r % 4) * 4 + (r / 4) * t.fill_sbo_b + (k % 8) * 16 + (k / 8) * t.fill_lbo_b
+            : (k / 4) * t.fill_lbo_b + (r / 8) * t.fill_sbo_b + (r % 8) * 16 + (k % 4) * 4;
         *reinterpret_cast<float *>(Bh + off) = hi;
         *reinterpret_cast<float *>(Bl + off) = lo;
     }
@@ -459,7 +464,7 @@ int pconv_forward_umma(const pcfb_pconv_shape *s, const float *feats, const int6
 
 // Hardware self-test of the UMMA descriptor conventions (used by tests/test_umma_selftest.py).
 extern "C" int pcfb_selftest_umma(const float *A, const float *B, float *raw, int M, int N, int K,
-                                  const uint32_t *h_params /* 11 host uint32 */, uint64_t desc_or, int split,
+                                  const uint32_t *h_params /* 12 host uint32 */, uint64_t desc_or, int split,
                                   int *status, void *stream)
 {
     using namespace pcfb;
@@ -470,7 +475,7 @@ extern "C" int pcfb_selftest_umma(const float *A, const float *B, float *raw, in
     t.A = A; t.B = B; t.raw = raw; t.M = M; t.N = N; t.K = K;
     t.fill_lbo_a = h_params[0]; t.fill_sbo_a = h_params[1]; t.fill_lbo_b = h_params[2]; t.fill_sbo_b = h_params[3];
     t.desc_lbo_a = h_params[4]; t.desc_sbo_a = h_params[5]; t.desc_lbo_b = h_params[6]; t.desc_sbo_b = h_params[7];
-    t.kstep_a = h_params[8]; t.kstep_b = h_params[9]; t.idesc = h_params[10];
+    t.kstep_a = h_params[8]; t.kstep_b = h_params[9]; t.idesc = h_params[10]; t.mn_flags = h_params[11];
     t.desc_or = desc_or; t.split = split; t.status = status;
     const size_t smem = 4 * 32 * 1024 + 64;
     PCFB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

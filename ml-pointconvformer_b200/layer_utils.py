@@ -247,6 +247,42 @@ def VI_coordinate_transform(localized_xyz, gathered_norm, sparse_xyz_norm, K):
 
 
 # ------------------------------------------------------------------------------------------------
+# dense Linear on the tensor cores (3xTF32: fp32-accurate; torch's fp32 path is a SIMT sgemm)
+# ------------------------------------------------------------------------------------------------
+class _LinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        y = pcf_cuda.gemm_nt(x2, weight, bias)
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad):
+        x2, weight = ctx.saved_tensors
+        g2 = grad.reshape(-1, weight.shape[0])
+        if g2.stride(-1) != 1 or g2.stride(0) < g2.shape[1]:
+            g2 = g2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = pcf_cuda.gemm_nt(g2, weight, None, w_is_kn=True).reshape(*grad.shape[:-1], weight.shape[1])
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gw, gb = pcf_cuda.gemm_tn(g2, x2, want_rowsum=ctx.has_bias)
+        return gx, gw, gb
+
+
+def linear(x, weight, bias=None):
+    """F.linear on the B200 tensor cores, fp32-accurate (pcfb_gemm_nt / pcfb_gemm_tn).  CUDA float32 only."""
+    if not x.is_cuda:
+        raise RuntimeError("pcf_b200.linear needs CUDA tensors (no CPU path)")
+    weight = weight.contiguous()
+    return _LinearFunction.apply(x, weight, bias)
+
+
+# ------------------------------------------------------------------------------------------------
 # Linear + BatchNorm blocks (layer_utils.py:241-319)
 # ------------------------------------------------------------------------------------------------
 class Linear_BN(nn.Module):
@@ -269,7 +305,7 @@ class Linear_BN(nn.Module):
         return fused
 
     def forward(self, x):
-        x = self.c(x)
+        x = linear(x, self.c.weight, self.c.bias)
         shape = x.shape
         if isinstance(self.bn, nn.SyncBatchNorm):          # after convert_sync_batchnorm (DDP, sync_bn: True)
             return self.bn(x.reshape(-1, shape[-1])).reshape(shape)
@@ -296,7 +332,8 @@ class UnaryBlock(nn.Module):
         self.leaky_relu = nn.Identity() if no_relu else nn.LeakyReLU(0.1)
 
     def forward(self, x):
-        return self.leaky_relu(self.mlp(x))
+        y = self.mlp(x) if isinstance(self.mlp, Linear_BN) else linear(x, self.mlp.weight, self.mlp.bias)
+        return self.leaky_relu(y)
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(

@@ -16,7 +16,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from .layer_utils import (FusedPConvFunction, PConvLinearOpt, Linear_BN, UnaryBlock, edge_geometry, gather_max,
-                          index_points, resolve_inverse)
+                          index_points, linear, resolve_inverse)
 
 
 def _drop_path(cfg):
@@ -64,7 +64,7 @@ def _contract(cfg, feats, nei_inds, inv, weights, additional, guidance, lin_w, l
     if additional is not None:
         g = torch.cat([g, additional], dim=-1)
     p = torch.matmul(g.permute(0, 1, 3, 2), weights).reshape(g.shape[0], g.shape[1], -1)
-    return p if lin_w is None else F.linear(p, lin_w, lin_b)
+    return p if lin_w is None else linear(p, lin_w, lin_b)
 
 
 class MultiHeadGuidance(nn.Module):
@@ -85,7 +85,7 @@ class MultiHeadGuidance(nn.Module):
         s = self.layer_norm_q(guidance_query) - self.layer_norm_k(guidance_key)
         last = len(self.mlp) - 1
         for i, layer in enumerate(self.mlp):
-            s = layer(s)
+            s = layer(s) if isinstance(layer, Linear_BN) else linear(s, layer.weight, layer.bias)
             s = torch.sigmoid(s) if i == last else F.relu(s)
         return s
 

@@ -16,7 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .layers import PCFLayer, PointConv, PointConvStridePE, PointConvTransposePE
-from .layer_utils import Linear_BN
+from .layer_utils import Linear_BN, linear
 
 
 class EasyDict(dict):
@@ -194,4 +194,4 @@ class PointConvFormer_Segmentation(nn.Module):
                 if vi is None:
                     vi = vi_new
             feat_list[lvl] = x
-        return self.fc2(self.dropout_fc(F.relu(self.fc1(x))))
+        return linear(self.dropout_fc(F.relu(self.fc1(x))), self.fc2.weight, self.fc2.bias)

@@ -254,6 +254,49 @@ def knn_packed(ref_xyz, ref_counts, qry_xyz, qry_counts, K, out=None):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# dense fp32-accurate products on the tensor cores (3xTF32)
+# ------------------------------------------------------------------------------------------------
+def gemm_nt(x, w, bias=None, w_is_kn=False, act=0):
+    """x [M,K] (row-major, last dim contiguous) times w^T (w [N,K]) or times w (w [K,N], w_is_kn) -> [M,N]."""
+    require(w, F32, "w")
+    if x.dtype != F32 or not x.is_cuda or x.stride(-1) != 1:
+        raise RuntimeError("gemm_nt: x must be a CUDA float32 matrix with contiguous rows")
+    M, K = x.shape
+    N = w.shape[1] if w_is_kn else w.shape[0]
+    if (w.shape[0] if w_is_kn else w.shape[1]) != K:
+        raise RuntimeError("gemm_nt: inner dimensions do not match")
+    out = torch.empty(M, N, device=x.device, dtype=F32)
+    if N > 192:                                   # column blocks (a 256-wide B ring does not fit next to the A tiles)
+        for n0 in range(0, N, 128):
+            wb = w[:, n0:n0 + 128] if w_is_kn else w[n0:n0 + 128]
+            out[:, n0:n0 + 128] = gemm_nt(x, wb.contiguous(), None if bias is None else bias[n0:n0 + 128].contiguous(), w_is_kn, act)
+        return out
+    ws_bytes = lib().pcfb_gemm_nt_workspace(N, K)
+    ws = workspace(ws_bytes, x.device)
+    check(lib().pcfb_gemm_nt(ptr(x), x.stride(0), ptr(w), w.stride(0), 1 if w_is_kn else 0, ptr(bias), ptr(out), N, M, N, K, int(act),
+                             ptr(ws), ws_bytes, stream_ptr()), "gemm_nt")
+    return out
+
+
+def gemm_tn(a, b, want_rowsum=False):
+    """a [M,N1], b [M,N2] -> (a^T b [N1,N2], sum_m a[m,:] [N1] or None); deterministic split over M."""
+    if a.dtype != F32 or b.dtype != F32 or not a.is_cuda or a.stride(-1) != 1 or b.stride(-1) != 1:
+        raise RuntimeError("gemm_tn: operands must be CUDA float32 matrices with contiguous rows")
+    M, N1 = a.shape
+    N2 = b.shape[1]
+    if N1 > 256:
+        parts = [gemm_tn(a[:, i:i + 256], b, want_rowsum) for i in range(0, N1, 256)]
+        return torch.cat([p[0] for p in parts]), (torch.cat([p[1] for p in parts]) if want_rowsum else None)
+    out = torch.empty(N1, N2, device=a.device, dtype=F32)
+    rs = torch.empty(N1, device=a.device, dtype=F32) if want_rowsum else None
+    ws_bytes = lib().pcfb_gemm_tn_workspace(M, N1, N2, 1 if want_rowsum else 0)
+    ws = workspace(ws_bytes, a.device)
+    check(lib().pcfb_gemm_tn(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), N2, ptr(rs), M, N1, N2, ptr(ws), ws_bytes,
+                             stream_ptr()), "gemm_tn")
+    return out, rs
+
+
 def _offsets(counts, dev):
     return torch.tensor([0] + list(counts), dtype=torch.int64).cumsum(0).to(torch.int32).to(dev, non_blocking=True)
 

@@ -1,8 +1,8 @@
 #!/bin/bash
 # usage: gpu_quick.sh "<pytest args>" [bench steps]   -- a subset of tests + optional bench
 mkdir -p gpurun_out
-timeout 1500 python -m pytest $1 -q -m gpu --no-header -p no:cacheprovider > gpurun_out/quick_test.log 2>&1; echo "tests exit $?"
-tail -n 25 gpurun_out/quick_test.log
+timeout 1500 python -m pytest $1 -q -m gpu --no-header -p no:cacheprovider -rP > gpurun_out/quick_test.log 2>&1; echo "tests exit $?"
+grep -E "^gemm_|passed|failed|FAILED|Error" gpurun_out/quick_test.log | tail -n 60
 if [ -n "$2" ]; then
   timeout 900 python bench.py --steps $2 --warmup 3 --no-cpu-baseline > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"
   python - <<'PY'

@@ -72,6 +72,16 @@ def t(x):
 
 
 def run_layer(name, ctor, call, n_in_feat, strided, transpose=False, seed=0):
+    """Retries with shifted seeds until the reference's own fp32 and fp64 evaluations agree on every gradient:
+    a draw where some ReLU pre-activation is ~1e-7 makes the fp32 gradients jump by percents (seen with seed 10)
+    and is useless as a parity target."""
+    for attempt in range(20):
+        if _run_layer(name, ctor, call, n_in_feat, strided, transpose, seed + 1000 * attempt):
+            return
+    raise RuntimeError("no stable draw for " + name)
+
+
+def _run_layer(name, ctor, call, n_in_feat, strided, transpose=False, seed=0):
     """Builds the reference layer, runs train-mode fwd + bwd and eval-mode fwd, saves everything."""
     L, _, _ = ref_shim.load()
     torch.manual_seed(seed)
@@ -128,8 +138,17 @@ def run_layer(name, ctor, call, n_in_feat, strided, transpose=False, seed=0):
     out["g_feats64"] = t64['feats'].grad.float().numpy()
     for k, p in layer64.named_parameters():
         out["grad64." + k] = p.grad.float().numpy().copy()
+    worst = float(np.abs(out["g_feats64"] - out["g_feats"]).max() / np.abs(out["g_feats64"]).max())
+    for k in list(out):
+        if k.startswith("grad64.") and not k.endswith(".c.bias"):
+            a, b = out[k], out["grad." + k[7:]]
+            worst = max(worst, float(np.abs(a - b).max() / max(np.abs(a).max(), 1.0)))
+    if worst > 5e-4:
+        print("layer_%s: seed %d unstable (fp32 vs fp64 gradients differ by %.1e), retrying" % (name, seed, worst))
+        return False
     np.savez_compressed(os.path.join(HERE, "layer_%s.npz" % name), **out)
-    print("layer_%s: y %s  |y|=%.4f" % (name, tuple(y.shape), float(y.abs().mean())))
+    print("layer_%s: y %s  |y|=%.4f (seed %d)" % (name, tuple(y.shape), float(y.abs().mean()), seed))
+    return True
 
 
 def make_layers():

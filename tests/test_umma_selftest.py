@@ -15,17 +15,22 @@ def idesc_tf32(M, N):
     return (1 << 4) | (2 << 7) | (2 << 10) | ((N >> 3) << 17) | ((M >> 4) << 24)
 
 
-def run(M, N, K, split, swap=False, desc_or=0):
+def run(M, N, K, split, swap=False, desc_or=0, a_mn=False, b_mn=False):
     from pcf_b200 import _lib
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g).cuda()
     B = torch.randn(N, K, generator=g).cuda()
     raw = torch.zeros(128, N, device="cuda")
     status = torch.zeros(1, dtype=torch.int32, device="cuda")
-    lbo_a, lbo_b, sbo = M * 16, N * 16, 128
-    fill = [lbo_a, sbo, lbo_b, sbo]
-    desc = [sbo, lbo_a, sbo, lbo_b] if swap else [lbo_a, sbo, lbo_b, sbo]
-    params = (ctypes.c_uint32 * 11)(*(fill + desc + [2 * lbo_a, 2 * lbo_b, idesc_tf32(M, N)]))
+    # K-major: LBO = stride between 16-byte K chunks (rows*16), SBO = 8-row group stride (128)
+    # MN-major: 4 rows share a 16-byte unit; 8 k's x 16 B = one 128-byte core (LBO = next 8 k's),
+    #           SBO = stride between 4-row units.  Here units are laid out [row/4][K][4] -> SBO = K*16.
+    la, sa, ka = (128, K * 16, 128) if a_mn else (M * 16, 128, 2 * M * 16)
+    lb, sb, kb = (128, K * 16, 128) if b_mn else (N * 16, 128, 2 * N * 16)
+    fill = [la, sa, lb, sb]
+    desc = [sa, la, sb, lb] if swap else [la, sa, lb, sb]
+    idesc = idesc_tf32(M, N) | ((1 << 15) if a_mn else 0) | ((1 << 16) if b_mn else 0)
+    params = (ctypes.c_uint32 * 12)(*(fill + desc + [ka, kb, idesc, (1 if a_mn else 0) | (2 if b_mn else 0)]))
     _lib.check(_lib.lib().pcfb_selftest_umma(A.data_ptr(), B.data_ptr(), raw.data_ptr(), M, N, K,
                                              ctypes.cast(params, ctypes.c_void_p), desc_or, split, status.data_ptr(),
                                              _lib.stream_ptr()), "selftest")
@@ -54,3 +59,13 @@ def test_umma_single_pass_tf32_is_tf32_accurate():
     raw, want = run(64, 32, 32, split=0)
     err = float((rows_of(raw, 64) - want).abs().max() / want.abs().max())
     assert 1e-6 < err < 5e-3, err           # tf32-sized error: proves the tensor path (not fp32 FMA) produced it
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(64, 32, 32), (128, 64, 16), (64, 128, 64)])
+def test_umma_mn_major_operands(M, N, K, a_mn, b_mn):
+    """MN-major (transposed) operands: a row-major [rows][cols] tile staged in 16-byte units of 4 columns is
+    both a K-major operand of one product and an MN-major operand of the transposed product."""
+    raw, want = run(M, N, K, split=1, a_mn=a_mn, b_mn=b_mn)
+    err = float((rows_of(raw, M) - want).abs().max() / want.abs().max())
+    assert err < 2e-6, err
