@@ -268,20 +268,19 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
 // ------------------------------------------------------------------------------------------------------------
 // gemm_tn: C[N1 x N2] (+ column N2 = row sums of A^T, i.e. sum_m A[m][n1]) = A^T B, reduction over rows m
 // ------------------------------------------------------------------------------------------------------------
-constexpr int TN_RC = 32;          // rows (reduction depth) per chunk
 
 struct GemmTnArgs {
     const float *A, *B;            // A [M][lda] (N1 used columns), B [M][ldb] (N2 used columns)
     float *partial;                // [slices][N1][ldp], ldp = N2 + (ones ? 1 : 0)
-    int M, N1, N1pad, N2, lda, ldb, ldp, ones, slice_rows, n2_tile, tmem_cols;
+    int M, N1, N1pad, N2, lda, ldb, ldp, ones, slice_rows, n2_tile, tmem_cols, RC;   // RC: rows per chunk
 };
 
 struct GemmTnPlan { uint32_t a_bytes, b_bytes; size_t off_A, off_B, off_bar, total; };
 
-__host__ __device__ inline GemmTnPlan gemm_tn_plan(int N1pad, int n2_tile) {
+__host__ __device__ inline GemmTnPlan gemm_tn_plan(int N1pad, int n2_tile, int RC) {
     GemmTnPlan pl;
-    pl.a_bytes = (uint32_t)N1pad * TN_RC * 4;
-    pl.b_bytes = (uint32_t)n2_tile * TN_RC * 4;
+    pl.a_bytes = (uint32_t)N1pad * RC * 4;
+    pl.b_bytes = (uint32_t)n2_tile * RC * 4;
     size_t o = 0;
     pl.off_A = o; o += 4 * (size_t)pl.a_bytes;
     pl.off_B = o; o += 4 * (size_t)pl.b_bytes;
@@ -291,28 +290,35 @@ __host__ __device__ inline GemmTnPlan gemm_tn_plan(int N1pad, int n2_tile) {
     return pl;
 }
 
-// stage a [TN_RC rows x ncols] block of a row-major matrix as the K-major operand of the transposed matrix:
-// element (col, row) -> (row/4)*(ncols_pad*16) + col*16 + (row%4)*4.  Each work item = 4 rows x 4 cols.
-__device__ __forceinline__ void tn_stage(const float *__restrict__ src, int ld, int m0, int m_end, int col0, int ncols,
-                                         int ncols_pad, int ones_col, unsigned char *dst_hi, unsigned char *dst_lo, int tid)
+// stage a [RC rows x ncols] block of a row-major matrix as the K-major operand of the transposed matrix:
+// element (col, row) -> (row/4)*(ncols_pad*16) + col*16 + (row%4)*4.  Each work item = 4 rows x 4 cols, transposed
+// in registers.  Only column groups that hold data are written; the padding columns were zeroed once.
+__device__ __forceinline__ void tn_stage(const float *__restrict__ src, int ld, int m0, int m_end, int RC, int col0, int ncols,
+                                         int ncols_pad, int ones_col, bool vec, unsigned char *dst_hi, unsigned char *dst_lo, int tid)
 {
-    const int cgroups = ncols_pad / 4;
-    for (int item = tid; item < cgroups * (TN_RC / 4); item += G_NT) {
+    const int used = ncols + ((ones_col >= col0 && ones_col < col0 + ncols_pad) ? 1 : 0);
+    const int cgroups = (used + 3) / 4;
+    for (int item = tid; item < cgroups * (RC / 4); item += G_NT) {
         const int cgp = item % cgroups, rg = item / cgroups;
         const int c = cgp * 4, r = rg * 4;
         float v[4][4];                                   // [row][col]
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
             const int m = m0 + r + rr;
+            if (vec && m < m_end && c + 3 < ncols) {
+                const float4 t = __ldg(reinterpret_cast<const float4 *>(src + (size_t)m * ld + col0 + c));
+                v[rr][0] = t.x; v[rr][1] = t.y; v[rr][2] = t.z; v[rr][3] = t.w;
+            } else {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int col = c + cc;
-                float x = 0.f;
-                if (m < m_end) {
-                    if (col < ncols) x = src[(size_t)m * ld + col0 + col];
-                    else if (col0 + col == ones_col) x = 1.f;
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int col = c + cc;
+                    float x = 0.f;
+                    if (m < m_end) {
+                        if (col < ncols) x = __ldg(src + (size_t)m * ld + col0 + col);
+                        else if (col0 + col == ones_col) x = 1.f;
+                    }
+                    v[rr][cc] = x;
                 }
-                v[rr][cc] = x;
             }
         }
 #pragma unroll
@@ -330,7 +336,8 @@ __device__ __forceinline__ void tn_stage(const float *__restrict__ src, int ld, 
 __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const GemmTnPlan pl = gemm_tn_plan(a.N1pad, a.n2_tile);
+    const GemmTnPlan pl = gemm_tn_plan(a.N1pad, a.n2_tile, a.RC);
+    const int RC = a.RC;
     unsigned char *A_base = smem_raw + pl.off_A;
     unsigned char *B_base = smem_raw + pl.off_B;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + pl.off_bar);
@@ -347,10 +354,15 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
         umma::mbar_init(&bars[1], 1);
         umma::fence_mbar_init();
     }
+    // operand buffers start zeroed: padding columns are never written again
+    for (uint32_t i = tid * 16; i < 4 * pl.a_bytes + 4 * pl.b_bytes; i += G_NT * 16)
+        *reinterpret_cast<float4 *>(smem_raw + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem_d = *tmem_slot;
+    const bool vec_a = ((a.lda & 3) == 0) && ((uintptr_t)a.A % 16 == 0);
+    const bool vec_b = ((a.ldb & 3) == 0) && ((uintptr_t)a.B % 16 == 0) && ((a.n2_tile & 3) == 0);
 
     const int n2_0 = blockIdx.x * a.n2_tile;                       // first B column of this CTA
     const int n2_cols = min(a.n2_tile, a.ldp - n2_0);              // incl. the ones column in the last tile
@@ -364,15 +376,15 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
     uint32_t uses0 = 0, uses1 = 0;
 
     int chunk = 0;
-    for (int m0 = m_begin; m0 < m_end; m0 += TN_RC, ++chunk) {
+    for (int m0 = m_begin; m0 < m_end; m0 += RC, ++chunk) {
         const int buf = chunk & 1;
         {
             const uint32_t u = buf ? uses1 : uses0;
             if (u > 0 && !umma::mbar_wait(&bars[buf], (u - 1) & 1)) __trap();
         }
-        tn_stage(a.A, a.lda, m0, m_end, 0, a.N1, a.N1pad, -1, A_base + (size_t)(buf * 2) * pl.a_bytes,
+        tn_stage(a.A, a.lda, m0, m_end, RC, 0, a.N1, a.N1pad, -1, vec_a, A_base + (size_t)(buf * 2) * pl.a_bytes,
                  A_base + (size_t)(buf * 2 + 1) * pl.a_bytes, tid);
-        tn_stage(a.B, a.ldb, m0, m_end, n2_0, min(a.n2_tile, a.N2 - n2_0), a.n2_tile, ones_col,
+        tn_stage(a.B, a.ldb, m0, m_end, RC, n2_0, max(0, min(a.n2_tile, a.N2 - n2_0)), a.n2_tile, ones_col, vec_b,
                  B_base + (size_t)(buf * 2) * pl.b_bytes, B_base + (size_t)(buf * 2 + 1) * pl.b_bytes, tid);
         umma::fence_proxy_async();
         umma::fence_before_sync();
@@ -386,8 +398,7 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
             for (int mb = 0; mb < n_mblk; ++mb) {
                 const uint32_t d = tmem_d + mb * a.n2_tile;
                 const uint32_t arow = mb * 128 * 16;               // rows of this block inside each 16-byte column
-#pragma unroll
-                for (int ks = 0; ks < TN_RC / 8; ++ks) {
+                for (int ks = 0; ks < RC / 8; ++ks) {
                     const uint32_t ao = ks * 2 * lbo_a + arow, bo = ks * 2 * lbo_b;
                     const uint64_t dah = umma::make_smem_desc(ah + ao, lbo_a, sbo);
                     const uint64_t dal = umma::make_smem_desc(al + ao, lbo_a, sbo);
@@ -481,7 +492,15 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     PCFB_REQUIRE(A && W && C && workspace, "pcfb_gemm_nt: null pointer");
     PCFB_REQUIRE(lda >= K && ldc >= N, "pcfb_gemm_nt: bad leading dimensions");
     NtSetup s = nt_setup(N, K);
-    PCFB_REQUIRE(s.plan.total <= 225 * 1024, "pcfb_gemm_nt: tile does not fit in shared memory (N=%d)", N);
+    if (s.plan.total > 225 * 1024) {
+        // a B ring this wide does not fit next to the A tiles: two column blocks (each re-reads A from L2)
+        PCFB_REQUIRE(N > 32, "pcfb_gemm_nt: tile does not fit in shared memory (N=%d)", N);
+        const int n_lo = ((N / 2 + 15) / 16) * 16;
+        int rc = pcfb_gemm_nt(A, lda, W, ldw, w_is_kn, bias, C, ldc, M, n_lo, K, act, workspace, workspace_bytes, stream);
+        if (rc) return rc;
+        return pcfb_gemm_nt(A, lda, w_is_kn ? W + n_lo : W + (size_t)n_lo * ldw, ldw, w_is_kn, bias ? bias + n_lo : nullptr,
+                            C + n_lo, ldc, M, N - n_lo, K, act, workspace, workspace_bytes, stream);
+    }
     if (workspace_bytes < s.prep_bytes) { set_error("pcfb_gemm_nt: workspace %zu < %zu", workspace_bytes, s.prep_bytes); return PCFB_ERR_WORKSPACE; }
     if (M == 0) return PCFB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -510,7 +529,7 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
 }
 
 namespace pcfb {
-struct TnSetup { int N1pad, n2_tile, n2_tiles, S, slice_rows, ldp; size_t ws_bytes; GemmTnPlan plan; };
+struct TnSetup { int N1pad, n2_tile, n2_tiles, S, slice_rows, ldp, RC; size_t ws_bytes; GemmTnPlan plan; };
 static TnSetup tn_setup(int M, int N1, int N2, int ones) {
     TnSetup s;
     s.N1pad = N1 <= 64 ? 64 : round_up(N1, 128);
@@ -519,14 +538,16 @@ static TnSetup tn_setup(int M, int N1, int N2, int ones) {
     s.n2_tile = round_up(s.ldp < max_tile ? s.ldp : max_tile, 16);
     if (s.n2_tile < 16) s.n2_tile = 16;
     s.n2_tiles = ceil_div(s.ldp, s.n2_tile);
+    s.RC = 128;                                                   // rows per chunk: as deep as shared memory allows
+    while (s.RC > 32 && gemm_tn_plan(s.N1pad, s.n2_tile, s.RC).total > 200 * 1024) s.RC >>= 1;
     int S = ceil_div(2 * kNumSMs, s.n2_tiles);
-    const int maxS = ceil_div(M > 0 ? M : 1, 8 * TN_RC);
+    const int maxS = ceil_div(M > 0 ? M : 1, 4 * s.RC);
     if (S > maxS) S = maxS;
     if (S < 1) S = 1;
-    s.slice_rows = round_up(ceil_div(M > 0 ? M : 1, S), TN_RC);
+    s.slice_rows = round_up(ceil_div(M > 0 ? M : 1, S), s.RC);
     s.S = ceil_div(M > 0 ? M : 1, s.slice_rows);
     s.ws_bytes = align_up((size_t)s.S * N1 * s.ldp * sizeof(float), 256);
-    s.plan = gemm_tn_plan(s.N1pad, s.n2_tile);
+    s.plan = gemm_tn_plan(s.N1pad, s.n2_tile, s.RC);
     return s;
 }
 }  // namespace pcfb
@@ -550,7 +571,7 @@ extern "C" int pcfb_gemm_tn(const float *A, int lda, const float *B, int ldb, fl
     GemmTnArgs a{};
     a.A = A; a.B = B; a.partial = static_cast<float *>(workspace);
     a.M = M; a.N1 = N1; a.N1pad = s.N1pad; a.N2 = N2; a.lda = lda; a.ldb = ldb; a.ldp = s.ldp; a.ones = rowsum != nullptr;
-    a.slice_rows = s.slice_rows; a.n2_tile = s.n2_tile;
+    a.slice_rows = s.slice_rows; a.n2_tile = s.n2_tile; a.RC = s.RC;
     int cols = 32;
     const int need_cols = (s.N1pad >= 128 ? s.N1pad / 128 : 1) * s.n2_tile;
     while (cols < need_cols) cols <<= 1;

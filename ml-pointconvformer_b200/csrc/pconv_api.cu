@@ -25,11 +25,24 @@ size_t pconv_forward_umma2_workspace(const pcfb_pconv_shape *s);
 int pconv_forward_umma2(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
                         const float *additional, const float *guidance, const float *lin_w, const float *lin_b,
                         float *out_y, float *out_p, void *workspace, size_t workspace_bytes, cudaStream_t st);
+// pconv_mid1.cu (C_mid == 1: weighted neighbour sum + tensor-core Linear)
+bool pconv_mid1_supported(const pcfb_pconv_shape *s);
+int pconv_mid1_forward_p(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
+                         const float *additional, float *P, cudaStream_t st);
+int pconv_mid1_backward(const pcfb_pconv_shape *s, const float *dP, const float *feats, const int64_t *nei,
+                        const int32_t *inv_n, const uint8_t *inv_k, const int32_t *inv_idx, const float *weights,
+                        const float *additional, float *grad_feats, float *grad_weights, float *grad_additional,
+                        cudaStream_t st);
 }  // namespace pcfb
+
+static bool mid1_path(const pcfb_pconv_shape *s, int variant) {
+    return variant != 1 && variant != 3 && s->C_out >= 1 && s->C_out <= 256 && pcfb::pconv_mid1_supported(s);
+}
 
 extern "C" int pcfb_pconv_forward_supported(const pcfb_pconv_shape *s, int variant)
 {
     if (!s) return 0;
+    if (variant == 2 && mid1_path(s, variant)) return 1;
     if (variant == 2 || variant == 3)
         return (pcfb::pconv_forward_umma_supported(s, s->C_out > 0) || pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) ? 1 : 0;
     return 1;
@@ -39,6 +52,8 @@ extern "C" size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int va
 {
     if (!s) return 0;
     if (variant == 1) return 0;
+    if (mid1_path(s, variant))
+        return pcfb::align_up((size_t)s->n_out * (s->C_in + s->C_add) * sizeof(float), 256) + pcfb_gemm_nt_workspace(s->C_out, s->C_in + s->C_add);
     if (variant != 3 && pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) return pcfb::pconv_forward_umma2_workspace(s);
     return pcfb::pconv_forward_umma_supported(s, s->C_out > 0) ? pcfb::pconv_forward_umma_workspace(s) : 0;
 }
@@ -58,6 +73,18 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // variants: 0 auto, 1 exact-fp32 SIMT, 2 tcgen05 (pipelined kernel when the tile fits, else the simple one),
     // 3 tcgen05 simple kernel only (kept for bisecting)
+    if (lin_w && mid1_path(s, variant)) {
+        // C_mid == 1: P = weighted neighbour sum (streaming kernel), Y = P W^T + b on tcgen05
+        const int C_cat = s->C_in + s->C_add;
+        const size_t p_bytes = align_up((size_t)s->n_out * C_cat * sizeof(float), 256);
+        const size_t nt_bytes = pcfb_gemm_nt_workspace(s->C_out, C_cat);
+        PCFB_REQUIRE(workspace && workspace_bytes >= p_bytes + nt_bytes, "pcfb_pconv_forward: workspace too small");
+        float *P = out_p ? out_p : static_cast<float *>(workspace);
+        int rc;
+        if ((rc = pconv_mid1_forward_p(s, feats, nei, weights, additional, P, st))) return rc;
+        return pcfb_gemm_nt(P, C_cat, lin_w, C_cat, 0, lin_b, out_y, s->C_out, s->n_out, s->C_out, C_cat, 0,
+                            static_cast<char *>(workspace) + p_bytes, nt_bytes, stream);
+    }
     const bool u1_ok = lin_w && pconv_forward_umma_supported(s, true);
     const bool u2_ok = lin_w && variant != 3 && pconv_forward_umma2_supported(s, true);
     if ((variant == 2 || variant == 3) && !u1_ok && !u2_ok) {
@@ -147,11 +174,16 @@ extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_
     if (need_w) {
         const float *P = pconv_out;
         if (need_p) {
-            if ((rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, w.p_re, st))) return rc;
+            if (pconv_mid1_supported(s)) rc = pconv_mid1_forward_p(s, feats, nei, weights, additional, w.p_re, st);
+            else rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, w.p_re, st);
+            if (rc) return rc;
             P = w.p_re;
         }
         if ((rc = pcfb_gemm_tn(grad_y, s->C_out, P, KK, grad_lin_w, KK, grad_lin_b, s->n_out, s->C_out, KK, w.tn_ws, w.tn_bytes, stream))) return rc;
     }
+    if (pconv_mid1_supported(s))
+        return pconv_mid1_backward(s, w.dP, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional, grad_feats,
+                                   grad_weights, grad_additional, st);
     pcfb_pconv_shape nolin = *s;
     nolin.C_out = 0;
     return pconv_backward_simt(&nolin, nullptr, w.dP, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional, guidance,

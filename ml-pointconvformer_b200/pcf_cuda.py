@@ -242,11 +242,9 @@ def knn_packed(ref_xyz, ref_counts, qry_xyz, qry_counts, K, out=None):
     dev = ref_xyz.device
     n_seg = len(ref_counts)
     assert len(qry_counts) == n_seg
-    ro = torch.tensor([0] + list(ref_counts), dtype=torch.int64).cumsum(0).to(torch.int32)
-    qo = torch.tensor([0] + list(qry_counts), dtype=torch.int64).cumsum(0).to(torch.int32)
-    if int(ro[-1]) != ref_xyz.shape[0] or int(qo[-1]) != qry_xyz.shape[0]:
+    if sum(map(int, ref_counts)) != ref_xyz.shape[0] or sum(map(int, qry_counts)) != qry_xyz.shape[0]:
         raise RuntimeError("scene counts do not add up to the packed cloud sizes")
-    ro_d, qo_d = ro.to(dev, non_blocking=True), qo.to(dev, non_blocking=True)
+    ro_d, qo_d = _offsets(ref_counts, dev), _offsets(qry_counts, dev)
     if out is None:
         out = torch.empty(qry_xyz.shape[0], K, device=dev, dtype=I64)
     check(lib().pcfb_knn_packed(ptr(ref_xyz), ptr(ro_d), ptr(qry_xyz), ptr(qo_d), n_seg, ref_xyz.shape[0],
@@ -297,8 +295,20 @@ def gemm_tn(a, b, want_rowsum=False):
     return out, rs
 
 
+_OFFSETS = {}
+
+
 def _offsets(counts, dev):
-    return torch.tensor([0] + list(counts), dtype=torch.int64).cumsum(0).to(torch.int32).to(dev, non_blocking=True)
+    """Device int32 prefix array of the per-scene counts, cached per (counts, device): the tiny H2D copy happens
+    once per distinct packing, never inside a captured CUDA graph."""
+    key = (tuple(int(c) for c in counts), str(dev))
+    t = _OFFSETS.get(key)
+    if t is None:
+        if len(_OFFSETS) > 4096:
+            _OFFSETS.clear()
+        t = torch.tensor([0] + list(key[0]), dtype=torch.int64).cumsum(0).to(torch.int32).to(dev)
+        _OFFSETS[key] = t
+    return t
 
 
 class KnnGrid:
