@@ -176,6 +176,42 @@ int pcfb_gemm_tn(const float *A, int lda, const float *B, int ldb, float *C, int
                  int M, int N1, int N2, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused small MLP layers with train-mode BatchNorm for the per-edge / per-point chains: WeightNet
+ * (layers.py:127-191), positional-encoding WeightNet (layers.py:575-577), mlp_conv (layers.py:240-243), the
+ * guidance MLP (layers.py:38-68) and UnaryBlock (layer_utils.py:281-319).  One layer = one streaming pass:
+ *   y[E,cout] = act_in(x*in_scale + in_shift) W^T + b     (the BatchNorm of the layer below is folded into the load)
+ * while sum(y-b), sum((y-b)^2) are accumulated per block (stat_partial [blocks][2][cout]); pcfb_bn_finalize
+ * turns them (reduced in double, fixed order) into the layer's own (scale, shift) = (gamma*invstd,
+ * beta - mean*gamma*invstd), updates the running statistics (momentum, unbiased variance) and saves mean / invstd.
+ * act codes: 0 none, 1 ReLU, 2 LeakyReLU(0.1), 3 sigmoid.  Sizes: cin, cout <= 64 (pcfb_mlp_supported).
+ * Backward per layer (pcfb_mlp_backward): dz = dA*act'(z), dy = scale*(dz - S1/E - xhat*S2/E) with sums = [S1|S2]
+ * from pcfb_mlp_backward_stats (or produced on the fly by the layer above through prev_sums); outputs dA_prev,
+ * dW, db; dgamma = S2, dbeta = S1.  All reductions are block partials summed in fixed order: deterministic.
+ * d_count (device double, may be NULL) overrides the row count with a global one (SyncBatchNorm across ranks).
+ * ------------------------------------------------------------------------------------------- */
+int pcfb_mlp_supported(int cin, int cout);
+size_t pcfb_mlp_workspace(int64_t E, int cin, int cout);
+int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int cout, const float *W, const float *b,
+                     const float *in_scale, const float *in_shift, int in_act, float *y, int ldy,
+                     float *stat_partial, int *h_nblocks, void *stream);
+int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, const double *d_count, const float *pivot,
+                     const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                     float *running_var, float *scale, float *shift, float *mean, float *invstd, void *stream);
+int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
+                void *stream);
+int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y, int ldy, int64_t E, int C, const float *scale,
+                            const float *shift, const float *mean, const float *invstd, int act, float *sums,
+                            void *workspace, size_t workspace_bytes, void *stream);
+int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int ldy, int64_t E, int cin, int cout,
+                      const float *W, const float *scale, const float *shift, const float *mean,
+                      const float *invstd, const float *sums, int act,
+                      const float *x_prev, int ldx, const float *in_scale, const float *in_shift, int in_act,
+                      const float *prev_mean, const float *prev_invstd,
+                      float *dA_prev, int ldp, float *prev_sums, float *dW, float *db, const double *d_count,
+                      void *workspace, size_t workspace_bytes, void *stream);
+int pcfb_sum_partials(const float *partial, int nblocks, int n, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Grid (voxel) subsampling with barycentres on packed scenes.  Replaces grid_subsampling()
  * (grid_subsampling.cpp:9-110) as called per level by subsample() (datasetCommon.py:384-420).
  * Three phases because the grid extent and the output size are data dependent (the host reads two

@@ -1,0 +1,638 @@
+// Fused per-edge / per-point MLP layers with train-mode BatchNorm (sm_100a).
+//
+// Covers SURVEY.md rows a8 / a9 / a13: WeightNet (Linear -> BN2d(batch stats) -> ReLU chains,
+// /root/reference/layers.py:127-191), the positional-encoding WeightNet (layers.py:575-577), mlp_conv
+// (layers.py:240-243) and the guidance MLP (layers.py:38-68), which the reference (and torch) run as ~5 full
+// HBM passes per layer (Linear, BN statistics, BN apply, ReLU, ...) over [E, C] tensors with E = 1.6 M edges.
+//
+// Here one layer is ONE streaming pass:  y = act_in(x * scale_in + shift_in) W^T + b  with the BatchNorm of the
+// *previous* layer folded into the load (scale/shift) and the batch statistics of y accumulated on the fly
+// (pivoted by the bias, block partials reduced in double by a finalize kernel -> deterministic).  The BatchNorm of
+// y itself is only a (scale, shift) pair that the next consumer applies.  Backward per layer: one pass producing
+// the input gradient (with the BN-backward sums of the layer below accumulated on the fly) and one pass producing
+// the weight / bias gradient (warps own output channels, rows live in lanes, fixed-order reductions, no atomics).
+// One thread owns one row; weights sit in shared memory, zero padded to the template maxima.
+#include "common.cuh"
+
+namespace pcfb {
+
+constexpr int ML_THREADS = 256;
+constexpr int ML_WARPS = ML_THREADS / 32;
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SIGMOID = 3 };
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    if (act == ACT_RELU) return fmaxf(z, 0.f);
+    if (act == ACT_LEAKY) return z > 0.f ? z : 0.1f * z;
+    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-z));
+    return z;
+}
+// derivative given pre-activation z and activation value a
+__device__ __forceinline__ float act_bwd(float z, float a, int act) {
+    if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    if (act == ACT_LEAKY) return z > 0.f ? 1.f : 0.1f;
+    if (act == ACT_SIGMOID) return a * (1.f - a);
+    return 1.f;
+}
+
+template <int CMAX>
+__device__ __forceinline__ void load_row(const float *__restrict__ base, int ld, int64_t row, int c, bool vec, float *out) {
+    const float *p = base + row * ld;
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < CMAX; i += 4) {
+            if (i < c) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(p + i));
+                out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; out[i + 3] = v.w;
+            } else { out[i] = out[i + 1] = out[i + 2] = out[i + 3] = 0.f; }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CMAX; ++i) out[i] = (i < c) ? __ldg(p + i) : 0.f;
+    }
+}
+
+template <int CMAX>
+__device__ __forceinline__ void store_row(float *__restrict__ base, int ld, int64_t row, int c, bool vec, const float *v) {
+    float *p = base + row * ld;
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < CMAX; i += 4)
+            if (i < c) *reinterpret_cast<float4 *>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CMAX; ++i) if (i < c) p[i] = v[i];
+    }
+}
+
+struct MlpLayer {            // everything one layer needs; pointers may be null where noted
+    const float *W, *b;      // [cout][cin], [cout] (b may be null)
+    int cin, cout;
+    const float *in_scale, *in_shift;   // folded BN of the layer below applied on load (null = identity)
+    int in_act;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// forward: y = act_in(x*s+t) W^T + b ; stats partial[block][2][cout] = sum (y-b), sum (y-b)^2
+// ------------------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(ML_THREADS)
+mlp_fwd_kernel(const float *__restrict__ x, int ldx, int64_t E, MlpLayer L, float *__restrict__ y, int ldy,
+               float *__restrict__ stat_partial, int rows_per_thread)
+{
+    __shared__ __align__(16) float W_s[COUT * CIN];
+    __shared__ float b_s[COUT], s_s[CIN], t_s[CIN];
+    __shared__ float red[ML_WARPS][2 * COUT];
+    for (int i = threadIdx.x; i < COUT * CIN; i += ML_THREADS) {
+        const int o = i / CIN, k = i - o * CIN;
+        W_s[i] = (o < L.cout && k < L.cin) ? L.W[o * L.cin + k] : 0.f;
+    }
+    for (int i = threadIdx.x; i < COUT; i += ML_THREADS) b_s[i] = (L.b && i < L.cout) ? L.b[i] : 0.f;
+    for (int i = threadIdx.x; i < CIN; i += ML_THREADS) {
+        s_s[i] = (L.in_scale && i < L.cin) ? L.in_scale[i] : 1.f;
+        t_s[i] = (L.in_shift && i < L.cin) ? L.in_shift[i] : 0.f;
+    }
+    __syncthreads();
+    const bool vec_in = ((ldx & 3) == 0) && ((L.cin & 3) == 0) && ((uintptr_t)x % 16 == 0);
+    const bool vec_out = ((ldy & 3) == 0) && ((L.cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
+    float s1[COUT], s2[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) { s1[o] = 0.f; s2[o] = 0.f; }
+    const int64_t block_row0 = (int64_t)blockIdx.x * ML_THREADS * rows_per_thread;
+    for (int r = 0; r < rows_per_thread; ++r) {
+        const int64_t row = block_row0 + (int64_t)r * ML_THREADS + threadIdx.x;
+        if (row >= E) break;
+        float a[CIN];
+        load_row<CIN>(x, ldx, row, L.cin, vec_in, a);
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) a[k] = act_fwd(fmaf(a[k], s_s[k], t_s[k]), L.in_act);
+        float acc[COUT];
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            float v = 0.f;
+#pragma unroll
+            for (int k = 0; k < CIN; k += 4) {
+                const float4 w = *reinterpret_cast<const float4 *>(&W_s[o * CIN + k]);
+                v = fmaf(a[k], w.x, v); v = fmaf(a[k + 1], w.y, v); v = fmaf(a[k + 2], w.z, v); v = fmaf(a[k + 3], w.w, v);
+            }
+            acc[o] = v;
+            s1[o] += v; s2[o] = fmaf(v, v, s2[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] += b_s[o];
+        store_row<COUT>(y, ldy, row, L.cout, vec_out, acc);
+    }
+    if (stat_partial) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            float a1 = s1[o], a2 = s2[o];
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, sft); a2 += __shfl_xor_sync(0xffffffffu, a2, sft); }
+            if (lane == 0) { red[warp][o] = a1; red[warp][COUT + o] = a2; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * COUT; i += ML_THREADS) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < ML_WARPS; ++w) v += red[w][i];
+            const int which = i / COUT, o = i - which * COUT;
+            if (o < L.cout) stat_partial[((size_t)blockIdx.x * 2 + which) * L.cout + o] = v;
+        }
+    }
+}
+
+// BN finalize: mean/var from pivoted partial sums (double), scale/shift, running-stat update, saved mean/invstd
+__global__ void bn_finalize_kernel(const float *__restrict__ partial, int nblocks, int C, double count_host,
+                                   const double *__restrict__ d_count, const float *__restrict__ pivot, const float *__restrict__ gamma,
+                                   const float *__restrict__ beta, float eps, float momentum, float *__restrict__ running_mean,
+                                   float *__restrict__ running_var, float *__restrict__ scale, float *__restrict__ shift,
+                                   float *__restrict__ mean_out, float *__restrict__ invstd_out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double count = d_count ? *d_count : count_host;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = 0; b < nblocks; ++b) {
+        s1 += (double)partial[((size_t)b * 2 + 0) * C + c];
+        s2 += (double)partial[((size_t)b * 2 + 1) * C + c];
+    }
+    const double m_p = s1 / count;                       // mean of (y - pivot)
+    double var = s2 / count - m_p * m_p;
+    if (var < 0.0) var = 0.0;
+    const double mean = m_p + (pivot ? (double)pivot[c] : 0.0);
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    scale[c] = g * invstd;
+    shift[c] = bt - (float)mean * g * invstd;
+    if (mean_out) mean_out[c] = (float)mean;
+    if (invstd_out) invstd_out[c] = invstd;
+    if (running_mean) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+    }
+}
+
+// a = act(y*scale+shift), elementwise (the chain's last BatchNorm + activation, materialised for its consumer)
+__global__ void bn_act_kernel(const float *__restrict__ y, int64_t n, int C, const float *__restrict__ scale,
+                              const float *__restrict__ shift, int act, float *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const float z = scale ? fmaf(y[i], scale[c], shift[c]) : y[i];
+        out[i] = act_fwd(z, act);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+struct MlpBnCtx {            // BatchNorm + activation of one layer's output y (train mode); no BN: scale = null
+    const float *scale, *shift, *mean, *invstd;   // scale = gamma*invstd, shift = beta - mean*scale
+    const float *sums;       // [2][C]: S1 = sum dz, S2 = sum dz * xhat   (null when no BN)
+    int act;
+    float inv_count;
+    const double *d_count;   // optional device-side global row count (SyncBatchNorm): overrides inv_count
+};
+
+__device__ __forceinline__ float ctx_inv_count(const MlpBnCtx &B) { return B.d_count ? (float)(1.0 / *B.d_count) : B.inv_count; }
+
+// stats of one layer's output gradient: partial[block][2][C] = sum dz, sum dz*xhat  (thread = row)
+template <int COUT>
+__global__ void __launch_bounds__(ML_THREADS)
+mlp_bwd_stats_kernel(const float *__restrict__ dA, int ldd, const float *__restrict__ y, int ldy, int64_t E, int C,
+                     MlpBnCtx B, float *__restrict__ partial, int rows_per_thread)
+{
+    __shared__ float red[ML_WARPS][2 * COUT];
+    const bool vec_d = ((ldd & 3) == 0) && ((C & 3) == 0) && ((uintptr_t)dA % 16 == 0);
+    const bool vec_y = ((ldy & 3) == 0) && ((C & 3) == 0) && ((uintptr_t)y % 16 == 0);
+    float s1[COUT], s2[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) { s1[o] = 0.f; s2[o] = 0.f; }
+    const int64_t block_row0 = (int64_t)blockIdx.x * ML_THREADS * rows_per_thread;
+    for (int r = 0; r < rows_per_thread; ++r) {
+        const int64_t row = block_row0 + (int64_t)r * ML_THREADS + threadIdx.x;
+        if (row >= E) break;
+        float d[COUT], yv[COUT];
+        load_row<COUT>(dA, ldd, row, C, vec_d, d);
+        load_row<COUT>(y, ldy, row, C, vec_y, yv);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            if (o < C) {
+                const float z = fmaf(yv[o], B.scale[o], B.shift[o]);
+                const float a = act_fwd(z, B.act);
+                const float dz = d[o] * act_bwd(z, a, B.act);
+                const float xhat = (yv[o] - B.mean[o]) * B.invstd[o];
+                s1[o] += dz; s2[o] = fmaf(dz, xhat, s2[o]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+        float a1 = s1[o], a2 = s2[o];
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, sft); a2 += __shfl_xor_sync(0xffffffffu, a2, sft); }
+        if (lane == 0) { red[warp][o] = a1; red[warp][COUT + o] = a2; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * COUT; i += ML_THREADS) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < ML_WARPS; ++w) v += red[w][i];
+        const int which = i / COUT, o = i - which * COUT;
+        if (o < C) partial[((size_t)blockIdx.x * 2 + which) * C + o] = v;
+    }
+}
+
+// sums[2][C] = fixed-order (double) reduction of the block partials; also used for dgamma (= S2) / dbeta (= S1)
+__global__ void sum_partials_kernel(const float *__restrict__ partial, int nblocks, int n, float *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * n + i];
+    out[i] = (float)s;
+}
+
+// input-gradient pass: dA_prev[row][k] = sum_o dy_o W[o][k]; optionally the BN-backward sums of the layer below
+// (S1 = sum dz_prev, S2 = sum dz_prev * xhat_prev with dz_prev = dA_prev * act'_prev) are accumulated on the fly
+template <int CIN, int COUT, bool FUSE_PREV>
+__global__ void __launch_bounds__(ML_THREADS)
+mlp_bwd_input_kernel(const float *__restrict__ dA, int ldd, const float *__restrict__ y, int ldy, int64_t E,
+                     const float *__restrict__ W, int cin, int cout, MlpBnCtx B,
+                     float *__restrict__ dA_prev, int ldp,
+                     const float *__restrict__ y_prev, int ldyp, MlpBnCtx Bp, float *__restrict__ prev_partial,
+                     int rows_per_thread)
+{
+    __shared__ __align__(16) float Wt_s[CIN * COUT];          // transposed: [k][o]
+    __shared__ float red[ML_WARPS][2 * CIN];
+    for (int i = threadIdx.x; i < CIN * COUT; i += ML_THREADS) {
+        const int k = i / COUT, o = i - k * COUT;
+        Wt_s[i] = (o < cout && k < cin) ? W[o * cin + k] : 0.f;
+    }
+    __syncthreads();
+    const bool vec_d = ((ldd & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)dA % 16 == 0);
+    const bool vec_y = ((ldy & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
+    const bool vec_p = ((ldp & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)dA_prev % 16 == 0);
+    const bool vec_yp = y_prev && ((ldyp & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)y_prev % 16 == 0);
+    const float inv_count = ctx_inv_count(B);
+    constexpr int SN = FUSE_PREV ? CIN : 1;
+    float s1[SN], s2[SN];
+#pragma unroll
+    for (int k = 0; k < SN; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    const int64_t block_row0 = (int64_t)blockIdx.x * ML_THREADS * rows_per_thread;
+    for (int r = 0; r < rows_per_thread; ++r) {
+        const int64_t row = block_row0 + (int64_t)r * ML_THREADS + threadIdx.x;
+        if (row >= E) break;
+        float d[COUT], yv[COUT];
+        load_row<COUT>(dA, ldd, row, cout, vec_d, d);
+        load_row<COUT>(y, ldy, row, cout, vec_y, yv);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) {
+            float dy = 0.f;
+            if (o < cout) {
+                float z = yv[o], xhat = 0.f;
+                if (B.scale) { z = fmaf(yv[o], B.scale[o], B.shift[o]); xhat = (yv[o] - B.mean[o]) * B.invstd[o]; }
+                const float a = act_fwd(z, B.act);
+                const float dz = d[o] * act_bwd(z, a, B.act);
+                dy = B.scale ? B.scale[o] * (dz - B.sums[o] * inv_count - xhat * B.sums[cout + o] * inv_count) : dz;
+            }
+            d[o] = dy;
+        }
+        float g[CIN];
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) {
+            float v = 0.f;
+#pragma unroll
+            for (int o = 0; o < COUT; o += 4) {
+                const float4 w = *reinterpret_cast<const float4 *>(&Wt_s[k * COUT + o]);
+                v = fmaf(d[o], w.x, v); v = fmaf(d[o + 1], w.y, v); v = fmaf(d[o + 2], w.z, v); v = fmaf(d[o + 3], w.w, v);
+            }
+            g[k] = v;
+        }
+        store_row<CIN>(dA_prev, ldp, row, cin, vec_p, g);
+        if (FUSE_PREV && prev_partial) {
+            float yp[CIN];
+            load_row<CIN>(y_prev, ldyp, row, cin, vec_yp, yp);
+#pragma unroll
+            for (int k = 0; k < CIN; ++k) {
+                if (k < cin) {
+                    const float z = fmaf(yp[k], Bp.scale[k], Bp.shift[k]);
+                    const float a = act_fwd(z, Bp.act);
+                    const float dz = g[k] * act_bwd(z, a, Bp.act);
+                    const float xhat = (yp[k] - Bp.mean[k]) * Bp.invstd[k];
+                    s1[k % SN] += dz; s2[k % SN] = fmaf(dz, xhat, s2[k % SN]);
+                }
+            }
+        }
+    }
+    if (FUSE_PREV && prev_partial) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < SN; ++k) {
+            float a1 = s1[k], a2 = s2[k];
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, sft); a2 += __shfl_xor_sync(0xffffffffu, a2, sft); }
+            if (lane == 0) { red[warp][k] = a1; red[warp][CIN + k] = a2; }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * CIN; i += ML_THREADS) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < ML_WARPS; ++w) v += red[w][i];
+            const int which = i / CIN, k = i - which * CIN;
+            if (k < cin) prev_partial[((size_t)blockIdx.x * 2 + which) * cin + k] = v;
+        }
+    }
+}
+
+// weight-gradient pass.  Tile = 128 rows: threads 0-127 turn (dA, y) of one row into dy[cout], threads 128-255 turn
+// the stored input of one row into a_prev[cin]; both land in shared memory.  Then every thread owns a 4x4 block of
+// the [cout x cin] gradient and a slice of the tile's rows (2 LDS.128 per 16 FMA), accumulating in registers over
+// all tiles of the CTA; slices are combined once at the end in fixed order.
+// partial[block][cout][cin+1]: dW[o][k] = sum dy_o * a_prev[k], last column = db[o] = sum dy_o
+constexpr int MW_TILE = 128;
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(ML_THREADS)
+mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__restrict__ y, int ldy, int64_t E, int cin, int cout,
+                      MlpBnCtx B, const float *__restrict__ x_prev, int ldx, const float *__restrict__ in_scale,
+                      const float *__restrict__ in_shift, int in_act, float *__restrict__ partial)
+{
+    constexpr int DS = COUT + 4, AS = CIN + 4;                  // padded row strides (floats), 16-byte aligned rows
+    constexpr int NPB = (COUT / 4) * (CIN / 4);                 // 4x4 blocks of the gradient
+    constexpr int NS = ML_THREADS / NPB;                        // row slices
+    static_assert(NPB <= ML_THREADS && ML_THREADS % NPB == 0, "bad tiling");
+    __shared__ __align__(16) float dy_s[MW_TILE * DS];
+    __shared__ __align__(16) float a_s[MW_TILE * AS];
+    const int t = threadIdx.x;
+    const int pb = t % NPB, slice = t / NPB;
+    const int o4 = (pb / (CIN / 4)) * 4, k4 = (pb % (CIN / 4)) * 4;
+    const bool vec_d = ((ldd & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)dA % 16 == 0);
+    const bool vec_y = ((ldy & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
+    const bool vec_x = ((ldx & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)x_prev % 16 == 0);
+    const float inv_count = ctx_inv_count(B);
+    float acc[4][4], accb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { accb[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
+    const int64_t n_tiles = (E + MW_TILE - 1) / MW_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * MW_TILE + (t & (MW_TILE - 1));
+        __syncthreads();                                        // previous tile consumed
+        if (t < MW_TILE) {
+            float d[COUT], yv[COUT];
+            if (row < E) { load_row<COUT>(dA, ldd, row, cout, vec_d, d); load_row<COUT>(y, ldy, row, cout, vec_y, yv); }
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                float dy = 0.f;
+                if (row < E && o < cout) {
+                    float z = yv[o], xhat = 0.f;
+                    if (B.scale) { z = fmaf(yv[o], B.scale[o], B.shift[o]); xhat = (yv[o] - B.mean[o]) * B.invstd[o]; }
+                    const float av = act_fwd(z, B.act);
+                    const float dz = d[o] * act_bwd(z, av, B.act);
+                    dy = B.scale ? B.scale[o] * (dz - B.sums[o] * inv_count - xhat * B.sums[cout + o] * inv_count) : dz;
+                }
+                d[o] = dy;
+            }
+#pragma unroll
+            for (int o = 0; o < COUT; o += 4)
+                *reinterpret_cast<float4 *>(&dy_s[t * DS + o]) = make_float4(d[o], d[o + 1], d[o + 2], d[o + 3]);
+        } else {
+            const int r = t - MW_TILE;
+            float a[CIN];
+            if (row < E) load_row<CIN>(x_prev, ldx, row, cin, vec_x, a);
+#pragma unroll
+            for (int k = 0; k < CIN; ++k) {
+                float v = 0.f;
+                if (row < E && k < cin) {
+                    v = in_scale ? fmaf(a[k], in_scale[k], in_shift[k]) : a[k];
+                    v = act_fwd(v, in_act);
+                }
+                a[k] = v;
+            }
+#pragma unroll
+            for (int k = 0; k < CIN; k += 4)
+                *reinterpret_cast<float4 *>(&a_s[r * AS + k]) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = slice; r < MW_TILE; r += NS) {
+            const float4 dv = *reinterpret_cast<const float4 *>(&dy_s[r * DS + o4]);
+            const float4 av = *reinterpret_cast<const float4 *>(&a_s[r * AS + k4]);
+            const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, aa[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                accb[i] += dd[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dd[i], aa[j], acc[i][j]);
+            }
+        }
+    }
+    // combine the NS row slices in fixed order (reuse dy_s / a_s as scratch: NS * NPB * 20 floats)
+    __syncthreads();
+    float *red = dy_s;                                          // [NS][NPB][20] <= MW_TILE*DS + MW_TILE*AS floats (contiguous arrays)
+    constexpr int RED_FLOATS = NS * NPB * 20;
+    static_assert(RED_FLOATS <= MW_TILE * DS + MW_TILE * AS, "reduction scratch does not fit");
+    float *mine = red + ((size_t)slice * NPB + pb) * 20;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mine[16 + i] = accb[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mine[i * 4 + j] = acc[i][j]; }
+    __syncthreads();
+    for (int e = t; e < NPB * 20; e += ML_THREADS) {
+        const int b2 = e / 20, idx = e - b2 * 20;
+        float v = 0.f;
+        for (int sl = 0; sl < NS; ++sl) v += red[((size_t)sl * NPB + b2) * 20 + idx];
+        const int bo = (b2 / (CIN / 4)) * 4, bk = (b2 % (CIN / 4)) * 4;
+        if (idx < 16) {
+            const int o = bo + idx / 4, k = bk + idx % 4;
+            if (o < cout && k < cin) partial[((size_t)blockIdx.x * cout + o) * (cin + 1) + k] = v;
+        } else if (bk == 0) {
+            const int o = bo + (idx - 16);
+            if (o < cout) partial[((size_t)blockIdx.x * cout + o) * (cin + 1) + cin] = v;
+        }
+    }
+}
+
+// dW[o][k], db[o] from block partials (fixed order, double)
+__global__ void mlp_weight_finalize_kernel(const float *__restrict__ partial, int nblocks, int cout, int cin,
+                                           float *__restrict__ dW, float *__restrict__ db)
+{
+    const int n = cout * (cin + 1);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * n + i];
+    const int o = i / (cin + 1), k = i - o * (cin + 1);
+    if (k < cin) { if (dW) dW[o * cin + k] = (float)s; }
+    else if (db) db[o] = (float)s;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static inline int cmax_of(int c) { return c <= 16 ? 16 : (c <= 32 ? 32 : 64); }
+constexpr int ML_RPT = 8;          // rows per thread in the streaming passes
+
+static inline int mlp_blocks(int64_t E) { return (int)((E + (int64_t)ML_THREADS * ML_RPT - 1) / ((int64_t)ML_THREADS * ML_RPT)); }
+static inline int mlp_wblocks(int64_t E, int *gpb) {
+    const int64_t tiles = (E + 127) / 128;
+    int64_t blocks = tiles < 3 * kNumSMs ? tiles : 3 * kNumSMs;
+    if (blocks < 1) blocks = 1;
+    *gpb = 0;
+    return (int)blocks;
+}
+
+}  // namespace pcfb
+
+using namespace pcfb;
+
+extern "C" int pcfb_mlp_supported(int cin, int cout)
+{
+    if (cin < 1 || cout < 1 || cin > 64 || cout > 64) return 0;
+    const int ci = cmax_of(cin), co = cmax_of(cout);
+    // template instances: (16,16) (16,32) (16,64) (32,16) (32,32) (64,16)
+    return (ci == 16) || (ci == 32 && co <= 32) || (ci == 64 && co == 16) ? 1 : 0;
+}
+
+// number of floats of scratch needed by the forward stats / backward partials for E rows
+extern "C" size_t pcfb_mlp_workspace(int64_t E, int cin, int cout)
+{
+    int gpb;
+    const size_t a = (size_t)mlp_blocks(E) * 2 * (size_t)(cout > cin ? cout : cin);
+    const size_t b = (size_t)mlp_wblocks(E, &gpb) * cout * (cin + 1);
+    return align_up((a > b ? a : b) * sizeof(float) + 1024, 256);
+}
+
+#define ML_DISPATCH_IO(CIN_V, COUT_V, CALL)                                         \
+    do {                                                                            \
+        if (CIN_V == 16 && COUT_V == 16) { constexpr int CI = 16, CO = 16; CALL; }   \
+        else if (CIN_V == 16 && COUT_V == 32) { constexpr int CI = 16, CO = 32; CALL; } \
+        else if (CIN_V == 16 && COUT_V == 64) { constexpr int CI = 16, CO = 64; CALL; } \
+        else if (CIN_V == 32 && COUT_V == 16) { constexpr int CI = 32, CO = 16; CALL; } \
+        else if (CIN_V == 32 && COUT_V == 32) { constexpr int CI = 32, CO = 32; CALL; } \
+        else { constexpr int CI = 64, CO = 16; CALL; }                               \
+    } while (0)
+
+// y[E,cout] = act_in(x*in_scale+in_shift) W^T + b ; stat_partial (optional): [blocks][2][cout]; returns #blocks via *nblocks
+extern "C" int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int cout, const float *W, const float *b,
+                                const float *in_scale, const float *in_shift, int in_act, float *y, int ldy,
+                                float *stat_partial, int *nblocks, void *stream)
+{
+    PCFB_REQUIRE(pcfb_mlp_supported(cin, cout), "pcfb_mlp_forward: unsupported layer size %d -> %d", cin, cout);
+    PCFB_REQUIRE(x && W && y && E >= 0, "pcfb_mlp_forward: null pointer");
+    const int blocks = mlp_blocks(E);
+    if (nblocks) *nblocks = blocks;
+    if (E == 0) return PCFB_OK;
+    MlpLayer L{W, b, cin, cout, in_scale, in_shift, in_act};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int ci = cmax_of(cin), co = cmax_of(cout);
+    ML_DISPATCH_IO(ci, co, (mlp_fwd_kernel<CI, CO><<<blocks, ML_THREADS, 0, st>>>(x, ldx, E, L, y, ldy, stat_partial, ML_RPT)));
+    return check_launch("mlp_fwd_kernel");
+}
+
+extern "C" int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, const double *d_count, const float *pivot,
+                                const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                                float *running_var, float *scale, float *shift, float *mean, float *invstd, void *stream)
+{
+    PCFB_REQUIRE(partial && scale && shift && C >= 1, "pcfb_bn_finalize: null pointer");
+    bn_finalize_kernel<<<ceil_div(C, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        partial, nblocks, C, (double)count, d_count, pivot, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
+    return check_launch("bn_finalize_kernel");
+}
+
+extern "C" int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
+                           void *stream)
+{
+    PCFB_REQUIRE(y && out, "pcfb_bn_act: null pointer");
+    const int64_t n = rows * C;
+    if (n == 0) return PCFB_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    bn_act_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, n, C, scale, shift, act, out);
+    return check_launch("bn_act_kernel");
+}
+
+// BN-backward sums of one layer: sums[2][C] = (sum dz, sum dz*xhat) for dz = dA * act'(y*scale+shift)
+extern "C" int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y, int ldy, int64_t E, int C, const float *scale,
+                                       const float *shift, const float *mean, const float *invstd, int act, float *sums,
+                                       void *workspace, size_t workspace_bytes, void *stream)
+{
+    PCFB_REQUIRE(C >= 1 && C <= 64 && dA && y && scale && shift && mean && invstd && sums && workspace, "pcfb_mlp_backward_stats: bad arguments");
+    const int blocks = mlp_blocks(E);
+    PCFB_REQUIRE(workspace_bytes >= (size_t)blocks * 2 * C * sizeof(float), "pcfb_mlp_backward_stats: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *partial = static_cast<float *>(workspace);
+    MlpBnCtx B{scale, shift, mean, invstd, nullptr, act, 0.f, nullptr};
+    int rc;
+    if (E > 0) {
+        const int co = cmax_of(C);
+        if (co == 16) mlp_bwd_stats_kernel<16><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, ML_RPT);
+        else if (co == 32) mlp_bwd_stats_kernel<32><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, ML_RPT);
+        else mlp_bwd_stats_kernel<64><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, ML_RPT);
+        if ((rc = check_launch("mlp_bwd_stats_kernel"))) return rc;
+    }
+    sum_partials_kernel<<<ceil_div(2 * C, 64), 64, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * C, sums);
+    return check_launch("sum_partials_kernel");
+}
+
+// One layer backward.  Inputs: dA (grad wrt this layer's activation output), y (its pre-BN output), BN context
+// (scale/shift/mean/invstd/sums; scale == NULL -> no BN), W.  Outputs: dA_prev [E,cin] (may be NULL), dW [cout,cin],
+// db [cout] (may be NULL).  x_prev (+ in_scale/in_shift/in_act) is the layer's input as stored (pre-BN output of the layer
+// below, or the raw chain input).  If prev_sums != NULL the BN-backward sums of the layer below (whose BN context is
+// prev_*) are produced on the fly: prev_sums[2][cin].
+extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int ldy, int64_t E, int cin, int cout,
+                                 const float *W, const float *scale, const float *shift, const float *mean,
+                                 const float *invstd, const float *sums, int act,
+                                 const float *x_prev, int ldx, const float *in_scale, const float *in_shift, int in_act,
+                                 const float *prev_mean, const float *prev_invstd,
+                                 float *dA_prev, int ldp, float *prev_sums, float *dW, float *db, const double *d_count,
+                                 void *workspace, size_t workspace_bytes, void *stream)
+{
+    PCFB_REQUIRE(pcfb_mlp_supported(cin, cout), "pcfb_mlp_backward: unsupported layer size %d -> %d", cin, cout);
+    PCFB_REQUIRE(dA && y && W && x_prev && workspace, "pcfb_mlp_backward: null pointer");
+    PCFB_REQUIRE(!scale || (shift && mean && invstd && sums), "pcfb_mlp_backward: incomplete BatchNorm context");
+    PCFB_REQUIRE(!prev_sums || (dA_prev && in_scale && in_shift && prev_mean && prev_invstd), "pcfb_mlp_backward: incomplete lower BatchNorm context");
+    PCFB_REQUIRE(!prev_sums || cin <= 32, "pcfb_mlp_backward: fused lower-layer sums need cin <= 32 (use pcfb_mlp_backward_stats)");
+    PCFB_REQUIRE(workspace_bytes >= pcfb_mlp_workspace(E, cin, cout), "pcfb_mlp_backward: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *partial = static_cast<float *>(workspace);
+    const float inv_count = E > 0 ? (float)(1.0 / (double)E) : 0.f;
+    MlpBnCtx B{scale, shift, mean, invstd, sums, act, inv_count, d_count};
+    MlpBnCtx Bp{in_scale, in_shift, prev_mean, prev_invstd, nullptr, in_act, inv_count, d_count};
+    const int ci = cmax_of(cin), co = cmax_of(cout);
+    int rc;
+    if (dA_prev) {
+        const int blocks = mlp_blocks(E);
+        if (E > 0) {
+            ML_DISPATCH_IO(ci, co, (mlp_bwd_input_kernel<CI, CO, (CI <= 32)><<<blocks, ML_THREADS, 0, st>>>(
+                dA, ldd, y, ldy, E, W, cin, cout, B, dA_prev, ldp, x_prev, ldx, Bp, prev_sums ? partial : nullptr, ML_RPT)));
+            if ((rc = check_launch("mlp_bwd_input_kernel"))) return rc;
+        }
+        if (prev_sums) {
+            sum_partials_kernel<<<ceil_div(2 * cin, 64), 64, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * cin, prev_sums);
+            if ((rc = check_launch("sum_partials_kernel"))) return rc;
+        }
+    }
+    if (dW || db) {
+        int gpb;
+        const int blocks = mlp_wblocks(E, &gpb);
+        (void)gpb;
+        if (E > 0) {
+            ML_DISPATCH_IO(ci, co, (mlp_bwd_weight_kernel<CI, CO><<<blocks, ML_THREADS, 0, st>>>(
+                dA, ldd, y, ldy, E, cin, cout, B, x_prev, ldx, in_scale, in_shift, in_act, partial)));
+            if ((rc = check_launch("mlp_bwd_weight_kernel"))) return rc;
+        }
+        mlp_weight_finalize_kernel<<<ceil_div(cout * (cin + 1), 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, cout, cin, dW, db);
+        if ((rc = check_launch("mlp_weight_finalize_kernel"))) return rc;
+    }
+    return PCFB_OK;
+}
+
+extern "C" int pcfb_sum_partials(const float *partial, int nblocks, int n, float *out, void *stream)
+{
+    PCFB_REQUIRE(partial && out && n >= 1, "pcfb_sum_partials: bad arguments");
+    sum_partials_kernel<<<ceil_div(n, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(partial, nblocks, n, out);
+    return check_launch("sum_partials_kernel");
+}

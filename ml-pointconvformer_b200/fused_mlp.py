@@ -1,0 +1,195 @@
+"""Fused small-MLP chains with BatchNorm (WeightNet, pe_convs, mlp_conv, guidance MLP, UnaryBlock) on top of
+pcfb_mlp_* (csrc/mlp.cu): one streaming kernel pass per layer in the forward, two in the backward, BatchNorm
+statistics accumulated on the fly, every reduction deterministic.  Mirrors what the reference computes with
+Linear_BN + activation sequences (/root/reference/layers.py:127-191, 38-68; layer_utils.py:241-319)."""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr, workspace
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
+F32 = torch.float32
+
+
+def supported(dims):
+    """dims: [(cin, cout), ...]"""
+    return all(lib().pcfb_mlp_supported(int(a), int(b)) for a, b in dims)
+
+
+def _sync_group(bn):
+    if isinstance(bn, torch.nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return True
+    return False
+
+
+class _ChainFunction(torch.autograd.Function):
+    """args: x2 [E, cin] (rows contiguous), spec (python: list of dict(act, has_bn, eps, momentum, sync)), training,
+    then per layer (W, b, gamma, beta) tensors (gamma/beta None without BN); running stats are passed through `buffers`."""
+
+    @staticmethod
+    def forward(ctx, x2, spec, training, buffers, *params):
+        E = x2.shape[0]
+        dev = x2.device
+        L = len(spec)
+        cur, ld = x2, x2.stride(0)
+        in_scale = in_shift = None
+        in_act = ACT_NONE
+        ys, ctxs = [], []
+        world = dist.get_world_size() if any(s["sync"] for s in spec) else 1
+        count, d_count = E, None
+        if world > 1:                                    # global row count stays on the device (no host sync)
+            d_count = torch.full((1,), float(E), device=dev, dtype=torch.float64)
+            dist.all_reduce(d_count)
+        for l, s in enumerate(spec):
+            W, b, gamma, beta = params[4 * l: 4 * l + 4]
+            cout, cin = W.shape
+            y = torch.empty(E, cout, device=dev, dtype=F32)
+            want_stats = s["has_bn"] and training
+            nblk = ctypes.c_int(0)
+            ws = workspace(lib().pcfb_mlp_workspace(E, cin, cout), dev) if want_stats else None
+            check(lib().pcfb_mlp_forward(ptr(cur), ld, E, cin, cout, ptr(W), ptr(b), ptr(in_scale), ptr(in_shift), in_act,
+                                         ptr(y), cout, ptr(ws), ctypes.addressof(nblk), stream_ptr()), "mlp_forward")
+            scale = shift = mean = invstd = None
+            if s["has_bn"]:
+                rm, rv = buffers[l]
+                if training:
+                    scale = torch.empty(cout, device=dev, dtype=F32); shift = torch.empty_like(scale)
+                    mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
+                    part, nb = ws, nblk.value
+                    if s["sync"] and world > 1:
+                        summed = torch.empty(2 * cout, device=dev, dtype=F32)
+                        check(lib().pcfb_sum_partials(ptr(ws), nblk.value, 2 * cout, ptr(summed), stream_ptr()), "sum_partials")
+                        dist.all_reduce(summed)
+                        part, nb = summed, 1
+                    check(lib().pcfb_bn_finalize(ptr(part), nb, cout, count, ptr(d_count) if s["sync"] else 0, ptr(b), ptr(gamma), ptr(beta), float(s["eps"]),
+                                                 float(s["momentum"]), ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean),
+                                                 ptr(invstd), stream_ptr()), "bn_finalize")
+                else:
+                    invstd = torch.rsqrt(rv + s["eps"])
+                    scale = (gamma * invstd).contiguous()
+                    shift = (beta - rm * scale).contiguous()
+                    mean = rm
+            ys.append(y)
+            ctxs.append((scale, shift, mean, invstd))
+            cur, ld = y, cout
+            in_scale, in_shift, in_act = scale, shift, s["act"]
+        out = torch.empty_like(ys[-1])
+        check(lib().pcfb_bn_act(ptr(ys[-1]), E, ys[-1].shape[1], ptr(in_scale), ptr(in_shift), in_act, ptr(out), stream_ptr()), "bn_act")
+        ctx.spec, ctx.training, ctx.d_count, ctx.world = spec, training, d_count, world
+        ctx.n_layers = L
+        saved = [x2] + ys + list(params)
+        for c in ctxs:
+            saved += list(c)
+        ctx.save_for_backward(*saved)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        spec, L = ctx.spec, ctx.n_layers
+        saved = ctx.saved_tensors
+        x2, ys = saved[0], saved[1:1 + L]
+        params = saved[1 + L: 1 + 5 * L]
+        cflat = saved[1 + 5 * L:]
+        ctxs = [cflat[4 * l: 4 * l + 4] for l in range(L)]
+        E = x2.shape[0]
+        dev = x2.device
+        dA = grad_out.reshape(E, -1)
+        if dA.stride(-1) != 1 or dA.stride(0) != dA.shape[1]:
+            dA = dA.contiguous()
+        grads = [None] * (4 * L)
+        train_bn = ctx.training
+        zeros_cache = {}
+
+        def bn_ctx(l):
+            """(scale, shift, mean, invstd) usable by the kernels; eval-mode BN = fixed affine (mean terms vanish)."""
+            scale, shift, mean, invstd = ctxs[l]
+            return scale, shift, mean, invstd
+
+        def stats(l, dA_l):
+            C = ys[l].shape[1]
+            scale, shift, mean, invstd = bn_ctx(l)
+            sums = torch.empty(2 * C, device=dev, dtype=F32)
+            if not train_bn:
+                sums.zero_()
+                return sums
+            ws = workspace(lib().pcfb_mlp_workspace(E, C, C), dev)
+            check(lib().pcfb_mlp_backward_stats(ptr(dA_l), dA_l.stride(0), ptr(ys[l]), C, E, C, ptr(scale), ptr(shift), ptr(mean),
+                                                ptr(invstd), spec[l]["act"], ptr(sums), ptr(ws), ws.numel(), stream_ptr()), "mlp_backward_stats")
+            if spec[l]["sync"] and ctx.world > 1:
+                dist.all_reduce(sums)
+            return sums
+
+        sums = stats(L - 1, dA) if spec[L - 1]["has_bn"] else None
+        need_x_grad = ctx.needs_input_grad[0]
+        for l in range(L - 1, -1, -1):
+            W, b, gamma, beta = params[4 * l: 4 * l + 4]
+            cout, cin = W.shape
+            scale, shift, mean, invstd = ctxs[l]
+            has_bn = spec[l]["has_bn"]
+            if l > 0:
+                x_prev, ldx = ys[l - 1], ys[l - 1].shape[1]
+                p_scale, p_shift, p_mean, p_invstd = ctxs[l - 1]
+                in_act = spec[l - 1]["act"]
+            else:
+                x_prev, ldx = x2, x2.stride(0)
+                p_scale = p_shift = p_mean = p_invstd = None
+                in_act = ACT_NONE
+            want_prev = l > 0 or need_x_grad
+            dA_prev = torch.empty(E, cin, device=dev, dtype=F32) if want_prev else None
+            prev_has_bn = l > 0 and spec[l - 1]["has_bn"]
+            fuse_prev = prev_has_bn and train_bn and cin <= 32 and not (spec[l - 1]["sync"] and ctx.world > 1)
+            prev_sums = torch.empty(2 * cin, device=dev, dtype=F32) if fuse_prev else None
+            dW = torch.empty_like(W)
+            db = torch.empty(cout, device=dev, dtype=F32) if b is not None else None
+            ws = workspace(lib().pcfb_mlp_workspace(E, cin, cout), dev)
+            inv_scale = 1.0
+            check(lib().pcfb_mlp_backward(
+                ptr(dA), dA.stride(0), ptr(ys[l]), cout, E, cin, cout, ptr(W),
+                ptr(scale) if has_bn else 0, ptr(shift) if has_bn else 0, ptr(mean) if has_bn else 0,
+                ptr(invstd) if has_bn else 0, ptr(sums) if has_bn else 0, spec[l]["act"],
+                ptr(x_prev), ldx, ptr(p_scale), ptr(p_shift), in_act, ptr(p_mean), ptr(p_invstd),
+                ptr(dA_prev), cin, ptr(prev_sums), ptr(dW), ptr(db), ptr(ctx.d_count) if (has_bn and spec[l]["sync"]) else 0,
+                ptr(ws), ws.numel(), stream_ptr()), "mlp_backward")
+            grads[4 * l] = dW
+            grads[4 * l + 1] = db
+            if has_bn and gamma is not None:
+                # dgamma = sum dz * xhat, dbeta = sum dz  (train mode); eval mode: recompute from dA is not needed
+                # because the affine is constant w.r.t. the batch -- dgamma/dbeta then come from the same sums
+                C = cout
+                if train_bn:
+                    grads[4 * l + 2] = sums[C:].clone()
+                    grads[4 * l + 3] = sums[:C].clone()
+            if l > 0:
+                if prev_has_bn:
+                    sums = prev_sums if fuse_prev else stats(l - 1, dA_prev)
+                else:
+                    sums = None
+                dA = dA_prev
+        gx = dA_prev if need_x_grad else None
+        return (gx, None, None, None) + tuple(grads)
+
+
+def mlp_chain(x, layers, training):
+    """x [..., cin]; layers: list of (linear_module, bn_module_or_None, act_code).  Returns act_L(BN_L(...)) with the
+    same leading shape.  Raises if a layer size is not supported (callers check `supported`)."""
+    if not x.is_cuda:
+        raise RuntimeError("pcf_b200 fused MLP needs CUDA tensors (no CPU path)")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    spec, params, buffers = [], [], []
+    for lin, bn, act in layers:
+        has_bn = bn is not None
+        spec.append(dict(act=act, has_bn=has_bn, eps=bn.eps if has_bn else 1e-5,
+                         momentum=(bn.momentum if bn.momentum is not None else 0.1) if has_bn else 0.1,
+                         sync=_sync_group(bn) if has_bn else False))
+        params += [lin.weight, lin.bias, bn.weight if has_bn else None, bn.bias if has_bn else None]
+        buffers.append((bn.running_mean, bn.running_var) if has_bn else (None, None))
+        if has_bn and training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+    out = _ChainFunction.apply(x2, spec, training, buffers, *params)
+    return out.reshape(*lead, out.shape[-1])

@@ -332,6 +332,11 @@ class UnaryBlock(nn.Module):
         self.leaky_relu = nn.Identity() if no_relu else nn.LeakyReLU(0.1)
 
     def forward(self, x):
+        from . import fused_mlp
+        lin, bn = (self.mlp.c, self.mlp.bn) if isinstance(self.mlp, Linear_BN) else (self.mlp, None)
+        if fused_mlp.supported([(lin.in_features, lin.out_features)]):
+            act = fused_mlp.ACT_NONE if self.no_relu else fused_mlp.ACT_LEAKY
+            return fused_mlp.mlp_chain(x, [(lin, bn, act)], self.training)
         y = self.mlp(x) if isinstance(self.mlp, Linear_BN) else linear(x, self.mlp.weight, self.mlp.bias)
         return self.leaky_relu(y)
 

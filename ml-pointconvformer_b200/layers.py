@@ -15,8 +15,20 @@ import torch
 from torch import nn
 import torch.nn.functional as F
 
+from . import fused_mlp
 from .layer_utils import (FusedPConvFunction, PConvLinearOpt, Linear_BN, UnaryBlock, edge_geometry, gather_max,
                           index_points, linear, resolve_inverse)
+
+
+def _chain_spec(mods, acts):
+    """[(linear, bn_or_None, act)] for a list of Linear_BN / nn.Linear modules, or None if a size is unsupported."""
+    out = []
+    for m, a in zip(mods, acts):
+        lin, bn = (m.c, m.bn) if isinstance(m, Linear_BN) else (m, None)
+        out.append((lin, bn, a))
+    if not fused_mlp.supported([(l.in_features, l.out_features) for l, _, _ in out]):
+        return None
+    return out
 
 
 def _drop_path(cfg):
@@ -84,6 +96,9 @@ class MultiHeadGuidance(nn.Module):
     def forward(self, guidance_query, guidance_key):
         s = self.layer_norm_q(guidance_query) - self.layer_norm_k(guidance_key)
         last = len(self.mlp) - 1
+        spec = _chain_spec(list(self.mlp), [fused_mlp.ACT_RELU] * last + [fused_mlp.ACT_SIGMOID])
+        if spec is not None:                       # one fused pass per layer (csrc/mlp.cu)
+            return fused_mlp.mlp_chain(s, spec, self.training)
         for i, layer in enumerate(self.mlp):
             s = layer(s) if isinstance(layer, Linear_BN) else linear(s, layer.weight, layer.bias)
             s = torch.sigmoid(s) if i == last else F.relu(s)
@@ -121,6 +136,9 @@ class WeightNet(nn.Module):
             self.mlp_convs.append(Linear_BN(cin, cout))
 
     def forward(self, localized_xyz):
+        spec = _chain_spec(list(self.mlp_convs), [fused_mlp.ACT_RELU] * len(self.mlp_convs))
+        if spec is not None:                       # fused Linear+BN(batch stats)+ReLU chain (csrc/mlp.cu)
+            return fused_mlp.mlp_chain(localized_xyz, spec, self.training)
         w = localized_xyz
         for conv in self.mlp_convs:
             w = F.relu(conv(w))
@@ -175,7 +193,8 @@ class PCFLayer(_PointLayerBase):
 
         feats_x = self.unary1(dense_feats)
         _, weightNetInput = self._geometry(dense_xyz, dense_xyz_norm, nei_inds, c_xyz, c_nrm, vi_features, self.cfg.USE_VI is True)
-        feat_pe = F.relu(self.mlp_conv(weightNetInput))
+        spec = _chain_spec([self.mlp_conv], [fused_mlp.ACT_RELU])
+        feat_pe = fused_mlp.mlp_chain(weightNetInput, spec, self.training) if spec is not None else F.relu(self.mlp_conv(weightNetInput))
         guidance_x = self.guidance_unary(feats_x)
         guidance_feature = torch.cat([index_points(guidance_x, nei_inds, inv), feat_pe], dim=-1)
         if M == N:

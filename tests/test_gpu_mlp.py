@@ -1,0 +1,101 @@
+"""GPU parity of the fused MLP chains (csrc/mlp.cu via fused_mlp.mlp_chain) against the same Linear -> BatchNorm ->
+activation sequence evaluated by torch in float64: outputs, input gradient, every parameter gradient, and the
+running-statistics update, in train and eval mode."""
+import pytest
+import torch
+import torch.nn as nn
+
+from gpu_util import max_err_scaled
+
+pytestmark = pytest.mark.gpu
+
+CASES = {  # name: (rows, [dims...], [acts...], bn)
+    "weightnet": (50001, [12, 8, 8, 16], [1, 1, 1], True),
+    "weightnet_decoder": (20000, [12, 8, 8, 1], [1, 1, 1], True),
+    "pe_convs": (33333, [3, 16, 16], [1, 1], True),
+    "pe_convs_32": (9000, [3, 32, 32], [1, 1], True),
+    "mlp_conv": (20000, [12, 32], [1], True),
+    "guidance": (20000, [64, 8, 8], [1, 3], True),
+    "unary_leaky": (7000, [64, 16], [2], True),
+    "unary_noact": (7000, [32, 64], [0], True),
+    "no_bn": (5000, [12, 8, 16], [1, 3], False),
+    "tiny": (37, [5, 7], [1], True),
+}
+
+
+def build(dims, bn, seed):
+    torch.manual_seed(seed)
+    mods = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        lin = nn.Linear(a, b)
+        norm = nn.BatchNorm1d(b, momentum=0.1) if bn else None
+        if bn:
+            with torch.no_grad():
+                norm.weight.copy_(1 + 0.3 * torch.randn(b)); norm.bias.copy_(0.3 * torch.randn(b))
+                norm.running_mean.copy_(0.2 * torch.randn(b)); norm.running_var.copy_(0.5 + torch.rand(b))
+        mods.append((lin, norm))
+    return mods
+
+
+def act_ref(z, a):
+    return [lambda t: t, torch.relu, lambda t: torch.nn.functional.leaky_relu(t, 0.1), torch.sigmoid][a](z)
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_chain_matches_float64(name, training):
+    from pcf_b200 import fused_mlp
+    rows, dims, acts, bn = CASES[name]
+    if not fused_mlp.supported(list(zip(dims[:-1], dims[1:]))):
+        pytest.skip("layer size outside the fused kernels' template table (callers fall back to GEMM + BatchNorm)")
+    mods = build(dims, bn, sum(map(ord, name)))
+    import copy
+    ref = copy.deepcopy(mods)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(rows, dims[0], generator=g) * 0.7 + 0.1
+    go = torch.randn(rows, dims[-1], generator=g)
+    # float64 reference on CPU
+    xr = x.double().requires_grad_(True)
+    h = xr
+    for (lin, norm), a in zip(ref, acts):
+        lin.double(); lin.train(training)
+        h = lin(h)
+        if norm is not None:
+            norm.double().train(training)
+            h = norm(h)
+        h = act_ref(h, a)
+    (h * go.double()).sum().backward()
+    # fused CUDA path
+    for lin, norm in mods:
+        lin.cuda()
+        if norm is not None:
+            norm.cuda().train(training)
+    xc = x.cuda().requires_grad_(True)
+    out = fused_mlp.mlp_chain(xc, [(lin, norm, a) for (lin, norm), a in zip(mods, acts)], training)
+    (out * go.cuda()).sum().backward()
+    assert max_err_scaled(out, h) < 2e-5, ("out", max_err_scaled(out, h))
+    assert max_err_scaled(xc.grad, xr.grad) < 2e-4, ("dx", max_err_scaled(xc.grad, xr.grad))
+    for li, ((lin, norm), (rl, rn)) in enumerate(zip(mods, ref)):
+        assert max_err_scaled(lin.weight.grad, rl.weight.grad) < 2e-4, ("dW", li, max_err_scaled(lin.weight.grad, rl.weight.grad))
+        if not (norm is not None and training):           # bias before a train-mode BN has zero gradient (noise only)
+            assert max_err_scaled(lin.bias.grad, rl.bias.grad) < 2e-4
+        if norm is not None:
+            if training:
+                assert max_err_scaled(norm.weight.grad, rn.weight.grad) < 2e-4
+                assert max_err_scaled(norm.bias.grad, rn.bias.grad) < 2e-4
+            assert max_err_scaled(norm.running_mean, rn.running_mean) < 1e-5
+            assert max_err_scaled(norm.running_var, rn.running_var) < 1e-5
+
+
+def test_chain_strided_input_and_determinism():
+    """The chain input may be a column slice of a wider tensor (pe_convs reads the last 3 VI channels in place)."""
+    from pcf_b200 import fused_mlp
+    mods = build([3, 16, 16], True, 3)
+    for lin, norm in mods:
+        lin.cuda(); norm.cuda()
+    vi = torch.randn(40000, 12, device="cuda")
+    x = vi[:, 9:12]
+    spec = [(lin, norm, 1) for lin, norm in mods]
+    a = fused_mlp.mlp_chain(x, spec, True)
+    b = fused_mlp.mlp_chain(x.contiguous(), spec, True)
+    assert torch.equal(a, b)
