@@ -33,6 +33,11 @@ int pconv_mid1_backward(const pcfb_pconv_shape *s, const float *dP, const float 
                         const int32_t *inv_n, const uint8_t *inv_k, const int32_t *inv_idx, const float *weights,
                         const float *additional, float *grad_feats, float *grad_weights, float *grad_additional,
                         cudaStream_t st);
+// pconv_bwd2.cu (pipelined contraction backward on dP)
+bool pconv_bwd2_supported(const pcfb_pconv_shape *s);
+int pconv_bwd2(const pcfb_pconv_shape *s, const float *dP, const float *feats, const int64_t *nei, const float *weights,
+               const float *additional, const float *guidance, float *grad_weights, float *grad_additional,
+               float *grad_guidance, float *grad_edge, cudaStream_t st);
 }  // namespace pcfb
 
 static bool mid1_path(const pcfb_pconv_shape *s, int variant) {
@@ -152,6 +157,18 @@ extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_
     PCFB_REQUIRE((s->H > 0) == (guidance != nullptr), "pcfb_pconv_backward: H and guidance disagree");
     PCFB_REQUIRE(variant >= 0 && variant <= 2, "pcfb_pconv_backward: unknown variant %d", variant);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (variant != 1 && !lin_w && grad_p && s->n_out > 0 && pconv_bwd2_supported(s)) {
+        pcfb_pconv_shape nolin0 = *s;
+        nolin0.C_out = 0;
+        const size_t need = pconv_backward_simt_workspace(&nolin0);
+        PCFB_REQUIRE(!grad_feats || (workspace && workspace_bytes >= need), "pcfb_pconv_backward: workspace too small");
+        PCFB_REQUIRE(!grad_feats || (inv_neighbors && inv_k && inv_idx), "pcfb_pconv_backward: grad_feats needs the inverse map");
+        float *grad_edge = grad_feats ? static_cast<float *>(workspace) : nullptr;
+        int rc0 = pconv_bwd2(s, grad_p, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance,
+                             grad_edge, st);
+        if (rc0 || !grad_feats) return rc0;
+        return pcfb_gather_backward(grad_edge, inv_neighbors, inv_k, inv_idx, s->n_in, s->n_out, s->K, s->C_in, grad_feats, stream);
+    }
     if (variant == 1 || !lin_w || s->C_out > 256 || s->n_out == 0)
         return pconv_backward_simt(s, grad_y, grad_p, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional,
                                    guidance, lin_w, pconv_out, grad_feats, grad_weights, grad_additional, grad_guidance,
@@ -184,6 +201,15 @@ extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_
     if (pconv_mid1_supported(s))
         return pconv_mid1_backward(s, w.dP, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional, grad_feats,
                                    grad_weights, grad_additional, st);
+    if (pconv_bwd2_supported(s)) {
+        float *grad_edge = grad_feats ? static_cast<float *>(w.simt_ws) : nullptr;     // [n_out, K, C_in] scratch
+        PCFB_REQUIRE(!grad_feats || (inv_neighbors && inv_k && inv_idx), "pcfb_pconv_backward: grad_feats needs the inverse map");
+        if ((rc = pconv_bwd2(s, w.dP, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance,
+                             grad_edge, st))) return rc;
+        if (grad_feats)
+            return pcfb_gather_backward(grad_edge, inv_neighbors, inv_k, inv_idx, s->n_in, s->n_out, s->K, s->C_in, grad_feats, stream);
+        return PCFB_OK;
+    }
     pcfb_pconv_shape nolin = *s;
     nolin.C_out = 0;
     return pconv_backward_simt(&nolin, nullptr, w.dP, feats, nei, inv_neighbors, inv_k, inv_idx, weights, additional, guidance,
