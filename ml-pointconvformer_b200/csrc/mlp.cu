@@ -149,14 +149,19 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partial, int nblock
                                    float *__restrict__ running_var, float *__restrict__ scale, float *__restrict__ shift,
                                    float *__restrict__ mean_out, float *__restrict__ invstd_out)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per channel: lanes stride over the block partials, then a fixed shuffle tree (deterministic)
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     const double count = d_count ? *d_count : count_host;
     double s1 = 0.0, s2 = 0.0;
-    for (int b = 0; b < nblocks; ++b) {
+    for (int b = lane; b < nblocks; b += 32) {
         s1 += (double)partial[((size_t)b * 2 + 0) * C + c];
         s2 += (double)partial[((size_t)b * 2 + 1) * C + c];
     }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, sft); s2 += __shfl_xor_sync(0xffffffffu, s2, sft); }
+    if (lane != 0) return;
     const double m_p = s1 / count;                       // mean of (y - pivot)
     double var = s2 / count - m_p * m_p;
     if (var < 0.0) var = 0.0;
@@ -249,11 +254,14 @@ mlp_bwd_stats_kernel(const float *__restrict__ dA, int ldd, const float *__restr
 // sums[2][C] = fixed-order (double) reduction of the block partials; also used for dgamma (= S2) / dbeta (= S1)
 __global__ void sum_partials_kernel(const float *__restrict__ partial, int nblocks, int n, float *__restrict__ out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= n) return;
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * n + i];
-    out[i] = (float)s;
+    for (int b = lane; b < nblocks; b += 32) s += (double)partial[(size_t)b * n + i];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
+    if (lane == 0) out[i] = (float)s;
 }
 
 // input-gradient pass: dA_prev[row][k] = sum_o dy_o W[o][k]; optionally the BN-backward sums of the layer below
@@ -462,10 +470,14 @@ __global__ void mlp_weight_finalize_kernel(const float *__restrict__ partial, in
                                            float *__restrict__ dW, float *__restrict__ db)
 {
     const int n = cout * (cin + 1);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= n) return;
     double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * n + i];
+    for (int b = lane; b < nblocks; b += 32) s += (double)partial[(size_t)b * n + i];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
+    if (lane != 0) return;
     const int o = i / (cin + 1), k = i - o * (cin + 1);
     if (k < cin) { if (dW) dW[o * cin + k] = (float)s; }
     else if (db) db[o] = (float)s;
@@ -537,7 +549,7 @@ extern "C" int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_
                                 float *running_var, float *scale, float *shift, float *mean, float *invstd, void *stream)
 {
     PCFB_REQUIRE(partial && scale && shift && C >= 1, "pcfb_bn_finalize: null pointer");
-    bn_finalize_kernel<<<ceil_div(C, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(
+    bn_finalize_kernel<<<ceil_div(C * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
         partial, nblocks, C, (double)count, d_count, pivot, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
     return check_launch("bn_finalize_kernel");
 }
@@ -573,7 +585,7 @@ extern "C" int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y,
         else mlp_bwd_stats_kernel<64><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, ML_RPT);
         if ((rc = check_launch("mlp_bwd_stats_kernel"))) return rc;
     }
-    sum_partials_kernel<<<ceil_div(2 * C, 64), 64, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * C, sums);
+    sum_partials_kernel<<<ceil_div(2 * C * 32, 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * C, sums);
     return check_launch("sum_partials_kernel");
 }
 
@@ -611,7 +623,7 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
             if ((rc = check_launch("mlp_bwd_input_kernel"))) return rc;
         }
         if (prev_sums) {
-            sum_partials_kernel<<<ceil_div(2 * cin, 64), 64, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * cin, prev_sums);
+            sum_partials_kernel<<<ceil_div(2 * cin * 32, 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * cin, prev_sums);
             if ((rc = check_launch("sum_partials_kernel"))) return rc;
         }
     }
@@ -624,7 +636,7 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
                 dA, ldd, y, ldy, E, cin, cout, B, x_prev, ldx, in_scale, in_shift, in_act, partial)));
             if ((rc = check_launch("mlp_bwd_weight_kernel"))) return rc;
         }
-        mlp_weight_finalize_kernel<<<ceil_div(cout * (cin + 1), 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, cout, cin, dW, db);
+        mlp_weight_finalize_kernel<<<ceil_div(cout * (cin + 1) * 32, 256), 256, 0, st>>>(partial, E > 0 ? blocks : 0, cout, cin, dW, db);
         if ((rc = check_launch("mlp_weight_finalize_kernel"))) return rc;
     }
     return PCFB_OK;
@@ -633,6 +645,6 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
 extern "C" int pcfb_sum_partials(const float *partial, int nblocks, int n, float *out, void *stream)
 {
     PCFB_REQUIRE(partial && out && n >= 1, "pcfb_sum_partials: bad arguments");
-    sum_partials_kernel<<<ceil_div(n, 64), 64, 0, static_cast<cudaStream_t>(stream)>>>(partial, nblocks, n, out);
+    sum_partials_kernel<<<ceil_div(n * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, nblocks, n, out);
     return check_launch("sum_partials_kernel");
 }
