@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--cpu-points", type=int, default=6000, help="level-0 points of the bounded CPU sample")
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="fused forward variant (0 auto, 1 SIMT, 2 tcgen05)")
+    ap.add_argument("--variant", type=int, default=0, help="fused forward variant (0 auto, 1 SIMT, 2 tcgen05 pipelined, 3 tcgen05 simple, 4 tcgen05 warp-specialised)")
+    ap.add_argument("--verbose", action="store_true", help="progress notes on stderr")
+    ap.add_argument("--watchdog", type=int, default=0, help="dump all Python stacks and exit after this many seconds (0 = off)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -125,11 +127,22 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    t_start = time.time()
+
+    def note(msg):                                                   # progress on stderr (stdout carries the JSON line only)
+        if args.verbose or world > 1:
+            sys.stderr.write("[bench rank %d +%.1fs] %s\n" % (rank, time.time() - t_start, msg))
+            sys.stderr.flush()
+
+    if args.watchdog > 0:                                            # a hung collective dumps every thread's stack and exits
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     pcf_cuda.FORWARD_VARIANT = args.variant
+    note("process group ready")
 
     cfgd = configs.CONFIG_PCF_OPT_10CM
     cfg = configs.make_cfg(cfgd)
@@ -176,6 +189,7 @@ def run_ours(args):
         return loss
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    note("model + host pyramid ready (%d level-0 points)" % n0)
 
     # ---- the whole step (edges -> fwd -> loss -> bwd -> all-reduce -> clip -> AdamW) as ONE CUDA graph: every shape
     # is fixed for a given packed batch, so after 3 eager warm-up steps the ~10k launches are captured once and
@@ -187,10 +201,12 @@ def run_ours(args):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(3):
+            for i in range(3):
                 step(*static_in)
+                note("eager warm-up step %d enqueued" % i)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        note("eager warm-up done, capturing")
         opt.zero_grad(set_to_none=True)
         l_before = _lib.launch_count()
         graph = torch.cuda.CUDAGraph()
@@ -198,6 +214,7 @@ def run_ours(args):
             static_loss = step(*static_in)
         launches_per_step = _lib.launch_count() - l_before
         torch.cuda.synchronize()
+        note("graph captured (%d launches of ours per step)" % launches_per_step)
 
     def graph_step(fresh):
         if fresh is not None:                                            # new host data -> static buffers
@@ -233,6 +250,7 @@ def run_ours(args):
         return sum(a.elapsed_time(b) for a, b in evs)
 
     timed(False, args.warmup)                                            # W untimed warm-up steps
+    note("warm-up steps done")
     sampler = ClockSampler(local)
     sampler.start()
     l0 = _lib.launch_count()
@@ -240,7 +258,9 @@ def run_ours(args):
     launches = _lib.launch_count() - l0
     if use_graph:
         launches = launches_per_step * args.steps                       # replayed from the graph, not re-enqueued
+    note("device-resident timing done")
     ms_e2e = timed(True, args.steps)
+    note("end-to-end timing done")
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -276,7 +296,7 @@ def run_ours(args):
             "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step (kNN x13 + inverse maps x13 + fwd + CE + bwd "
                                    "+ grad-clip + AdamW), %d synthetic scene(s) of ~%d level-0 points per GPU, K=16" % (args.scenes, args.points),
                        "points_per_gpu": int(n0), "levels": [int(t.shape[0]) for t in h_pts], "parallelism": "dp%d" % world,
-                       "sync_bn": bool(sync_bn), "cuda_graph": bool(use_graph), "forward_variant": {0: "auto(tcgen05)", 1: "simt_fp32", 2: "tcgen05"}[args.variant],
+                       "sync_bn": bool(sync_bn), "cuda_graph": bool(use_graph), "forward_variant": {0: "auto(tcgen05)", 1: "simt_fp32", 2: "tcgen05 pipelined", 3: "tcgen05 simple", 4: "tcgen05 warp-specialised"}[args.variant],
                        "l2": "256 MiB buffer written between timed steps; per-step working set >> 126 MB L2"},
             "scenes_per_s": total_scenes * args.steps / (ms_dev / 1e3),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
@@ -289,8 +309,18 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
     if world > 1:
+        # The JSON line goes out first; then every rank leaves through os._exit.  Tearing the NCCL communicator down
+        # while a captured graph still references its kernels blocks in destroy_process_group (seen on 2xB200).
+        torch.cuda.synchronize()
         dist.barrier()
+        if out is not None:
+            print(json.dumps(out))
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if use_graph:
+            os._exit(0)
         dist.destroy_process_group()
+        return None
     return out
 
 
@@ -334,8 +364,8 @@ def kernel_rooflines(dev, host, cfgd, args):
 
     res = {}
     fwd_bytes_pt = 8 * K + 4 * C_in + 4 * K * C_mid + 4 * K * C_add + 4 * C_out
-    for name, variant, save_p in (("fused_fwd", args.variant if args.variant else 2, False), ("fused_fwd_saveP", args.variant if args.variant else 2, True),
-                                  ("fused_fwd_simt", 1, False)):
+    for name, variant, save_p in (("fused_fwd", args.variant, False), ("fused_fwd_saveP", args.variant, True),
+                                  ("fused_fwd_umma2", 2, False), ("fused_fwd_simt", 1, False)):
         try:
             ms = time_op(lambda: pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, None, W, b, want_p=save_p, variant=variant))
         except RuntimeError as e:
@@ -362,7 +392,9 @@ def kernel_rooflines(dev, host, cfgd, args):
 
     key = "fused_fwd_saveP" if "ms" in res.get("fused_fwd_saveP", {}) else "fused_fwd_simt"
     r = res[key]
-    roof = {"kernel": "pconv_fwd_umma_kernel<16,16>" if key != "fused_fwd_simt" else "pconv_fwd_simt_kernel<16>",
+    kname = {0: "pconv_fwd_ws_kernel<4,0>", 4: "pconv_fwd_ws_kernel<4,0>", 2: "pconv_fwd_umma2_kernel<16,false>",
+             3: "pconv_fwd_umma_kernel<16,4>", 1: "pconv_fwd_simt_kernel<16>"}[args.variant]
+    roof = {"kernel": kname if key != "fused_fwd_simt" else "pconv_fwd_simt_kernel<16>",
             "shape": "level-0 PointConvStridePE contraction: N=%d K=16 C_in=16 C_add=16 C_mid=16 C_out=32, P saved" % n,
             "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["frac_hbm"],
             "traffic": None, "peak_source": peaks["src"], "ms": r["ms"], "alg_bytes_per_launch": r["alg_bytes"]}

@@ -124,7 +124,8 @@ int pcfb_edge_geometry(const float *xyz_in, const float *nrm_in, const float *xy
  * (pcf.h:131-138), pconv_forward (pcf.h:81-86; lin_w == NULL -> only P) and pcf_forward (pcf.h:38-43;
  * guidance != NULL).  out_y [n_out,C_out] (NULL iff lin_w NULL), out_p [n_out,C_cat*C_mid] (may be NULL
  * when lin_w given).  `variant`: 0 = auto, 1 = exact fp32 SIMT, 2 = tcgen05 (3xTF32 split Linear; pipelined
- * kernel when the tile fits in shared memory, else the simple one), 3 = tcgen05 simple kernel (bisecting).
+ * kernel when the tile fits in shared memory, else the simple one), 3 = tcgen05 simple kernel (bisecting),
+ * 4 = warp-specialised tcgen05 kernel only (K = 16, C_mid = 16, C_out % 16 == 0, C_out <= 128; what auto prefers).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     int n_in, n_out, K, C_in, C_add, C_mid, C_out, H; /* H = guidance heads (0 if none) */
@@ -164,7 +165,8 @@ int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_y, const fl
  * around the contraction (Linear_BN / UnaryBlock, layer_utils.py:241-319; torch runs them as SIMT sgemm) and
  * for the two dense products of the fused backward (dP = dY W, dW = dY^T P; pconv_ops.cu:434-440,516-533).
  *   pcfb_gemm_nt : C[M,N] = act(A[M,K] * Wt + bias);  W is [N,K] (w_is_kn = 0, y = x W^T) or [K,N]
- *                  (w_is_kn = 1, dx = dy W); 1 <= N <= 256; act 0 none / 1 ReLU / 2 LeakyReLU(0.1).
+ *                  (w_is_kn = 1, dx = dy W); any N >= 1 (wide outputs run as column blocks of one launch);
+ *                  act 0 none / 1 ReLU / 2 LeakyReLU(0.1).
  *   pcfb_gemm_tn : C[N1,N2] = A[M,N1]^T * B[M,N2], optionally rowsum[N1] = sum_m A[m,:] (bias gradient);
  *                  1 <= N1 <= 256; reduction over M split across CTAs, partials summed in fixed order.
  * ------------------------------------------------------------------------------------------- */

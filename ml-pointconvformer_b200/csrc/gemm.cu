@@ -31,9 +31,15 @@ __device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group 
 
 // ---- B preparation: weight matrix -> (hi, lo) tf32, K-major core-matrix order, zero padded ----
 // out[chunk][hi|lo][q = k/4 within chunk][n][4];  src element (n, k) = trans ? W[k*ldw + n] : W[n*ldw + k]
-__global__ void gemm_prep_b_kernel(const float *__restrict__ W, int ldw, int trans, int N, int Npad, int K, int n_chunks,
-                                   float *__restrict__ out)
+// Column blocks (blockIdx.y): block y covers weight columns n in [y*Nblk, min(N_total, (y+1)*Nblk)) and writes its own
+// prepared image of block_floats floats.
+__global__ void gemm_prep_b_kernel(const float *__restrict__ W, int ldw, int trans, int N_total, int Nblk, int Npad, int K, int n_chunks,
+                                   size_t block_floats, float *__restrict__ out)
 {
+    const int n_col0 = blockIdx.y * Nblk;
+    const int N = min(Nblk, N_total - n_col0);
+    W += trans ? (size_t)n_col0 : (size_t)n_col0 * ldw;
+    out += (size_t)blockIdx.y * block_floats;
     const int units = GT_KC / 4;
     const int64_t total = (int64_t)n_chunks * units * Npad;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -63,6 +69,8 @@ struct GemmNtArgs {
     const float *bias;       // [N] or null
     float *C;                // [M][ldc]
     int M, N, Npad, K, lda, ldc, n_chunks, tmem_cols;
+    int Nblk;                // columns per column block (blockIdx.y); N is the total
+    size_t b_block_floats;   // prepared-B floats per column block
     int b_resident;          // whole prepared B lives in shared memory
     int vec_a;               // 16-byte loads of A rows allowed
     int act;                 // 0 none, 1 relu, 2 leaky relu 0.1
@@ -93,7 +101,11 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + pl.off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + pl.off_bar + 32);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int M = a.M, N = a.N, Npad = a.Npad, K = a.K, n_chunks = a.n_chunks;
+    const int n_col0 = blockIdx.y * a.Nblk;                    // this CTA's column block
+    const int M = a.M, N = min(a.Nblk, a.N - n_col0), Npad = a.Npad, K = a.K, n_chunks = a.n_chunks;
+    a.b_prep += (size_t)blockIdx.y * a.b_block_floats;
+    a.C += n_col0;
+    if (a.bias) a.bias += n_col0;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
@@ -464,16 +476,28 @@ __global__ void gemm_tn_reduce_kernel(const float *__restrict__ partial, int S, 
 // ---- host side ---------------------------------------------------------------------------------------------
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-struct NtSetup { int Npad, n_chunks, resident; size_t prep_bytes; GemmNtPlan plan; };
+struct NtSetup { int Nblk, n_blocks, Npad, n_chunks, resident; size_t block_bytes, prep_bytes; GemmNtPlan plan; };
 
+// One column block when the tile (A double buffer + B ring or resident B) fits for the whole width, else column
+// blocks of 128 (64 for very long K) handled by blockIdx.y of the same launch.
 static NtSetup nt_setup(int N, int K) {
     NtSetup s;
-    s.Npad = round_up(N < 16 ? 16 : N, 16);
     s.n_chunks = ceil_div(K, GT_KC);
-    s.prep_bytes = align_up((size_t)s.n_chunks * 2 * s.Npad * GT_KC * sizeof(float), 256);
-    s.resident = (s.prep_bytes <= 128 * 1024) ? 1 : 0;
-    s.plan = gemm_nt_plan(s.Npad, s.n_chunks, s.resident != 0);
-    if (s.plan.total > 225 * 1024) { s.resident = 0; s.plan = gemm_nt_plan(s.Npad, s.n_chunks, false); }
+    const int widths[] = {N, 128, 64, 32, 16};
+    for (int wi = 0; wi < 5; ++wi) {
+        const int nb = widths[wi];
+        if (wi > 0 && nb >= N) continue;
+        if (nb > 256) continue;
+        s.Nblk = nb;
+        s.n_blocks = ceil_div(N, nb);
+        s.Npad = round_up(nb < 16 ? 16 : nb, 16);
+        s.block_bytes = align_up((size_t)s.n_chunks * 2 * s.Npad * GT_KC * sizeof(float), 256);
+        s.prep_bytes = s.block_bytes * s.n_blocks;
+        s.resident = (s.block_bytes <= 128 * 1024) ? 1 : 0;
+        s.plan = gemm_nt_plan(s.Npad, s.n_chunks, s.resident != 0);
+        if (s.plan.total > 225 * 1024) { s.resident = 0; s.plan = gemm_nt_plan(s.Npad, s.n_chunks, false); }
+        if (s.plan.total <= 225 * 1024) break;
+    }
     return s;
 }
 
@@ -488,19 +512,12 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
                             int M, int N, int K, int act, void *workspace, size_t workspace_bytes, void *stream)
 {
     using namespace pcfb;
-    PCFB_REQUIRE(M >= 0 && N >= 1 && N <= 256 && K >= 1, "pcfb_gemm_nt: need 1 <= N <= 256, K >= 1 (N=%d K=%d)", N, K);
+    PCFB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "pcfb_gemm_nt: need N >= 1, K >= 1 (N=%d K=%d)", N, K);
     PCFB_REQUIRE(A && W && C && workspace, "pcfb_gemm_nt: null pointer");
     PCFB_REQUIRE(lda >= K && ldc >= N, "pcfb_gemm_nt: bad leading dimensions");
     NtSetup s = nt_setup(N, K);
-    if (s.plan.total > 225 * 1024) {
-        // a B ring this wide does not fit next to the A tiles: two column blocks (each re-reads A from L2)
-        PCFB_REQUIRE(N > 32, "pcfb_gemm_nt: tile does not fit in shared memory (N=%d)", N);
-        const int n_lo = ((N / 2 + 15) / 16) * 16;
-        int rc = pcfb_gemm_nt(A, lda, W, ldw, w_is_kn, bias, C, ldc, M, n_lo, K, act, workspace, workspace_bytes, stream);
-        if (rc) return rc;
-        return pcfb_gemm_nt(A, lda, w_is_kn ? W + n_lo : W + (size_t)n_lo * ldw, ldw, w_is_kn, bias ? bias + n_lo : nullptr,
-                            C + n_lo, ldc, M, N - n_lo, K, act, workspace, workspace_bytes, stream);
-    }
+    PCFB_REQUIRE(s.plan.total <= 225 * 1024, "pcfb_gemm_nt: tile does not fit in shared memory (N=%d K=%d)", N, K);
+    PCFB_REQUIRE(s.n_blocks <= 65535, "pcfb_gemm_nt: too many column blocks");
     if (workspace_bytes < s.prep_bytes) { set_error("pcfb_gemm_nt: workspace %zu < %zu", workspace_bytes, s.prep_bytes); return PCFB_ERR_WORKSPACE; }
     if (M == 0) return PCFB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -508,12 +525,14 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     {
         const int64_t total = (int64_t)s.n_chunks * (GT_KC / 4) * s.Npad;
         const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
-        gemm_prep_b_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(W, ldw, w_is_kn, N, s.Npad, K, s.n_chunks, static_cast<float *>(workspace));
+        gemm_prep_b_kernel<<<dim3(blocks < 1 ? 1 : blocks, s.n_blocks), 256, 0, st>>>(W, ldw, w_is_kn, N, s.Nblk, s.Npad, K, s.n_chunks,
+                                                                              s.block_bytes / sizeof(float), static_cast<float *>(workspace));
         if ((rc = check_launch("gemm_prep_b_kernel"))) return rc;
     }
     GemmNtArgs a{};
     a.A = A; a.b_prep = static_cast<const float *>(workspace); a.bias = bias; a.C = C;
     a.M = M; a.N = N; a.Npad = s.Npad; a.K = K; a.lda = lda; a.ldc = ldc; a.n_chunks = s.n_chunks;
+    a.Nblk = s.Nblk; a.b_block_floats = s.block_bytes / sizeof(float);
     a.b_resident = s.resident; a.act = act;
     a.vec_a = ((lda & 3) == 0) && ((uintptr_t)A % 16 == 0);
     int cols = 32;
@@ -523,8 +542,10 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     if (!attr) { PCFB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr = true; }
     const int tiles = ceil_div(M, GT_M);
     const int per_sm = (s.plan.total + 1024 <= 113 * 1024) ? 2 : 1;
-    const int grid = tiles < kNumSMs * per_sm ? tiles : kNumSMs * per_sm;
-    gemm_nt_kernel<<<grid, G_NT, s.plan.total, st>>>(a);
+    int gx = ceil_div(kNumSMs * per_sm, s.n_blocks);               // CTAs per column block: the whole grid is about one wave
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    gemm_nt_kernel<<<dim3(gx, s.n_blocks), G_NT, s.plan.total, st>>>(a);
     return check_launch("gemm_nt_kernel");
 }
 

@@ -25,6 +25,12 @@ size_t pconv_forward_umma2_workspace(const pcfb_pconv_shape *s);
 int pconv_forward_umma2(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
                         const float *additional, const float *guidance, const float *lin_w, const float *lin_b,
                         float *out_y, float *out_p, void *workspace, size_t workspace_bytes, cudaStream_t st);
+// pconv_ws.cu (warp-specialised tcgen05 forward, C_mid == 16)
+bool pconv_forward_ws_supported(const pcfb_pconv_shape *s, bool has_lin);
+size_t pconv_forward_ws_workspace(const pcfb_pconv_shape *s);
+int pconv_forward_ws(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
+                     const float *additional, const float *guidance, const float *lin_w, const float *lin_b,
+                     float *out_y, float *out_p, void *workspace, size_t workspace_bytes, cudaStream_t st);
 // pconv_mid1.cu (C_mid == 1: weighted neighbour sum + tensor-core Linear)
 bool pconv_mid1_supported(const pcfb_pconv_shape *s);
 int pconv_mid1_forward_p(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
@@ -41,13 +47,14 @@ int pconv_bwd2(const pcfb_pconv_shape *s, const float *dP, const float *feats, c
 }  // namespace pcfb
 
 static bool mid1_path(const pcfb_pconv_shape *s, int variant) {
-    return variant != 1 && variant != 3 && s->C_out >= 1 && s->C_out <= 256 && pcfb::pconv_mid1_supported(s);
+    return variant != 1 && variant != 3 && variant != 4 && s->C_out >= 1 && s->C_out <= 256 && pcfb::pconv_mid1_supported(s);
 }
 
 extern "C" int pcfb_pconv_forward_supported(const pcfb_pconv_shape *s, int variant)
 {
     if (!s) return 0;
     if (variant == 2 && mid1_path(s, variant)) return 1;
+    if (variant == 4) return pcfb::pconv_forward_ws_supported(s, s->C_out > 0) ? 1 : 0;
     if (variant == 2 || variant == 3)
         return (pcfb::pconv_forward_umma_supported(s, s->C_out > 0) || pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) ? 1 : 0;
     return 1;
@@ -59,7 +66,14 @@ extern "C" size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int va
     if (variant == 1) return 0;
     if (mid1_path(s, variant))
         return pcfb::align_up((size_t)s->n_out * (s->C_in + s->C_add) * sizeof(float), 256) + pcfb_gemm_nt_workspace(s->C_out, s->C_in + s->C_add);
-    if (variant != 3 && pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) return pcfb::pconv_forward_umma2_workspace(s);
+    size_t ws = 0;                                      // auto may fall from one tcgen05 kernel to the next: size for all
+    if ((variant == 0 || variant == 4) && pcfb::pconv_forward_ws_supported(s, s->C_out > 0)) ws = pcfb::pconv_forward_ws_workspace(s);
+    if (variant == 4) return ws;
+    if (variant != 3 && pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) {
+        const size_t w2 = pcfb::pconv_forward_umma2_workspace(s);
+        return w2 > ws ? w2 : ws;
+    }
+    if (ws) return ws;
     return pcfb::pconv_forward_umma_supported(s, s->C_out > 0) ? pcfb::pconv_forward_umma_workspace(s) : 0;
 }
 
@@ -74,10 +88,10 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
     PCFB_REQUIRE(s->C_add == 0 || additional, "pcfb_pconv_forward: C_add=%d but additional is NULL", s->C_add);
     PCFB_REQUIRE((s->H > 0) == (guidance != nullptr), "pcfb_pconv_forward: H and guidance disagree");
     PCFB_REQUIRE(lin_w ? out_y != nullptr : out_p != nullptr, "pcfb_pconv_forward: no output requested");
-    PCFB_REQUIRE(variant >= 0 && variant <= 3, "pcfb_pconv_forward: unknown variant %d", variant);
+    PCFB_REQUIRE(variant >= 0 && variant <= 4, "pcfb_pconv_forward: unknown variant %d", variant);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // variants: 0 auto, 1 exact-fp32 SIMT, 2 tcgen05 (pipelined kernel when the tile fits, else the simple one),
-    // 3 tcgen05 simple kernel only (kept for bisecting)
+    // 3 tcgen05 simple kernel only (kept for bisecting), 4 warp-specialised tcgen05 kernel only
     if (lin_w && mid1_path(s, variant)) {
         // C_mid == 1: P = weighted neighbour sum (streaming kernel), Y = P W^T + b on tcgen05
         const int C_cat = s->C_in + s->C_add;
@@ -89,6 +103,17 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
         if ((rc = pconv_mid1_forward_p(s, feats, nei, weights, additional, P, st))) return rc;
         return pcfb_gemm_nt(P, C_cat, lin_w, C_cat, 0, lin_b, out_y, s->C_out, s->n_out, s->C_out, C_cat, 0,
                             static_cast<char *>(workspace) + p_bytes, nt_bytes, stream);
+    }
+    if (variant == 0 || variant == 4) {
+        const bool aligned = ((uintptr_t)feats % 16 == 0) && (s->C_add == 0 || (uintptr_t)additional % 16 == 0) &&
+                             (s->H == 0 || (uintptr_t)guidance % 16 == 0);
+        if (lin_w && (variant == 4 || aligned) && pconv_forward_ws_supported(s, true))
+            return pconv_forward_ws(s, feats, nei, weights, additional, guidance, lin_w, lin_b, out_y, out_p,
+                                    workspace, workspace_bytes, st);
+        if (variant == 4) {
+            set_error("pcfb_pconv_forward: the warp-specialised variant does not support this shape");
+            return PCFB_ERR_UNSUPPORTED;
+        }
     }
     const bool u1_ok = lin_w && pconv_forward_umma_supported(s, true);
     const bool u2_ok = lin_w && variant != 3 && pconv_forward_umma2_supported(s, true);
@@ -117,7 +142,7 @@ static BwdCompose carve_compose(void *ws, const pcfb_pconv_shape &s, bool need_w
     BwdCompose w{};
     const int KK = (s.C_in + s.C_add) * s.C_mid;
     w.dP = c.take<float>((size_t)s.n_out * KK);
-    w.nt_bytes = pcfb_gemm_nt_workspace(128, s.C_out);
+    w.nt_bytes = pcfb_gemm_nt_workspace((s.C_in + s.C_add) * s.C_mid, s.C_out);
     w.nt_ws = c.take<char>(w.nt_bytes);
     if (need_w) {
         w.tn_bytes = pcfb_gemm_tn_workspace(s.n_out, s.C_out, KK, 1);
@@ -183,11 +208,9 @@ extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_
     }
     const int KK = (s->C_in + s->C_add) * s->C_mid;
     int rc;
-    for (int n0 = 0; n0 < KK; n0 += 128) {                    // dP[:, n0:n0+128] = dY * W[:, n0:n0+128]
-        const int nb = KK - n0 < 128 ? KK - n0 : 128;
-        if ((rc = pcfb_gemm_nt(grad_y, s->C_out, lin_w + n0, KK, 1, nullptr, w.dP + n0, KK, s->n_out, nb, s->C_out, 0,
-                               w.nt_ws, w.nt_bytes, stream))) return rc;
-    }
+    // dP = dY * W  (one launch; column blocks of the KK outputs ride on blockIdx.y)
+    if ((rc = pcfb_gemm_nt(grad_y, s->C_out, lin_w, KK, 1, nullptr, w.dP, KK, s->n_out, KK, s->C_out, 0,
+                           w.nt_ws, w.nt_bytes, stream))) return rc;
     if (need_w) {
         const float *P = pconv_out;
         if (need_p) {

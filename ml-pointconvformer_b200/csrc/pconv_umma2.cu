@@ -121,6 +121,12 @@ __global__ void prep_w_kernel(const float *__restrict__ W, int C_out, int KK, in
     }
 }
 
+void prep_w_launch(const float *lin_w, int C_out, int KK, int CK, int n_chunks, float *out, cudaStream_t st) {
+    const int64_t total = (int64_t)n_chunks * (CK / 4) * C_out;
+    const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    prep_w_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(lin_w, C_out, KK, CK, n_chunks, out);
+}
+
 // Tiling of one chunk (CK = 32 kk columns = CC channels x CMID weights) over the 4 thread groups of a point:
 //   TJ = min(CMID, 4) weights x TC = 8 / TJ channels per thread; NJ = CMID / TJ weight groups, NCG = 4 / NJ
 //   channel groups.  The TJ x 16 weightnet values a thread needs are the same for every chunk of the tile, so

@@ -9,6 +9,7 @@ CPU extension) are exposed with plain names: knn_packed, gather, gather_max, edg
 grid_subsample.
 """
 import ctypes
+import os
 
 import torch
 
@@ -38,6 +39,9 @@ def _batched(t):
 # ------------------------------------------------------------------------------------------------
 # fused PConv(+guidance)(+Linear) core
 # ------------------------------------------------------------------------------------------------
+_TRACE_SHAPES = os.environ.get("PCFB_TRACE_SHAPES")      # debug aid: append every fused-forward shape to this file
+
+
 def _pconv_fwd(inp, nei, weights, additional, guidance, lin_w, lin_b, want_p, variant=None):
     require(inp, F32, "input"); require(nei, I64, "neighbor_inds"); require(weights, F32, "weights")
     B, N_in, C_in = inp.shape
@@ -66,6 +70,10 @@ def _pconv_fwd(inp, nei, weights, additional, guidance, lin_w, lin_b, want_p, va
     out_p = torch.empty(B, M, KK, device=dev, dtype=F32) if (want_p or lin_w is None) else None
     v = FORWARD_VARIANT if variant is None else variant
     sh = _shape(N_in, M, K, C_in, C_add, C_mid, C_out, H)
+    if _TRACE_SHAPES:
+        with open(_TRACE_SHAPES, "a") as f:
+            f.write("pconv_forward n_in=%d n_out=%d K=%d C_in=%d C_add=%d C_mid=%d C_out=%d H=%d want_p=%d\n"
+                    % (N_in, M, K, C_in, C_add, C_mid, C_out, H, int(out_p is not None)))
     ws_bytes = lib().pcfb_pconv_forward_workspace(ctypes.byref(sh), v)
     ws = workspace(ws_bytes, dev) if ws_bytes else None
     for b in range(B):
@@ -265,11 +273,6 @@ def gemm_nt(x, w, bias=None, w_is_kn=False, act=0):
     if (w.shape[0] if w_is_kn else w.shape[1]) != K:
         raise RuntimeError("gemm_nt: inner dimensions do not match")
     out = torch.empty(M, N, device=x.device, dtype=F32)
-    if N > 192:                                   # column blocks (a 256-wide B ring does not fit next to the A tiles)
-        for n0 in range(0, N, 128):
-            wb = w[:, n0:n0 + 128] if w_is_kn else w[n0:n0 + 128]
-            out[:, n0:n0 + 128] = gemm_nt(x, wb.contiguous(), None if bias is None else bias[n0:n0 + 128].contiguous(), w_is_kn, act)
-        return out
     ws_bytes = lib().pcfb_gemm_nt_workspace(N, K)
     ws = workspace(ws_bytes, x.device)
     check(lib().pcfb_gemm_nt(ptr(x), x.stride(0), ptr(w), w.stride(0), 1 if w_is_kn else 0, ptr(bias), ptr(out), N, M, N, K, int(act),

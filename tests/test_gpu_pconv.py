@@ -57,6 +57,8 @@ def oracle_eval(d, grad_out=None):
     return P.detach(), (Y.detach() if Y is not None else None), grads
 
 
+PADDED = ("level1_pcf", "ws_multi_tile_h8", "ws_h2")      # cases with -1 entries in the neighbour table
+
 SHAPES = {  # name: (n_in, n_out, K, C_in, C_add, C_mid, C_out, H)
     "level0_pointconv": (3000, 3000, 16, 6, 12, 16, 64, 0),
     "level0_stridepe": (3000, 3000, 16, 16, 16, 16, 32, 0),
@@ -68,16 +70,25 @@ SHAPES = {  # name: (n_in, n_out, K, C_in, C_add, C_mid, C_out, H)
     "lite_mid4": (2000, 501, 16, 32, 16, 4, 64, 4),
     "mid8_k32": (1000, 333, 32, 24, 8, 8, 40, 0),
     "ref_test_k64": (2000, 2000, 64, 16, 16, 16, 64, 0),          # test_kernels.py:1086-1120 channel sizes
+    # warp-specialised kernel: several tiles per CTA (> 148 * 120 points), ragged last tile, every guidance width
+    "ws_multi_tile": (30000, 40003, 16, 16, 16, 16, 32, 0),
+    "ws_multi_tile_h8": (9000, 19001, 16, 32, 0, 16, 64, 8),
+    "ws_h1_cout128": (500, 1234, 16, 8, 4, 16, 128, 1),
+    "ws_h2": (500, 130, 16, 12, 8, 16, 16, 2),
+    "ws_h4_one_group": (64, 119, 16, 4, 0, 16, 48, 4),
 }
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("name", sorted(SHAPES))
 def test_forward_matches_oracle(name, variant):
     if not _pc().forward_variant_supported(*SHAPES[name], variant):
+        if variant == 4:
+            assert not name.startswith("ws_") and name not in ("level0_stridepe", "level1_pcf", "level2_pcf")
+            pytest.skip("shape not covered by the warp-specialised variant (needs K=16, C_mid=16, C_out%16==0, C_out<=128)")
         assert variant in (2, 3) and name == "ref_test_k64"       # the only shape the tcgen05 tile cannot hold
         pytest.skip("shape not covered by the tcgen05 variant (K*C_mid tile exceeds shared memory)")
-    d = make_case(sum(map(ord, name)), *SHAPES[name], pad=(name == "level1_pcf"))
+    d = make_case(sum(map(ord, name)), *SHAPES[name], pad=(name in PADDED))
     P, Y, _ = oracle_eval(d)
     dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
     y, p = _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], dc["gd"], dc["W"], dc["b"], want_p=True, variant=variant)
@@ -100,7 +111,7 @@ def test_forward_mid3_falls_back_to_simt():
 @pytest.mark.parametrize("name", sorted(SHAPES))
 def test_backward_matches_autograd(name):
     shp = SHAPES[name]
-    d = make_case(sum(map(ord, name)) + 1, *shp, pad=(name == "level1_pcf"))
+    d = make_case(sum(map(ord, name)) + 1, *shp, pad=(name in PADDED))
     go = torch.randn(1, shp[1], shp[6], generator=torch.Generator().manual_seed(9))
     P, Y, G = oracle_eval(d, go)
     dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
