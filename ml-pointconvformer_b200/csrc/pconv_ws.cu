@@ -5,13 +5,13 @@
 //
 // What changed against pconv_umma2.cu (whose ncu profile showed 13% FFMA2 among 934 warp instructions per point,
 // the rest address arithmetic of 8-byte gather pieces, block barriers and the tf32 split):
-//   * no block barrier in the main loop.  15 compute warps own 8 points each and run a PRIVATE cp.async ring for the
+//   * no block barrier in the main loop.  11 compute warps own 8 points each and run a PRIVATE cp.async ring for the
 //     gathered rows (warp-level sync only); one extra warp issues every tcgen05.mma and streams the prepared Linear
 //     weights with cp.async.bulk; hand-offs are mbarriers (A full/empty, B full/empty, D full/empty);
 //   * gathers are issued from per-lane row pointers held in registers (4 neighbour rows per lane), 16 bytes per
 //     cp.async, no index arithmetic, no shared-memory copy of the neighbour table;
 //   * the accumulator in TMEM is double buffered, the epilogue of tile t runs inside tile t+1;
-//   * tile = 120 points (rows 120..127 of the M=128 UMMA read stale shared memory and are never stored).
+//   * tile = 88 points (rows 88..127 of the M=128 UMMA read stale shared memory and are never stored).
 // Lane l of a compute warp: point pl = l / 4 of the warp's 8, weight quarter jq = l % 4 (weights 4jq .. 4jq+3).  Its
 // 16x4 weightnet values stay in registers for the whole tile.
 #include "common.cuh"
@@ -19,7 +19,7 @@
 
 namespace pcfb {
 
-constexpr int WS_NW = 15;                        // compute warps (16 warps x 128 registers fill the register file)
+constexpr int WS_NW = 11;                        // compute warps (12 warps -> 168 registers per thread: no spills, no rematerialised indices)
 constexpr int WS_PT = WS_NW * 8;                 // points per tile
 constexpr int WS_EPI = (WS_PT + 31) / 32;        // warps that drain the accumulator
 constexpr int WS_NT = (WS_NW + 1) * 32;          // threads
@@ -39,7 +39,7 @@ struct WsArgs {
     const int64_t *nei;
     float *out_y, *out_p;
     int tmem_cols;             // columns of ONE accumulator buffer (power of two >= 32)
-    int n_groups, n_chunks, n_tiles, sb;
+    int n_groups, n_chunks, n_tiles, sb, na;   // sb: B ring slots, na: A buffers
 };
 
 struct WsPlan {
@@ -47,14 +47,14 @@ struct WsPlan {
     size_t off_ring, off_A, off_B, off_bar, total;
 };
 
-__host__ __device__ inline WsPlan ws_plan(int C_out, int stages, int sb) {
+__host__ __device__ inline WsPlan ws_plan(int C_out, int stages, int sb, int na) {
     WsPlan pl;
     pl.b_bytes = (uint32_t)C_out * WS_CK * 4 * 2;
     size_t o = 0;
     pl.off_ring = o; o += (size_t)WS_NW * stages * WS_STAGE * 4;
     o = align_up(o, 128);
-    pl.off_A = o;    o += 2 * 2 * (size_t)WS_A_HALF;
-    pl.off_B = o;    o += (size_t)sb * pl.b_bytes;          // also the overrun area of the last A unit (rows 120..127)
+    pl.off_A = o;    o += (size_t)na * 2 * WS_A_HALF;
+    pl.off_B = o;    o += (size_t)sb * pl.b_bytes;          // also the overrun area of the last A unit (rows 88..127)
     o = align_up(o, 16);
     pl.off_bar = o;  o += 256;
     pl.total = o;
@@ -110,7 +110,7 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 }  // namespace ws
 
 // barrier slots
-enum { WS_A_FULL = 0, WS_A_EMPTY = 2, WS_D_FULL = 4, WS_D_EMPTY = 6, WS_B_FULL = 8, WS_B_EMPTY = 16 };   // up to 8 B slots
+enum { WS_A_FULL = 0, WS_A_EMPTY = 3, WS_D_FULL = 6, WS_D_EMPTY = 8, WS_B_FULL = 10, WS_B_EMPTY = 18, WS_NBAR = 26 };   // <= 3 A buffers, <= 8 B slots
 
 // GQ: 0 = no guidance, 1 = H in {1,2,4} (one quad of head values per neighbour), 2 = H == 8 (two quads)
 template <int STAGES, int GQ>
@@ -121,13 +121,13 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
     const pcfb_pconv_shape &s = a.s;
     const int C_in = s.C_in, C_add = s.C_add, C_cat = C_in + C_add, KK = C_cat * 16, C_out = s.C_out, H = s.H;
     const int n_in = s.n_in, n_out = s.n_out;
-    const int NG = a.n_groups, n_chunks = a.n_chunks, n_tiles = a.n_tiles, SB = a.sb;
-    const WsPlan pl_ = ws_plan(C_out, S, SB);
+    const int NG = a.n_groups, n_chunks = a.n_chunks, n_tiles = a.n_tiles, SB = a.sb, NA = a.na;
+    const WsPlan pl_ = ws_plan(C_out, S, SB, NA);
     float *ring_all = reinterpret_cast<float *>(smem_raw + pl_.off_ring);
     unsigned char *A_base = smem_raw + pl_.off_A;
     unsigned char *B_base = smem_raw + pl_.off_B;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + pl_.off_bar);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + pl_.off_bar + 24 * 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + pl_.off_bar + WS_NBAR * 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == WS_NW) {
@@ -136,9 +136,11 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 3; ++i) {
             umma::mbar_init(&bars[WS_A_FULL + i], WS_NW);
             umma::mbar_init(&bars[WS_A_EMPTY + i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             umma::mbar_init(&bars[WS_D_FULL + i], 1);
             umma::mbar_init(&bars[WS_D_EMPTY + i], WS_EPI);
         }
@@ -168,15 +170,15 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
             }
             long long i = 0;
             int bs = 0, bs_use = 0;                                   // slot of chunk i and how often it was used before
+            int ab = 0, ab_use = 0;                                   // A buffer of chunk i, ditto
             for (int t = 0; t < my_tiles; ++t) {
                 const int db = t & 1;
                 if (t >= 2) ws::wait_or_trap(&bars[WS_D_EMPTY + db], ((t >> 1) - 1) & 1);
                 umma::fence_after_sync();
                 const uint32_t dcol = tmem_d + (uint32_t)(db * a.tmem_cols);
                 for (int ch = 0; ch < n_chunks; ++ch, ++i) {
-                    const int ab = (int)(i & 1);
                     ws::wait_or_trap(&bars[WS_B_FULL + bs], bs_use & 1);
-                    ws::wait_or_trap(&bars[WS_A_FULL + ab], (uint32_t)(i >> 1) & 1);
+                    ws::wait_or_trap(&bars[WS_A_FULL + ab], ab_use & 1);
                     umma::fence_after_sync();
                     const uint32_t ah = umma::smem_u32(A_base + (size_t)ab * 2 * WS_A_HALF);
                     const uint32_t al = ah + WS_A_HALF;
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                                      wsrc + (size_t)((i - 1 + SB) % n_chunks) * bbytes, bbytes, &bars[WS_B_FULL + ps]);
                     }
                     if (++bs == SB) { bs = 0; ++bs_use; }
+                    if (++ab == NA) { ab = 0; ++ab_use; }
                 }
             }
         }
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
 #pragma unroll 1
         for (int p = 0; p < S - 1; ++p) issue_next();
 
-        long long chunk_i = 0;
+        int ab = 0, ab_use = 0;                                           // A buffer of the next chunk and its use count
         int c_slot = 0;
         int pend_tile = -1, pend_it = 0;                                  // epilogue owed by warps 0..WS_EPI-1
         auto epilogue = [&](int tile, int t_it) {
@@ -384,10 +387,8 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                 }
                 // ---- two A chunks (2 channels each): split to (hi, lo), hand to the MMA warp ----
 #pragma unroll
-                for (int h = 0; h < 2; ++h, ++chunk_i) {
-                    const int ab = (int)(chunk_i & 1);
-                    const long long use = chunk_i >> 1;
-                    if (use > 0) ws::wait_or_trap(&bars[WS_A_EMPTY + ab], (uint32_t)(use - 1) & 1);
+                for (int h = 0; h < 2; ++h) {
+                    if (ab_use > 0) ws::wait_or_trap(&bars[WS_A_EMPTY + ab], (uint32_t)(ab_use - 1) & 1);
                     unsigned char *Ah = A_base + (size_t)ab * 2 * WS_A_HALF;
                     unsigned char *Al = Ah + WS_A_HALF;
 #pragma unroll
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                     umma::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) ws::mbar_arrive(&bars[WS_A_FULL + ab]);
+                    if (++ab == NA) { ab = 0; ++ab_use; }
                 }
                 if (g == 0 && pend_tile >= 0 && warp < WS_EPI) { epilogue(pend_tile, pend_it); }
                 if (g == 0) pend_tile = -1;
@@ -424,11 +426,11 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
 // ---- host side ---------------------------------------------------------------------------------
 void prep_w_launch(const float *lin_w, int C_out, int KK, int CK, int n_chunks, float *out, cudaStream_t st);   // pconv_umma2.cu
 
-static bool ws_config(const pcfb_pconv_shape *s, int *stages, int *sb) {
-    // (ring stages, B slots) in order of preference; the first that fits wins
-    const int cand[][2] = {{4, 4}, {3, 4}, {3, 3}, {3, 2}};
+static bool ws_config(const pcfb_pconv_shape *s, int *stages, int *sb, int *na) {
+    // (ring stages, B slots, A buffers) in order of preference; the first that fits wins
+    const int cand[][3] = {{4, 4, 3}, {4, 3, 3}, {4, 2, 3}, {4, 2, 2}, {3, 2, 2}};
     for (auto &c : cand)
-        if (ws_plan(s->C_out, c[0], c[1]).total <= WS_SMEM_MAX) { *stages = c[0]; *sb = c[1]; return true; }
+        if (ws_plan(s->C_out, c[0], c[1], c[2]).total <= WS_SMEM_MAX) { *stages = c[0]; *sb = c[1]; *na = c[2]; return true; }
     return false;
 }
 
@@ -440,8 +442,8 @@ bool pconv_forward_ws_supported(const pcfb_pconv_shape *s, bool has_lin) {
     if (s->H != 0 && !((s->H == 1 || s->H == 2 || s->H == 4 || s->H == 8) && s->C_in % s->H == 0)) return false;
     if ((uint64_t)s->n_in * (uint64_t)s->C_in >= (1ull << 32)) return false;
     if ((uint64_t)s->n_out * WS_K * (uint64_t)(s->C_add > 0 ? s->C_add : 1) >= (1ull << 32)) return false;
-    int st, sb;
-    return ws_config(s, &st, &sb);
+    int st, sb, na;
+    return ws_config(s, &st, &sb, &na);
 }
 
 size_t pconv_forward_ws_workspace(const pcfb_pconv_shape *s) {
@@ -470,9 +472,9 @@ int pconv_forward_ws(const pcfb_pconv_shape *s, const float *feats, const int64_
     const size_t need = pconv_forward_ws_workspace(s);
     if (!workspace || workspace_bytes < need) { set_error("pcfb_pconv_forward: workspace %zu < %zu", workspace_bytes, need); return PCFB_ERR_WORKSPACE; }
     if (s->n_out == 0) return PCFB_OK;
-    int stages = 0, sb = 0;
-    ws_config(s, &stages, &sb);
-    const WsPlan pl = ws_plan(s->C_out, stages, sb);
+    int stages = 0, sb = 0, na = 0;
+    ws_config(s, &stages, &sb, &na);
+    const WsPlan pl = ws_plan(s->C_out, stages, sb, na);
     const int C_cat = s->C_in + s->C_add, KK = C_cat * 16;
     WsArgs a{};
     a.s = *s;
@@ -482,7 +484,7 @@ int pconv_forward_ws(const pcfb_pconv_shape *s, const float *feats, const int64_
     a.n_groups = C_cat / WS_CG;
     a.n_chunks = KK / WS_CK;
     a.n_tiles = ceil_div(s->n_out, WS_PT);
-    a.sb = sb;
+    a.sb = sb; a.na = na;
     int cols = 32;
     while (cols < s->C_out) cols <<= 1;
     a.tmem_cols = cols;
