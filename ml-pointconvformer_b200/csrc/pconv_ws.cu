@@ -16,6 +16,7 @@
 // 16x4 weightnet values stay in registers for the whole tile.
 #include "common.cuh"
 #include "umma.cuh"
+#include <cstdlib>
 
 namespace pcfb {
 
@@ -28,7 +29,10 @@ constexpr int WS_CG = 4;                         // channels per ring stage
 constexpr int WS_PSTRIDE = WS_K * WS_CG + 4;     // floats per point per stage; +4 shifts each point by 4 banks
 constexpr int WS_STAGE = 8 * WS_PSTRIDE;         // floats per warp per stage
 constexpr int WS_CK = 32;                        // kk columns per MMA chunk (= 2 channels x 16 weights)
-constexpr uint32_t WS_LBO_A = WS_PT * 16;        // bytes between K-units of the A operand (rows x 16 B)
+// bytes between K-units of the A operand: rows x 16 B, +32 so that the four K-units a quarter-warp stores to (one per
+// weight quarter jq) start 8 banks apart -- with the unpadded stride every STS.128 of the tile was a 4-way bank conflict
+// (ncu: 16 wavefronts per instruction instead of 4, 47% of all shared-memory wavefronts of the kernel)
+constexpr uint32_t WS_LBO_A = WS_PT * 16 + 32;
 constexpr uint32_t WS_A_HALF = (WS_CK / 4) * WS_LBO_A;   // bytes of one (hi | lo) A chunk
 constexpr size_t WS_SMEM_MAX = 227 * 1024;
 
@@ -40,6 +44,7 @@ struct WsArgs {
     float *out_y, *out_p;
     int tmem_cols;             // columns of ONE accumulator buffer (power of two >= 32)
     int n_groups, n_chunks, n_tiles, sb, na;   // sb: B ring slots, na: A buffers
+    int dbg;                   // ablation switches for profiling (PCFB_WS_DEBUG): 1 no gather, 2 no MMA hand-off, 4 no FMA loop
 };
 
 struct WsPlan {
@@ -93,6 +98,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {          // true in exactly one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+// lane-predicated forms (pred != 0 executes): the predicate lives inside the asm so the caller's control flow stays warp-uniform
+__device__ __forceinline__ void mbar_expect_tx_if(uint64_t *bar, uint32_t bytes, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n"
+                 :: "r"(umma::smem_u32(bar)), "r"(bytes), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_if(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %4, 0;\n\t"
+                 "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}\n"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void mma_if(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void commit_if(uint64_t *bar, uint32_t pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
+                 :: "r"(umma::smem_u32(bar)), "r"(pred) : "memory");
+}
 __device__ __forceinline__ void wait_or_trap(uint64_t *bar, uint32_t parity) {
     if (!umma::mbar_wait(bar, parity)) __trap();
 }
@@ -128,7 +158,8 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
     unsigned char *B_base = smem_raw + pl_.off_B;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + pl_.off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem_raw + pl_.off_bar + WS_NBAR * 8);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // broadcast: the compiler can treat the role branch as warp-uniform
 
     if (warp == WS_NW) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
@@ -153,63 +184,83 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
 
     if (warp == WS_NW) {
-        // ============================ MMA issuer + Linear-weight producer (one thread) ============================
-        if (lane == 0) {
-            const uint32_t idesc = umma::make_idesc_tf32(128, C_out);
-            const uint32_t lbo_b = (uint32_t)C_out * 16, sbo = 128;
-            const uint32_t bbytes = pl_.b_bytes;
-            const unsigned char *wsrc = reinterpret_cast<const unsigned char *>(a.w_prep);
-            const long long total = (long long)my_tiles * n_chunks;
+        // ==================== MMA issuer + Linear-weight producer ====================
+        // The whole warp walks the loop in uniform control flow (the role branch is on a shuffled, hence provably
+        // uniform, warp index; waits, counters and descriptors stay in uniform registers); one elected lane issues the
+        // tcgen05 / bulk-copy instructions.  With a plain `if (lane == 0)` loop every UTCHMMA was wrapped in
+        // R2UR x6 + ELECT + BRA.U.ANY and this single thread limited the kernel (~1000 cycles per 12-MMA chunk).
+        const uint32_t idesc = umma::make_idesc_tf32(128, C_out);
+        const uint32_t lbo_b = (uint32_t)C_out * 16, sbo = 128;
+        const uint32_t bbytes = pl_.b_bytes;
+        const unsigned char *wsrc = reinterpret_cast<const unsigned char *>(a.w_prep);
+        const int total = my_tiles * n_chunks;
+        const uint32_t a_u32 = umma::smem_u32(A_base), b_u32 = umma::smem_u32(B_base);
+        // descriptors without the start address; the address field is the low 14 bits (bytes >> 4) and never carries
+        // out of it for shared-memory addresses
+        const uint64_t da0 = umma::make_smem_desc(0, WS_LBO_A, sbo), db0 = umma::make_smem_desc(0, lbo_b, sbo);
+        if (ws::elect_one()) {
             for (int j = 0; j < SB && j < total; ++j) {
                 ws::mbar_expect_tx(&bars[WS_B_FULL + j], bbytes);
-                ws::bulk_g2s(umma::smem_u32(B_base + (size_t)j * bbytes), wsrc + (size_t)(j % n_chunks) * bbytes, bbytes, &bars[WS_B_FULL + j]);
+                ws::bulk_g2s(b_u32 + (uint32_t)j * bbytes, wsrc + (size_t)(j % n_chunks) * bbytes, bbytes, &bars[WS_B_FULL + j]);
             }
-            long long i = 0;
-            int bs = 0, bs_use = 0;                                   // slot of chunk i and how often it was used before
-            int ab = 0, ab_use = 0;                                   // A buffer of chunk i, ditto
-            for (int t = 0; t < my_tiles; ++t) {
-                const int db = t & 1;
-                if (t >= 2) ws::wait_or_trap(&bars[WS_D_EMPTY + db], ((t >> 1) - 1) & 1);
+        }
+        __syncwarp();
+        const int lag = (SB >= 3) ? 2 : 1;
+        int i = 0, wch = SB % n_chunks;                               // wch: W chunk of the next refill (chunk i-lag+SB)
+        int bs = 0, bs_use = 0;                                       // slot of chunk i and how often it was used before
+        int ab = 0, ab_use = 0;                                       // A buffer of chunk i, ditto
+        for (int t = 0; t < ((a.dbg & 2) ? 0 : my_tiles); ++t) {
+            const int db = t & 1;
+            if (t >= 2) ws::wait_or_trap(&bars[WS_D_EMPTY + db], ((t >> 1) - 1) & 1);
+            umma::fence_after_sync();
+            const uint32_t dcol = tmem_d + (uint32_t)(db * a.tmem_cols);
+            for (int ch = 0; ch < n_chunks; ++ch, ++i) {
+                if (!(a.dbg & 32) || bs_use == 0) ws::wait_or_trap(&bars[WS_B_FULL + bs], bs_use & 1);
+                ws::wait_or_trap(&bars[WS_A_FULL + ab], ab_use & 1);
+                if (!(a.dbg & 64)) umma::fence_proxy_async();         // A tile written with st.shared by the compute warps
                 umma::fence_after_sync();
-                const uint32_t dcol = tmem_d + (uint32_t)(db * a.tmem_cols);
-                for (int ch = 0; ch < n_chunks; ++ch, ++i) {
-                    ws::wait_or_trap(&bars[WS_B_FULL + bs], bs_use & 1);
-                    ws::wait_or_trap(&bars[WS_A_FULL + ab], ab_use & 1);
-                    umma::fence_after_sync();
-                    const uint32_t ah = umma::smem_u32(A_base + (size_t)ab * 2 * WS_A_HALF);
-                    const uint32_t al = ah + WS_A_HALF;
-                    const uint32_t bh = umma::smem_u32(B_base + (size_t)bs * bbytes);
-                    const uint32_t bl = bh + bbytes / 2;
+                const uint64_t dah = da0 + ((a_u32 + (uint32_t)ab * 2 * WS_A_HALF) >> 4);
+                const uint64_t dal = dah + (WS_A_HALF >> 4);
+                const uint64_t dbh = db0 + ((b_u32 + (uint32_t)bs * bbytes) >> 4);
+                const uint64_t dbl = dbh + (bbytes >> 5);
+                if (ws::elect_one()) {
+                    if (!(a.dbg & 8)) {
 #pragma unroll
-                    for (int ks = 0; ks < WS_CK / 8; ++ks) {
-                        const uint32_t ao = ks * 2 * WS_LBO_A, bo = ks * 2 * lbo_b;
-                        const uint64_t dah = umma::make_smem_desc(ah + ao, WS_LBO_A, sbo);
-                        const uint64_t dal = umma::make_smem_desc(al + ao, WS_LBO_A, sbo);
-                        const uint64_t dbh = umma::make_smem_desc(bh + bo, lbo_b, sbo);
-                        const uint64_t dbl = umma::make_smem_desc(bl + bo, lbo_b, sbo);
-                        umma::mma_tf32_ss(dcol, dal, dbh, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
-                        umma::mma_tf32_ss(dcol, dah, dbl, idesc, 1u);
-                        umma::mma_tf32_ss(dcol, dah, dbh, idesc, 1u);
+                        for (int ks = 0; ks < WS_CK / 8; ++ks) {
+                            const uint32_t ao = (ks * 2 * WS_LBO_A) >> 4, bo = (ks * 2 * lbo_b) >> 4;
+                            umma::mma_tf32_ss(dcol, dal + ao, dbh + bo, idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+                            umma::mma_tf32_ss(dcol, dah + ao, dbl + bo, idesc, 1u);
+                            umma::mma_tf32_ss(dcol, dah + ao, dbh + bo, idesc, 1u);
+                        }
+                        umma::commit(&bars[WS_A_EMPTY + ab]);
+                        umma::commit(&bars[WS_B_EMPTY + bs]);
+                        if (ch == n_chunks - 1) umma::commit(&bars[WS_D_FULL + db]);
+                    } else {                                          // ablation 8: no MMAs, plain arrives instead of commits
+                        ws::mbar_arrive(&bars[WS_A_EMPTY + ab]);
+                        ws::mbar_arrive(&bars[WS_B_EMPTY + bs]);
+                        if (ch == n_chunks - 1) ws::mbar_arrive(&bars[WS_D_FULL + db]);
                     }
-                    umma::commit(&bars[WS_A_EMPTY + ab]);
-                    umma::commit(&bars[WS_B_EMPTY + bs]);
-                    if (ch == n_chunks - 1) umma::commit(&bars[WS_D_FULL + db]);
-                    // refill the slot chunk i-1 used (its MMAs were committed one iteration ago) with chunk i-1+SB
-                    if (i >= 1 && i - 1 + SB < total) {
-                        const int ps = (bs == 0) ? SB - 1 : bs - 1;
-                        const int ps_use = (bs == 0) ? bs_use - 1 : bs_use;
-                        ws::wait_or_trap(&bars[WS_B_EMPTY + ps], ps_use & 1);
-                        ws::mbar_expect_tx(&bars[WS_B_FULL + ps], bbytes);
-                        ws::bulk_g2s(umma::smem_u32(B_base + (size_t)ps * bbytes),
-                                     wsrc + (size_t)((i - 1 + SB) % n_chunks) * bbytes, bbytes, &bars[WS_B_FULL + ps]);
-                    }
-                    if (++bs == SB) { bs = 0; ++bs_use; }
-                    if (++ab == NA) { ab = 0; ++ab_use; }
                 }
+                __syncwarp();
+                // Refill the slot that chunk i-LAG used with chunk i-LAG+SB.  LAG = 2 when the ring has >= 3 slots: those
+                // MMAs were committed two iterations ago, so the wait below does not drain the tensor pipe.
+                if (i >= lag && i - lag + SB < total && !(a.dbg & 32)) {
+                    int ps = bs - lag, ps_use = bs_use;
+                    if (ps < 0) { ps += SB; --ps_use; }
+                    ws::wait_or_trap(&bars[WS_B_EMPTY + ps], ps_use & 1);
+                    if (ws::elect_one()) {
+                        ws::mbar_expect_tx(&bars[WS_B_FULL + ps], bbytes);
+                        ws::bulk_g2s(b_u32 + (uint32_t)ps * bbytes, wsrc + (size_t)wch * bbytes, bbytes, &bars[WS_B_FULL + ps]);
+                    }
+                    __syncwarp();
+                    if (++wch == n_chunks) wch = 0;
+                }
+                if (++bs == SB) { bs = 0; ++bs_use; }
+                if (++ab == NA) { ab = 0; ++ab_use; }
             }
         }
     } else {
@@ -244,7 +295,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
         load_rows(i_tile, q_off, vmask, add_off);
         load_rows(i_tile + gridDim.x, qn_off, vmaskn, addn_off);
         auto issue_next = [&]() {
-            if (i_tile < n_tiles) {
+            if (i_tile < n_tiles && !(a.dbg & 1)) {
                 const int c0 = i_g * CG;
                 const uint32_t dst = ring_u32 + (uint32_t)i_slot * (WS_STAGE * 4) + my_dst;
                 if (c0 < C_in) {
@@ -266,6 +317,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                     load_rows(i_tile + gridDim.x, qn_off, vmaskn, addn_off);
                 }
             }
+            if (a.dbg & 1) { if (++i_g == NG) { i_g = 0; i_tile += gridDim.x; } }
             if (++i_slot == S) i_slot = 0;
             ws::commit_group();
         };
@@ -370,7 +422,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                 for (int c = 0; c < CG; ++c)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
-                {
+                if (!(a.dbg & 4)) {
                     const float4 *gp = reinterpret_cast<const float4 *>(slot + pl * WS_PSTRIDE);
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
@@ -388,11 +440,15 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                 // ---- two A chunks (2 channels each): split to (hi, lo), hand to the MMA warp ----
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if (ab_use > 0) ws::wait_or_trap(&bars[WS_A_EMPTY + ab], (uint32_t)(ab_use - 1) & 1);
+                    if (a.dbg & 2) {                              // ablation: keep the values alive, skip the hand-off
+                        if (acc[2 * h][0] + acc[2 * h + 1][3] == 123.456f) a.out_y[0] = 1.f;
+                        continue;
+                    }
+                    if (ab_use > 0 && !(a.dbg & 16)) ws::wait_or_trap(&bars[WS_A_EMPTY + ab], (uint32_t)(ab_use - 1) & 1);
                     unsigned char *Ah = A_base + (size_t)ab * 2 * WS_A_HALF;
                     unsigned char *Al = Ah + WS_A_HALF;
 #pragma unroll
-                    for (int cl = 0; cl < 2; ++cl) {
+                    for (int cl = 0; cl < ((a.dbg & 128) ? 0 : 2); ++cl) {
                         const int c = 2 * h + cl;
                         float4 hi, lo;
                         ws::split(acc[c][0], hi.x, lo.x); ws::split(acc[c][1], hi.y, lo.y);
@@ -404,17 +460,19 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                             *reinterpret_cast<float4 *>(a.out_p + (size_t)m * KK + (size_t)(c0 + c) * 16 + jq * 4) =
                                 make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
                     }
-                    umma::fence_proxy_async();
+                    // hand-off: the warp's stores are ordered before lane 0's release-arrive by __syncwarp; the generic->async
+                    // proxy fence is executed once by the consumer (MMA thread) after its acquire.  A writer-side
+                    // fence.proxy.async here compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and cost 20% of the kernel (ncu).
                     __syncwarp();
                     if (lane == 0) ws::mbar_arrive(&bars[WS_A_FULL + ab]);
                     if (++ab == NA) { ab = 0; ++ab_use; }
                 }
-                if (g == 0 && pend_tile >= 0 && warp < WS_EPI) { epilogue(pend_tile, pend_it); }
+                if (g == 0 && pend_tile >= 0 && warp < WS_EPI && !(a.dbg & 2)) { epilogue(pend_tile, pend_it); }
                 if (g == 0) pend_tile = -1;
             }
             pend_tile = tile; pend_it = t_it;
         }
-        if (pend_tile >= 0 && warp < WS_EPI) epilogue(pend_tile, pend_it);
+        if (pend_tile >= 0 && warp < WS_EPI && !(a.dbg & 2)) epilogue(pend_tile, pend_it);
         ws::wait_group<0>();
     }
     umma::fence_before_sync();
@@ -485,6 +543,7 @@ int pconv_forward_ws(const pcfb_pconv_shape *s, const float *feats, const int64_
     a.n_chunks = KK / WS_CK;
     a.n_tiles = ceil_div(s->n_out, WS_PT);
     a.sb = sb; a.na = na;
+    { const char *e = getenv("PCFB_WS_DEBUG"); a.dbg = e ? atoi(e) : 0; }
     int cols = 32;
     while (cols < s->C_out) cols <<= 1;
     a.tmem_cols = cols;

@@ -30,6 +30,20 @@ def main():
     inv = pcf_cuda.compute_knn_inverse(nei[None], n)
     y, p = pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, gd, W, b, want_p=True)
     torch.cuda.synchronize()
+    if what == "fwd_time":                      # CUDA-event timing of the fused forward (L2 flushed before every launch)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, gd, W, b, want_p=False)
+            b_.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_))
+        ts.sort()
+        print("fwd_time ms median %.4f min %.4f" % (ts[len(ts) // 2], ts[0]))
+        return
     for _ in range(reps):
         if what == "fwd":
             pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, gd, W, b, want_p=False)
