@@ -18,6 +18,14 @@
 #include "umma.cuh"
 #include <cstdlib>
 
+// Ablation switches used while profiling (scripts/ws_ablate.sh): compile with -DPCFB_WS_ABLATE=1 and set PCFB_WS_DEBUG
+// to a bit mask (1 no gather, 2 no MMA hand-off, 4 no FMA loop, 8 no MMAs, 32 no B refill, 64 no proxy fence, 128 no A
+// stores).  Results are wrong with any bit set; the shipped library compiles them out.
+#ifndef PCFB_WS_ABLATE
+#define PCFB_WS_ABLATE 0
+#endif
+#define WS_DBG(bit) (PCFB_WS_ABLATE && (a.dbg & (bit)))
+
 namespace pcfb {
 
 constexpr int WS_NW = 11;                        // compute warps (12 warps -> 168 registers per thread: no spills, no rematerialised indices)
@@ -25,8 +33,8 @@ constexpr int WS_PT = WS_NW * 8;                 // points per tile
 constexpr int WS_EPI = (WS_PT + 31) / 32;        // warps that drain the accumulator
 constexpr int WS_NT = (WS_NW + 1) * 32;          // threads
 constexpr int WS_K = 16;
-constexpr int WS_CG = 4;                         // channels per ring stage
-constexpr int WS_PSTRIDE = WS_K * WS_CG + 4;     // floats per point per stage; +4 shifts each point by 4 banks
+constexpr int WS_CG = 8;                         // channels per ring stage (x 8 neighbours)
+constexpr int WS_PSTRIDE = 8 * WS_CG + 4;        // floats per point per stage; +4 shifts each point by 4 banks
 constexpr int WS_STAGE = 8 * WS_PSTRIDE;         // floats per warp per stage
 constexpr int WS_CK = 32;                        // kk columns per MMA chunk (= 2 channels x 16 weights)
 // bytes between K-units of the A operand: rows x 16 B, +32 so that the four K-units a quarter-warp stores to (one per
@@ -140,18 +148,18 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 }  // namespace ws
 
 // barrier slots
-enum { WS_A_FULL = 0, WS_A_EMPTY = 3, WS_D_FULL = 6, WS_D_EMPTY = 8, WS_B_FULL = 10, WS_B_EMPTY = 18, WS_NBAR = 26 };   // <= 3 A buffers, <= 8 B slots
+enum { WS_A_FULL = 0, WS_A_EMPTY = 4, WS_D_FULL = 8, WS_D_EMPTY = 10, WS_B_FULL = 12, WS_B_EMPTY = 20, WS_NBAR = 28 };   // <= 4 A buffers, <= 8 B slots
 
 // GQ: 0 = no guidance, 1 = H in {1,2,4} (one quad of head values per neighbour), 2 = H == 8 (two quads)
 template <int STAGES, int GQ>
 __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
 {
-    constexpr int K = WS_K, CG = WS_CG, S = STAGES;
+    constexpr int K = WS_K, S = STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const pcfb_pconv_shape &s = a.s;
     const int C_in = s.C_in, C_add = s.C_add, C_cat = C_in + C_add, KK = C_cat * 16, C_out = s.C_out, H = s.H;
     const int n_in = s.n_in, n_out = s.n_out;
-    const int NG = a.n_groups, n_chunks = a.n_chunks, n_tiles = a.n_tiles, SB = a.sb, NA = a.na;
+    const int n_chunks = a.n_chunks, n_tiles = a.n_tiles, SB = a.sb, NA = a.na;
     const WsPlan pl_ = ws_plan(C_out, S, SB, NA);
     float *ring_all = reinterpret_cast<float *>(smem_raw + pl_.off_ring);
     unsigned char *A_base = smem_raw + pl_.off_A;
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 4; ++i) {
             umma::mbar_init(&bars[WS_A_FULL + i], WS_NW);
             umma::mbar_init(&bars[WS_A_EMPTY + i], 1);
         }
@@ -213,22 +221,22 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
         int i = 0, wch = SB % n_chunks;                               // wch: W chunk of the next refill (chunk i-lag+SB)
         int bs = 0, bs_use = 0;                                       // slot of chunk i and how often it was used before
         int ab = 0, ab_use = 0;                                       // A buffer of chunk i, ditto
-        for (int t = 0; t < ((a.dbg & 2) ? 0 : my_tiles); ++t) {
+        for (int t = 0; t < (WS_DBG(2) ? 0 : my_tiles); ++t) {
             const int db = t & 1;
             if (t >= 2) ws::wait_or_trap(&bars[WS_D_EMPTY + db], ((t >> 1) - 1) & 1);
             umma::fence_after_sync();
             const uint32_t dcol = tmem_d + (uint32_t)(db * a.tmem_cols);
             for (int ch = 0; ch < n_chunks; ++ch, ++i) {
-                if (!(a.dbg & 32) || bs_use == 0) ws::wait_or_trap(&bars[WS_B_FULL + bs], bs_use & 1);
+                if (!WS_DBG(32) || bs_use == 0) ws::wait_or_trap(&bars[WS_B_FULL + bs], bs_use & 1);
                 ws::wait_or_trap(&bars[WS_A_FULL + ab], ab_use & 1);
-                if (!(a.dbg & 64)) umma::fence_proxy_async();         // A tile written with st.shared by the compute warps
+                if (!WS_DBG(64)) umma::fence_proxy_async();         // A tile written with st.shared by the compute warps
                 umma::fence_after_sync();
                 const uint64_t dah = da0 + ((a_u32 + (uint32_t)ab * 2 * WS_A_HALF) >> 4);
                 const uint64_t dal = dah + (WS_A_HALF >> 4);
                 const uint64_t dbh = db0 + ((b_u32 + (uint32_t)bs * bbytes) >> 4);
                 const uint64_t dbl = dbh + (bbytes >> 5);
                 if (ws::elect_one()) {
-                    if (!(a.dbg & 8)) {
+                    if (!WS_DBG(8)) {
 #pragma unroll
                         for (int ks = 0; ks < WS_CK / 8; ++ks) {
                             const uint32_t ao = (ks * 2 * WS_LBO_A) >> 4, bo = (ks * 2 * lbo_b) >> 4;
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                 __syncwarp();
                 // Refill the slot that chunk i-LAG used with chunk i-LAG+SB.  LAG = 2 when the ring has >= 3 slots: those
                 // MMAs were committed two iterations ago, so the wait below does not drain the tensor pipe.
-                if (i >= lag && i - lag + SB < total && !(a.dbg & 32)) {
+                if (i >= lag && i - lag + SB < total && !WS_DBG(32)) {
                     int ps = bs - lag, ps_use = bs_use;
                     if (ps < 0) { ps += SB; --ps_use; }
                     ws::wait_or_trap(&bars[WS_B_EMPTY + ps], ps_use & 1);
@@ -265,59 +273,64 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
         }
     } else {
         // ================================================ compute warps ================================================
+        // Ring stage = [8 points][8 neighbours][8 channels] (32 B per gathered row piece = one L2 sector; the two 16 B
+        // halves are requested by adjacent lanes of the same cp.async so they land as one shared-memory wavefront --
+        // with 16 B pieces of 32 different rows every piece was its own wavefront, ncu: 28 per LDGSTS).  A channel octet
+        // therefore takes two stages (neighbour halves kh = 0, 1); its 8x4 accumulators live across both.
         const int pl = lane >> 2, jq = lane & 3;
+        const int hh = jq & 1, ks = jq >> 1;                            // gather role: 16 B half of the piece, neighbour block
         const int row = warp * 8 + pl;                                  // row of the tile
         float *ring = ring_all + (size_t)warp * S * WS_STAGE;
         const uint32_t ring_u32 = umma::smem_u32(ring);
-        const uint32_t my_dst = (uint32_t)(pl * WS_PSTRIDE + jq * 4 * CG) * 4;     // byte offset of this lane's first row in a stage
+        const uint32_t my_dst = (uint32_t)(pl * WS_PSTRIDE + ks * 4 * 8 + hh * 4) * 4;   // this lane's first piece in a stage (bytes)
+        const int NO = (C_cat + 7) >> 3;                                // channel octets per tile
 
-        // ---- issue cursor: (tile, group) of the next stage to request, with the lane's 4 row offsets ----
-        uint32_t q_off[4], qn_off[4];
-        uint32_t vmask = 0, vmaskn = 0;                                   // bits 0..3 neighbour valid, bit 4 point valid
-        uint32_t add_off = 0, addn_off = 0;
-        auto load_rows = [&](int tile, uint32_t *qo, uint32_t &vm, uint32_t &ao) {
-            vm = 0; ao = 0;
+        // ---- issue cursor: (tile, octet, neighbour half) of the next stage to request; the lane's 8 row offsets ----
+        uint32_t q_off[8];                                              // rows k = 8 ks + kk, kk = 0..7
+        uint32_t vmask = 0, add_off = 0;                                // bits 0..7 neighbour valid, bit 8 point valid
+        auto load_rows = [&](int tile) {
+            vmask = 0; add_off = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) qo[i] = 0;
+            for (int i = 0; i < 8; ++i) q_off[i] = 0;
             const int m = tile * WS_PT + row;
             if (tile < n_tiles && m < n_out) {
-                const longlong2 *src = reinterpret_cast<const longlong2 *>(a.nei + (size_t)m * K + jq * 4);
-                const longlong2 v0 = __ldg(src), v1 = __ldg(src + 1);
-                const long long q[4] = {v0.x, v0.y, v1.x, v1.y};
+                const longlong2 *src = reinterpret_cast<const longlong2 *>(a.nei + (size_t)m * K + ks * 8);
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (q[i] >= 0 && q[i] < n_in) { qo[i] = (uint32_t)q[i] * (uint32_t)C_in; vm |= 1u << i; }
-                vm |= 16u;
-                ao = ((uint32_t)m * K + jq * 4) * (uint32_t)C_add;
+                for (int i = 0; i < 4; ++i) {
+                    const longlong2 v = __ldg(src + i);
+                    if (v.x >= 0 && v.x < n_in) { q_off[2 * i] = (uint32_t)v.x * (uint32_t)C_in; vmask |= 1u << (2 * i); }
+                    if (v.y >= 0 && v.y < n_in) { q_off[2 * i + 1] = (uint32_t)v.y * (uint32_t)C_in; vmask |= 2u << (2 * i); }
+                }
+                vmask |= 256u;
+                add_off = ((uint32_t)m * K + ks * 8) * (uint32_t)C_add;
             }
         };
-        int i_tile = blockIdx.x, i_g = 0, i_slot = 0;
-        load_rows(i_tile, q_off, vmask, add_off);
-        load_rows(i_tile + gridDim.x, qn_off, vmaskn, addn_off);
+        int i_tile = blockIdx.x, i_o = 0, i_kh = 0, i_slot = 0;
+        load_rows(i_tile);
         auto issue_next = [&]() {
-            if (i_tile < n_tiles && !(a.dbg & 1)) {
-                const int c0 = i_g * CG;
+            if (i_tile < n_tiles && !WS_DBG(1)) {
+                const int c = i_o * 8 + hh * 4;                         // this lane's 4 channels of the octet
                 const uint32_t dst = ring_u32 + (uint32_t)i_slot * (WS_STAGE * 4) + my_dst;
-                if (c0 < C_in) {
+                if (c < C_in) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        ws::cp16(dst + i * CG * 4, a.feats + q_off[i] + c0, (vmask >> i) & 1u);
+                    for (int i = 0; i < 4; ++i) {
+                        const int kk = i_kh * 4 + i;
+                        ws::cp16(dst + i * 32, a.feats + (i_kh ? q_off[4 + i] : q_off[i]) + c, (vmask >> kk) & 1u);
+                    }
                 } else {
-                    const float *src = a.additional + add_off + (c0 - C_in);
+                    const bool ok = c < C_cat && (vmask & 256u);
+                    const float *src = ok ? a.additional + add_off + (size_t)(i_kh * 4) * C_add + (c - C_in) : a.feats;
+                    const int step = ok ? C_add : 0;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        ws::cp16(dst + i * CG * 4, src + i * C_add, (vmask >> 4) & 1u);
-                }
-                if (++i_g == NG) {
-                    i_g = 0;
-                    i_tile += gridDim.x;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) q_off[i] = qn_off[i];
-                    vmask = vmaskn; add_off = addn_off;
-                    load_rows(i_tile + gridDim.x, qn_off, vmaskn, addn_off);
+                    for (int i = 0; i < 4; ++i) ws::cp16(dst + i * 32, src + i * step, ok);
                 }
             }
-            if (a.dbg & 1) { if (++i_g == NG) { i_g = 0; i_tile += gridDim.x; } }
+            if (i_tile < n_tiles) {
+                if (++i_kh == 2) {
+                    i_kh = 0;
+                    if (++i_o == NO) { i_o = 0; i_tile += gridDim.x; load_rows(i_tile); }
+                }
+            }
             if (++i_slot == S) i_slot = 0;
             ws::commit_group();
         };
@@ -352,104 +365,115 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
             if (lane == 0) ws::mbar_arrive(&bars[WS_D_EMPTY + db]);
         };
 
+        // this lane's weightnet values w[m][k][4jq .. 4jq+3], all 16 k, in registers for the tile
+        float wreg[K][4];
+        auto load_w = [&](int tile) {
+            const int m = tile * WS_PT + row;
+            const bool ok = tile < n_tiles && m < n_out;
+            const float *wsrc = a.weights + (size_t)(ok ? m : 0) * K * 16 + jq * 4;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(wsrc + k * 16));
+                wreg[k][0] = ok ? v.x : 0.f; wreg[k][1] = ok ? v.y : 0.f;
+                wreg[k][2] = ok ? v.z : 0.f; wreg[k][3] = ok ? v.w : 0.f;
+            }
+        };
+        load_w(blockIdx.x);
+
         int t_it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
             const int m = tile * WS_PT + row;
             const bool pvalid = m < n_out;
-            // ---- this lane's weightnet values (and guidance quads) for the tile ----
-            float wreg[K][4];
-            {
-                const float *wsrc = a.weights + (size_t)(pvalid ? m : 0) * K * 16 + jq * 4;
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(wsrc + k * 16));
-                    wreg[k][0] = pvalid ? v.x : 0.f; wreg[k][1] = pvalid ? v.y : 0.f;
-                    wreg[k][2] = pvalid ? v.z : 0.f; wreg[k][3] = pvalid ? v.w : 0.f;
-                }
-            }
-            {   // pull the next tile's weightnet rows towards L2 while this tile computes (8 points x 1 KB per warp)
-                const int mn = (tile + (int)gridDim.x) * WS_PT + warp * 8;
+            {   // pull the tile after next towards L2 (weightnet rows 8 x 1 KB per warp, neighbour table, guidance)
+                const int mn = (tile + 2 * (int)gridDim.x) * WS_PT + warp * 8;
                 if (mn + 8 <= n_out) {
                     const char *pn = reinterpret_cast<const char *>(a.weights + (size_t)mn * K * 16);
                     ws::prefetch_l2(pn + lane * 256);
                     ws::prefetch_l2(pn + lane * 256 + 128);
+                    if (lane < 8) ws::prefetch_l2(reinterpret_cast<const char *>(a.nei + (size_t)mn * K) + lane * 128);
                     if (GQ > 0) {
                         const char *gn = reinterpret_cast<const char *>(a.guidance + (size_t)mn * K * H);
                         if (lane * 128 < 8 * K * H * 4) ws::prefetch_l2(gn + lane * 128);
                     }
                 }
             }
-            const float *gsrc = (GQ > 0) ? a.guidance + ((size_t)(pvalid ? m : 0) * K + jq * 4) * H : nullptr;
+            const float *gsrc = (GQ > 0) ? a.guidance + ((size_t)(pvalid ? m : 0) * K + ks * 8) * H : nullptr;
 
-            for (int g = 0; g < NG; ++g) {
-                float4 gq[4];                                             // guidance of the lane's rows k = 4jq + i for this group
-                if (GQ > 0 && g * CG < C_in) {
+            for (int o = 0; o < NO; ++o) {
+                float acc[8][4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (GQ == 2) {
-                            gq[i] = __ldg(reinterpret_cast<const float4 *>(gsrc + i * 8) + (g & 1));
-                        } else if (H == 4) {
-                            gq[i] = __ldg(reinterpret_cast<const float4 *>(gsrc + i * 4));
-                        } else if (H == 2) {
-                            const float2 v = __ldg(reinterpret_cast<const float2 *>(gsrc + i * 2));
-                            gq[i] = make_float4(v.x, v.y, v.x, v.y);
-                        } else {
-                            const float v = __ldg(gsrc + i);
-                            gq[i] = make_float4(v, v, v, v);
+                for (int c = 0; c < 8; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
+#pragma unroll
+                for (int kh = 0; kh < 2; ++kh) {
+                    float4 gq[4];                                         // guidance of the lane's pieces (rows 8ks + 4kh + i)
+                    const bool guided = GQ > 0 && (o * 8 + hh * 4) < C_in;
+                    if (guided) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float *gp_ = gsrc + (kh * 4 + i) * H;
+                            if (GQ == 2) {
+                                gq[i] = __ldg(reinterpret_cast<const float4 *>(gp_) + hh);
+                            } else if (H == 4) {
+                                gq[i] = __ldg(reinterpret_cast<const float4 *>(gp_));
+                            } else if (H == 2) {
+                                const float2 v = __ldg(reinterpret_cast<const float2 *>(gp_));
+                                gq[i] = make_float4(v.x, v.y, v.x, v.y);
+                            } else {
+                                const float v = __ldg(gp_);
+                                gq[i] = make_float4(v, v, v, v);
+                            }
+                        }
+                    }
+                    ws::wait_group<S - 2>();
+                    __syncwarp();
+                    issue_next();
+                    float *slot = ring + (size_t)c_slot * WS_STAGE;
+                    if (++c_slot == S) c_slot = 0;
+                    if (GQ > 0) {                                         // guidance multiply, each lane on the pieces it fetched
+                        if (guided) {
+                            unsigned char *rp = reinterpret_cast<unsigned char *>(slot) + my_dst;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                float4 v = *reinterpret_cast<float4 *>(rp + i * 32);
+                                v.x *= gq[i].x; v.y *= gq[i].y; v.z *= gq[i].z; v.w *= gq[i].w;
+                                *reinterpret_cast<float4 *>(rp + i * 32) = v;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    // ---- contraction 1 over this stage's 8 neighbours: acc[c][j] += G[k][c] w[k][j] ----
+                    if (!WS_DBG(4)) {
+                        const float4 *gp = reinterpret_cast<const float4 *>(slot + pl * WS_PSTRIDE);
+#pragma unroll
+                        for (int kl = 0; kl < 8; ++kl) {
+                            const int k = (kl >> 2) * 8 + kh * 4 + (kl & 3);
+                            const float4 v0 = gp[2 * kl], v1 = gp[2 * kl + 1];
+                            const float g8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                ws::ffma2(acc[c][0], acc[c][1], g8[c], wreg[k][0], wreg[k][1]);
+                                ws::ffma2(acc[c][2], acc[c][3], g8[c], wreg[k][2], wreg[k][3]);
+                            }
                         }
                     }
                 }
-                ws::wait_group<S - 2>();
-                __syncwarp();
-                issue_next();
-                float *slot = ring + (size_t)c_slot * WS_STAGE;
-                if (++c_slot == S) c_slot = 0;
-                const int c0 = g * CG;
-                if (GQ > 0 && c0 < C_in) {                                // guidance multiply, each lane on the rows it fetched
-                    float4 *rp = reinterpret_cast<float4 *>(reinterpret_cast<unsigned char *>(slot) + my_dst);
+                if (o == NO - 1) load_w(tile + (int)gridDim.x);           // next tile's weightnet values fly during the hand-off
+                // ---- four A chunks (2 channels each): split to (hi, lo), hand to the MMA warp ----
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float4 v = rp[i];
-                        const float4 gv = gq[i];
-                        v.x *= gv.x; v.y *= gv.y; v.z *= gv.z; v.w *= gv.w;
-                        rp[i] = v;
-                    }
-                    __syncwarp();
-                }
-                // ---- contraction 1 over the 16 neighbours: acc[c][j] ----
-                float acc[CG][4];
-#pragma unroll
-                for (int c = 0; c < CG; ++c)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[c][j] = 0.f;
-                if (!(a.dbg & 4)) {
-                    const float4 *gp = reinterpret_cast<const float4 *>(slot + pl * WS_PSTRIDE);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const float4 v = gp[k];
-                        ws::ffma2(acc[0][0], acc[0][1], v.x, wreg[k][0], wreg[k][1]);
-                        ws::ffma2(acc[0][2], acc[0][3], v.x, wreg[k][2], wreg[k][3]);
-                        ws::ffma2(acc[1][0], acc[1][1], v.y, wreg[k][0], wreg[k][1]);
-                        ws::ffma2(acc[1][2], acc[1][3], v.y, wreg[k][2], wreg[k][3]);
-                        ws::ffma2(acc[2][0], acc[2][1], v.z, wreg[k][0], wreg[k][1]);
-                        ws::ffma2(acc[2][2], acc[2][3], v.z, wreg[k][2], wreg[k][3]);
-                        ws::ffma2(acc[3][0], acc[3][1], v.w, wreg[k][0], wreg[k][1]);
-                        ws::ffma2(acc[3][2], acc[3][3], v.w, wreg[k][2], wreg[k][3]);
-                    }
-                }
-                // ---- two A chunks (2 channels each): split to (hi, lo), hand to the MMA warp ----
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (a.dbg & 2) {                              // ablation: keep the values alive, skip the hand-off
-                        if (acc[2 * h][0] + acc[2 * h + 1][3] == 123.456f) a.out_y[0] = 1.f;
+                for (int cp = 0; cp < 4; ++cp) {
+                    if (o * 8 + 2 * cp >= C_cat) break;                   // octet padded past the last channel
+                    if WS_DBG(2) {                              // ablation: keep the values alive, skip the hand-off
+                        if (acc[2 * cp][0] + acc[2 * cp + 1][3] == 123.456f) a.out_y[0] = 1.f;
                         continue;
                     }
-                    if (ab_use > 0 && !(a.dbg & 16)) ws::wait_or_trap(&bars[WS_A_EMPTY + ab], (uint32_t)(ab_use - 1) & 1);
+                    if (ab_use > 0 && !WS_DBG(16)) ws::wait_or_trap(&bars[WS_A_EMPTY + ab], (uint32_t)(ab_use - 1) & 1);
                     unsigned char *Ah = A_base + (size_t)ab * 2 * WS_A_HALF;
                     unsigned char *Al = Ah + WS_A_HALF;
 #pragma unroll
-                    for (int cl = 0; cl < ((a.dbg & 128) ? 0 : 2); ++cl) {
-                        const int c = 2 * h + cl;
+                    for (int cl = 0; cl < (WS_DBG(128) ? 0 : 2); ++cl) {
+                        const int c = 2 * cp + cl;
                         float4 hi, lo;
                         ws::split(acc[c][0], hi.x, lo.x); ws::split(acc[c][1], hi.y, lo.y);
                         ws::split(acc[c][2], hi.z, lo.z); ws::split(acc[c][3], hi.w, lo.w);
@@ -457,22 +481,22 @@ __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
                         *reinterpret_cast<float4 *>(Ah + off) = hi;
                         *reinterpret_cast<float4 *>(Al + off) = lo;
                         if (a.out_p && pvalid)
-                            *reinterpret_cast<float4 *>(a.out_p + (size_t)m * KK + (size_t)(c0 + c) * 16 + jq * 4) =
+                            *reinterpret_cast<float4 *>(a.out_p + (size_t)m * KK + (size_t)(o * 8 + c) * 16 + jq * 4) =
                                 make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
                     }
                     // hand-off: the warp's stores are ordered before lane 0's release-arrive by __syncwarp; the generic->async
-                    // proxy fence is executed once by the consumer (MMA thread) after its acquire.  A writer-side
+                    // proxy fence is executed once by the consumer (MMA warp) after its acquire.  A writer-side
                     // fence.proxy.async here compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and cost 20% of the kernel (ncu).
                     __syncwarp();
                     if (lane == 0) ws::mbar_arrive(&bars[WS_A_FULL + ab]);
                     if (++ab == NA) { ab = 0; ++ab_use; }
                 }
-                if (g == 0 && pend_tile >= 0 && warp < WS_EPI && !(a.dbg & 2)) { epilogue(pend_tile, pend_it); }
-                if (g == 0) pend_tile = -1;
+                if (o == 0 && pend_tile >= 0 && warp < WS_EPI && !WS_DBG(2)) { epilogue(pend_tile, pend_it); }
+                if (o == 0) pend_tile = -1;
             }
             pend_tile = tile; pend_it = t_it;
         }
-        if (pend_tile >= 0 && warp < WS_EPI && !(a.dbg & 2)) epilogue(pend_tile, pend_it);
+        if (pend_tile >= 0 && warp < WS_EPI && !WS_DBG(2)) epilogue(pend_tile, pend_it);
         ws::wait_group<0>();
     }
     umma::fence_before_sync();
@@ -486,7 +510,7 @@ void prep_w_launch(const float *lin_w, int C_out, int KK, int CK, int n_chunks, 
 
 static bool ws_config(const pcfb_pconv_shape *s, int *stages, int *sb, int *na) {
     // (ring stages, B slots, A buffers) in order of preference; the first that fits wins
-    const int cand[][3] = {{4, 4, 3}, {4, 3, 3}, {4, 2, 3}, {4, 2, 2}, {3, 2, 2}};
+    const int cand[][3] = {{4, 4, 4}, {3, 4, 4}, {3, 3, 4}, {3, 3, 3}, {3, 2, 3}, {3, 2, 2}};
     for (auto &c : cand)
         if (ws_plan(s->C_out, c[0], c[1], c[2]).total <= WS_SMEM_MAX) { *stages = c[0]; *sb = c[1]; *na = c[2]; return true; }
     return false;
@@ -539,11 +563,13 @@ int pconv_forward_ws(const pcfb_pconv_shape *s, const float *feats, const int64_
     a.feats = feats; a.nei = nei; a.weights = weights; a.additional = additional; a.guidance = guidance;
     a.lin_b = lin_b; a.out_y = out_y; a.out_p = out_p;
     a.w_prep = static_cast<const float *>(workspace);
-    a.n_groups = C_cat / WS_CG;
+    a.n_groups = (C_cat + WS_CG - 1) / WS_CG;
     a.n_chunks = KK / WS_CK;
     a.n_tiles = ceil_div(s->n_out, WS_PT);
     a.sb = sb; a.na = na;
+#if PCFB_WS_ABLATE
     { const char *e = getenv("PCFB_WS_DEBUG"); a.dbg = e ? atoi(e) : 0; }
+#endif
     int cols = 32;
     while (cols < s->C_out) cols <<= 1;
     a.tmem_cols = cols;
