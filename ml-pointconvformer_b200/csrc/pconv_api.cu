@@ -50,6 +50,13 @@ static bool mid1_path(const pcfb_pconv_shape *s, int variant) {
     return variant != 1 && variant != 3 && variant != 4 && s->C_out >= 1 && s->C_out <= 256 && pcfb::pconv_mid1_supported(s);
 }
 
+// auto only: shapes that neither pipelined tcgen05 kernel holds (wide C_out at the deep levels, a few hundred points):
+// P by the CUDA-core contraction kernel, Y = P W^T + b as a column-block tensor-core GEMM.  The simple tcgen05 kernel
+// these shapes used before keeps 2-3 CTAs busy for ~0.4 ms.
+static bool compose_path(const pcfb_pconv_shape *s) {
+    return s->C_out > 0 && s->C_mid > 1 && !pcfb::pconv_forward_ws_supported(s, true) && !pcfb::pconv_forward_umma2_supported(s, true);
+}
+
 extern "C" int pcfb_pconv_forward_supported(const pcfb_pconv_shape *s, int variant)
 {
     if (!s) return 0;
@@ -74,6 +81,9 @@ extern "C" size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int va
         return w2 > ws ? w2 : ws;
     }
     if (ws) return ws;
+    if (variant == 0 && compose_path(s))
+        return pcfb::align_up((size_t)s->n_out * (s->C_in + s->C_add) * s->C_mid * sizeof(float), 256) +
+               pcfb_gemm_nt_workspace(s->C_out, (s->C_in + s->C_add) * s->C_mid);
     return pcfb::pconv_forward_umma_supported(s, s->C_out > 0) ? pcfb::pconv_forward_umma_workspace(s) : 0;
 }
 
@@ -114,6 +124,17 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
             set_error("pcfb_pconv_forward: the warp-specialised variant does not support this shape");
             return PCFB_ERR_UNSUPPORTED;
         }
+    }
+    if (variant == 0 && lin_w && compose_path(s)) {
+        const int KK = (s->C_in + s->C_add) * s->C_mid;
+        const size_t p_bytes = align_up((size_t)s->n_out * KK * sizeof(float), 256);
+        const size_t nt_bytes = pcfb_gemm_nt_workspace(s->C_out, KK);
+        PCFB_REQUIRE(workspace && workspace_bytes >= p_bytes + nt_bytes, "pcfb_pconv_forward: workspace too small");
+        float *P = out_p ? out_p : static_cast<float *>(workspace);
+        int rc;
+        if ((rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, P, st))) return rc;
+        return pcfb_gemm_nt(P, KK, lin_w, KK, 0, lin_b, out_y, s->C_out, s->n_out, s->C_out, KK, 0,
+                            static_cast<char *>(workspace) + p_bytes, nt_bytes, stream);
     }
     const bool u1_ok = lin_w && pconv_forward_umma_supported(s, true);
     const bool u2_ok = lin_w && variant != 3 && pconv_forward_umma2_supported(s, true);
