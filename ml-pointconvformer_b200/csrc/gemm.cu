@@ -26,6 +26,11 @@ __device__ __forceinline__ void g_cp_async16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(umma::smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void g_cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ bool g_elect_one() {          // true in exactly one lane of the converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred px;\n\telect.sync _|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
 template <int N>
 __device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
@@ -120,9 +125,12 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);          // provably warp-uniform copy for the MMA-issue branch
     const uint32_t idesc = umma::make_idesc_tf32(GT_M, Npad);
     const uint32_t lbo_a = GT_M * 16, lbo_b = (uint32_t)Npad * 16, sbo = 128;
+    const uint64_t da0 = umma::make_smem_desc(0, lbo_a, sbo), db0 = umma::make_smem_desc(0, lbo_b, sbo);
+    const uint32_t a_u32 = umma::smem_u32(A_base), b_u32 = umma::smem_u32(B_base);
     uint32_t uses0 = 0, uses1 = 0;
 
     auto issue_b = [&](int chunk, int slot) {
@@ -197,25 +205,24 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
             umma::fence_proxy_async();
             umma::fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp_u == 0) {                                       // warp-uniform branch: the MMAs issue back to back from one elected lane
                 umma::fence_after_sync();
                 const int slot = a.b_resident ? chunk : (chunk % 3);
-                const uint32_t ah = umma::smem_u32(A_base + (size_t)(buf * 2 + 0) * pl.a_bytes);
-                const uint32_t al = umma::smem_u32(A_base + (size_t)(buf * 2 + 1) * pl.a_bytes);
-                const uint32_t bh = umma::smem_u32(B_base + (size_t)(slot * 2 + 0) * pl.b_bytes);
-                const uint32_t bl = umma::smem_u32(B_base + (size_t)(slot * 2 + 1) * pl.b_bytes);
+                const uint64_t dah0 = da0 + ((a_u32 + (uint32_t)(buf * 2 + 0) * pl.a_bytes) >> 4);
+                const uint64_t dal0 = da0 + ((a_u32 + (uint32_t)(buf * 2 + 1) * pl.a_bytes) >> 4);
+                const uint64_t dbh0 = db0 + ((b_u32 + (uint32_t)(slot * 2 + 0) * pl.b_bytes) >> 4);
+                const uint64_t dbl0 = db0 + ((b_u32 + (uint32_t)(slot * 2 + 1) * pl.b_bytes) >> 4);
+                if (g_elect_one()) {
 #pragma unroll
-                for (int ks = 0; ks < GT_KC / 8; ++ks) {
-                    const uint32_t ao = ks * 2 * lbo_a, bo = ks * 2 * lbo_b;
-                    const uint64_t dah = umma::make_smem_desc(ah + ao, lbo_a, sbo);
-                    const uint64_t dal = umma::make_smem_desc(al + ao, lbo_a, sbo);
-                    const uint64_t dbh = umma::make_smem_desc(bh + bo, lbo_b, sbo);
-                    const uint64_t dbl = umma::make_smem_desc(bl + bo, lbo_b, sbo);
-                    umma::mma_tf32_ss(tmem_d, dal, dbh, idesc, (chunk > 0 || ks > 0) ? 1u : 0u);
-                    umma::mma_tf32_ss(tmem_d, dah, dbl, idesc, 1u);
-                    umma::mma_tf32_ss(tmem_d, dah, dbh, idesc, 1u);
+                    for (int ks = 0; ks < GT_KC / 8; ++ks) {
+                        const uint32_t ao = (ks * 2 * lbo_a) >> 4, bo = (ks * 2 * lbo_b) >> 4;
+                        umma::mma_tf32_ss(tmem_d, dal0 + ao, dbh0 + bo, idesc, (chunk > 0 || ks > 0) ? 1u : 0u);
+                        umma::mma_tf32_ss(tmem_d, dah0 + ao, dbl0 + bo, idesc, 1u);
+                        umma::mma_tf32_ss(tmem_d, dah0 + ao, dbh0 + bo, idesc, 1u);
+                    }
+                    umma::commit(&bars[buf]);
                 }
-                umma::commit(&bars[buf]);
+                __syncwarp();
             }
             if (buf) ++uses1; else ++uses0;
             if (!a.b_resident) {
@@ -285,14 +292,18 @@ struct GemmTnArgs {
     const float *A, *B;            // A [M][lda] (N1 used columns), B [M][ldb] (N2 used columns)
     float *partial;                // [slices][N1][ldp], ldp = N2 + (ones ? 1 : 0)
     int M, N1, N1pad, N2, lda, ldb, ldp, ones, slice_rows, n2_tile, tmem_cols, RC;   // RC: rows per chunk
+    int N1blk;                     // A columns per blockIdx.z block (N1pad pads one block)
 };
 
+constexpr uint32_t TN_SBO = 144;
 struct GemmTnPlan { uint32_t a_bytes, b_bytes; size_t off_A, off_B, off_bar, total; };
 
 __host__ __device__ inline GemmTnPlan gemm_tn_plan(int N1pad, int n2_tile, int RC) {
     GemmTnPlan pl;
-    pl.a_bytes = (uint32_t)N1pad * RC * 4;
-    pl.b_bytes = (uint32_t)n2_tile * RC * 4;
+    // 8-column groups (the UMMA core matrices, 128 B) sit TN_SBO = 144 B apart: with the dense 128 B stride the staging
+    // stores of a warp (16 B every 64 B) were 4-way bank conflicts (ncu: 14.8 wavefronts per STS.128)
+    pl.a_bytes = (uint32_t)(N1pad / 8) * TN_SBO * (RC / 4);
+    pl.b_bytes = (uint32_t)(n2_tile / 8) * TN_SBO * (RC / 4);
     size_t o = 0;
     pl.off_A = o; o += 4 * (size_t)pl.a_bytes;
     pl.off_B = o; o += 4 * (size_t)pl.b_bytes;
@@ -302,50 +313,7 @@ __host__ __device__ inline GemmTnPlan gemm_tn_plan(int N1pad, int n2_tile, int R
     return pl;
 }
 
-// stage a [RC rows x ncols] block of a row-major matrix as the K-major operand of the transposed matrix:
-// element (col, row) -> (row/4)*(ncols_pad*16) + col*16 + (row%4)*4.  Each work item = 4 rows x 4 cols, transposed
-// in registers.  Only column groups that hold data are written; the padding columns were zeroed once.
-__device__ __forceinline__ void tn_stage(const float *__restrict__ src, int ld, int m0, int m_end, int RC, int col0, int ncols,
-                                         int ncols_pad, int ones_col, bool vec, unsigned char *dst_hi, unsigned char *dst_lo, int tid)
-{
-    const int used = ncols + ((ones_col >= col0 && ones_col < col0 + ncols_pad) ? 1 : 0);
-    const int cgroups = (used + 3) / 4;
-    for (int item = tid; item < cgroups * (RC / 4); item += G_NT) {
-        const int cgp = item % cgroups, rg = item / cgroups;
-        const int c = cgp * 4, r = rg * 4;
-        float v[4][4];                                   // [row][col]
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int m = m0 + r + rr;
-            if (vec && m < m_end && c + 3 < ncols) {
-                const float4 t = __ldg(reinterpret_cast<const float4 *>(src + (size_t)m * ld + col0 + c));
-                v[rr][0] = t.x; v[rr][1] = t.y; v[rr][2] = t.z; v[rr][3] = t.w;
-            } else {
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const int col = c + cc;
-                    float x = 0.f;
-                    if (m < m_end) {
-                        if (col < ncols) x = __ldg(src + (size_t)m * ld + col0 + col);
-                        else if (col0 + col == ones_col) x = 1.f;
-                    }
-                    v[rr][cc] = x;
-                }
-            }
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            float4 hi, lo;
-            umma::split_tf32(v[0][cc], hi.x, lo.x); umma::split_tf32(v[1][cc], hi.y, lo.y);
-            umma::split_tf32(v[2][cc], hi.z, lo.z); umma::split_tf32(v[3][cc], hi.w, lo.w);
-            const size_t off = (size_t)rg * ncols_pad * 16 + (size_t)(c + cc) * 16;
-            *reinterpret_cast<float4 *>(dst_hi + off) = hi;
-            *reinterpret_cast<float4 *>(dst_lo + off) = lo;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
+__global__ void __launch_bounds__(G_NT, 2) gemm_tn_kernel(GemmTnArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GemmTnPlan pl = gemm_tn_plan(a.N1pad, a.n2_tile, a.RC);
@@ -372,10 +340,13 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
-    const uint32_t tmem_d = *tmem_slot;
-    const bool vec_a = ((a.lda & 3) == 0) && ((uintptr_t)a.A % 16 == 0);
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const bool vec_a = ((a.lda & 3) == 0) && ((uintptr_t)a.A % 16 == 0) && ((a.N1blk & 3) == 0);
     const bool vec_b = ((a.ldb & 3) == 0) && ((uintptr_t)a.B % 16 == 0) && ((a.n2_tile & 3) == 0);
 
+    const int n1_0 = blockIdx.z * a.N1blk;                         // first A column (= output row) of this CTA
+    const int n1_cols = min(a.N1blk, a.N1 - n1_0);
     const int n2_0 = blockIdx.x * a.n2_tile;                       // first B column of this CTA
     const int n2_cols = min(a.n2_tile, a.ldp - n2_0);              // incl. the ones column in the last tile
     const int slice = blockIdx.y;
@@ -383,9 +354,91 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
     const int n_mblk = a.N1pad / 128 > 0 ? a.N1pad / 128 : 1;      // MMA row blocks of 128 (or one of 64)
     const int mma_m = a.N1pad >= 128 ? 128 : 64;
     const uint32_t idesc = umma::make_idesc_tf32(mma_m, a.n2_tile);
-    const uint32_t lbo_a = (uint32_t)a.N1pad * 16, lbo_b = (uint32_t)a.n2_tile * 16, sbo = 128;
+    const uint32_t lbo_a = (uint32_t)(a.N1pad / 8) * TN_SBO, lbo_b = (uint32_t)(a.n2_tile / 8) * TN_SBO, sbo = TN_SBO;
+    const uint64_t da0 = umma::make_smem_desc(0, lbo_a, sbo), db0 = umma::make_smem_desc(0, lbo_b, sbo);
+    const uint32_t a_u32 = umma::smem_u32(A_base), b_u32 = umma::smem_u32(B_base);
     const int ones_col = a.ones ? a.N2 : -1;
     uint32_t uses0 = 0, uses1 = 0;
+
+    // ---- staging as work items of 4 rows x 4 columns (transposed in registers).  Items [0, items_a) belong to A, the rest
+    // to B.  The global loads of the NEXT chunk are issued into registers (TN_PRE items per thread) right after this
+    // chunk's registers went to shared memory, so they fly while the MMAs of this chunk run and the buffer of the next one
+    // frees up; the first version loaded and stored item by item and ran at 0.9 TB/s. ----
+    const int b_cols = max(0, min(a.n2_tile, a.N2 - n2_0));
+    const int cg_a = (n1_cols + 3) / 4;
+    const int cg_b = (b_cols + ((ones_col >= n2_0 && ones_col < n2_0 + a.n2_tile) ? 1 : 0) + 3) / 4;
+    const int rg = RC / 4;
+    const int items_a = cg_a * rg, items = items_a + cg_b * rg;
+    // Per-thread item descriptors are fixed for the whole kernel (the divisions happen once): source pointer of the
+    // item's first element at row 0 of a chunk, row offset inside the chunk, shared-memory offset, and whether the four
+    // float4 loads are legal (else the generic element-wise path).
+    struct Item { const float *p; uint32_t off; int r, ld, flags; };          // flags: 1 = A operand, 2 = vector loads
+    auto make_item = [&](int item) {
+        Item t;
+        const bool is_a = item < items_a;
+        const int it = is_a ? item : item - items_a;
+        const int cgroups = is_a ? cg_a : cg_b;
+        const int c = (it % cgroups) * 4;
+        t.r = (it / cgroups) * 4;
+        t.ld = is_a ? a.lda : a.ldb;
+        t.p = (is_a ? a.A + n1_0 : a.B + n2_0) + c;
+        const bool full = c + 3 < (is_a ? n1_cols : b_cols);
+        t.flags = (is_a ? 1 : 0) | (((is_a ? vec_a : vec_b) && full) ? 2 : 0);
+        // (hi) byte offset of column c of row group r/4: K-unit * LBO + (c/8) * SBO + (c%8) * 16 ; lo = hi + operand bytes
+        t.off = (uint32_t)(is_a ? pl.off_A : pl.off_B) + (uint32_t)(t.r / 4) * (is_a ? lbo_a : lbo_b) + (uint32_t)(c / 8) * TN_SBO + (uint32_t)(c % 8) * 16;
+        return t;
+    };
+    auto load_item = [&](const Item &t, int item, int m0, float (&v)[4][4]) {
+        if (t.flags & 2) {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int m = m0 + t.r + rr;
+                float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < m_end) t4 = __ldg(reinterpret_cast<const float4 *>(t.p + (size_t)m * t.ld));
+                v[rr][0] = t4.x; v[rr][1] = t4.y; v[rr][2] = t4.z; v[rr][3] = t4.w;
+            }
+        } else {                                                       // ragged / unaligned columns, the ones column
+            const bool is_a = (t.flags & 1) != 0;
+            const int it = is_a ? item : item - items_a;
+            const int c = (it % (is_a ? cg_a : cg_b)) * 4;
+            const int ncols = is_a ? n1_cols : b_cols, col0 = is_a ? n1_0 : n2_0, oc = is_a ? -1 : ones_col;
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int m = m0 + t.r + rr;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const int col = c + cc;
+                    float x = 0.f;
+                    if (m < m_end) {
+                        if (col < ncols) x = __ldg(t.p + (size_t)m * t.ld + cc);
+                        else if (col0 + col == oc) x = 1.f;
+                    }
+                    v[rr][cc] = x;
+                }
+            }
+        }
+    };
+    auto store_item = [&](const Item &t, const float (&v)[4][4], int buf) {
+        const uint32_t opb = (t.flags & 1) ? pl.a_bytes : pl.b_bytes;
+        unsigned char *dst_hi = smem_raw + t.off + (size_t)(buf * 2) * opb;
+        unsigned char *dst_lo = dst_hi + opb;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float4 hi, lo;
+            umma::split_tf32(v[0][cc], hi.x, lo.x); umma::split_tf32(v[1][cc], hi.y, lo.y);
+            umma::split_tf32(v[2][cc], hi.z, lo.z); umma::split_tf32(v[3][cc], hi.w, lo.w);
+            *reinterpret_cast<float4 *>(dst_hi + cc * 16) = hi;     // c % 8 is 0 or 4: the four columns stay inside one group
+            *reinterpret_cast<float4 *>(dst_lo + cc * 16) = lo;
+        }
+    };
+    constexpr int TN_PRE = 3;
+    float pre[TN_PRE][4][4];
+    Item its[TN_PRE];
+#pragma unroll
+    for (int i = 0; i < TN_PRE; ++i) {
+        its[i] = make_item(min(tid + i * G_NT, items - 1));
+        if (tid + i * G_NT < items && m_begin < m_end) load_item(its[i], tid + i * G_NT, m_begin, pre[i]);
+    }
 
     int chunk = 0;
     for (int m0 = m_begin; m0 < m_end; m0 += RC, ++chunk) {
@@ -394,34 +447,43 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
             const uint32_t u = buf ? uses1 : uses0;
             if (u > 0 && !umma::mbar_wait(&bars[buf], (u - 1) & 1)) __trap();
         }
-        tn_stage(a.A, a.lda, m0, m_end, RC, 0, a.N1, a.N1pad, -1, vec_a, A_base + (size_t)(buf * 2) * pl.a_bytes,
-                 A_base + (size_t)(buf * 2 + 1) * pl.a_bytes, tid);
-        tn_stage(a.B, a.ldb, m0, m_end, RC, n2_0, max(0, min(a.n2_tile, a.N2 - n2_0)), a.n2_tile, ones_col, vec_b,
-                 B_base + (size_t)(buf * 2) * pl.b_bytes, B_base + (size_t)(buf * 2 + 1) * pl.b_bytes, tid);
+#pragma unroll
+        for (int i = 0; i < TN_PRE; ++i)
+            if (tid + i * G_NT < items) store_item(its[i], pre[i], buf);
+        for (int item = tid + TN_PRE * G_NT; item < items; item += G_NT) {      // tiles wider than the register window
+            float v[4][4];
+            const Item t = make_item(item);
+            load_item(t, item, m0, v);
+            store_item(t, v, buf);
+        }
+        if (m0 + RC < m_end) {
+#pragma unroll
+            for (int i = 0; i < TN_PRE; ++i)
+                if (tid + i * G_NT < items) load_item(its[i], tid + i * G_NT, m0 + RC, pre[i]);
+        }
         umma::fence_proxy_async();
         umma::fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp_u == 0) {                                           // warp-uniform branch, one elected lane issues
             umma::fence_after_sync();
-            const uint32_t ah = umma::smem_u32(A_base + (size_t)(buf * 2 + 0) * pl.a_bytes);
-            const uint32_t al = umma::smem_u32(A_base + (size_t)(buf * 2 + 1) * pl.a_bytes);
-            const uint32_t bh = umma::smem_u32(B_base + (size_t)(buf * 2 + 0) * pl.b_bytes);
-            const uint32_t bl = umma::smem_u32(B_base + (size_t)(buf * 2 + 1) * pl.b_bytes);
-            for (int mb = 0; mb < n_mblk; ++mb) {
-                const uint32_t d = tmem_d + mb * a.n2_tile;
-                const uint32_t arow = mb * 128 * 16;               // rows of this block inside each 16-byte column
-                for (int ks = 0; ks < RC / 8; ++ks) {
-                    const uint32_t ao = ks * 2 * lbo_a + arow, bo = ks * 2 * lbo_b;
-                    const uint64_t dah = umma::make_smem_desc(ah + ao, lbo_a, sbo);
-                    const uint64_t dal = umma::make_smem_desc(al + ao, lbo_a, sbo);
-                    const uint64_t dbh = umma::make_smem_desc(bh + bo, lbo_b, sbo);
-                    const uint64_t dbl = umma::make_smem_desc(bl + bo, lbo_b, sbo);
-                    umma::mma_tf32_ss(d, dal, dbh, idesc, (chunk > 0 || ks > 0) ? 1u : 0u);
-                    umma::mma_tf32_ss(d, dah, dbl, idesc, 1u);
-                    umma::mma_tf32_ss(d, dah, dbh, idesc, 1u);
+            const uint64_t dah0 = da0 + ((a_u32 + (uint32_t)(buf * 2 + 0) * pl.a_bytes) >> 4);
+            const uint64_t dal0 = da0 + ((a_u32 + (uint32_t)(buf * 2 + 1) * pl.a_bytes) >> 4);
+            const uint64_t dbh0 = db0 + ((b_u32 + (uint32_t)(buf * 2 + 0) * pl.b_bytes) >> 4);
+            const uint64_t dbl0 = db0 + ((b_u32 + (uint32_t)(buf * 2 + 1) * pl.b_bytes) >> 4);
+            if (g_elect_one()) {
+                for (int mb = 0; mb < n_mblk; ++mb) {
+                    const uint32_t d = tmem_d + mb * a.n2_tile;
+                    const uint32_t arow = (uint32_t)(mb * 16) * TN_SBO;   // 128 rows = 16 column groups further inside each K-unit
+                    for (int ks = 0; ks < RC / 8; ++ks) {
+                        const uint32_t ao = (ks * 2 * lbo_a + arow) >> 4, bo = (ks * 2 * lbo_b) >> 4;
+                        umma::mma_tf32_ss(d, dal0 + ao, dbh0 + bo, idesc, (chunk > 0 || ks > 0) ? 1u : 0u);
+                        umma::mma_tf32_ss(d, dah0 + ao, dbl0 + bo, idesc, 1u);
+                        umma::mma_tf32_ss(d, dah0 + ao, dbh0 + bo, idesc, 1u);
+                    }
                 }
+                umma::commit(&bars[buf]);
             }
-            umma::commit(&bars[buf]);
+            __syncwarp();
         }
         if (buf) ++uses1; else ++uses0;
     }
@@ -446,8 +508,8 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = 0.f;
                 }
-                if (lane_ok && n1 < a.N1) {
-                    float *dst = a.partial + ((size_t)slice * a.N1 + n1) * a.ldp + n2_0 + c0;
+                if (lane_ok && n1 < n1_cols) {
+                    float *dst = a.partial + ((size_t)slice * a.N1 + n1_0 + n1) * a.ldp + n2_0 + c0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) if (c0 + j < n2_cols) dst[j] = v[j];
                 }
@@ -461,16 +523,42 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_tn_kernel(GemmTnArgs a)
 }
 
 __global__ void gemm_tn_reduce_kernel(const float *__restrict__ partial, int S, int N1, int N2, int ldp,
-                                      float *__restrict__ C, int ldc, float *__restrict__ rowsum)
+                                      float *__restrict__ C, int ldc, float *__restrict__ rowsum, int transposed)
 {
     const int total = N1 * ldp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float s = 0.f;
         for (int z = 0; z < S; ++z) s += partial[(size_t)z * total + i];          // fixed order: deterministic
         const int n1 = i / ldp, c = i - n1 * ldp;
-        if (c < N2) { if (C) C[(size_t)n1 * ldc + c] = s; }
+        if (c < N2) { if (C) C[transposed ? (size_t)c * ldc + n1 : (size_t)n1 * ldc + c] = s; }
         else if (rowsum) rowsum[n1] = s;
     }
+}
+
+// column sums of a row-major [M x N] matrix (N <= 256), two deterministic stages: partial[slice][n], then out[n]
+__global__ void gemm_colsum_kernel(const float *__restrict__ A, int lda, int M, int N, int slice_rows, float *__restrict__ partial)
+{
+    __shared__ float red[256];
+    const int n = threadIdx.x % N, sub = threadIdx.x / N, nsub = blockDim.x / N;
+    const int m_begin = blockIdx.x * slice_rows, m_end = min(M, m_begin + slice_rows);
+    float s = 0.f;
+    if (sub < nsub)
+        for (int m = m_begin + sub; m < m_end; m += nsub) s += __ldg(A + (size_t)m * lda + n);
+    red[threadIdx.x] = (sub < nsub) ? s : 0.f;
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float t = 0.f;
+        for (int q = 0; q < nsub; ++q) t += red[q * N + threadIdx.x];
+        partial[(size_t)blockIdx.x * N + threadIdx.x] = t;
+    }
+}
+__global__ void gemm_colsum_reduce_kernel(const float *__restrict__ partial, int S, int N, float *__restrict__ out)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int z = 0; z < S; ++z) s += partial[(size_t)z * N + n];
+    out[n] = s;
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------
@@ -550,24 +638,40 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
 }
 
 namespace pcfb {
-struct TnSetup { int N1pad, n2_tile, n2_tiles, S, slice_rows, ldp, RC; size_t ws_bytes; GemmTnPlan plan; };
-static TnSetup tn_setup(int M, int N1, int N2, int ones) {
+struct TnSetup { int swap, n1, n2, N1blk, n1_blocks, N1pad, n2_tile, n2_tiles, S, slice_rows, ldp, RC, ones; size_t ws_bytes, colsum_off; GemmTnPlan plan; };
+// The UMMA M side (TMEM lanes) holds up to 256 output rows per CTA, the N side up to 256 columns.  An MMA costs
+// max(M,128)*N/256 cycles, so the LONG output dimension belongs on the M side: dW = dY^T P (32 x 512) runs as
+// (P^T dY)^T -- four 128-row blocks of N = 32 instead of one half-empty 64-row block of N = 256 twice (2x the tensor time).
+static TnSetup tn_setup(int M, int N1, int N2, int want_rowsum) {
     TnSetup s;
-    s.N1pad = N1 <= 64 ? 64 : round_up(N1, 128);
-    s.ldp = N2 + (ones ? 1 : 0);
+    s.swap = 0;   // (N2 > N1 && N2 >= 128): measured slower on B200 at every model shape (the staging, not the tensor pipe, bounds this kernel)
+    s.n1 = s.swap ? N2 : N1;                                      // rows of the product the kernel computes
+    s.n2 = s.swap ? N1 : N2;
+    s.ones = (want_rowsum && !s.swap) ? 1 : 0;                    // swapped: the bias gradient is a separate column sum
+    s.N1blk = s.n1 <= 256 ? s.n1 : 256;
+    s.n1_blocks = ceil_div(s.n1, s.N1blk);
+    s.N1pad = s.N1blk <= 64 ? 64 : round_up(s.N1blk, 128);
+    s.ldp = s.n2 + s.ones;
     const int max_tile = s.N1pad > 128 ? 128 : 256;               // TMEM columns: n_mblk * n2_tile <= 512; smem
     s.n2_tile = round_up(s.ldp < max_tile ? s.ldp : max_tile, 16);
     if (s.n2_tile < 16) s.n2_tile = 16;
     s.n2_tiles = ceil_div(s.ldp, s.n2_tile);
     s.RC = 128;                                                   // rows per chunk: as deep as shared memory allows
     while (s.RC > 32 && gemm_tn_plan(s.N1pad, s.n2_tile, s.RC).total > 200 * 1024) s.RC >>= 1;
-    int S = ceil_div(2 * kNumSMs, s.n2_tiles);
+    // two co-resident CTAs per SM hide each other's stage -> barrier -> MMA bubbles: take a shallower chunk if that is
+    // what it costs to get under half of the shared memory
+    int per_sm = 1;
+    if (gemm_tn_plan(s.N1pad, s.n2_tile, s.RC).total > 110 * 1024 && s.RC >= 32 &&
+        gemm_tn_plan(s.N1pad, s.n2_tile, s.RC / 2).total <= 110 * 1024 && M >= 16384) { s.RC >>= 1; per_sm = 2; }
+    else if (gemm_tn_plan(s.N1pad, s.n2_tile, s.RC).total <= 110 * 1024) per_sm = 2;
+    int S = ceil_div(2 * per_sm * kNumSMs, s.n2_tiles * s.n1_blocks);
     const int maxS = ceil_div(M > 0 ? M : 1, 4 * s.RC);
     if (S > maxS) S = maxS;
     if (S < 1) S = 1;
     s.slice_rows = round_up(ceil_div(M > 0 ? M : 1, S), s.RC);
     s.S = ceil_div(M > 0 ? M : 1, s.slice_rows);
-    s.ws_bytes = align_up((size_t)s.S * N1 * s.ldp * sizeof(float), 256);
+    s.colsum_off = align_up((size_t)s.S * s.n1 * s.ldp * sizeof(float), 256);
+    s.ws_bytes = s.colsum_off + ((want_rowsum && s.swap) ? align_up((size_t)s.S * N1 * sizeof(float), 256) : 0);
     s.plan = gemm_tn_plan(s.N1pad, s.n2_tile, s.RC);
     return s;
 }
@@ -590,8 +694,9 @@ extern "C" int pcfb_gemm_tn(const float *A, int lda, const float *B, int ldb, fl
     if (workspace_bytes < s.ws_bytes) { set_error("pcfb_gemm_tn: workspace %zu < %zu", workspace_bytes, s.ws_bytes); return PCFB_ERR_WORKSPACE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GemmTnArgs a{};
-    a.A = A; a.B = B; a.partial = static_cast<float *>(workspace);
-    a.M = M; a.N1 = N1; a.N1pad = s.N1pad; a.N2 = N2; a.lda = lda; a.ldb = ldb; a.ldp = s.ldp; a.ones = rowsum != nullptr;
+    a.A = s.swap ? B : A; a.B = s.swap ? A : B; a.partial = static_cast<float *>(workspace);
+    a.M = M; a.N1 = s.n1; a.N1pad = s.N1pad; a.N1blk = s.N1blk; a.N2 = s.n2;
+    a.lda = s.swap ? ldb : lda; a.ldb = s.swap ? lda : ldb; a.ldp = s.ldp; a.ones = s.ones;
     a.slice_rows = s.slice_rows; a.n2_tile = s.n2_tile; a.RC = s.RC;
     int cols = 32;
     const int need_cols = (s.N1pad >= 128 ? s.N1pad / 128 : 1) * s.n2_tile;
@@ -600,10 +705,19 @@ extern "C" int pcfb_gemm_tn(const float *A, int lda, const float *B, int ldb, fl
     static bool attr = false;
     if (!attr) { PCFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr = true; }
     int rc;
-    dim3 grid(s.n2_tiles, s.S);
+    dim3 grid(s.n2_tiles, s.S, s.n1_blocks);
     gemm_tn_kernel<<<grid, G_NT, s.plan.total, st>>>(a);
     if ((rc = check_launch("gemm_tn_kernel"))) return rc;
-    const int total = N1 * s.ldp;
-    gemm_tn_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(a.partial, s.S, N1, N2, s.ldp, C, ldc, rowsum);
-    return check_launch("gemm_tn_reduce_kernel");
+    const int total = s.n1 * s.ldp;
+    gemm_tn_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(a.partial, s.S, s.n1, s.n2, s.ldp, C, ldc,
+                                                                            s.swap ? nullptr : rowsum, s.swap);
+    if ((rc = check_launch("gemm_tn_reduce_kernel"))) return rc;
+    if (rowsum && s.swap) {
+        float *cpart = reinterpret_cast<float *>(static_cast<char *>(workspace) + s.colsum_off);
+        gemm_colsum_kernel<<<s.S, 256, 0, st>>>(A, lda, M, N1, s.slice_rows, cpart);
+        if ((rc = check_launch("gemm_colsum_kernel"))) return rc;
+        gemm_colsum_reduce_kernel<<<ceil_div(N1, 128), 128, 0, st>>>(cpart, s.S, N1, rowsum);
+        if ((rc = check_launch("gemm_colsum_reduce_kernel"))) return rc;
+    }
+    return PCFB_OK;
 }

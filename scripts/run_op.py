@@ -10,6 +10,17 @@ def main():
     what = sys.argv[1]
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     dev = torch.device("cuda", 0)
+    if what in ("gemm_tn", "gemm_nt"):          # the dense products of the fused backward at the level-0 shape
+        M, C_out, KK = 102095, 32, 512
+        dy = torch.randn(M, C_out, device=dev); Wm = torch.randn(C_out, KK, device=dev); P = torch.randn(M, KK, device=dev)
+        for _ in range(reps):
+            if what == "gemm_tn":
+                pcf_cuda.gemm_tn(dy, P, want_rowsum=True)
+            else:
+                pcf_cuda.gemm_nt(dy, Wm, None, w_is_kn=True)
+        torch.cuda.synchronize()
+        print("ok", what)
+        return
     xyz, _, _ = synthetic.make_scene(1, 100000)
     xyz = torch.from_numpy(xyz).to(dev)
     n = xyz.shape[0]
