@@ -324,6 +324,26 @@ def run_ours(args):
     return out
 
 
+def ncu_traffic(op, kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the named kernel, from the newest committed
+    `profiles/ncu_<op>_*.txt` (an `ncu --set full` capture summarised by scripts/summarize_profiles.py); None if absent."""
+    import glob
+    import re
+    best = None
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_%s_*.txt" % op)), key=os.path.getmtime):
+        txt = open(fn).read()
+        for block in txt.split("== launch")[1:]:
+            if kernel_substr not in block.splitlines()[0]:
+                continue
+            vals = {}
+            for m in re.finditer(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", block):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
+                vals[m.group(1)] = float(m.group(2)) * scale
+            if len(vals) == 2:
+                best = {"bytes": vals["read"] + vals["write"], "source": os.path.relpath(fn, ROOT)}
+    return best
+
+
 def kernel_rooflines(dev, host, cfgd, args):
     """Live CUDA-event timing of the hot kernels on this rank's data (each timed alone, L2 flushed before every
     launch): the fused forward at the level-0 StridePE shape (HBM-bound, reported as `roofline`), plus kNN,
@@ -391,13 +411,15 @@ def kernel_rooflines(dev, host, cfgd, args):
     res["knn_inverse_level0"] = {"ms": ms, "alg_bytes": inv_bytes, "GBps": inv_bytes / ms / 1e6, "frac_hbm": inv_bytes / ms / 1e6 / peaks["hbm_gbs"]}
 
     key = "fused_fwd_saveP" if "ms" in res.get("fused_fwd_saveP", {}) else "fused_fwd_simt"
+    traffic = ncu_traffic("fwdp", "pconv_fwd_ws") if args.variant in (0, 4) else None
     r = res[key]
     kname = {0: "pconv_fwd_ws_kernel<4,0>", 4: "pconv_fwd_ws_kernel<4,0>", 2: "pconv_fwd_umma2_kernel<16,false>",
              3: "pconv_fwd_umma_kernel<16,4>", 1: "pconv_fwd_simt_kernel<16>"}[args.variant]
     roof = {"kernel": kname if key != "fused_fwd_simt" else "pconv_fwd_simt_kernel<16>",
             "shape": "level-0 PointConvStridePE contraction: N=%d K=16 C_in=16 C_add=16 C_mid=16 C_out=32, P saved" % n,
             "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["frac_hbm"],
-            "traffic": None, "peak_source": peaks["src"], "ms": r["ms"], "alg_bytes_per_launch": r["alg_bytes"]}
+            "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
+            "peak_source": peaks["src"], "ms": r["ms"], "alg_bytes_per_launch": r["alg_bytes"]}
     return roof, {"kernels": res, "knn_mpts_per_s": res["knn_grid_self_level0"]["Mqueries_per_s"],
                   "knn_bruteforce_mpts_per_s": res["knn_self_level0"]["Mqueries_per_s"]}
 

@@ -16,7 +16,7 @@ timeout 900 python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > 
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$R.csv \
     python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 echo "ncu launches exit $?" >> gpurun_out/summary.log
-for op in fwd bwd; do
+for op in fwd fwdp bwd; do
   python scripts/run_op.py $op 3 > gpurun_out/run_op.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:"pconv_fwd_ws|pconv_fwd_umma2|pconv_bwd2" -s 1 -c 1 -o gpurun_out/prof_${op}_$R -f python scripts/run_op.py $op 3 > gpurun_out/ncu_$op.log 2>&1
   echo "ncu $op exit $?" >> gpurun_out/summary.log

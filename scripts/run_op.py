@@ -58,6 +58,8 @@ def main():
     for _ in range(reps):
         if what == "fwd":
             pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, gd, W, b, want_p=False)
+        elif what == "fwdp":                  # training-mode forward: P saved for the backward (the bench's roofline entry)
+            pcf_cuda.pconv_fused_forward(feats, nei[None], w, add, gd, W, b, want_p=True)
         elif what == "bwd":
             pcf_cuda.pconv_fused_backward(go, None, feats, inv, nei[None], w, add, gd, W, p, (True,) * 6)
         elif what == "knn":
