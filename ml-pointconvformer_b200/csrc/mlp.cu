@@ -661,6 +661,33 @@ __global__ void mlp_weight_finalize_kernel(const float *__restrict__ partial, in
     else if (db) db[o] = (float)s;
 }
 
+// fused-backward finalize: dW / db from the weight partials AND the lower layer's BatchNorm-backward sums from theirs,
+// one launch (warp per output element, fixed order, double accumulation)
+__global__ void mlp_fused_finalize_kernel(const float *__restrict__ w_partial, const float *__restrict__ p_partial, int nblocks,
+                                          int cout, int cin, float *__restrict__ dW, float *__restrict__ db,
+                                          float *__restrict__ prev_sums)
+{
+    const int n_w = cout * (cin + 1), n_p = p_partial ? 2 * cin : 0;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_w + n_p) return;
+    const bool is_w = i < n_w;
+    const float *src = is_w ? w_partial + i : p_partial + (i - n_w);
+    const int stride = is_w ? n_w : n_p;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += (double)src[(size_t)b * stride];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
+    if (lane != 0) return;
+    if (is_w) {
+        const int o = i / (cin + 1), k = i - o * (cin + 1);
+        if (k < cin) { if (dW) dW[o * cin + k] = (float)s; }
+        else if (db) db[o] = (float)s;
+    } else {
+        prev_sums[i - n_w] = (float)s;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 static inline int cmax_of(int c) { return c <= 16 ? 16 : (c <= 32 ? 32 : 64); }
 constexpr int ML_RPT = 8;          // rows per thread in the streaming passes
@@ -806,12 +833,10 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
         ML_FUSED_CASE(16, 16) ML_FUSED_CASE(16, 32)
 #undef ML_FUSED_CASE
         if ((rc = check_launch("mlp_bwd_fused_kernel"))) return rc;
-        if (prev_sums) {
-            sum_partials_kernel<<<ceil_div(2 * cin * 32, 128), 128, 0, st>>>(p_part, blocks, 2 * cin, prev_sums);
-            if ((rc = check_launch("sum_partials_kernel"))) return rc;
-        }
-        mlp_weight_finalize_kernel<<<ceil_div(cout * (cin + 1) * 32, 256), 256, 0, st>>>(w_part, blocks, cout, cin, dW, db);
-        return check_launch("mlp_weight_finalize_kernel");
+        const int n_fin = cout * (cin + 1) + (prev_sums ? 2 * cin : 0);
+        mlp_fused_finalize_kernel<<<ceil_div(n_fin * 32, 256), 256, 0, st>>>(w_part, prev_sums ? p_part : nullptr, blocks, cout, cin,
+                                                                            dW, db, prev_sums);
+        return check_launch("mlp_fused_finalize_kernel");
     }
     if (dA_prev) {
         const int blocks = mlp_blocks(E);

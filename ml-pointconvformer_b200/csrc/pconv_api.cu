@@ -31,6 +31,10 @@ size_t pconv_forward_ws_workspace(const pcfb_pconv_shape *s);
 int pconv_forward_ws(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
                      const float *additional, const float *guidance, const float *lin_w, const float *lin_b,
                      float *out_y, float *out_p, void *workspace, size_t workspace_bytes, cudaStream_t st);
+// pconv_small.cu (P for small outputs, one thread per (point, channel, 4 weights))
+bool pconv_p_small_supported(const pcfb_pconv_shape *s, const float *weights, const float *P);
+int pconv_p_small(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
+                  const float *additional, const float *guidance, float *P, cudaStream_t st);
 // pconv_mid1.cu (C_mid == 1: weighted neighbour sum + tensor-core Linear)
 bool pconv_mid1_supported(const pcfb_pconv_shape *s);
 int pconv_mid1_forward_p(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
@@ -132,7 +136,9 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
         PCFB_REQUIRE(workspace && workspace_bytes >= p_bytes + nt_bytes, "pcfb_pconv_forward: workspace too small");
         float *P = out_p ? out_p : static_cast<float *>(workspace);
         int rc;
-        if ((rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, P, st))) return rc;
+        if (s->n_out <= 16384 && pconv_p_small_supported(s, weights, P)) rc = pconv_p_small(s, feats, nei, weights, additional, guidance, P, st);
+        else rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, P, st);
+        if (rc) return rc;
         return pcfb_gemm_nt(P, KK, lin_w, KK, 0, lin_b, out_y, s->C_out, s->n_out, s->C_out, KK, 0,
                             static_cast<char *>(workspace) + p_bytes, nt_bytes, stream);
     }
