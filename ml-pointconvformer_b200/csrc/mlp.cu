@@ -481,11 +481,13 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
     constexpr int DS = COUT + 4, AS = CIN + 4;
     constexpr int NPB = (COUT / 4) * (CIN / 4);
     constexpr int NS = ML_THREADS / NPB;
+    constexpr int KH = CIN / 2;                                 // input channels per thread in the input-gradient phase
     static_assert(NPB <= ML_THREADS && ML_THREADS % NPB == 0, "bad tiling");
     __shared__ __align__(16) float dy_s[MW_TILE * DS];
-    __shared__ __align__(16) float a_s[MW_TILE * AS];
+    __shared__ __align__(16) float a_s[MW_TILE * AS];           // activated input (operand of dW)
+    __shared__ __align__(16) float x_s[MW_TILE * AS];           // raw stored input (BatchNorm-backward sums of the layer below)
     __shared__ __align__(16) float Wt_s[CIN * COUT];            // transposed: [k][o]
-    __shared__ float red[ML_WARPS / 2][2 * CIN];
+    __shared__ float red[ML_WARPS][2 * KH];
     const int t = threadIdx.x;
     for (int i = t; i < CIN * COUT; i += ML_THREADS) {
         const int k = i / COUT, o = i - k * COUT;
@@ -493,10 +495,11 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
     }
     const int pb = t % NPB, slice = t / NPB;
     const int o4 = (pb / (CIN / 4)) * 4, k4 = (pb % (CIN / 4)) * 4;
+    const int r_in = t & (MW_TILE - 1), kh0 = (t >> 7) * KH;    // input-gradient phase: row of the tile, first input channel
     const bool vec_d = ((ldd & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)dA % 16 == 0);
     const bool vec_y = ((ldy & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
     const bool vec_x = ((ldx & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)x_prev % 16 == 0);
-    const bool vec_p = ((ldp & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)dA_prev % 16 == 0);
+    const bool vec_p = ((ldp & 3) == 0) && ((uintptr_t)dA_prev % 16 == 0) && (KH % 4 == 0) && cin == CIN;
     const float inv_count = ctx_inv_count(B);
     const bool prev_bn = prev_partial != nullptr;
     float acc[4][4], accb[4];
@@ -504,13 +507,12 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
     for (int i = 0; i < 4; ++i) { accb[i] = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f; }
-    float s1[CIN], s2[CIN];
+    float s1[KH], s2[KH];
 #pragma unroll
-    for (int k = 0; k < CIN; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
+    for (int k = 0; k < KH; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
     const int64_t n_tiles = (E + MW_TILE - 1) / MW_TILE;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * MW_TILE + (t & (MW_TILE - 1));
-        float xr[CIN];                                          // raw input row (threads 128-255)
+        const int64_t row = tile * MW_TILE + r_in;
         __syncthreads();                                        // previous tile consumed (and Wt_s written, first time)
         if (t < MW_TILE) {
             float d[COUT], yv[COUT];
@@ -531,11 +533,10 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
             for (int o = 0; o < COUT; o += 4)
                 *reinterpret_cast<float4 *>(&dy_s[t * DS + o]) = make_float4(d[o], d[o + 1], d[o + 2], d[o + 3]);
         } else {
-            const int r = t - MW_TILE;
+            float xr[CIN], a[CIN];
 #pragma unroll
             for (int k = 0; k < CIN; ++k) xr[k] = 0.f;
             if (row < E) load_row<CIN>(x_prev, ldx, row, cin, vec_x, xr);
-            float a[CIN];
 #pragma unroll
             for (int k = 0; k < CIN; ++k) {
                 float v = 0.f;
@@ -546,38 +547,48 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
                 a[k] = v;
             }
 #pragma unroll
-            for (int k = 0; k < CIN; k += 4)
-                *reinterpret_cast<float4 *>(&a_s[r * AS + k]) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+            for (int k = 0; k < CIN; k += 4) {
+                *reinterpret_cast<float4 *>(&a_s[r_in * AS + k]) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+                *reinterpret_cast<float4 *>(&x_s[r_in * AS + k]) = make_float4(xr[k], xr[k + 1], xr[k + 2], xr[k + 3]);
+            }
         }
         __syncthreads();
-        if (t >= MW_TILE && row < E) {                          // input gradient of this row (+ sums of the layer below)
-            const int r = t - MW_TILE;
+        if (row < E) {                                          // input gradient: every thread does KH channels of one row
             float d[COUT];
 #pragma unroll
             for (int o = 0; o < COUT; o += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(&dy_s[r * DS + o]);
+                const float4 v = *reinterpret_cast<const float4 *>(&dy_s[r_in * DS + o]);
                 d[o] = v.x; d[o + 1] = v.y; d[o + 2] = v.z; d[o + 3] = v.w;
             }
-            float g[CIN];
+            float g[KH];
 #pragma unroll
-            for (int k = 0; k < CIN; ++k) {
+            for (int k = 0; k < KH; ++k) {
                 float v = 0.f;
 #pragma unroll
                 for (int o = 0; o < COUT; o += 4) {
-                    const float4 w = *reinterpret_cast<const float4 *>(&Wt_s[k * COUT + o]);
+                    const float4 w = *reinterpret_cast<const float4 *>(&Wt_s[(kh0 + k) * COUT + o]);
                     v = fmaf(d[o], w.x, v); v = fmaf(d[o + 1], w.y, v); v = fmaf(d[o + 2], w.z, v); v = fmaf(d[o + 3], w.w, v);
                 }
                 g[k] = v;
             }
-            store_row<CIN>(dA_prev, ldp, row, cin, vec_p, g);
+            if (vec_p) {
+#pragma unroll
+                for (int k = 0; k < KH; k += 4)
+                    *reinterpret_cast<float4 *>(dA_prev + (size_t)row * ldp + kh0 + k) = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KH; ++k) if (kh0 + k < cin) dA_prev[(size_t)row * ldp + kh0 + k] = g[k];
+            }
             if (prev_bn) {
 #pragma unroll
-                for (int k = 0; k < CIN; ++k) {
-                    if (k < cin) {
-                        const float z = fmaf(xr[k], Bp.scale[k], Bp.shift[k]);
+                for (int k = 0; k < KH; ++k) {
+                    const int kk = kh0 + k;
+                    if (kk < cin) {
+                        const float xv = x_s[r_in * AS + kk];
+                        const float z = fmaf(xv, Bp.scale[kk], Bp.shift[kk]);
                         const float av = act_fwd(z, Bp.act);
                         const float dz = g[k] * act_bwd(z, av, Bp.act);
-                        const float xhat = (xr[k] - Bp.mean[k]) * Bp.invstd[k];
+                        const float xhat = (xv - Bp.mean[kk]) * Bp.invstd[kk];
                         s1[k] += dz; s2[k] = fmaf(dz, xhat, s2[k]);
                     }
                 }
@@ -596,24 +607,23 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
             }
         }
     }
-    // ---- BatchNorm-backward sums of the layer below: warps 4-7 hold them ----
+    // ---- BatchNorm-backward sums of the layer below: warps 0-3 hold channels [0, KH), warps 4-7 hold [KH, CIN) ----
     if (prev_bn) {
         const int lane = t & 31, warp = t >> 5;
-        if (warp >= ML_WARPS / 2) {
 #pragma unroll
-            for (int k = 0; k < CIN; ++k) {
-                float a1 = s1[k], a2 = s2[k];
+        for (int k = 0; k < KH; ++k) {
+            float a1 = s1[k], a2 = s2[k];
 #pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, sft); a2 += __shfl_xor_sync(0xffffffffu, a2, sft); }
-                if (lane == 0) { red[warp - ML_WARPS / 2][k] = a1; red[warp - ML_WARPS / 2][CIN + k] = a2; }
-            }
+            for (int sft = 16; sft > 0; sft >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, sft); a2 += __shfl_xor_sync(0xffffffffu, a2, sft); }
+            if (lane == 0) { red[warp][k] = a1; red[warp][KH + k] = a2; }
         }
         __syncthreads();
         for (int i = t; i < 2 * CIN; i += ML_THREADS) {
+            const int which = i / CIN, k = i - which * CIN;
+            const int half = k / KH, kl = k - half * KH;
             float v = 0.f;
 #pragma unroll
-            for (int w = 0; w < ML_WARPS / 2; ++w) v += red[w][i];
-            const int which = i / CIN, k = i - which * CIN;
+            for (int w = 0; w < ML_WARPS / 2; ++w) v += red[half * (ML_WARPS / 2) + w][which * KH + kl];
             if (k < cin) prev_partial[((size_t)blockIdx.x * 2 + which) * cin + k] = v;
         }
     }
