@@ -153,8 +153,8 @@ def run_ours(args):
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     model.train()
     use_graph = not args.no_graph
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=cfgd["adamw_decay"], fused=True, capturable=use_graph)
-    params = [p for p in model.parameters()]
+    flat = sharding.FlatParameters(model)                              # one buffer: optimizer / clip / all-reduce see one tensor
+    opt = torch.optim.AdamW([flat.flat], lr=1e-3, weight_decay=cfgd["adamw_decay"], fused=True, capturable=use_graph)
 
     host = host_pyramid(1 + rank, args.points, cfgd["grid_size"], args.scenes)
     L = cfgd["num_level"]
@@ -180,11 +180,9 @@ def run_ours(args):
         logits = model(col.unsqueeze(0), pcs, es, ef, ep, nrms, inv_s, inv_f, inv_p)
         loss = torch.nn.functional.cross_entropy(logits[0], lab, ignore_index=cfgd["ignore_label"],
                                                  label_smoothing=cfgd["label_smoothing"])
-        opt.zero_grad(set_to_none=True)
         loss.backward()
-        if world > 1:
-            sharding.allreduce_gradients(params, world)
-        torch.nn.utils.clip_grad_norm_(params, 10.0)
+        flat.gather_grads(world)                                       # flat gradient (+ the DDP all-reduce, mean over ranks)
+        torch.nn.utils.clip_grad_norm_([flat.flat], 10.0)
         opt.step()
         return loss
 

@@ -33,3 +33,39 @@ def allreduce_gradients(params, world_size=None, group=None):
         n = p.grad.numel()
         p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
+
+
+class FlatParameters:
+    """All trainable parameters of a module as views into ONE contiguous buffer, so that the optimizer, the gradient
+    clipping and the DDP all-reduce each touch a single tensor (PCF_Normal has 382 parameter tensors: the per-tensor
+    optimizer bookkeeping alone was ~3 ms of a 48 ms training step).  The module keeps using its own parameter
+    objects; only their storage moves.  Call after any module surgery (e.g. SyncBatchNorm conversion)."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        if not self.params:
+            raise ValueError("module has no trainable parameters")
+        ref = self.params[0]
+        total = sum(p.numel() for p in self.params)
+        flat = torch.empty(total, device=ref.device, dtype=ref.dtype)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                flat[off:off + n].copy_(p.data.reshape(-1))
+                p.data = flat[off:off + n].view(p.shape)
+                off += n
+        self.flat = torch.nn.Parameter(flat)
+
+    def gather_grads(self, world_size=1, group=None):
+        """Concatenate the per-parameter gradients into the flat gradient (mean over ranks when world_size > 1), attach
+        it to the flat parameter and drop the per-parameter ones."""
+        pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
+        g = torch.cat(pieces)
+        if world_size > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+            g.div_(world_size)
+        self.flat.grad = g
+        for p in self.params:
+            p.grad = None
+        return g

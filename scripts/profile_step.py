@@ -16,7 +16,9 @@ def main():
     dev = torch.device("cuda", 0)
     cfgd = configs.CONFIG_PCF_OPT_10CM
     model = MA.PointConvFormer_Segmentation(configs.make_cfg(cfgd)).to(dev).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True)
+    from pcf_b200 import sharding
+    flat = sharding.FlatParameters(model)
+    opt = torch.optim.AdamW([flat.flat], lr=1e-3, weight_decay=0.05, fused=True)
     host = bench.host_pyramid(1, args.points, cfgd["grid_size"], args.scenes)
     pts = [torch.from_numpy(p).to(dev) for p in host["points"]]
     nrm = [torch.from_numpy(p).to(dev) for p in host["normals"]]
@@ -30,11 +32,11 @@ def main():
         with torch.profiler.record_function("forward"):
             logits = model(col.unsqueeze(0), pcs, es, ef, ep, nrms, *inv)
             loss = torch.nn.functional.cross_entropy(logits[0], lab, label_smoothing=0.2)
-        opt.zero_grad(set_to_none=True)
         with torch.profiler.record_function("backward"):
             loss.backward()
         with torch.profiler.record_function("optimizer"):
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+            flat.gather_grads()
+            torch.nn.utils.clip_grad_norm_([flat.flat], 10.0)
             opt.step()
     for _ in range(2):
         step()
