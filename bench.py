@@ -140,6 +140,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # SyncBatchNorm makes ~450 all-reduces of a few hundred bytes per step: latency, not bandwidth.  The NVLink-SHARP
+        # (NVLS) path costs more per tiny message than the LL ring/tree (measured at N=2: 55.4 -> 53.7 ms/step).
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
         dist.init_process_group("nccl", device_id=dev)
     pcf_cuda.FORWARD_VARIANT = args.variant
     note("process group ready")

@@ -466,11 +466,15 @@ mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__rest
 }
 
 
-// Fused backward of one layer: the weight-gradient pass above plus the input-gradient pass in the same sweep over the
-// rows -- (dA, y, x_prev) are read ONCE instead of twice (the two separate kernels were 9 ms of the 51 ms training step).
-// Tile = 128 rows as in mlp_bwd_weight_kernel; after the tile is staged, threads 128-255 (which hold the raw input row
-// x_prev) also turn their row's dy into dA_prev = dy W, store it, and accumulate the BatchNorm-backward sums of the layer
-// below; then all threads accumulate their 4x4 block of dW.  Same fixed-order reductions, no atomics.
+// Fused backward of one layer: weight gradient + input gradient (+ the BatchNorm-backward sums of the layer below) in
+// ONE sweep over the rows -- (dA, y, x_prev) are read once instead of twice.  Every WARP is autonomous: it owns 16 rows
+// per iteration, stages them in its private slice of shared memory and only ever executes __syncwarp in the main loop
+// (the first version staged 128-row tiles per CTA behind two block barriers and sat at the barrier 40% of the time, ncu).
+//   lanes 0-15 : dy[row] from (dA, y) with this layer's BatchNorm/activation backward      -> dy_s
+//   lanes 16-31: stored input row -> x_s (raw) and a_s = act(bn(x))
+//   then every lane: CIN/2 input-gradient channels of one row (+ lower-BN sums), and its 4x4 block of dW over 8 or 16 rows.
+// Block partials are combined once at the end in fixed order (no atomics).
+constexpr int MF_ROWS = 16;
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(ML_THREADS, 2)
 mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restrict__ y, int ldy, int64_t E,
@@ -479,29 +483,33 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
                      float *__restrict__ dA_prev, int ldp, float *__restrict__ prev_partial, float *__restrict__ w_partial)
 {
     constexpr int DS = COUT + 4, AS = CIN + 4;
-    constexpr int NPB = (COUT / 4) * (CIN / 4);
-    constexpr int NS = ML_THREADS / NPB;
-    constexpr int KH = CIN / 2;                                 // input channels per thread in the input-gradient phase
-    static_assert(NPB <= ML_THREADS && ML_THREADS % NPB == 0, "bad tiling");
-    __shared__ __align__(16) float dy_s[MW_TILE * DS];
-    __shared__ __align__(16) float a_s[MW_TILE * AS];           // activated input (operand of dW)
-    __shared__ __align__(16) float x_s[MW_TILE * AS];           // raw stored input (BatchNorm-backward sums of the layer below)
+    constexpr int NPB = (COUT / 4) * (CIN / 4);                 // 4x4 blocks of dW: 16 or 32
+    constexpr int RH = 32 / NPB;                                // row halves per block (2 when NPB == 16, else 1)
+    constexpr int RPL = MF_ROWS / RH;                           // rows each lane accumulates per iteration
+    constexpr int KH = CIN / 2;
+    static_assert(NPB == 16 || NPB == 32, "warp tiling needs 16 or 32 blocks");
+    constexpr int SLICE = MF_ROWS * (DS + 2 * AS);              // floats of one warp's staging slice
+    constexpr int STAGE_FLOATS = ML_WARPS * SLICE, RED_FLOATS = ML_WARPS * NPB * 20;
+    __shared__ __align__(16) float stage_s[STAGE_FLOATS > RED_FLOATS ? STAGE_FLOATS : RED_FLOATS];   // staging, then the dW reduction scratch
     __shared__ __align__(16) float Wt_s[CIN * COUT];            // transposed: [k][o]
-    __shared__ float red[ML_WARPS][2 * KH];
-    const int t = threadIdx.x;
+    __shared__ float reds[ML_WARPS][2][2 * KH];
+    float (*redw)[NPB * 20] = reinterpret_cast<float (*)[NPB * 20]>(stage_s);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     for (int i = t; i < CIN * COUT; i += ML_THREADS) {
         const int k = i / COUT, o = i - k * COUT;
         Wt_s[i] = (o < cout && k < cin) ? W[o * cin + k] : 0.f;
     }
-    const int pb = t % NPB, slice = t / NPB;
+    __syncthreads();
+    const int pb = lane % NPB, rh = lane / NPB;
     const int o4 = (pb / (CIN / 4)) * 4, k4 = (pb % (CIN / 4)) * 4;
-    const int r_in = t & (MW_TILE - 1), kh0 = (t >> 7) * KH;    // input-gradient phase: row of the tile, first input channel
+    const int r_in = lane & (MF_ROWS - 1), kh0 = (lane >> 4) * KH;
     const bool vec_d = ((ldd & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)dA % 16 == 0);
     const bool vec_y = ((ldy & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
     const bool vec_x = ((ldx & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)x_prev % 16 == 0);
     const bool vec_p = ((ldp & 3) == 0) && ((uintptr_t)dA_prev % 16 == 0) && (KH % 4 == 0) && cin == CIN;
     const float inv_count = ctx_inv_count(B);
     const bool prev_bn = prev_partial != nullptr;
+    float *dyw = stage_s + warp * SLICE, *aw = dyw + MF_ROWS * DS, *xw = aw + MF_ROWS * AS;
     float acc[4][4], accb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { accb[i] = 0.f;
@@ -510,57 +518,87 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
     float s1[KH], s2[KH];
 #pragma unroll
     for (int k = 0; k < KH; ++k) { s1[k] = 0.f; s2[k] = 0.f; }
-    const int64_t n_tiles = (E + MW_TILE - 1) / MW_TILE;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * MW_TILE + r_in;
-        __syncthreads();                                        // previous tile consumed (and Wt_s written, first time)
-        if (t < MW_TILE) {
-            float d[COUT], yv[COUT];
-            if (row < E) { load_row<COUT>(dA, ldd, row, cout, vec_d, d); load_row<COUT>(y, ldy, row, cout, vec_y, yv); }
+    const int64_t n_groups = (E + MF_ROWS - 1) / MF_ROWS;
+    for (int64_t g = (int64_t)blockIdx.x * ML_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * ML_WARPS) {
+        const int64_t row = g * MF_ROWS + r_in;
+        __syncwarp();                                           // the previous group's reads of the warp's slice are done
+        {   // staging, uniform over the warp: lane (row, half) handles half of the row's output and input channels
+            constexpr int OH = COUT / 2;
+            const int oh0 = (lane >> 4) * OH;
+            float d[OH], yv[OH];
 #pragma unroll
-            for (int o = 0; o < COUT; ++o) {
+            for (int o = 0; o < OH; ++o) { d[o] = 0.f; yv[o] = 0.f; }
+            if (row < E) {
+                if (vec_d && vec_y && cout == COUT) {
+#pragma unroll
+                    for (int o = 0; o < OH; o += 4) {
+                        const float4 dv = __ldg(reinterpret_cast<const float4 *>(dA + (size_t)row * ldd + oh0 + o));
+                        const float4 yy = __ldg(reinterpret_cast<const float4 *>(y + (size_t)row * ldy + oh0 + o));
+                        d[o] = dv.x; d[o + 1] = dv.y; d[o + 2] = dv.z; d[o + 3] = dv.w;
+                        yv[o] = yy.x; yv[o + 1] = yy.y; yv[o + 2] = yy.z; yv[o + 3] = yy.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int o = 0; o < OH; ++o)
+                        if (oh0 + o < cout) { d[o] = __ldg(dA + (size_t)row * ldd + oh0 + o); yv[o] = __ldg(y + (size_t)row * ldy + oh0 + o); }
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < OH; ++o) {
+                const int oo = oh0 + o;
                 float dy = 0.f;
-                if (row < E && o < cout) {
+                if (row < E && oo < cout) {
                     float z = yv[o], xhat = 0.f;
-                    if (B.scale) { z = fmaf(yv[o], B.scale[o], B.shift[o]); xhat = (yv[o] - B.mean[o]) * B.invstd[o]; }
+                    if (B.scale) { z = fmaf(yv[o], B.scale[oo], B.shift[oo]); xhat = (yv[o] - B.mean[oo]) * B.invstd[oo]; }
                     const float av = act_fwd(z, B.act);
                     const float dz = d[o] * act_bwd(z, av, B.act);
-                    dy = B.scale ? B.scale[o] * (dz - B.sums[o] * inv_count - xhat * B.sums[cout + o] * inv_count) : dz;
+                    dy = B.scale ? B.scale[oo] * (dz - B.sums[oo] * inv_count - xhat * B.sums[cout + oo] * inv_count) : dz;
                 }
                 d[o] = dy;
             }
 #pragma unroll
-            for (int o = 0; o < COUT; o += 4)
-                *reinterpret_cast<float4 *>(&dy_s[t * DS + o]) = make_float4(d[o], d[o + 1], d[o + 2], d[o + 3]);
-        } else {
-            float xr[CIN], a[CIN];
+            for (int o = 0; o < OH; o += 4)
+                *reinterpret_cast<float4 *>(&dyw[r_in * DS + oh0 + o]) = make_float4(d[o], d[o + 1], d[o + 2], d[o + 3]);
+            float xr[KH], a[KH];
 #pragma unroll
-            for (int k = 0; k < CIN; ++k) xr[k] = 0.f;
-            if (row < E) load_row<CIN>(x_prev, ldx, row, cin, vec_x, xr);
+            for (int k = 0; k < KH; ++k) xr[k] = 0.f;
+            if (row < E) {
+                if (vec_x && cin == CIN) {
 #pragma unroll
-            for (int k = 0; k < CIN; ++k) {
+                    for (int k = 0; k < KH; k += 4) {
+                        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_prev + (size_t)row * ldx + kh0 + k));
+                        xr[k] = xv.x; xr[k + 1] = xv.y; xr[k + 2] = xv.z; xr[k + 3] = xv.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KH; ++k) if (kh0 + k < cin) xr[k] = __ldg(x_prev + (size_t)row * ldx + kh0 + k);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KH; ++k) {
+                const int kk = kh0 + k;
                 float v = 0.f;
-                if (row < E && k < cin) {
-                    v = Bp.scale ? fmaf(xr[k], Bp.scale[k], Bp.shift[k]) : xr[k];
+                if (row < E && kk < cin) {
+                    v = Bp.scale ? fmaf(xr[k], Bp.scale[kk], Bp.shift[kk]) : xr[k];
                     v = act_fwd(v, Bp.act);
                 }
                 a[k] = v;
             }
 #pragma unroll
-            for (int k = 0; k < CIN; k += 4) {
-                *reinterpret_cast<float4 *>(&a_s[r_in * AS + k]) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
-                *reinterpret_cast<float4 *>(&x_s[r_in * AS + k]) = make_float4(xr[k], xr[k + 1], xr[k + 2], xr[k + 3]);
+            for (int k = 0; k < KH; k += 4) {
+                *reinterpret_cast<float4 *>(&aw[r_in * AS + kh0 + k]) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+                *reinterpret_cast<float4 *>(&xw[r_in * AS + kh0 + k]) = make_float4(xr[k], xr[k + 1], xr[k + 2], xr[k + 3]);
             }
         }
-        __syncthreads();
-        if (row < E) {                                          // input gradient: every thread does KH channels of one row
+        __syncwarp();
+        if (row < E) {                                          // input gradient: KH channels of one row per lane
             float d[COUT];
 #pragma unroll
             for (int o = 0; o < COUT; o += 4) {
-                const float4 v = *reinterpret_cast<const float4 *>(&dy_s[r_in * DS + o]);
+                const float4 v = *reinterpret_cast<const float4 *>(&dyw[r_in * DS + o]);
                 d[o] = v.x; d[o + 1] = v.y; d[o + 2] = v.z; d[o + 3] = v.w;
             }
-            float g[KH];
+            float gk[KH];
 #pragma unroll
             for (int k = 0; k < KH; ++k) {
                 float v = 0.f;
@@ -569,35 +607,36 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
                     const float4 w = *reinterpret_cast<const float4 *>(&Wt_s[(kh0 + k) * COUT + o]);
                     v = fmaf(d[o], w.x, v); v = fmaf(d[o + 1], w.y, v); v = fmaf(d[o + 2], w.z, v); v = fmaf(d[o + 3], w.w, v);
                 }
-                g[k] = v;
+                gk[k] = v;
             }
             if (vec_p) {
 #pragma unroll
                 for (int k = 0; k < KH; k += 4)
-                    *reinterpret_cast<float4 *>(dA_prev + (size_t)row * ldp + kh0 + k) = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
+                    *reinterpret_cast<float4 *>(dA_prev + (size_t)row * ldp + kh0 + k) = make_float4(gk[k], gk[k + 1], gk[k + 2], gk[k + 3]);
             } else {
 #pragma unroll
-                for (int k = 0; k < KH; ++k) if (kh0 + k < cin) dA_prev[(size_t)row * ldp + kh0 + k] = g[k];
+                for (int k = 0; k < KH; ++k) if (kh0 + k < cin) dA_prev[(size_t)row * ldp + kh0 + k] = gk[k];
             }
             if (prev_bn) {
 #pragma unroll
                 for (int k = 0; k < KH; ++k) {
                     const int kk = kh0 + k;
                     if (kk < cin) {
-                        const float xv = x_s[r_in * AS + kk];
+                        const float xv = xw[r_in * AS + kk];
                         const float z = fmaf(xv, Bp.scale[kk], Bp.shift[kk]);
                         const float av = act_fwd(z, Bp.act);
-                        const float dz = g[k] * act_bwd(z, av, Bp.act);
+                        const float dz = gk[k] * act_bwd(z, av, Bp.act);
                         const float xhat = (xv - Bp.mean[kk]) * Bp.invstd[kk];
                         s1[k] += dz; s2[k] = fmaf(dz, xhat, s2[k]);
                     }
                 }
             }
         }
-#pragma unroll 4
-        for (int r = slice; r < MW_TILE; r += NS) {
-            const float4 dv = *reinterpret_cast<const float4 *>(&dy_s[r * DS + o4]);
-            const float4 av = *reinterpret_cast<const float4 *>(&a_s[r * AS + k4]);
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {                      // dW: this lane's 4x4 block over its rows of the group
+            const int r = rh * RPL + rr;
+            const float4 dv = *reinterpret_cast<const float4 *>(&dyw[r * DS + o4]);
+            const float4 av = *reinterpret_cast<const float4 *>(&aw[r * AS + k4]);
             const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, aa[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -607,41 +646,38 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
             }
         }
     }
-    // ---- BatchNorm-backward sums of the layer below: warps 0-3 hold channels [0, KH), warps 4-7 hold [KH, CIN) ----
-    if (prev_bn) {
-        const int lane = t & 31, warp = t >> 5;
+    // ---- block partials, fixed order: lanes -> warps ----
+    __syncthreads();                                            // every warp is out of its staging slice: reuse it as scratch
+    if (RH == 2) {                                              // the two row halves of a block sit 16 lanes apart
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            accb[i] += __shfl_xor_sync(0xffffffffu, accb[i], 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+        }
+    }
+    if (lane < NPB) {
+        float *mine = &redw[warp][pb * 20];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { mine[16 + i] = accb[i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mine[i * 4 + j] = acc[i][j]; }
+    }
+    if (prev_bn) {                                              // lanes 0-15 hold channels [0, KH), lanes 16-31 [KH, CIN)
 #pragma unroll
         for (int k = 0; k < KH; ++k) {
             float a1 = s1[k], a2 = s2[k];
 #pragma unroll
-            for (int sft = 16; sft > 0; sft >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, sft); a2 += __shfl_xor_sync(0xffffffffu, a2, sft); }
-            if (lane == 0) { red[warp][k] = a1; red[warp][KH + k] = a2; }
-        }
-        __syncthreads();
-        for (int i = t; i < 2 * CIN; i += ML_THREADS) {
-            const int which = i / CIN, k = i - which * CIN;
-            const int half = k / KH, kl = k - half * KH;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < ML_WARPS / 2; ++w) v += red[half * (ML_WARPS / 2) + w][which * KH + kl];
-            if (k < cin) prev_partial[((size_t)blockIdx.x * 2 + which) * cin + k] = v;
+            for (int sft = 8; sft > 0; sft >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, sft); a2 += __shfl_xor_sync(0xffffffffu, a2, sft); }
+            if ((lane & 15) == 0) { reds[warp][lane >> 4][k] = a1; reds[warp][lane >> 4][KH + k] = a2; }
         }
     }
-    // ---- combine the NS row slices of dW in fixed order (dy_s / a_s reused as scratch) ----
-    __syncthreads();
-    float *redw = dy_s;
-    constexpr int RED_FLOATS = NS * NPB * 20;
-    static_assert(RED_FLOATS <= MW_TILE * DS + MW_TILE * AS, "reduction scratch does not fit");
-    float *mine = redw + ((size_t)slice * NPB + pb) * 20;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { mine[16 + i] = accb[i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mine[i * 4 + j] = acc[i][j]; }
     __syncthreads();
     for (int e = t; e < NPB * 20; e += ML_THREADS) {
         const int b2 = e / 20, idx = e - b2 * 20;
         float v = 0.f;
-        for (int sl = 0; sl < NS; ++sl) v += redw[((size_t)sl * NPB + b2) * 20 + idx];
+#pragma unroll
+        for (int w = 0; w < ML_WARPS; ++w) v += redw[w][e];
         const int bo = (b2 / (CIN / 4)) * 4, bk = (b2 % (CIN / 4)) * 4;
         if (idx < 16) {
             const int o = bo + idx / 4, k = bk + idx % 4;
@@ -649,6 +685,16 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
         } else if (bk == 0) {
             const int o = bo + (idx - 16);
             if (o < cout) w_partial[((size_t)blockIdx.x * cout + o) * (cin + 1) + cin] = v;
+        }
+    }
+    if (prev_bn) {
+        for (int i = t; i < 2 * CIN; i += ML_THREADS) {
+            const int which = i / CIN, k = i - which * CIN;
+            const int half = k / KH, kl = k - half * KH;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < ML_WARPS; ++w) v += reds[w][half][which * KH + kl];
+            if (k < cin) prev_partial[((size_t)blockIdx.x * 2 + which) * cin + k] = v;
         }
     }
 }

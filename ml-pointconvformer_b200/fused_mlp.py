@@ -140,7 +140,7 @@ class _ChainFunction(torch.autograd.Function):
             want_prev = l > 0 or need_x_grad
             dA_prev = torch.empty(E, cin, device=dev, dtype=F32) if want_prev else None
             prev_has_bn = l > 0 and spec[l - 1]["has_bn"]
-            fuse_prev = prev_has_bn and train_bn and cin <= 32 and not (spec[l - 1]["sync"] and ctx.world > 1)
+            fuse_prev = prev_has_bn and train_bn and cin <= 32
             prev_sums = torch.empty(2 * cin, device=dev, dtype=F32) if fuse_prev else None
             dW = torch.empty_like(W)
             db = torch.empty(cout, device=dev, dtype=F32) if b is not None else None
@@ -160,10 +160,12 @@ class _ChainFunction(torch.autograd.Function):
                 # because the affine is constant w.r.t. the batch -- dgamma/dbeta then come from the same sums
                 C = cout
                 if train_bn:
-                    grads[4 * l + 2] = sums[C:].clone()
-                    grads[4 * l + 3] = sums[:C].clone()
+                    grads[4 * l + 2] = sums[C:]          # views: AccumulateGrad takes them as they are (no copy kernels)
+                    grads[4 * l + 3] = sums[:C]
             if l > 0:
                 if prev_has_bn:
+                    if fuse_prev and spec[l - 1]["sync"] and ctx.world > 1:
+                        dist.all_reduce(prev_sums)                 # SyncBatchNorm: the sums are over the global batch
                     sums = prev_sums if fuse_prev else stats(l - 1, dA_prev)
                 else:
                     sums = None

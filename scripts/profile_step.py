@@ -7,6 +7,7 @@ import bench
 from torch.profiler import profile, ProfilerActivity
 
 def main():
+    stacks = "stacks" in os.environ.get("PROFILE_STEP_FLAGS", "")
     sys.argv = ["bench.py", "--steps", "1", "--warmup", "2", "--no-cpu-baseline"] + sys.argv[1:]
     args = bench.parse()
     # reuse bench internals: run_ours builds everything; instead replicate the step here
@@ -41,13 +42,20 @@ def main():
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=stacks) as prof:
         step()
         torch.cuda.synchronize()
     out = os.path.join(ROOT, "gpurun_out", "prof_table.txt")
     with open(out, "w") as f:
         f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
     print(open(out).read()[:6000])
+    if stacks:                                      # who launches the small elementwise kernels?
+        with open(os.path.join(ROOT, "gpurun_out", "prof_stacks.txt"), "w") as f:
+            for ev in sorted(prof.key_averages(group_by_stack_n=8), key=lambda e: -e.count):
+                if ev.key in ("aten::fill_", "aten::zero_", "aten::copy_", "aten::add_", "aten::clone", "aten::contiguous", "aten::cat", "aten::mul", "aten::add") and ev.count >= 8:
+                    f.write("%s count=%d cuda=%.1fus\n" % (ev.key, ev.count, ev.device_time_total))
+                    for fr in ev.stack[:8]:
+                        f.write("    %s\n" % fr)
 
 if __name__ == "__main__":
     main()
