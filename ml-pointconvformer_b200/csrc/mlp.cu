@@ -476,7 +476,7 @@ mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__rest
 // Block partials are combined once at the end in fixed order (no atomics).
 constexpr int MF_ROWS = 16;
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(ML_THREADS, 2)
+__global__ void __launch_bounds__(ML_THREADS, 3)
 mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restrict__ y, int ldy, int64_t E,
                      const float *__restrict__ W, int cin, int cout, MlpBnCtx B,
                      const float *__restrict__ x_prev, int ldx, MlpBnCtx Bp,
