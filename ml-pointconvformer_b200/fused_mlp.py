@@ -114,15 +114,19 @@ class _ChainFunction(torch.autograd.Function):
             sums = torch.empty(2 * C, device=dev, dtype=F32)
             if not train_bn:
                 sums.zero_()
-                return sums
+                return sums, sums
             ws = workspace(lib().pcfb_mlp_workspace(E, C, C), dev)
             check(lib().pcfb_mlp_backward_stats(ptr(dA_l), dA_l.stride(0), ptr(ys[l]), C, E, C, ptr(scale), ptr(shift), ptr(mean),
                                                 ptr(invstd), spec[l]["act"], ptr(sums), ptr(ws), ws.numel(), stream_ptr()), "mlp_backward_stats")
+            local = sums
             if spec[l]["sync"] and ctx.world > 1:
+                # dx needs the sums over the GLOBAL batch; dgamma / dbeta stay LOCAL (the DDP gradient all-reduce adds the
+                # ranks up, exactly as torch.nn.SyncBatchNorm does)
+                local = sums.clone()
                 dist.all_reduce(sums)
-            return sums
+            return sums, local
 
-        sums = stats(L - 1, dA) if spec[L - 1]["has_bn"] else None
+        sums, sums_local = stats(L - 1, dA) if spec[L - 1]["has_bn"] else (None, None)
         need_x_grad = ctx.needs_input_grad[0]
         for l in range(L - 1, -1, -1):
             W, b, gamma, beta = params[4 * l: 4 * l + 4]
@@ -160,15 +164,19 @@ class _ChainFunction(torch.autograd.Function):
                 # because the affine is constant w.r.t. the batch -- dgamma/dbeta then come from the same sums
                 C = cout
                 if train_bn:
-                    grads[4 * l + 2] = sums[C:]          # views: AccumulateGrad takes them as they are (no copy kernels)
-                    grads[4 * l + 3] = sums[:C]
+                    grads[4 * l + 2] = sums_local[C:]    # views: AccumulateGrad takes them as they are (no copy kernels)
+                    grads[4 * l + 3] = sums_local[:C]
             if l > 0:
                 if prev_has_bn:
-                    if fuse_prev and spec[l - 1]["sync"] and ctx.world > 1:
-                        dist.all_reduce(prev_sums)                 # SyncBatchNorm: the sums are over the global batch
-                    sums = prev_sums if fuse_prev else stats(l - 1, dA_prev)
+                    if fuse_prev:
+                        sums = sums_local = prev_sums
+                        if spec[l - 1]["sync"] and ctx.world > 1:
+                            sums_local = prev_sums.clone()
+                            dist.all_reduce(prev_sums)             # SyncBatchNorm: dx uses the sums over the global batch
+                    else:
+                        sums, sums_local = stats(l - 1, dA_prev)
                 else:
-                    sums = None
+                    sums = sums_local = None
                 dA = dA_prev
         gx = dA_prev if need_x_grad else None
         return (gx, None, None, None) + tuple(grads)

@@ -1,0 +1,89 @@
+"""Two-GPU parity of the SyncBatchNorm path of the fused MLP chain: two ranks with different row counts must produce
+the outputs / gradients of ONE process that sees the concatenated batch (torch float64 reference).  Needs >= 2 GPUs
+(skipped otherwise; the single-GPU driver box skips it, `scripts/gpu_n2.sh`-style 2-GPU runs execute it)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import pcf_b200  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _build(dtype, device, sync):
+    torch.manual_seed(5)
+    lins = [torch.nn.Linear(12, 16), torch.nn.Linear(16, 16), torch.nn.Linear(16, 32)]
+    bns = [torch.nn.BatchNorm1d(16), torch.nn.BatchNorm1d(16), torch.nn.BatchNorm1d(32)]
+    for bn in bns:
+        torch.nn.init.uniform_(bn.weight, 0.5, 1.5)
+        torch.nn.init.uniform_(bn.bias, -0.5, 0.5)
+    mods = torch.nn.ModuleList(lins + bns).to(device=device, dtype=dtype)
+    if sync:
+        mods = torch.nn.SyncBatchNorm.convert_sync_batchnorm(mods)
+    return list(mods[:3]), list(mods[3:])
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from pcf_b200 import fused_mlp
+    g = torch.Generator().manual_seed(11)
+    rows = [3000, 1777]
+    xs = [torch.randn(n, 12, generator=g) for n in rows]
+    gos = [torch.randn(n, 32, generator=g) for n in rows]
+    lins, bns = _build(torch.float32, dev, sync=True)
+    x = xs[rank].to(dev).requires_grad_(True)
+    y = fused_mlp.mlp_chain(x, [(lins[i], bns[i], fused_mlp.ACT_RELU) for i in range(3)], training=True)
+    (y * gos[rank].to(dev)).sum().backward()
+    out = {"y": y.detach().cpu(), "gx": x.grad.cpu(), "gw0": lins[0].weight.grad.cpu(), "gw2": lins[2].weight.grad.cpu(),
+           "gg1": bns[1].weight.grad.cpu(), "gb2": bns[2].bias.grad.cpu()}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        # single-process float64 reference over the concatenated batch
+        rl, rb = _build(torch.float64, dev, sync=False)
+        X = torch.cat(xs).to(dev, torch.float64).requires_grad_(True)
+        h = X
+        for i in range(3):
+            h = torch.relu(rb[i](rl[i](h)))
+        (h * torch.cat(gos).to(dev, torch.float64)).sum().backward()
+        ref = {"y": h.detach().cpu(), "gx": X.grad.cpu(), "gw0": rl[0].weight.grad.cpu(), "gw2": rl[2].weight.grad.cpu(),
+               "gg1": rb[1].weight.grad.cpu(), "gb2": rb[2].bias.grad.cpu()}
+        errs = {}
+        got_y = torch.cat([o["y"] for o in gathered]).double()
+        got_gx = torch.cat([o["gx"] for o in gathered]).double()
+        errs["y"] = float((got_y - ref["y"]).abs().max() / ref["y"].abs().max())
+        errs["gx"] = float((got_gx - ref["gx"]).abs().max() / ref["gx"].abs().max())
+        for k in ("gw0", "gw2", "gg1", "gb2"):                     # parameter gradients: sum over ranks = global gradient
+            tot = sum(o[k].double() for o in gathered)
+            errs[k] = float((tot - ref[k]).abs().max() / ref[k].abs().max())
+        ret["errs"] = errs
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_fused_chain_syncbn_two_ranks_match_single_process():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    errs = dict(ret["errs"])
+    print(errs)
+    assert errs["y"] < 2e-5 and errs["gx"] < 2e-4, errs
+    for k in ("gw0", "gw2", "gg1", "gb2"):
+        assert errs[k] < 1e-3, errs                                # fp32 sums behind three train-mode BatchNorms
