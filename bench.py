@@ -39,7 +39,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=100000, help="level-0 points per scene")
     ap.add_argument("--scenes", type=int, default=1, help="scenes per GPU (packed)")
-    ap.add_argument("--cpu-points", type=int, default=6000, help="level-0 points of the bounded CPU sample")
+    ap.add_argument("--cpu-points", type=int, default=0,
+                    help="level-0 points of the bounded CPU sample (0 = the largest of 100k/50k/25k/12k/6k that fits --cpu-budget)")
+    ap.add_argument("--cpu-budget", type=float, default=0.0,
+                    help="seconds of CPU work the CPU arm may take in total (0 = 30 s for the cpu_baseline leg, 150 s for --impl reference)")
+    ap.add_argument("--knn-sweep", action="store_true",
+                    help="only run the kNN sweep of BASELINE.json configs[4] (N x K grid of self-kNN, knn_post_benchmark shapes) and print it")
     ap.add_argument("--no-sync-bn", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=0, help="fused forward variant (0 auto, 1 SIMT, 2 tcgen05 pipelined, 3 tcgen05 simple, 4 tcgen05 warp-specialised)")
@@ -425,6 +430,49 @@ def kernel_rooflines(dev, host, cfgd, args):
                   "knn_bruteforce_mpts_per_s": res["knn_self_level0"]["Mqueries_per_s"]}
 
 
+def knn_sweep(args):
+    """BASELINE.json configs[4]: self-kNN over N in {25k..250k} x K in {16, 32, 64} (the shapes of the reference's
+    kNN benchmark, test_kernels.py:2425-2429) on `randn` clouds (seed 42) and on synthetic room surfaces (10 cm voxels);
+    exact grid search (build + query) for every cell, brute force for K = 16.  One GPU; scenes shard over ranks with no
+    collective, so N GPUs run N of these side by side."""
+    import pcf_b200  # noqa: F401
+    from pcf_b200 import pcf_cuda, synthetic
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def time_op(fn, reps=3):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts))
+
+    rows = []
+    for n_target in (25000, 50000, 100000, 200000, 250000):
+        clouds = {"randn": torch.randn(n_target, 3, generator=torch.Generator().manual_seed(42)).to(dev),
+                  "room": torch.from_numpy(synthetic.make_scene(7, n_target)[0]).to(dev)}
+        for kind, xyz in clouds.items():
+            n = xyz.shape[0]
+            for K in (16, 32, 64):
+                hint = 0.25 if kind == "room" else 0.0
+                ms = time_op(lambda: pcf_cuda.KnnGrid(xyz, [n], hint).query(xyz, [n], K))
+                row = {"cloud": kind, "N": int(n), "K": K, "grid_ms": ms, "grid_Mpts_per_s": n / ms / 1e3}
+                if K == 16:
+                    msb = time_op(lambda: pcf_cuda.knn_packed(xyz, [n], xyz, [n], K), reps=2)
+                    same = bool(torch.equal(pcf_cuda.KnnGrid(xyz, [n], hint).query(xyz, [n], K), pcf_cuda.knn_packed(xyz, [n], xyz, [n], K)))
+                    row.update(brute_ms=msb, brute_Mpts_per_s=n / msb / 1e3, brute_Gpairs_per_s=float(n) * n / msb / 1e6,
+                               grid_equals_brute=same)
+                rows.append(row)
+    return {"metric": "knn_self_Mpts_per_s", "unit": "Mpts/s", "n_gpus": 1, "data": "synthetic", "dtype": "f32",
+            "config": {"workload": "self-kNN sweep, N x K grid, exact (ties by index), int64 output"}, "rows": rows}
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference's PyTorch path + C kNN, on a bounded sample
 # ---------------------------------------------------------------------------------------------------
@@ -467,7 +515,29 @@ def cpu_step_factory(args):
     return step, n0, cores, sample
 
 
-def cpu_baseline(args, steps, warmup):
+def choose_cpu_points(args, n_steps, budget_s):
+    """Largest sample of the ladder 100k..6k level-0 points whose `n_steps` steps fit `budget_s` seconds on this host.
+    Cost model: one calibration step at 6k points gives the per-point cost of the layers (linear in N); the brute-force
+    kNN of the port is quadratic: 13 edge sets ~ 1.6 N0^2 pair evaluations, rate measured on a 20k-point self query."""
+    from oracle import knn as OK
+    import copy
+    a6 = copy.copy(args)
+    a6.cpu_points = 6000
+    step, n6, _, _ = cpu_step_factory(a6)
+    t0 = time.perf_counter(); step(); t_lin = (time.perf_counter() - t0) / n6
+    pts = np.random.default_rng(0).random((20000, 3)).astype(np.float32)
+    t0 = time.perf_counter(); OK.compute_knn(pts, pts, 16, use_c=True); pair_s = (time.perf_counter() - t0) / 4e8
+    for n in (100000, 50000, 25000, 12000):
+        if n_steps * (t_lin * n + 1.6 * pair_s * n * n) <= budget_s:
+            return n
+    return 6000
+
+
+def cpu_baseline(args, steps, warmup, budget_s=30.0):
+    if args.cpu_points <= 0:
+        import copy
+        args = copy.copy(args)
+        args.cpu_points = choose_cpu_points(args, steps + warmup, args.cpu_budget or budget_s)
     step, n0, cores, sample = cpu_step_factory(args)
     for _ in range(warmup):
         step()
@@ -483,7 +553,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
-    base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1))
+    base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1), budget_s=150.0)
     return {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": base["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -496,7 +566,10 @@ def run_reference(args):
 
 def main():
     args = parse()
-    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if args.knn_sweep:
+        out = knn_sweep(args)
+    else:
+        out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
         print(json.dumps(out))
 

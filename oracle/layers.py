@@ -235,8 +235,8 @@ def backbone(params, prefix, cfg, features, pcs, e_self, e_fwd, norms, training=
 
 
 def segmentation_model(params, cfg, features, pcs, e_self, e_fwd, e_prop, norms, training=True):
-    """PointConvFormer_Segmentation.forward (model_architecture.py:406-502); resblocks_back all 0 in
-    every shipped config, so decoder res-blocks are restated only for that case."""
+    """PointConvFormer_Segmentation.forward (model_architecture.py:406-502), decoder res-blocks included
+    (resblocks_back is all 0 in every shipped config; tests/golden/model_routing.npz exercises them)."""
     feats = backbone(params, "pcf_backbone.", cfg, features, pcs, e_self, e_fwd, norms, training)
     x = feats[-1]
     L = cfg["num_level"]
@@ -244,7 +244,12 @@ def segmentation_model(params, cfg, features, pcs, e_self, e_fwd, e_prop, norms,
         lvl = L - 2 - i
         x, _ = point_conv_transpose_pe(params, "pointdeconv.%d" % i, cfg, pcs[lvl + 1], x, e_prop[lvl],
                                        norms[lvl + 1], pcs[lvl], norms[lvl], feats[lvl], training=training)
-        assert sum(cfg.get("resblocks_back", [0])) == 0, "decoder res-blocks not restated"
+        n_res = cfg.get("resblocks_back", [0] * L)[lvl] if cfg["resblocks"][lvl] != 0 else 0
+        vi = None                                  # decoder res-blocks (model_architecture.py:391-398, 466-494)
+        for b in range(n_res):
+            x, vi_new = point_conv_stride_pe(params, "pointdeconv_res.%d.%d" % (i, b), cfg, pcs[lvl], x, e_self[lvl],
+                                             norms[lvl], vi_features=vi, training=training)
+            vi = vi_new if vi is None else vi
         feats[lvl] = x
     h = F.relu(linear_bn(x, params, "fc1", training))
     return F.linear(h, params["fc2.weight"], params["fc2.bias"])

@@ -10,6 +10,10 @@ Only runnable in the build container (needs /root/reference and oracle/_ref/libg
 Files:
   layer_<name>.npz      reference layer modules (layers.py) fwd (train + eval) and autograd grads
   model_small.npz       PointConvFormer_Segmentation (model_architecture.py) logits + grads, small dims
+  model_lite.npz / model_ptf2.npz / model_routing.npz   same, with the structure of configPCF_10cm_lite (mid_dim 4),
+                        configPCF_2cm_PTF2 (use_level_1 False, mid_dim_back 3) and the guided_level / resblocks_back
+                        branches (`python tests/golden/make_golden.py --model lite ptf2 routing`); they share
+                        model_small.npz's pyramid and edges
   inverse.npz           reference create_inverse_python (test_kernels.py:177-213) on a kNN table
   grid_subsample.npz    reference C++ grid_subsampling (grid_subsampling.cpp:9-110) via oracle/_ref
   pconv_linear_seed42.npz  the reference's torch formulation (layers.py:713-719 + Linear) on the
@@ -200,16 +204,35 @@ def small_pyramid(seed=100):
     return pcs, nrms, stored
 
 
-def make_model():
+MODEL_VARIANTS = {
+    # name: (cfg overrides, torch seed) -- model_small is the PCF_Normal structure (configPCF_Opt_10cm / configPCF_5cm) at
+    # small dims (the reference's torch path needs (out/4) % num_heads == 0, layers.py:387); the others restate the remaining shipped configs' structure and the routing branches none of them takes
+    "small": (dict(), 200),
+    # configPCF_10cm_lite.yaml: mid_dim 4 (C_mid = 4 kernels), 8 heads
+    "lite": (dict(mid_dim=[4] * 5, num_heads=8, feat_dim=[16, 32, 64, 64, 96], resblocks=[0, 1, 1, 1, 1]), 210),
+    # configPCF_2cm_PTF2.yaml: no level-1 PointConv stack (selfmlp), mid_dim_back 3, 8 heads, 6-entry resblocks
+    "ptf2": (dict(use_level_1=False, mid_dim_back=3, num_heads=8, feat_dim=[16, 32, 64, 64, 96],
+                  resblocks=[0, 1, 2, 1, 1, 1]), 220),
+    # branches no shipped config takes: PointConvStridePE encoder level (guided_level=1) and decoder res-blocks
+    "routing": (dict(guided_level=1, resblocks_back=[0, 1, 1, 0, 0], resblocks=[0, 1, 1, 1, 1]), 230),
+}
+GRAD_KEY_PATTERNS = ["selfpointconv.linear.c.weight", "selfmlp.c.weight", "selfpointconv_res1.linear.c.weight",
+                     "pointconv.0.linear.c.weight", "pointconv_res.1.0.guidance_weight.mlp.0.c.weight",
+                     "pointconv_res.3.0.weightnet.mlp_convs.0.c.weight", "pointdeconv.3.linear.c.weight",
+                     "pointdeconv.0.weightnet.mlp_convs.2.c.weight", "pointdeconv_res.2.0.linear.c.weight", "fc2.weight"]
+
+
+def make_model(variant="small"):
     _, _, MA = ref_shim.load()
-    cfg = ref_shim.EasyDict(SMALL_MODEL_CFG)
+    over, seed = MODEL_VARIANTS[variant]
+    cfg = ref_shim.EasyDict(dict(SMALL_MODEL_CFG, **over))
     cfg = MA.get_default_configs(cfg, cfg.num_level, cfg.base_dim)
-    torch.manual_seed(200)
+    torch.manual_seed(seed)
     model = MA.PointConvFormer_Segmentation(cfg)
-    randomize_bn(model, 201)
+    randomize_bn(model, seed + 1)
     pcs, nrms, stored = small_pyramid()
     es, ef, ep = oknn.compute_knn_packed(pcs, stored, cfg.K_self, cfg.K_forward, cfg.K_propagate)
-    rng = np.random.default_rng(202)
+    rng = np.random.default_rng(seed + 2)
     feats = rng.random((1, pcs[0].shape[1], 3)).astype(np.float32)
     target = rng.integers(0, 20, pcs[0].shape[1])
     tt = lambda lst: [t(x) for x in lst]
@@ -219,30 +242,35 @@ def make_model():
     loss.backward()
     out = dict(feats=feats, target=target, logits_train=logits.detach().numpy(), loss=np.float32(loss.item()),
                stored=np.asarray(stored))
-    for l in range(5):
-        out["pc%d" % l] = pcs[l]
-        out["nrm%d" % l] = nrms[l]
-        out["es%d" % l] = es[l]
-    for l in range(4):
-        out["ef%d" % l] = ef[l]
-        out["ep%d" % l] = ep[l]
+    if variant == "small":                      # the other variants reuse model_small.npz's pyramid and edges
+        for l in range(5):
+            out["pc%d" % l] = pcs[l]
+            out["nrm%d" % l] = nrms[l]
+            out["es%d" % l] = es[l]
+        for l in range(4):
+            out["ef%d" % l] = ef[l]
+            out["ep%d" % l] = ep[l]
     gn = {k: p.grad for k, p in model.named_parameters()}
     # gradients: keep full tensors for a representative subset, norms for all
     out["grad_names"] = np.array(sorted(gn.keys()))
     out["grad_norms"] = np.array([float(gn[k].norm()) for k in sorted(gn.keys())], np.float32)
-    for k in ["pcf_backbone.selfpointconv.linear.c.weight", "pcf_backbone.selfpointconv_res1.linear.c.weight",
-              "pcf_backbone.pointconv.0.linear.c.weight", "pcf_backbone.pointconv_res.1.1.guidance_weight.mlp.0.c.weight",
-              "pcf_backbone.pointconv_res.3.0.weightnet.mlp_convs.0.c.weight", "pointdeconv.3.linear.c.weight",
-              "pointdeconv.0.weightnet.mlp_convs.2.c.weight", "fc2.weight"]:
+    if variant == "small":
+        keys = ["pcf_backbone.selfpointconv.linear.c.weight", "pcf_backbone.selfpointconv_res1.linear.c.weight",
+                "pcf_backbone.pointconv.0.linear.c.weight", "pcf_backbone.pointconv_res.1.1.guidance_weight.mlp.0.c.weight",
+                "pcf_backbone.pointconv_res.3.0.weightnet.mlp_convs.0.c.weight", "pointdeconv.3.linear.c.weight",
+                "pointdeconv.0.weightnet.mlp_convs.2.c.weight", "fc2.weight"]
+    else:
+        keys = [k for pat in GRAD_KEY_PATTERNS for k in sorted(gn) if k.endswith(pat)]
+    for k in keys:
         out["grad." + k] = gn[k].numpy()
     model.eval()
     with torch.no_grad():
         out["logits_eval"] = model(t(feats), tt(pcs), tt(es), tt(ef), tt(ep), tt(nrms)).numpy()
     for k, v in model.state_dict().items():
         out["param." + k] = v.numpy()
-    np.savez_compressed(os.path.join(HERE, "model_small.npz"), **out)
-    print("model_small: N per level", [p.shape[1] for p in pcs], "loss", loss.item(),
-          "params", sum(p.numel() for p in model.parameters()))
+    np.savez_compressed(os.path.join(HERE, "model_%s.npz" % variant), **out)
+    print("model_%s: N per level" % variant, [p.shape[1] for p in pcs], "loss", loss.item(),
+          "params", sum(p.numel() for p in model.parameters()), "full grads", len(keys))
 
 
 def make_inverse():
@@ -312,8 +340,13 @@ def make_pconv_linear():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 2 and sys.argv[1] == "--model":     # regenerate single model variants only
+        for v in sys.argv[2:]:
+            make_model(v)
+        sys.exit(0)
     make_pconv_linear()
     make_inverse()
     make_grid_subsample()
     make_layers()
-    make_model()
+    for v in MODEL_VARIANTS:
+        make_model(v)

@@ -82,20 +82,14 @@ def test_layer_matches_reference_golden(golden_dir, name, use_kernel):
     torch.testing.assert_close(ye.cpu(), torch.from_numpy(g["y_eval"]), rtol=2e-4, atol=2e-4)
 
 
-@pytest.mark.parametrize("pconv_opt", [False, True])
-def test_model_matches_reference_golden(golden_dir, pconv_opt):
-    """Whole PointConvFormer_Segmentation (small dims) fwd + bwd vs the reference; with PCONV_OPT the parameters
-    are renamed to the reference's other spelling (linear.c -> pconv_linear_opt.linear, linear.bn -> bn)."""
+def _build_model(g, variant, pconv_opt, **extra):
+    """Our PointConvFormer_Segmentation for a golden variant with the reference's parameters loaded (strict)."""
+    import model_variants
     from pcf_b200 import model_architecture as MA
-    g = np.load(os.path.join(golden_dir, "model_small.npz"))
-    cfg = MA.EasyDict(USE_VI=True, USE_PE=True, BATCH_NORM=True, USE_CUDA_KERNEL=True, PCONV_OPT=pconv_opt, USE_XYZ=True,
-                      drop_path_rate=0., dropout_rate=0., dropout_fc=0., attention_type='subtraction',
-                      layer_norm_guidance=False, transformer_type='PCF', point_dim=3, feat_dim=[16, 32, 48, 64, 96],
-                      mid_dim=[16] * 5, mid_dim_back=1, guided_level=0, num_heads=4, resblocks=[0, 1, 2, 1, 1],
-                      resblocks_back=[0] * 5, use_level_1=True, num_classes=20)
-    cfg = MA.get_default_configs(cfg, 5, 16)
+    c = dict(model_variants.cfg_of(variant), USE_CUDA_KERNEL=True, PCONV_OPT=pconv_opt, **extra)
+    cfg = MA.get_default_configs(MA.EasyDict(c), c["num_level"], c["base_dim"])
     model = MA.PointConvFormer_Segmentation(cfg).cuda()
-    sd = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")}
+    sd = {k[6:]: torch.from_numpy(g[k]) for k in g if k.startswith("param.")}
     if pconv_opt:
         own = set(model.state_dict().keys())
         ren = {}
@@ -104,11 +98,29 @@ def test_model_matches_reference_golden(golden_dir, pconv_opt):
             ren[k2 if (k2 in own and k not in own) else k] = v
         sd = ren
     model.load_state_dict(sd, strict=True)
+    return model, sd
+
+
+def _model_inputs(g):
     pcs = [cuda(g["pc%d" % l]) for l in range(5)]
     nrm = [cuda(g["nrm%d" % l]) for l in range(5)]
     es = [cuda(g["es%d" % l]) for l in range(5)]
     ef = [cuda(g["ef%d" % l]) for l in range(4)]
     ep = [cuda(g["ep%d" % l]) for l in range(4)]
+    return pcs, nrm, es, ef, ep
+
+
+@pytest.mark.parametrize("pconv_opt", [False, True])
+@pytest.mark.parametrize("variant", ["small", "lite", "ptf2", "routing"])
+def test_model_matches_reference_golden(golden_dir, variant, pconv_opt):
+    """Whole PointConvFormer_Segmentation (small dims) fwd + bwd vs the reference, for the structure of every shipped
+    config family (tests/model_variants.py: PCF_Normal 10cm/5cm, 10cm_lite with mid_dim 4, 2cm_PTF2 with
+    use_level_1 False + mid_dim_back 3, and the guided_level / resblocks_back branches); with PCONV_OPT the parameters
+    are renamed to the reference's other spelling (linear.c -> pconv_linear_opt.linear, linear.bn -> bn)."""
+    import model_variants
+    g = model_variants.load(golden_dir, variant)
+    model, sd = _build_model(g, variant, pconv_opt)
+    pcs, nrm, es, ef, ep = _model_inputs(g)
     from pcf_b200 import common_util as CU
     inv = CU.compute_knn_inverse(pcs, es, ef, ep) if pconv_opt else (None, None, None)
     model.train()
@@ -133,3 +145,41 @@ def test_model_matches_reference_golden(golden_dir, pconv_opt):
     with torch.no_grad():
         le = model(cuda(g["feats"]), pcs, es, ef, ep, nrm)
     torch.testing.assert_close(le.cpu(), torch.from_numpy(g["logits_eval"]), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("variant", ["small", "ptf2"])
+def test_bn_folded_inference_matches_reference_golden(golden_dir, variant):
+    """replace_batchnorm (util/common_util.py:237-247, the reference's inference path in test_ScanNet_simple.py) folds
+    every Linear_BN into a Linear; the folded model must reproduce the reference's eval-mode logits."""
+    import model_variants
+    from pcf_b200 import common_util as CU
+    from pcf_b200.layer_utils import Linear_BN
+    g = model_variants.load(golden_dir, variant)
+    model, _ = _build_model(g, variant, False)
+    pcs, nrm, es, ef, ep = _model_inputs(g)
+    model.eval()
+    CU.replace_batchnorm(model)
+    assert not any(isinstance(m, Linear_BN) for m in model.modules())
+    with torch.no_grad():
+        le = model(cuda(g["feats"]), pcs, es, ef, ep, nrm)
+    torch.testing.assert_close(le.cpu(), torch.from_numpy(g["logits_eval"]), rtol=2e-3, atol=2e-3)
+
+
+def test_eval_scene_independence(golden_dir):
+    """Edges never cross scenes (knn_post_dataloader_utils.py:194-212) and eval-mode BatchNorm is a fixed affine, so the
+    logits of a scene must not depend on what it is packed with: run the two packed scenes of the golden pyramid together
+    and scene 0 alone."""
+    import model_variants
+    g = model_variants.load(golden_dir, "small")
+    model, _ = _build_model(g, "small", False)
+    model.eval()
+    pcs, nrm, es, ef, ep = _model_inputs(g)
+    with torch.no_grad():
+        both = model(cuda(g["feats"]), pcs, es, ef, ep, nrm)
+    n = [int(g["stored"][l][0]) for l in range(5)]            # scene 0 comes first at every level: its indices need no shift
+    with torch.no_grad():
+        alone = model(cuda(g["feats"])[:, :n[0]], [p[:, :n[l]] for l, p in enumerate(pcs)],
+                      [e[:, :n[l]].contiguous() for l, e in enumerate(es)],
+                      [e[:, :n[l + 1]].contiguous() for l, e in enumerate(ef)],
+                      [e[:, :n[l]].contiguous() for l, e in enumerate(ep)], [x[:, :n[l]] for l, x in enumerate(nrm)])
+    torch.testing.assert_close(alone, both[:, :n[0]], rtol=1e-5, atol=1e-5)

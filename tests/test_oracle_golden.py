@@ -7,6 +7,7 @@ import pytest
 import torch
 
 from oracle import layers as OL, inverse as OI, grid_subsample as OG, knn as OK
+import model_variants
 
 TOL = dict(rtol=1e-4, atol=1e-4)        # the reference's own tolerance (test_kernels.py:1756-1764)
 
@@ -114,16 +115,15 @@ def model_inputs(g):
     return t(g["feats"]), pcs, es, ef, ep, nrms
 
 
-def small_cfg():
-    return dict(USE_VI=True, USE_PE=True, USE_XYZ=True, use_level_1=True, num_level=5, guided_level=0,
-                resblocks=[0, 1, 2, 1, 1], resblocks_back=[0] * 5)
-
-
-def test_model_matches_reference(golden_dir):
-    g = load(golden_dir, "model_small.npz")
+@pytest.mark.parametrize("variant", ["small", "lite", "ptf2", "routing"])
+def test_model_matches_reference(golden_dir, variant):
+    """Whole-model oracle vs the unmodified reference for the structures of every shipped config family
+    (tests/model_variants.py) plus the guided_level / resblocks_back branches."""
+    g = model_variants.load(golden_dir, variant)
+    cfg = model_variants.cfg_of(variant)
     P = params_of(g, requires_grad=True)
     feats, pcs, es, ef, ep, nrms = model_inputs(g)
-    logits = OL.segmentation_model(P, small_cfg(), feats, pcs, es, ef, ep, nrms, training=True)
+    logits = OL.segmentation_model(P, cfg, feats, pcs, es, ef, ep, nrms, training=True)
     torch.testing.assert_close(logits, torch.from_numpy(g["logits_train"]), rtol=1e-3, atol=1e-3)
     loss = torch.nn.functional.cross_entropy(logits[0], torch.from_numpy(g["target"]), label_smoothing=0.2)
     assert abs(loss.item() - float(g["loss"])) < 1e-4
@@ -137,7 +137,7 @@ def test_model_matches_reference(golden_dir):
             ref = torch.from_numpy(v)
             assert float((P[k[5:]].grad - ref).abs().max()) <= 1e-2 * max(1e-3, float(ref.abs().max())), k
     with torch.no_grad():
-        le = OL.segmentation_model(params_of(g), small_cfg(), feats, pcs, es, ef, ep, nrms, training=False)
+        le = OL.segmentation_model(params_of(g), cfg, feats, pcs, es, ef, ep, nrms, training=False)
     torch.testing.assert_close(le, torch.from_numpy(g["logits_eval"]), rtol=1e-3, atol=1e-3)
 
 
