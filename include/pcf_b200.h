@@ -214,6 +214,30 @@ int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int ldy, int64_t
 int pcfb_sum_partials(const float *partial, int nblocks, int n, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * BatchNorm (+ activation) over a contiguous [rows, C] tensor, C % 4 == 0, C <= 1024: the BatchNorm + ReLU that
+ * follows the fused contraction (layers.py:708-709, 721, 893-898, 1086-1092; `self.bn` / `linear.bn`) and the
+ * Linear_BN (+ LeakyReLU) of the wide per-point blocks (layer_utils.py:241-319), replacing torch's
+ * batch_norm + activation kernels (5 passes forward, 8 backward) by 3 and 5.
+ *   forward (train): pcfb_bn_stats -> partial[blocks][2][C] = sum(x - pivot), sum((x - pivot)^2)  (pivot: any
+ *     per-channel offset near the mean, e.g. the Linear bias; may be NULL) -> pcfb_bn_finalize (scale, shift,
+ *     running statistics, mean, invstd) -> pcfb_bn_act (out = act(x*scale + shift)).  Eval: pcfb_bn_act only.
+ *   backward: pcfb_bn_backward_stats -> sums[2][C] = (sum dz, sum dz*xhat) = (dbeta, dgamma), dz = dA*act'(z);
+ *     pcfb_bn_backward: dX = scale*(dz - S1/E - xhat*S2/E) (sums == NULL: eval mode, dX = scale*dz).
+ *     d_count (device double, may be NULL) = global row count for SyncBatchNorm.
+ * Every reduction is block partials summed in fixed order (deterministic).
+ * ------------------------------------------------------------------------------------------- */
+int pcfb_bn_supported(int C);
+size_t pcfb_bn_workspace(int64_t rows, int C);
+int pcfb_bn_stats(const float *x, int64_t rows, int C, const float *pivot, float *partial, size_t partial_bytes,
+                  int *h_nblocks, void *stream);
+int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
+                           const float *mean, const float *invstd, int act, float *sums, void *workspace,
+                           size_t workspace_bytes, void *stream);
+int pcfb_bn_backward(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
+                     const float *mean, const float *invstd, const float *sums, int act, const double *d_count,
+                     float *dX, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Grid (voxel) subsampling with barycentres on packed scenes.  Replaces grid_subsampling()
  * (grid_subsampling.cpp:9-110) as called per level by subsample() (datasetCommon.py:384-420).
  * Three phases because the grid extent and the output size are data dependent (the host reads two

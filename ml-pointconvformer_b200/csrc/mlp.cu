@@ -190,6 +190,10 @@ __global__ void bn_act_kernel(const float *__restrict__ y, int64_t n, int C, con
     }
 }
 
+__global__ void __launch_bounds__(256)
+bn_act4_kernel(const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale, const float *__restrict__ shift,
+               int act, float *__restrict__ out, int c4, int ry);                          // float4 form, defined below
+
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
@@ -823,6 +827,14 @@ extern "C" int pcfb_bn_act(const float *y, int64_t rows, int C, const float *sca
     if (n == 0) return PCFB_OK;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    if ((C & 3) == 0 && C <= 1024 && ((uintptr_t)y % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+        (!scale || (((uintptr_t)scale % 16 == 0) && ((uintptr_t)shift % 16 == 0)))) {
+        const int c4 = C >> 2, ry = 256 / c4;
+        int64_t b4 = (rows + ry - 1) / ry;
+        if (b4 > (int64_t)kNumSMs * 8) b4 = (int64_t)kNumSMs * 8;
+        bn_act4_kernel<<<(int)b4, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, rows, C, scale, shift, act, out, c4, ry);
+        return check_launch("bn_act4_kernel");
+    }
     bn_act_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, n, C, scale, shift, act, out);
     return check_launch("bn_act_kernel");
 }
@@ -926,4 +938,222 @@ extern "C" int pcfb_sum_partials(const float *partial, int nblocks, int n, float
     PCFB_REQUIRE(partial && out && n >= 1, "pcfb_sum_partials: bad arguments");
     sum_partials_kernel<<<ceil_div(n * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, nblocks, n, out);
     return check_launch("sum_partials_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// BatchNorm (+ activation) over a contiguous [rows, C] tensor for any C % 4 == 0, C <= 1024: the BatchNorm + ReLU
+// behind the fused contraction (/root/reference/layers.py:708-709,721, 893-898, 1086-1092) and the Linear_BN of the
+// wide per-point blocks (layer_utils.py:241-319) whose Linear runs on gemm_nt.  Train mode = 2 reads + 1 write in the
+// forward (statistics, apply + activation), 2 + 2 reads + 1 write in the backward; all sums are block partials reduced
+// in fixed order (deterministic, no atomics).
+// Thread layout: tx = float4 column group (C/4 of them), ty = row lane (256 / (C/4) rows in flight per block).
+// ------------------------------------------------------------------------------------------------------------
+namespace pcfb {
+
+constexpr int BA_THREADS = 256;
+
+struct BaGeom { int c4, ry, rows_per_block, blocks; };
+
+static BaGeom ba_geom(int64_t rows, int C) {
+    BaGeom g;
+    g.c4 = C >> 2;
+    g.ry = BA_THREADS / g.c4;
+    int64_t rpb = (rows + (int64_t)kNumSMs * 8 - 1) / ((int64_t)kNumSMs * 8);        // <= 8 blocks per SM
+    if (rpb < (int64_t)g.ry * 4) rpb = (int64_t)g.ry * 4;
+    rpb = (rpb + g.ry - 1) / g.ry * g.ry;
+    g.rows_per_block = (int)rpb;
+    g.blocks = rows > 0 ? (int)((rows + rpb - 1) / rpb) : 0;
+    return g;
+}
+
+// fixed-order reduction of the per-row-lane accumulators of one block: partial[block][which][C]
+__device__ __forceinline__ void ba_block_reduce(float4 s1, float4 s2, int tx, int ty, int c4, int ry, bool active,
+                                                float4 *sm, float *__restrict__ partial, int C)
+{
+    if (active) { sm[ty * c4 + tx] = s1; sm[(ry + ty) * c4 + tx] = s2; }
+    __syncthreads();
+    if (active && ty == 0) {
+        float4 a = sm[tx], b = sm[ry * c4 + tx];
+        for (int r = 1; r < ry; ++r) {
+            const float4 u = sm[r * c4 + tx], v = sm[(ry + r) * c4 + tx];
+            a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+            b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+        }
+        *reinterpret_cast<float4 *>(partial + ((size_t)blockIdx.x * 2 + 0) * C + 4 * tx) = a;
+        *reinterpret_cast<float4 *>(partial + ((size_t)blockIdx.x * 2 + 1) * C + 4 * tx) = b;
+    }
+}
+
+// partial[block][2][C] = sum (x - pivot), sum (x - pivot)^2 over the block's rows
+__global__ void __launch_bounds__(BA_THREADS)
+bn_stats_kernel(const float *__restrict__ x, int64_t rows, int C, const float *__restrict__ pivot, float *__restrict__ partial,
+                int c4, int ry, int rows_per_block)
+{
+    extern __shared__ float4 ba_sm[];
+    const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
+    const bool active = ty < ry;
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    if (active) {
+        // scalar loads: the pivot is usually a bias parameter, which may be a 4-byte aligned view into a flat buffer
+        const float4 pv = pivot ? make_float4(__ldg(pivot + 4 * tx), __ldg(pivot + 4 * tx + 1), __ldg(pivot + 4 * tx + 2), __ldg(pivot + 4 * tx + 3))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+        const int64_t r1 = min(rows, r0 + rows_per_block);
+        for (int64_t r = r0 + ty; r < r1; r += ry) {
+            float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * C) + tx);
+            v.x -= pv.x; v.y -= pv.y; v.z -= pv.z; v.w -= pv.w;
+            s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+            s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+        }
+    }
+    ba_block_reduce(s1, s2, tx, ty, c4, ry, active, ba_sm, partial, C);
+}
+
+// out = act(y * scale + shift), float4 columns (the vector form of bn_act_kernel)
+__global__ void __launch_bounds__(BA_THREADS)
+bn_act4_kernel(const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale, const float *__restrict__ shift,
+               int act, float *__restrict__ out, int c4, int ry)
+{
+    const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
+    if (ty >= ry) return;
+    const float4 sc = scale ? __ldg(reinterpret_cast<const float4 *>(scale) + tx) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 sh = scale ? __ldg(reinterpret_cast<const float4 *>(shift) + tx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = (int64_t)blockIdx.x * ry + ty; r < rows; r += (int64_t)gridDim.x * ry) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * C) + tx);
+        float4 o;
+        o.x = act_fwd(fmaf(v.x, sc.x, sh.x), act); o.y = act_fwd(fmaf(v.y, sc.y, sh.y), act);
+        o.z = act_fwd(fmaf(v.z, sc.z, sh.z), act); o.w = act_fwd(fmaf(v.w, sc.w, sh.w), act);
+        *(reinterpret_cast<float4 *>(out + r * C) + tx) = o;
+    }
+}
+
+__device__ __forceinline__ float ba_dz(float d, float yv, float sc, float sh, int act) {
+    const float z = fmaf(yv, sc, sh);
+    return d * act_bwd(z, act_fwd(z, act), act);
+}
+
+// partial[block][2][C] = sum dz, sum dz * xhat   with dz = dA * act'(y*scale+shift), xhat = (y - mean) * invstd
+__global__ void __launch_bounds__(BA_THREADS)
+bn_bwd_stats_kernel(const float *__restrict__ dA, const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale,
+                    const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd, int act,
+                    float *__restrict__ partial, int c4, int ry, int rows_per_block)
+{
+    extern __shared__ float4 ba_sm[];
+    const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
+    const bool active = ty < ry;
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    if (active) {
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + tx), sh = __ldg(reinterpret_cast<const float4 *>(shift) + tx);
+        const float4 mu = __ldg(reinterpret_cast<const float4 *>(mean) + tx), is = __ldg(reinterpret_cast<const float4 *>(invstd) + tx);
+        const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+        const int64_t r1 = min(rows, r0 + rows_per_block);
+        for (int64_t r = r0 + ty; r < r1; r += ry) {
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(dA + r * C) + tx);
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * C) + tx);
+            const float dx_ = ba_dz(d.x, v.x, sc.x, sh.x, act), dy_ = ba_dz(d.y, v.y, sc.y, sh.y, act);
+            const float dz_ = ba_dz(d.z, v.z, sc.z, sh.z, act), dw_ = ba_dz(d.w, v.w, sc.w, sh.w, act);
+            s1.x += dx_; s1.y += dy_; s1.z += dz_; s1.w += dw_;
+            s2.x = fmaf(dx_, (v.x - mu.x) * is.x, s2.x); s2.y = fmaf(dy_, (v.y - mu.y) * is.y, s2.y);
+            s2.z = fmaf(dz_, (v.z - mu.z) * is.z, s2.z); s2.w = fmaf(dw_, (v.w - mu.w) * is.w, s2.w);
+        }
+    }
+    ba_block_reduce(s1, s2, tx, ty, c4, ry, active, ba_sm, partial, C);
+}
+
+// train (sums != null): dX = scale * (dz - S1/E - xhat * S2/E);  eval: dX = scale * dz
+__global__ void __launch_bounds__(BA_THREADS)
+bn_bwd_kernel(const float *__restrict__ dA, const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale,
+              const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd,
+              const float *__restrict__ sums, int act, float inv_count, const double *__restrict__ d_count,
+              float *__restrict__ dX, int c4, int ry)
+{
+    const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
+    if (ty >= ry) return;
+    const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + tx), sh = __ldg(reinterpret_cast<const float4 *>(shift) + tx);
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu, m1 = mu, m2 = mu;
+    if (sums) {
+        const float ic = d_count ? (float)(1.0 / *d_count) : inv_count;
+        mu = __ldg(reinterpret_cast<const float4 *>(mean) + tx); is = __ldg(reinterpret_cast<const float4 *>(invstd) + tx);
+        m1 = __ldg(reinterpret_cast<const float4 *>(sums) + tx); m2 = __ldg(reinterpret_cast<const float4 *>(sums + C) + tx);
+        m1.x *= ic; m1.y *= ic; m1.z *= ic; m1.w *= ic;
+        m2.x *= ic; m2.y *= ic; m2.z *= ic; m2.w *= ic;
+    }
+    for (int64_t r = (int64_t)blockIdx.x * ry + ty; r < rows; r += (int64_t)gridDim.x * ry) {
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(dA + r * C) + tx);
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * C) + tx);
+        float4 o;
+        o.x = sc.x * (ba_dz(d.x, v.x, sc.x, sh.x, act) - m1.x - (v.x - mu.x) * is.x * m2.x);
+        o.y = sc.y * (ba_dz(d.y, v.y, sc.y, sh.y, act) - m1.y - (v.y - mu.y) * is.y * m2.y);
+        o.z = sc.z * (ba_dz(d.z, v.z, sc.z, sh.z, act) - m1.z - (v.z - mu.z) * is.z * m2.z);
+        o.w = sc.w * (ba_dz(d.w, v.w, sc.w, sh.w, act) - m1.w - (v.w - mu.w) * is.w * m2.w);
+        *(reinterpret_cast<float4 *>(dX + r * C) + tx) = o;
+    }
+}
+
+static int ba_stream_blocks(int64_t rows, int ry) {
+    int64_t b = (rows + ry - 1) / ry;
+    if (b > (int64_t)kNumSMs * 8) b = (int64_t)kNumSMs * 8;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace pcfb
+
+using namespace pcfb;
+
+extern "C" int pcfb_bn_supported(int C) { return C >= 4 && C <= 1024 && (C & 3) == 0; }
+
+extern "C" size_t pcfb_bn_workspace(int64_t rows, int C)
+{
+    if (!pcfb_bn_supported(C)) return 0;
+    return align_up((size_t)(ba_geom(rows, C).blocks + 1) * 2 * C * sizeof(float), 256);
+}
+
+extern "C" int pcfb_bn_stats(const float *x, int64_t rows, int C, const float *pivot, float *partial, size_t partial_bytes,
+                             int *nblocks, void *stream)
+{
+    PCFB_REQUIRE(pcfb_bn_supported(C), "pcfb_bn_stats: C = %d unsupported (multiple of 4, <= 1024)", C);
+    PCFB_REQUIRE(x && partial && rows >= 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)partial % 16 == 0),
+                 "pcfb_bn_stats: null or misaligned pointer");
+    const BaGeom g = ba_geom(rows, C);
+    PCFB_REQUIRE(partial_bytes >= (size_t)g.blocks * 2 * C * sizeof(float), "pcfb_bn_stats: workspace too small");
+    if (nblocks) *nblocks = g.blocks;
+    if (g.blocks == 0) return PCFB_OK;
+    bn_stats_kernel<<<g.blocks, BA_THREADS, (size_t)2 * g.ry * g.c4 * sizeof(float4), static_cast<cudaStream_t>(stream)>>>(
+        x, rows, C, pivot, partial, g.c4, g.ry, g.rows_per_block);
+    return check_launch("bn_stats_kernel");
+}
+
+extern "C" int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
+                                      const float *mean, const float *invstd, int act, float *sums, void *workspace,
+                                      size_t workspace_bytes, void *stream)
+{
+    PCFB_REQUIRE(pcfb_bn_supported(C), "pcfb_bn_backward_stats: C = %d unsupported (multiple of 4, <= 1024)", C);
+    PCFB_REQUIRE(dA && y && scale && shift && mean && invstd && sums && workspace && ((uintptr_t)dA % 16 == 0) &&
+                 ((uintptr_t)y % 16 == 0), "pcfb_bn_backward_stats: null or misaligned pointer");
+    const BaGeom g = ba_geom(rows, C);
+    PCFB_REQUIRE(workspace_bytes >= (size_t)g.blocks * 2 * C * sizeof(float), "pcfb_bn_backward_stats: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float *partial = static_cast<float *>(workspace);
+    int rc;
+    if (g.blocks > 0) {
+        bn_bwd_stats_kernel<<<g.blocks, BA_THREADS, (size_t)2 * g.ry * g.c4 * sizeof(float4), st>>>(
+            dA, y, rows, C, scale, shift, mean, invstd, act, partial, g.c4, g.ry, g.rows_per_block);
+        if ((rc = check_launch("bn_bwd_stats_kernel"))) return rc;
+    }
+    sum_partials_kernel<<<ceil_div(2 * C * 32, 128), 128, 0, st>>>(partial, g.blocks, 2 * C, sums);
+    return check_launch("sum_partials_kernel");
+}
+
+extern "C" int pcfb_bn_backward(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
+                                const float *mean, const float *invstd, const float *sums, int act, const double *d_count,
+                                float *dX, void *stream)
+{
+    PCFB_REQUIRE(pcfb_bn_supported(C), "pcfb_bn_backward: C = %d unsupported (multiple of 4, <= 1024)", C);
+    PCFB_REQUIRE(dA && y && scale && shift && dX && (!sums || (mean && invstd)) && ((uintptr_t)dA % 16 == 0) &&
+                 ((uintptr_t)y % 16 == 0) && ((uintptr_t)dX % 16 == 0), "pcfb_bn_backward: null or misaligned pointer");
+    if (rows == 0) return PCFB_OK;
+    const int c4 = C >> 2, ry = BA_THREADS / c4;
+    bn_bwd_kernel<<<ba_stream_blocks(rows, ry), BA_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        dA, y, rows, C, scale, shift, mean, invstd, sums, act, (float)(1.0 / (double)rows), d_count, dX, c4, ry);
+    return check_launch("bn_bwd_kernel");
 }

@@ -25,12 +25,49 @@ def _sync_group(bn):
     return False
 
 
+# ---- global row counts for SyncBatchNorm -------------------------------------------------------------------------
+# A BatchNorm over [1, N_l, (K,) C] needs the row count summed over all ranks.  Every tensor of the model has N_l rows
+# of some pyramid level l, so ONE all-reduce of the per-level point counts at the start of a forward
+# (register_levels, called by PointConvFormer_Segmentation.forward) serves all ~190 BatchNorms of the step; a chain
+# whose leading shape is not a registered level falls back to its own all-reduce.
+_LEVEL_ROWS = {}          # local N_l -> (1-element double tensor with the global N_l)
+_DERIVED_ROWS = {}        # (local N_l, factor) -> global N_l * factor
+
+
+def register_levels(point_counts, device):
+    """point_counts: local per-level point counts of this rank's packed batch.  No-op without an initialised
+    process group.  Levels whose local counts coincide are left unregistered (their global counts may differ)."""
+    _LEVEL_ROWS.clear()
+    _DERIVED_ROWS.clear()
+    counts = [int(c) for c in point_counts]
+    if not counts or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    g = torch.tensor(counts, device=device, dtype=torch.float64)
+    dist.all_reduce(g)
+    for i, c in enumerate(counts):
+        if counts.count(c) == 1:
+            _LEVEL_ROWS[c] = g[i:i + 1]
+
+
+def global_rows(lead_shape, rows, device):
+    """1-element device double with the number of rows summed over all ranks (stays on the device: no host sync)."""
+    m = int(lead_shape[1]) if len(lead_shape) >= 2 else -1
+    if m > 0 and m in _LEVEL_ROWS and rows % m == 0:
+        key = (m, rows // m)
+        if key not in _DERIVED_ROWS:
+            _DERIVED_ROWS[key] = _LEVEL_ROWS[m] * float(rows // m)
+        return _DERIVED_ROWS[key]
+    d = torch.full((1,), float(rows), device=device, dtype=torch.float64)
+    dist.all_reduce(d)
+    return d
+
+
 class _ChainFunction(torch.autograd.Function):
     """args: x2 [E, cin] (rows contiguous), spec (python: list of dict(act, has_bn, eps, momentum, sync)), training,
     then per layer (W, b, gamma, beta) tensors (gamma/beta None without BN); running stats are passed through `buffers`."""
 
     @staticmethod
-    def forward(ctx, x2, spec, training, buffers, *params):
+    def forward(ctx, x2, spec, training, buffers, lead, *params):
         E = x2.shape[0]
         dev = x2.device
         L = len(spec)
@@ -40,9 +77,8 @@ class _ChainFunction(torch.autograd.Function):
         ys, ctxs = [], []
         world = dist.get_world_size() if any(s["sync"] for s in spec) else 1
         count, d_count = E, None
-        if world > 1:                                    # global row count stays on the device (no host sync)
-            d_count = torch.full((1,), float(E), device=dev, dtype=torch.float64)
-            dist.all_reduce(d_count)
+        if world > 1 and training:                       # global row count stays on the device (no host sync)
+            d_count = global_rows(lead, E, dev)
         for l, s in enumerate(spec):
             W, b, gamma, beta = params[4 * l: 4 * l + 4]
             cout, cin = W.shape
@@ -179,7 +215,7 @@ class _ChainFunction(torch.autograd.Function):
                     sums = sums_local = None
                 dA = dA_prev
         gx = dA_prev if need_x_grad else None
-        return (gx, None, None, None) + tuple(grads)
+        return (gx, None, None, None, None) + tuple(grads)
 
 
 def mlp_chain(x, layers, training):
@@ -201,5 +237,99 @@ def mlp_chain(x, layers, training):
         buffers.append((bn.running_mean, bn.running_var) if has_bn else (None, None))
         if has_bn and training and bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
-    out = _ChainFunction.apply(x2, spec, training, buffers, *params)
+    out = _ChainFunction.apply(x2, spec, training, buffers, tuple(lead), *params)
+    return out.reshape(*lead, out.shape[-1])
+
+
+# ---- BatchNorm (+ activation) on wide / post-contraction tensors (csrc/mlp.cu, pcfb_bn_*) ---------------------------
+def bn_supported(C):
+    return bool(lib().pcfb_bn_supported(int(C)))
+
+
+class _BnActFunction(torch.autograd.Function):
+    """out = act(BatchNorm(x2)) for contiguous x2 [rows, C]; cfg = dict(act, training, eps, momentum, sync, lead)."""
+
+    @staticmethod
+    def forward(ctx, x2, gamma, beta, pivot, running_mean, running_var, cfg):
+        rows, C = x2.shape
+        dev = x2.device
+        act, training = cfg["act"], cfg["training"]
+        world = dist.get_world_size() if cfg["sync"] else 1
+        d_count = None
+        if training:
+            if world > 1:
+                d_count = global_rows(cfg["lead"], rows, dev)
+            ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
+            nblk = ctypes.c_int(0)
+            check(lib().pcfb_bn_stats(ptr(x2), rows, C, ptr(pivot), ptr(ws), ws.numel(), ctypes.addressof(nblk), stream_ptr()), "bn_stats")
+            part, nb = ws, nblk.value
+            if world > 1:
+                summed = torch.empty(2 * C, device=dev, dtype=F32)
+                check(lib().pcfb_sum_partials(ptr(ws), nblk.value, 2 * C, ptr(summed), stream_ptr()), "sum_partials")
+                dist.all_reduce(summed)
+                part, nb = summed, 1
+            scale = torch.empty(C, device=dev, dtype=F32); shift = torch.empty_like(scale)
+            mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
+            check(lib().pcfb_bn_finalize(ptr(part), nb, C, rows, ptr(d_count), ptr(pivot), ptr(gamma), ptr(beta), float(cfg["eps"]),
+                                         float(cfg["momentum"]), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift),
+                                         ptr(mean), ptr(invstd), stream_ptr()), "bn_finalize")
+        else:
+            invstd = torch.rsqrt(running_var + cfg["eps"])
+            scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
+            shift = ((beta if beta is not None else 0.) - running_mean * scale).contiguous()
+            mean = running_mean
+        out = torch.empty_like(x2)
+        check(lib().pcfb_bn_act(ptr(x2), rows, C, ptr(scale), ptr(shift), act, ptr(out), stream_ptr()), "bn_act")
+        ctx.cfg, ctx.d_count, ctx.world = cfg, d_count, world
+        ctx.has_affine = gamma is not None
+        ctx.save_for_backward(x2, scale, shift, mean, invstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x2, scale, shift, mean, invstd = ctx.saved_tensors
+        rows, C = x2.shape
+        dev = x2.device
+        cfg = ctx.cfg
+        dA = grad_out.reshape(rows, C)
+        if not dA.is_contiguous():
+            dA = dA.contiguous()
+        need_affine = ctx.has_affine and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        sums = local = None
+        if cfg["training"] or need_affine:
+            sums = torch.empty(2 * C, device=dev, dtype=F32)
+            ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
+            check(lib().pcfb_bn_backward_stats(ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cfg["act"],
+                                               ptr(sums), ptr(ws), ws.numel(), stream_ptr()), "bn_backward_stats")
+            local = sums
+            if cfg["training"] and ctx.world > 1:          # dx: sums over the global batch; dgamma / dbeta stay local
+                local = sums.clone()
+                dist.all_reduce(sums)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x2)
+            check(lib().pcfb_bn_backward(ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                                         ptr(sums) if cfg["training"] else 0, cfg["act"], ptr(ctx.d_count), ptr(dx), stream_ptr()), "bn_backward")
+        dgamma = local[C:] if need_affine else None
+        dbeta = local[:C] if need_affine else None
+        return dx, dgamma, dbeta, None, None, None, None
+
+
+def bn_act(x, bn, act, pivot=None):
+    """act(bn(x)) over the last dim of x [..., C] with a BatchNorm1d/2d/SyncBatchNorm-like module `bn` (batch statistics
+    over all leading dims when bn.training, running statistics otherwise; running stats / num_batches_tracked updated
+    like torch).  pivot: optional per-channel offset near the mean (the bias of the Linear that produced x)."""
+    if not x.is_cuda:
+        raise RuntimeError("pcf_b200 BatchNorm needs CUDA tensors (no CPU path)")
+    lead = tuple(x.shape[:-1])
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    training = bn.training or not bn.track_running_stats
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    cfg = dict(act=act, training=training, eps=bn.eps, momentum=0.1 if bn.momentum is None else bn.momentum,
+               sync=_sync_group(bn), lead=lead)
+    rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
+    out = _BnActFunction.apply(x2, bn.weight, bn.bias, pivot.detach() if pivot is not None else None, rm, rv, cfg)
     return out.reshape(*lead, out.shape[-1])

@@ -304,21 +304,39 @@ class Linear_BN(nn.Module):
         fused.bias.copy_(self.bn.bias + (self.c.bias - self.bn.running_mean) * scale)
         return fused
 
-    def forward(self, x):
+    def forward(self, x, act=0):
+        """act (fused_mlp.ACT_*): activation applied after the BatchNorm in the same kernel pass (0 = none, the
+        reference's module; callers that follow the block with ReLU / LeakyReLU pass it here)."""
+        from . import fused_mlp
         x = linear(x, self.c.weight, self.c.bias)
+        if fused_mlp.bn_supported(x.shape[-1]):
+            # BatchNorm over the last dim == the reference's permute(0,3,2,1) -> BN2d -> permute back / BN1d over a
+            # [rows, C] view (layer_utils.py:272-277): statistics + apply(+activation) as two passes of pcfb_bn_*
+            return fused_mlp.bn_act(x, self.bn, act, pivot=self.c.bias)
         shape = x.shape
         if isinstance(self.bn, nn.SyncBatchNorm):          # after convert_sync_batchnorm (DDP, sync_bn: True)
-            return self.bn(x.reshape(-1, shape[-1])).reshape(shape)
-        # BatchNorm over the last dim == BatchNorm1d over a [rows, C] view (same statistics as the
-        # reference's permute(0,3,2,1) -> BN2d -> permute back, layer_utils.py:272-277)
-        return F.batch_norm(x.reshape(-1, shape[-1]), self.bn.running_mean, self.bn.running_var, self.bn.weight,
-                            self.bn.bias, self.bn.training or not self.bn.track_running_stats,
-                            self._momentum(), self.bn.eps).reshape(shape)
+            y = self.bn(x.reshape(-1, shape[-1])).reshape(shape)
+        else:
+            y = F.batch_norm(x.reshape(-1, shape[-1]), self.bn.running_mean, self.bn.running_var, self.bn.weight,
+                             self.bn.bias, self.bn.training or not self.bn.track_running_stats,
+                             self._momentum(), self.bn.eps).reshape(shape)
+        return _activate(y, act)
 
     def _momentum(self):
         if self.bn.training and self.bn.track_running_stats and self.bn.num_batches_tracked is not None:
             self.bn.num_batches_tracked.add_(1)
         return 0.0 if self.bn.momentum is None else self.bn.momentum
+
+
+def _activate(y, act):
+    """torch form of the fused_mlp.ACT_* codes (channel counts the pcfb_bn_* kernels do not take)."""
+    if act == 1:
+        return F.relu(y)
+    if act == 2:
+        return F.leaky_relu(y, 0.1)
+    if act == 3:
+        return torch.sigmoid(y)
+    return y
 
 
 class UnaryBlock(nn.Module):
@@ -337,8 +355,9 @@ class UnaryBlock(nn.Module):
         if fused_mlp.supported([(lin.in_features, lin.out_features)]):
             act = fused_mlp.ACT_NONE if self.no_relu else fused_mlp.ACT_LEAKY
             return fused_mlp.mlp_chain(x, [(lin, bn, act)], self.training)
-        y = self.mlp(x) if isinstance(self.mlp, Linear_BN) else linear(x, self.mlp.weight, self.mlp.bias)
-        return self.leaky_relu(y)
+        if isinstance(self.mlp, Linear_BN):                # wide block: tcgen05 GEMM + BatchNorm/LeakyReLU in one apply pass
+            return self.mlp(x, act=fused_mlp.ACT_NONE if self.no_relu else fused_mlp.ACT_LEAKY)
+        return self.leaky_relu(linear(x, self.mlp.weight, self.mlp.bias))
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(

@@ -210,26 +210,27 @@ class PCFLayer(_PointLayerBase):
         else:
             lin, post_bn = self.linear, None
         new_feat = _contract(self.cfg, feats_x, nei_inds, inv, weights, None, guidance_score, lin.weight, lin.bias)
-        if post_bn is not None:
-            new_feat = _apply_bn(post_bn.bn, new_feat)
-        new_feat = self.dropout(F.relu(new_feat))
+        new_feat = _bn_relu(post_bn.bn, new_feat, lin.bias) if post_bn is not None else F.relu(new_feat)
+        new_feat = self.dropout(new_feat)
         new_feat = self.unary2(new_feat)
         sparse_feats = gather_max(dense_feats, nei_inds, inv) if strided else dense_feats
         shortcut = self.unary_shortcut(sparse_feats)
         return self.leaky_relu(self.drop_path(new_feat) + shortcut), weightNetInput
 
 
-def _apply_bn(bn, x):
-    """BatchNorm over the last dim of [B,N,C] with a BatchNorm1d-like module `bn` (batch statistics over all
-    points of the packed batch when training, layer_utils.py:276-277)."""
+def _bn_relu(bn, x, pivot=None):
+    """ReLU(BatchNorm(x)) over the last dim of [B,N,C] with a BatchNorm1d-like module `bn` (batch statistics over all
+    points of the packed batch when training, layer_utils.py:276-277; layers.py:708-709,721): two passes of pcfb_bn_*."""
+    if fused_mlp.bn_supported(x.shape[-1]):
+        return fused_mlp.bn_act(x, bn, fused_mlp.ACT_RELU, pivot=pivot)
     shape = x.shape
     if isinstance(bn, nn.SyncBatchNorm):
-        return bn(x.reshape(-1, shape[-1])).reshape(shape)
+        return F.relu(bn(x.reshape(-1, shape[-1])).reshape(shape))
     if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    return F.batch_norm(x.reshape(-1, shape[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
-                        bn.training or not bn.track_running_stats, 0.0 if bn.momentum is None else bn.momentum,
-                        bn.eps).reshape(shape)
+    return F.relu(F.batch_norm(x.reshape(-1, shape[-1]), bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                               bn.training or not bn.track_running_stats, 0.0 if bn.momentum is None else bn.momentum,
+                               bn.eps).reshape(shape))
 
 
 class _PConvLinearMixin:
@@ -245,6 +246,8 @@ class _PConvLinearMixin:
             self.linear = Linear_BN(lin_in, lin_out, bn_ver='1d') if cfg.BATCH_NORM else nn.Linear(lin_in, lin_out)
 
     def _contract_linear(self, feats, nei_inds, inv, weights, additional):
+        """-> ReLU(BN(Linear(contraction))): every caller in the reference applies ReLU right after the BatchNorm
+        (layers.py:709,721, 898, 1092), so the activation rides in the BatchNorm's apply pass."""
         cfg = self.cfg
         if cfg.PCONV_OPT:
             lin, bn = self.pconv_linear_opt.linear, (self.bn if cfg.BATCH_NORM else None)
@@ -253,7 +256,7 @@ class _PConvLinearMixin:
         else:
             lin, bn = self.linear, None
         y = _contract(cfg, feats, nei_inds, inv, weights, additional, None, lin.weight, lin.bias)
-        return y if bn is None else _apply_bn(bn, y)
+        return F.relu(y) if bn is None else _bn_relu(bn, y, lin.bias)
 
 
 class PointConvStridePE(_PointLayerBase, _PConvLinearMixin):
@@ -289,8 +292,7 @@ class PointConvStridePE(_PointLayerBase, _PConvLinearMixin):
                                                        self.cfg.USE_VI is True)
         feat_pe = self.pe_convs(localized_xyz)
         weights = self.weightnet(weightNetInput)
-        new_feat = self._contract_linear(feats_x, nei_inds, inv, weights, feat_pe)
-        new_feat = self.dropout(F.relu(new_feat))
+        new_feat = self.dropout(self._contract_linear(feats_x, nei_inds, inv, weights, feat_pe))
         new_feat = self.unary2(new_feat)
         sparse_feats = gather_max(dense_feats, nei_inds, inv) if strided else dense_feats
         shortcut = self.unary_shortcut(sparse_feats)
@@ -319,7 +321,7 @@ class PointConv(_PointLayerBase, _PConvLinearMixin):
         additional = weightNetInput if self.cfg.USE_PE else None
         weights = self.weightnet(weightNetInput)
         new_feat = self._contract_linear(dense_feats, nei_inds, inv, weights, additional)
-        return self.dropout(F.relu(new_feat)), weightNetInput
+        return self.dropout(new_feat), weightNetInput
 
 
 class PointConvTransposePE(_PointLayerBase, _PConvLinearMixin):
@@ -359,10 +361,11 @@ class PointConvTransposePE(_PointLayerBase, _PConvLinearMixin):
                                                        vi_features, self.cfg.USE_VI is True)
         feat_pe = self.pe_convs(localized_xyz) if self.cfg.USE_PE else None
         weights = self.weightnet(weightNetInput)
-        new_feat = F.relu(self._contract_linear(sparse_feats, nei_inds, inv, weights, feat_pe))
+        new_feat = self._contract_linear(sparse_feats, nei_inds, inv, weights, feat_pe)
         if dense_feats is not None:
             new_feat = new_feat + dense_feats
         new_feat = self.dropout(new_feat)
         for conv in self.mlp2_convs:
-            new_feat = F.relu(conv(new_feat))
+            new_feat = conv(new_feat, act=fused_mlp.ACT_RELU) if isinstance(conv, Linear_BN) else \
+                F.relu(linear(new_feat, conv.weight, conv.bias))
         return new_feat, weightNetInput

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused_mlp
 from .layers import PCFLayer, PointConv, PointConvStridePE, PointConvTransposePE
 from .layer_utils import Linear_BN, linear
 
@@ -104,7 +105,8 @@ class PCF_Backbone(nn.Module):
             x, _ = self.selfpointconv_res1(pointclouds[0], x, edges_self[0], norms[0], vi_features=vi, **kw)
             x, _ = self.selfpointconv_res2(pointclouds[0], x, edges_self[0], norms[0], vi_features=vi, **kw)
         else:
-            x = F.relu(self.selfmlp(x))
+            x = self.selfmlp(x, act=fused_mlp.ACT_RELU) if isinstance(self.selfmlp, Linear_BN) else \
+                F.relu(linear(x, self.selfmlp.weight, self.selfmlp.bias))          # after replace_batchnorm
         feat_list = [x]
         for i, conv in enumerate(self.pointconv):
             kw = _inv_kwargs(opt, inv_neighbors_forward, inv_k_forward, inv_idx_forward, i)
@@ -176,6 +178,17 @@ class PointConvFormer_Segmentation(nn.Module):
 
     def forward(self, features, pointclouds, edges_self, edges_forward, edges_propagate, norms,
                 inv_self=None, inv_forward=None, inv_propagate=None):
+        # SyncBatchNorm needs the row counts summed over ranks: one all-reduce of the per-level point counts here
+        # serves every BatchNorm of the step (no-op on one GPU); cleared again so nothing stale outlives the forward
+        fused_mlp.register_levels([p.shape[1] for p in pointclouds], features.device)
+        try:
+            return self._forward(features, pointclouds, edges_self, edges_forward, edges_propagate, norms,
+                                 inv_self, inv_forward, inv_propagate)
+        finally:
+            fused_mlp.register_levels([], features.device)
+
+    def _forward(self, features, pointclouds, edges_self, edges_forward, edges_propagate, norms,
+                 inv_self=None, inv_forward=None, inv_propagate=None):
         opt = bool(self.cfg.PCONV_OPT)
         ins, iks, iis = inv_self if (opt and inv_self is not None) else (None, None, None)
         inf, ikf, iif = inv_forward if (opt and inv_forward is not None) else (None, None, None)
@@ -194,4 +207,5 @@ class PointConvFormer_Segmentation(nn.Module):
                 if vi is None:
                     vi = vi_new
             feat_list[lvl] = x
-        return linear(self.dropout_fc(F.relu(self.fc1(x))), self.fc2.weight, self.fc2.bias)
+        h = self.fc1(x, act=fused_mlp.ACT_RELU) if isinstance(self.fc1, Linear_BN) else F.relu(linear(x, self.fc1.weight, self.fc1.bias))
+        return linear(self.dropout_fc(h), self.fc2.weight, self.fc2.bias)

@@ -51,6 +51,19 @@ def _worker(rank, world, port, ret):
     (y * gos[rank].to(dev)).sum().backward()
     out = {"y": y.detach().cpu(), "gx": x.grad.cpu(), "gw0": lins[0].weight.grad.cpu(), "gw2": lins[2].weight.grad.cpu(),
            "gg1": bns[1].weight.grad.cpu(), "gb2": bns[2].bias.grad.cpu()}
+    # the wide BatchNorm + ReLU (pcfb_bn_*) under SyncBatchNorm, with the row counts coming from register_levels
+    torch.manual_seed(7)
+    wbn = torch.nn.SyncBatchNorm.convert_sync_batchnorm(torch.nn.BatchNorm1d(96)).to(dev)
+    torch.nn.init.uniform_(wbn.weight, 0.5, 1.5)
+    xw_all = [torch.randn(1, n, 96, generator=g) * 2 + 0.3 for n in rows]
+    gw_all = [torch.randn(1, n, 96, generator=g) for n in rows]
+    fused_mlp.register_levels([rows[rank]], dev)
+    xw = xw_all[rank].to(dev).requires_grad_(True)
+    yw = fused_mlp.bn_act(xw, wbn, fused_mlp.ACT_RELU)
+    fused_mlp.register_levels([], dev)
+    (yw * gw_all[rank].to(dev)).sum().backward()
+    out.update(wy=yw.detach().cpu()[0], wgx=xw.grad.cpu()[0], wgg=wbn.weight.grad.cpu(), wgb=wbn.bias.grad.cpu(),
+               wrm=wbn.running_mean.cpu(), wrv=wbn.running_var.cpu())
     gathered = [None] * world
     dist.all_gather_object(gathered, out)
     if rank == 0:
@@ -71,6 +84,20 @@ def _worker(rank, world, port, ret):
         for k in ("gw0", "gw2", "gg1", "gb2"):                     # parameter gradients: sum over ranks = global gradient
             tot = sum(o[k].double() for o in gathered)
             errs[k] = float((tot - ref[k]).abs().max() / ref[k].abs().max())
+        torch.manual_seed(7)
+        rbn = torch.nn.BatchNorm1d(96).to(dev)
+        torch.nn.init.uniform_(rbn.weight, 0.5, 1.5)
+        rbn = rbn.double()
+        XW = torch.cat([t[0] for t in xw_all]).to(dev, torch.float64).requires_grad_(True)
+        hw = torch.relu(rbn(XW))
+        (hw * torch.cat([t[0] for t in gw_all]).to(dev, torch.float64)).sum().backward()
+        rel = lambda a, b: float((a.double().cpu() - b.cpu()).abs().max() / b.abs().max())
+        errs["wy"] = rel(torch.cat([o["wy"] for o in gathered]), hw.detach())
+        errs["wgx"] = rel(torch.cat([o["wgx"] for o in gathered]), XW.grad)
+        errs["wgg"] = rel(sum(o["wgg"].double() for o in gathered), rbn.weight.grad)
+        errs["wgb"] = rel(sum(o["wgb"].double() for o in gathered), rbn.bias.grad)
+        errs["wrm"] = rel(gathered[1]["wrm"], rbn.running_mean)
+        errs["wrv"] = rel(gathered[1]["wrv"], rbn.running_var)
         ret["errs"] = errs
     dist.barrier()
     dist.destroy_process_group()
@@ -87,3 +114,5 @@ def test_fused_chain_syncbn_two_ranks_match_single_process():
     assert errs["y"] < 2e-5 and errs["gx"] < 2e-4, errs
     for k in ("gw0", "gw2", "gg1", "gb2"):
         assert errs[k] < 1e-3, errs                                # fp32 sums behind three train-mode BatchNorms
+    assert errs["wy"] < 1e-5 and errs["wgx"] < 1e-4 and errs["wgg"] < 1e-4 and errs["wgb"] < 1e-4, errs
+    assert errs["wrm"] < 1e-5 and errs["wrv"] < 1e-5, errs

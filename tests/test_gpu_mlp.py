@@ -99,3 +99,49 @@ def test_chain_strided_input_and_determinism():
     a = fused_mlp.mlp_chain(x, spec, True)
     b = fused_mlp.mlp_chain(x.contiguous(), spec, True)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("rows,C", [(102095, 32), (5153, 96), (1026, 128), (184, 384), (7, 64), (40000, 20)])
+def test_bn_act_matches_float64(rows, C, act, training):
+    """pcfb_bn_* (the BatchNorm + activation behind the fused contraction and the wide per-point blocks) vs
+    torch BatchNorm1d + activation in float64: output, input gradient, dgamma / dbeta, running statistics."""
+    from pcf_b200 import fused_mlp
+    assert fused_mlp.bn_supported(C)
+    torch.manual_seed(rows + C)
+    bn = nn.BatchNorm1d(C, momentum=0.1)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.3 * torch.randn(C)); bn.bias.copy_(0.3 * torch.randn(C))
+        bn.running_mean.copy_(0.2 * torch.randn(C)); bn.running_var.copy_(0.5 + torch.rand(C))
+    import copy
+    ref = copy.deepcopy(bn).double().train(training)
+    pivot = torch.randn(C) * 0.5
+    x = torch.randn(1, rows, C) * (0.5 + torch.rand(C)) + pivot + 0.1 * torch.randn(C)      # mean near the pivot, like y = xW^T + b
+    go = torch.randn(1, rows, C)
+    xr = x.double().requires_grad_(True)
+    h = act_ref(ref(xr[0]), act)
+    (h * go[0].double()).sum().backward()
+    bn.cuda().train(training)
+    xc = x.cuda().requires_grad_(True)
+    out = fused_mlp.bn_act(xc, bn, act, pivot=pivot.cuda() if C != 20 else None)
+    assert out.shape == xc.shape
+    (out * go.cuda()).sum().backward()
+    assert max_err_scaled(out[0], h) < 1e-5, ("out", max_err_scaled(out[0], h))
+    assert max_err_scaled(xc.grad, xr.grad) < 1e-4, ("dx", max_err_scaled(xc.grad, xr.grad))
+    assert max_err_scaled(bn.weight.grad, ref.weight.grad) < 1e-4
+    assert max_err_scaled(bn.bias.grad, ref.bias.grad) < 1e-4
+    assert max_err_scaled(bn.running_mean, ref.running_mean) < 1e-5
+    assert max_err_scaled(bn.running_var, ref.running_var) < 1e-5
+    assert int(bn.num_batches_tracked) == int(ref.num_batches_tracked)
+
+
+def test_bn_act_deterministic_and_rejects_cpu():
+    from pcf_b200 import fused_mlp
+    bn = nn.BatchNorm1d(64).cuda().train()
+    x = torch.randn(1, 30000, 64, device="cuda")
+    a = fused_mlp.bn_act(x, bn, 1)
+    b = fused_mlp.bn_act(x, bn, 1)
+    assert torch.equal(a, b)
+    with pytest.raises(RuntimeError):
+        fused_mlp.bn_act(x.cpu(), bn, 1)
