@@ -750,9 +750,19 @@ __global__ void mlp_fused_finalize_kernel(const float *__restrict__ w_partial, c
 
 // ---- host side ---------------------------------------------------------------------------------------------
 static inline int cmax_of(int c) { return c <= 16 ? 16 : (c <= 32 ? 32 : 64); }
-constexpr int ML_RPT = 8;          // rows per thread in the streaming passes
-
-static inline int mlp_blocks(int64_t E) { return (int)((E + (int64_t)ML_THREADS * ML_RPT - 1) / ((int64_t)ML_THREADS * ML_RPT)); }
+constexpr int ML_RPT = 8;          // most rows per thread in the streaming passes
+// Rows per thread: 8 for the level-0 edge tensors (1.6 M rows), fewer as the tensor shrinks so that the coarse levels
+// (3 k .. 80 k rows) still spread over the SMs -- with a fixed 8 a 16 k-row pass ran as 9 blocks whose threads walked
+// 8 rows one after the other (ncu: 47-56 us for a pass that moves 4 MB; 14 of the model's 25 PointConvFormer layers
+// live on those levels).
+static inline int mlp_rpt(int64_t E) {
+    const int64_t r = (E + (int64_t)ML_THREADS * kNumSMs * 4 - 1) / ((int64_t)ML_THREADS * kNumSMs * 4);
+    return r < 1 ? 1 : (r > ML_RPT ? ML_RPT : (int)r);
+}
+static inline int mlp_blocks(int64_t E) {
+    const int64_t per = (int64_t)ML_THREADS * mlp_rpt(E);
+    return (int)((E + per - 1) / per);
+}
 static inline int mlp_wblocks(int64_t E, int *gpb) {
     const int64_t tiles = (E + 127) / 128;
     int64_t blocks = tiles < 3 * kNumSMs ? tiles : 3 * kNumSMs;
@@ -805,7 +815,7 @@ extern "C" int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int
     MlpLayer L{W, b, cin, cout, in_scale, in_shift, in_act};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int ci = cmax_of(cin), co = cmax_of(cout);
-    ML_DISPATCH_IO(ci, co, (mlp_fwd_kernel<CI, CO><<<blocks, ML_THREADS, 0, st>>>(x, ldx, E, L, y, ldy, stat_partial, ML_RPT)));
+    ML_DISPATCH_IO(ci, co, (mlp_fwd_kernel<CI, CO><<<blocks, ML_THREADS, 0, st>>>(x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E))));
     return check_launch("mlp_fwd_kernel");
 }
 
@@ -853,9 +863,9 @@ extern "C" int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y,
     int rc;
     if (E > 0) {
         const int co = cmax_of(C);
-        if (co == 16) mlp_bwd_stats_kernel<16><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, ML_RPT);
-        else if (co == 32) mlp_bwd_stats_kernel<32><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, ML_RPT);
-        else mlp_bwd_stats_kernel<64><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, ML_RPT);
+        if (co == 16) mlp_bwd_stats_kernel<16><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
+        else if (co == 32) mlp_bwd_stats_kernel<32><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
+        else mlp_bwd_stats_kernel<64><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
         if ((rc = check_launch("mlp_bwd_stats_kernel"))) return rc;
     }
     sum_partials_kernel<<<ceil_div(2 * C * 32, 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * C, sums);
@@ -910,7 +920,7 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
         const int blocks = mlp_blocks(E);
         if (E > 0) {
             ML_DISPATCH_IO(ci, co, (mlp_bwd_input_kernel<CI, CO, (CI <= 32)><<<blocks, ML_THREADS, 0, st>>>(
-                dA, ldd, y, ldy, E, W, cin, cout, B, dA_prev, ldp, x_prev, ldx, Bp, prev_sums ? partial : nullptr, ML_RPT)));
+                dA, ldd, y, ldy, E, W, cin, cout, B, dA_prev, ldp, x_prev, ldx, Bp, prev_sums ? partial : nullptr, mlp_rpt(E))));
             if ((rc = check_launch("mlp_bwd_input_kernel"))) return rc;
         }
         if (prev_sums) {
