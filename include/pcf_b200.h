@@ -198,7 +198,8 @@ int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int cout, cons
                      float *stat_partial, int *h_nblocks, void *stream);
 int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, const double *d_count, const float *pivot,
                      const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
-                     float *running_var, float *scale, float *shift, float *mean, float *invstd, void *stream);
+                     float *running_var, float *scale, float *shift, float *mean, float *invstd,
+                     int64_t *batches_tracked /* BatchNorm.num_batches_tracked, incremented; may be NULL */, void *stream);
 int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
                 void *stream);
 int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y, int ldy, int64_t E, int C, const float *scale,

@@ -49,7 +49,7 @@ SIGNATURES = {
     "pcfb_mlp_supported": (c_int, [c_int, c_int]),
     "pcfb_mlp_workspace": (c_size_t, [c_int64, c_int, c_int]),
     "pcfb_mlp_forward": (c_int, [_P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, c_int, _P, c_int, _P, _P, _P]),
-    "pcfb_bn_finalize": (c_int, [_P, c_int, c_int, c_int64, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P]),
+    "pcfb_bn_finalize": (c_int, [_P, c_int, c_int, c_int64, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pcfb_bn_act": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P]),
     "pcfb_mlp_backward_stats": (c_int, [_P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, c_size_t, _P]),
     "pcfb_mlp_backward": (c_int, [_P, c_int, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int,

@@ -147,7 +147,7 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partial, int nblock
                                    const double *__restrict__ d_count, const float *__restrict__ pivot, const float *__restrict__ gamma,
                                    const float *__restrict__ beta, float eps, float momentum, float *__restrict__ running_mean,
                                    float *__restrict__ running_var, float *__restrict__ scale, float *__restrict__ shift,
-                                   float *__restrict__ mean_out, float *__restrict__ invstd_out)
+                                   float *__restrict__ mean_out, float *__restrict__ invstd_out, long long *__restrict__ batches_tracked)
 {
     // one warp per channel: lanes stride over the block partials, then a fixed shuffle tree (deterministic)
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -155,13 +155,23 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partial, int nblock
     if (c >= C) return;
     const double count = d_count ? *d_count : count_host;
     double s1 = 0.0, s2 = 0.0;
-    for (int b = lane; b < nblocks; b += 32) {
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {                 // four independent loads per sum in flight (the loop is pure latency)
+        const float a0 = partial[((size_t)b * 2 + 0) * C + c], a1 = partial[((size_t)(b + 32) * 2 + 0) * C + c];
+        const float a2 = partial[((size_t)(b + 64) * 2 + 0) * C + c], a3 = partial[((size_t)(b + 96) * 2 + 0) * C + c];
+        const float q0 = partial[((size_t)b * 2 + 1) * C + c], q1 = partial[((size_t)(b + 32) * 2 + 1) * C + c];
+        const float q2 = partial[((size_t)(b + 64) * 2 + 1) * C + c], q3 = partial[((size_t)(b + 96) * 2 + 1) * C + c];
+        s1 += (double)a0; s1 += (double)a1; s1 += (double)a2; s1 += (double)a3;
+        s2 += (double)q0; s2 += (double)q1; s2 += (double)q2; s2 += (double)q3;
+    }
+    for (; b < nblocks; b += 32) {
         s1 += (double)partial[((size_t)b * 2 + 0) * C + c];
         s2 += (double)partial[((size_t)b * 2 + 1) * C + c];
     }
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, sft); s2 += __shfl_xor_sync(0xffffffffu, s2, sft); }
     if (lane != 0) return;
+    if (c == 0 && batches_tracked) *batches_tracked += 1;          // BatchNorm.num_batches_tracked (int64), one writer
     const double m_p = s1 / count;                       // mean of (y - pivot)
     double var = s2 / count - m_p * m_p;
     if (var < 0.0) var = 0.0;
@@ -262,7 +272,13 @@ __global__ void sum_partials_kernel(const float *__restrict__ partial, int nbloc
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += (double)partial[(size_t)b * n + i];
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {
+        const float a0 = partial[(size_t)b * n + i], a1 = partial[(size_t)(b + 32) * n + i];
+        const float a2 = partial[(size_t)(b + 64) * n + i], a3 = partial[(size_t)(b + 96) * n + i];
+        s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+    }
+    for (; b < nblocks; b += 32) s += (double)partial[(size_t)b * n + i];
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
     if (lane == 0) out[i] = (float)s;
@@ -712,7 +728,13 @@ __global__ void mlp_weight_finalize_kernel(const float *__restrict__ partial, in
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
     double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += (double)partial[(size_t)b * n + i];
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {
+        const float a0 = partial[(size_t)b * n + i], a1 = partial[(size_t)(b + 32) * n + i];
+        const float a2 = partial[(size_t)(b + 64) * n + i], a3 = partial[(size_t)(b + 96) * n + i];
+        s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+    }
+    for (; b < nblocks; b += 32) s += (double)partial[(size_t)b * n + i];
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
     if (lane != 0) return;
@@ -821,11 +843,13 @@ extern "C" int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int
 
 extern "C" int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, const double *d_count, const float *pivot,
                                 const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
-                                float *running_var, float *scale, float *shift, float *mean, float *invstd, void *stream)
+                                float *running_var, float *scale, float *shift, float *mean, float *invstd,
+                                int64_t *batches_tracked, void *stream)
 {
     PCFB_REQUIRE(partial && scale && shift && C >= 1, "pcfb_bn_finalize: null pointer");
     bn_finalize_kernel<<<ceil_div(C * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        partial, nblocks, C, (double)count, d_count, pivot, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd);
+        partial, nblocks, C, (double)count, d_count, pivot, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd,
+        reinterpret_cast<long long *>(batches_tracked));
     return check_launch("bn_finalize_kernel");
 }
 

@@ -17,8 +17,9 @@
 
 namespace pcfb {
 
-constexpr int BT = 64;         // points per tile
-constexpr int BNT = 256;
+constexpr int BT = 64;         // points per tile (level-0/1 sized launches)
+constexpr int BT_SMALL = 16;   // points per tile on the coarse levels: the tile's work is a serial FMA stream per CTA, so a 184-point
+                               // level that ran as 3 CTAs for 115 us runs as 12 (and a 1 k-point level as 65 instead of 17)
 constexpr int BK = 16;         // neighbours
 constexpr int BCC = 4;         // channels per chunk
 
@@ -38,7 +39,7 @@ __host__ __device__ inline int b2_pad4odd(int x) {
 
 struct Bwd2Plan { int GS, DS, GDS; size_t off_g, off_d, off_gd, off_nei, total; };
 
-__host__ __device__ inline Bwd2Plan b2_plan(const pcfb_pconv_shape &s) {
+__host__ __device__ inline Bwd2Plan b2_plan(const pcfb_pconv_shape &s, int BT = 64) {
     Bwd2Plan pl;
     pl.GS = b2_pad4odd(BK * BCC);
     pl.DS = b2_pad4odd(BCC * s.C_mid);
@@ -66,12 +67,13 @@ __device__ __forceinline__ void b2_commit() { asm volatile("cp.async.commit_grou
 template <int N>
 __device__ __forceinline__ void b2_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
 
-template <int CMID, bool GUIDE>
-__global__ void __launch_bounds__(BNT, 1) pconv_bwd2_kernel(Bwd2Args a)
+template <int CMID, bool GUIDE, int BT>
+__global__ void __launch_bounds__(4 * BT, 1) pconv_bwd2_kernel(Bwd2Args a)
 {
+    constexpr int BNT = 4 * BT;                                 // thread = (point, quarter of the 16 neighbours)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const pcfb_pconv_shape &s = a.s;
-    const Bwd2Plan pl = b2_plan(s);
+    const Bwd2Plan pl = b2_plan(s, BT);
     float *g_s = reinterpret_cast<float *>(smem_raw + pl.off_g);
     float *d_s = reinterpret_cast<float *>(smem_raw + pl.off_d);
     float *gd_s = reinterpret_cast<float *>(smem_raw + pl.off_gd);
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(BNT, 1) pconv_bwd2_kernel(Bwd2Args a)
     const int C_in = s.C_in, C_add = s.C_add, C_cat = C_in + C_add, KK = C_cat * CMID, H = s.H;
     const int n_in = s.n_in, n_out = s.n_out, n_chunks = a.n_chunks;
     const int tid = threadIdx.x;
-    const int p = tid & (BT - 1), kg = tid >> 6;
+    const int p = tid & (BT - 1), kg = tid / BT;
     const int GS = pl.GS, DS = pl.DS;
 
     auto issue_nei = [&](int m0, long long *dst) {
@@ -282,11 +284,20 @@ bool pconv_bwd2_supported(const pcfb_pconv_shape *s) {
 }
 
 template <int CMID, bool GUIDE>
-static int launch_bwd2(const Bwd2Args &a, const Bwd2Plan &pl, cudaStream_t st) {
-    PCFB_CUDA(cudaFuncSetAttribute(pconv_bwd2_kernel<CMID, GUIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+static int launch_bwd2(const Bwd2Args &a, const Bwd2Plan &, cudaStream_t st) {
+    // fewer 64-point tiles than ~1.5 per SM: the launch is bounded by one CTA's serial work, use 16-point tiles
+    if (ceil_div(a.s.n_out, BT) < kNumSMs * 3 / 2) {
+        const Bwd2Plan pl = b2_plan(a.s, BT_SMALL);
+        PCFB_CUDA(cudaFuncSetAttribute(pconv_bwd2_kernel<CMID, GUIDE, BT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        const int grid = max(1, min(ceil_div(a.s.n_out, BT_SMALL), kNumSMs * 6));
+        pconv_bwd2_kernel<CMID, GUIDE, BT_SMALL><<<grid, 4 * BT_SMALL, pl.total, st>>>(a);
+        return check_launch("pconv_bwd2_kernel");
+    }
+    const Bwd2Plan pl = b2_plan(a.s, BT);
+    PCFB_CUDA(cudaFuncSetAttribute(pconv_bwd2_kernel<CMID, GUIDE, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int per_sm = (pl.total + 1024 <= 113 * 1024) ? 2 : 1;   // register use decides the real residency
     const int grid = max(1, min(ceil_div(a.s.n_out, BT), kNumSMs * per_sm));
-    pconv_bwd2_kernel<CMID, GUIDE><<<grid, BNT, pl.total, st>>>(a);
+    pconv_bwd2_kernel<CMID, GUIDE, BT><<<grid, 4 * BT, pl.total, st>>>(a);
     return check_launch("pconv_bwd2_kernel");
 }
 

@@ -90,7 +90,7 @@ class _ChainFunction(torch.autograd.Function):
                                          ptr(y), cout, ptr(ws), ctypes.addressof(nblk), stream_ptr()), "mlp_forward")
             scale = shift = mean = invstd = None
             if s["has_bn"]:
-                rm, rv = buffers[l]
+                rm, rv, nbt = buffers[l]
                 if training:
                     scale = torch.empty(cout, device=dev, dtype=F32); shift = torch.empty_like(scale)
                     mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
@@ -102,7 +102,7 @@ class _ChainFunction(torch.autograd.Function):
                         part, nb = summed, 1
                     check(lib().pcfb_bn_finalize(ptr(part), nb, cout, count, ptr(d_count) if s["sync"] else 0, ptr(b), ptr(gamma), ptr(beta), float(s["eps"]),
                                                  float(s["momentum"]), ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean),
-                                                 ptr(invstd), stream_ptr()), "bn_finalize")
+                                                 ptr(invstd), ptr(nbt), stream_ptr()), "bn_finalize")
                 else:
                     invstd = torch.rsqrt(rv + s["eps"])
                     scale = (gamma * invstd).contiguous()
@@ -234,9 +234,8 @@ def mlp_chain(x, layers, training):
                          momentum=(bn.momentum if bn.momentum is not None else 0.1) if has_bn else 0.1,
                          sync=_sync_group(bn) if has_bn else False))
         params += [lin.weight, lin.bias, bn.weight if has_bn else None, bn.bias if has_bn else None]
-        buffers.append((bn.running_mean, bn.running_var) if has_bn else (None, None))
-        if has_bn and training and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        # num_batches_tracked is incremented by the finalize kernel (one tiny torch add_ per BatchNorm was 273 launches a step)
+        buffers.append((bn.running_mean, bn.running_var, bn.num_batches_tracked) if has_bn else (None, None, None))
     out = _ChainFunction.apply(x2, spec, training, buffers, tuple(lead), *params)
     return out.reshape(*lead, out.shape[-1])
 
@@ -272,7 +271,7 @@ class _BnActFunction(torch.autograd.Function):
             mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
             check(lib().pcfb_bn_finalize(ptr(part), nb, C, rows, ptr(d_count), ptr(pivot), ptr(gamma), ptr(beta), float(cfg["eps"]),
                                          float(cfg["momentum"]), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift),
-                                         ptr(mean), ptr(invstd), stream_ptr()), "bn_finalize")
+                                         ptr(mean), ptr(invstd), ptr(cfg["nbt"]), stream_ptr()), "bn_finalize")
         else:
             invstd = torch.rsqrt(running_var + cfg["eps"])
             scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
@@ -326,10 +325,9 @@ def bn_act(x, bn, act, pivot=None):
     if not x2.is_contiguous():
         x2 = x2.contiguous()
     training = bn.training or not bn.track_running_stats
-    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
     cfg = dict(act=act, training=training, eps=bn.eps, momentum=0.1 if bn.momentum is None else bn.momentum,
-               sync=_sync_group(bn), lead=lead)
+               sync=_sync_group(bn), lead=lead,
+               nbt=bn.num_batches_tracked if bn.track_running_stats else None)      # incremented by the finalize kernel
     rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
     out = _BnActFunction.apply(x2, bn.weight, bn.bias, pivot.detach() if pivot is not None else None, rm, rv, cfg)
     return out.reshape(*lead, out.shape[-1])

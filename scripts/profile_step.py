@@ -49,6 +49,20 @@ def main():
     with open(out, "w") as f:
         f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
     print(open(out).read()[:6000])
+    # per (kernel, grid) durations from the chrome trace: separates the level-0 launches from the latency-bound coarse levels
+    import collections, re
+    trace = os.path.join(ROOT, "gpurun_out", "prof_trace.json")
+    prof.export_chrome_trace(trace)
+    agg = collections.defaultdict(list)
+    for ev in json.load(open(trace))["traceEvents"]:
+        if ev.get("cat") == "kernel":
+            name = re.sub(r"\(.*$", "", ev["name"]).replace("void ", "").replace("pcfb::", "")
+            agg[(name[:60], str(ev.get("args", {}).get("grid")))].append(ev["dur"])
+    os.remove(trace)
+    with open(os.path.join(ROOT, "gpurun_out", "prof_kernels_by_grid.txt"), "w") as f:
+        f.write("# one training step, CUPTI kernel durations grouped by (kernel, grid): calls, mean us, total us\n")
+        for (name, grid), d in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write("%-62s %-16s %4d %9.1f %10.1f\n" % (name, grid, len(d), sum(d) / len(d), sum(d)))
     if stacks:                                      # who launches the small elementwise kernels?
         with open(os.path.join(ROOT, "gpurun_out", "prof_stacks.txt"), "w") as f:
             for ev in sorted(prof.key_averages(group_by_stack_n=8), key=lambda e: -e.count):
