@@ -42,7 +42,7 @@ def compute_knn(ref_points, query_points, K, dilated_rate=1, method='keops'):
 # 'grid' (default): exact uniform-grid search; 'brute': the shared-memory tiled brute-force kernel.  Both return
 # identical tables (tests/test_gpu_knn.py); brute force is O(N^2) per scene.
 KNN_METHOD = "grid"
-BRUTE_MAX_REFS = 6000          # per-scene reference count below which brute force beats the grid search
+BRUTE_MAX_REFS = 256           # per-scene reference count below which brute force beats the grid search
 
 
 def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagate, grid_size=None, method=None):
@@ -63,9 +63,9 @@ def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagat
                 e_fwd.append(pcf_cuda.knn_packed(pcs[j - 1], counts[j - 1], pcs[j], counts[j], K_forward[j]))
                 e_prop.append(pcf_cuda.knn_packed(pcs[j], counts[j], pcs[j - 1], counts[j - 1], K_propagate[j]))
         return [e_self], [e_fwd], [e_prop]
-    # Coarse levels (every scene <= BRUTE_MAX_REFS reference points): the tiled brute-force kernel.  One thread walks all
-    # references of its scene in a few tens of microseconds, while the grid search is a chain of dependent cell look-ups
-    # (measured per query set: 128 us at 1 k points, 185 us at 5 k) -- same table either way.
+    # Tiny levels (every scene <= BRUTE_MAX_REFS reference points) use the tiled brute-force kernel; above that the grid
+    # search wins even when it is latency bound (measured per query set, grid vs brute force: 128 vs 232 us at 1 k
+    # references, 185 vs 287 us at 5 k, 105 vs 84 us at 184) -- same table either way.
     small = [max(counts[j]) <= BRUTE_MAX_REFS for j in range(L)]
     grids = [None if small[j] else pcf_cuda.KnnGrid(pcs[j], counts[j], 2.5 * float(grid_size[j]) if grid_size is not None else 0.0)
              for j in range(L)]
