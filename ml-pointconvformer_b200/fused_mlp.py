@@ -32,6 +32,7 @@ def _sync_group(bn):
 # whose leading shape is not a registered level falls back to its own all-reduce.
 _LEVEL_ROWS = {}          # local N_l -> (1-element double tensor with the global N_l)
 _DERIVED_ROWS = {}        # (local N_l, factor) -> global N_l * factor
+_LOCAL_COUNTS = {}        # (counts, device) -> device tensor of the local counts
 
 
 def register_levels(point_counts, device):
@@ -42,7 +43,13 @@ def register_levels(point_counts, device):
     counts = [int(c) for c in point_counts]
     if not counts or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
         return
-    g = torch.tensor(counts, device=device, dtype=torch.float64)
+    key = (tuple(counts), str(device))
+    local = _LOCAL_COUNTS.get(key)
+    if local is None:                                 # H2D copy once per distinct packing, never inside a captured graph
+        if len(_LOCAL_COUNTS) > 1024:
+            _LOCAL_COUNTS.clear()
+        local = _LOCAL_COUNTS[key] = torch.tensor(counts, dtype=torch.float64).to(device)
+    g = local.clone()
     dist.all_reduce(g)
     for i, c in enumerate(counts):
         if counts.count(c) == 1:
