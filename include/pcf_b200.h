@@ -215,6 +215,20 @@ int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int ldy, int64_t
 int pcfb_sum_partials(const float *partial, int nblocks, int n, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Small all-reduce (sum, <= pcfb_peer_max_floats() floats) over NVLink / NVSwitch peer memory: the SyncBatchNorm
+ * statistics exchange (torch.nn.SyncBatchNorm after convert_sync_batchnorm, train_ScanNet_DDP_WarmUP.py:190-195;
+ * sync_bn: True in configs/configPCF_Opt_10cm.yaml) as ONE single-CTA kernel instead of an NCCL call: every rank
+ * stores its values into its slot of every peer's buffer, publishes an epoch flag (st.release.sys), waits for the
+ * peers' flags (ld.acquire.sys) and sums the slots in rank order (bit-identical on all ranks).
+ * peer_bases: device array of `world` pointers, entry r = rank r's symmetric buffer of pcfb_peer_buffer_bytes(world)
+ * bytes as mapped into THIS process (all-zero before the first call).  Every rank must make the same sequence of
+ * calls; in/out may alias; the kernel traps after 20 s if a peer never arrives.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcfb_peer_buffer_bytes(int world);
+int pcfb_peer_max_floats(void);
+int pcfb_peer_allreduce(const float *in, float *out, int n, const void *peer_bases, int rank, int world, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * BatchNorm (+ activation) over a contiguous [rows, C] tensor, C % 4 == 0, C <= 1024: the BatchNorm + ReLU that
  * follows the fused contraction (layers.py:708-709, 721, 893-898, 1086-1092; `self.bn` / `linear.bn`) and the
  * Linear_BN (+ LeakyReLU) of the wide per-point blocks (layer_utils.py:241-319), replacing torch's

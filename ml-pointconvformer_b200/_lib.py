@@ -55,6 +55,9 @@ SIGNATURES = {
     "pcfb_mlp_backward": (c_int, [_P, c_int, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int,
                                   _P, c_int, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "pcfb_sum_partials": (c_int, [_P, c_int, c_int, _P, _P]),
+    "pcfb_peer_buffer_bytes": (c_size_t, [c_int]),
+    "pcfb_peer_max_floats": (c_int, []),
+    "pcfb_peer_allreduce": (c_int, [_P, _P, c_int, _P, c_int, c_int, _P]),
     "pcfb_bn_supported": (c_int, [c_int]),
     "pcfb_bn_workspace": (c_size_t, [c_int64, c_int]),
     "pcfb_bn_stats": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P, _P]),

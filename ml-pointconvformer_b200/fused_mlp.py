@@ -25,6 +25,57 @@ def _sync_group(bn):
     return False
 
 
+# ---- the SyncBatchNorm statistics exchange --------------------------------------------------------------------------
+# ~540 all-reduces of <= 2 x 384 floats per training step: latency only.  When the ranks share an NVLink / NVSwitch domain
+# the exchange runs as one single-CTA kernel over symmetric peer memory (csrc/peer_reduce.cu, ~1/3 of the latency of an
+# NCCL call inside the captured step); otherwise -- other backend, no peer access, PCFB_PEER_REDUCE=0 -- it is
+# dist.all_reduce.  torch.distributed._symmetric_memory only provides the allocation + address exchange (plumbing).
+_PEER = {"state": None}       # None = not tried, False = unavailable, dict = ready
+
+
+def _peer_setup(device):
+    import os
+    st = {"ok": False}
+    try:
+        if os.environ.get("PCFB_PEER_REDUCE", "1") == "0" or dist.get_backend() != "nccl":
+            raise RuntimeError("disabled")
+        import torch.distributed._symmetric_memory as symm_mem
+        world, rank = dist.get_world_size(), dist.get_rank()
+        nbytes = int(lib().pcfb_peer_buffer_bytes(world))
+        if nbytes == 0:
+            raise RuntimeError("world size not supported")
+        buf = symm_mem.empty(nbytes // 4, dtype=F32, device=device)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        bases = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64).to(device)
+        torch.cuda.synchronize(device)
+        st = {"ok": True, "buf": buf, "hdl": hdl, "bases": bases, "rank": rank, "world": world,
+              "maxn": int(lib().pcfb_peer_max_floats())}
+    except Exception as e:                                    # every rank must agree: vote below
+        st = {"ok": False, "why": "%s: %s" % (type(e).__name__, e)}
+    vote = torch.tensor([1.0 if st["ok"] else 0.0], device=device)
+    dist.all_reduce(vote, op=dist.ReduceOp.MIN)               # also orders the zero-fill of every buffer before its first use
+    if float(vote.item()) < 1.0:
+        return False
+    return st
+
+
+def sync_all_reduce(t):
+    """In-place sum of a small contiguous float32 CUDA tensor over all ranks (the BatchNorm sums)."""
+    st = _PEER["state"]
+    if st is None:
+        if torch.cuda.is_current_stream_capturing():          # set-up needs host syncs: do it in the eager warm-up steps
+            st = False
+        else:
+            st = _PEER["state"] = _peer_setup(t.device)
+    if st and t.dtype == F32 and t.is_contiguous() and t.numel() <= st["maxn"]:
+        check(lib().pcfb_peer_allreduce(ptr(t), ptr(t), t.numel(), ptr(st["bases"]), st["rank"], st["world"], stream_ptr()),
+              "peer_allreduce")
+        return t
+    dist.all_reduce(t)
+    return t
+
+
 # ---- global row counts for SyncBatchNorm -------------------------------------------------------------------------
 # A BatchNorm over [1, N_l, (K,) C] needs the row count summed over all ranks.  Every tensor of the model has N_l rows
 # of some pyramid level l, so ONE all-reduce of the per-level point counts at the start of a forward
@@ -105,7 +156,7 @@ class _ChainFunction(torch.autograd.Function):
                     if s["sync"] and world > 1:
                         summed = torch.empty(2 * cout, device=dev, dtype=F32)
                         check(lib().pcfb_sum_partials(ptr(ws), nblk.value, 2 * cout, ptr(summed), stream_ptr()), "sum_partials")
-                        dist.all_reduce(summed)
+                        sync_all_reduce(summed)
                         part, nb = summed, 1
                     check(lib().pcfb_bn_finalize(ptr(part), nb, cout, count, ptr(d_count) if s["sync"] else 0, ptr(b), ptr(gamma), ptr(beta), float(s["eps"]),
                                                  float(s["momentum"]), ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean),
@@ -166,7 +217,7 @@ class _ChainFunction(torch.autograd.Function):
                 # dx needs the sums over the GLOBAL batch; dgamma / dbeta stay LOCAL (the DDP gradient all-reduce adds the
                 # ranks up, exactly as torch.nn.SyncBatchNorm does)
                 local = sums.clone()
-                dist.all_reduce(sums)
+                sync_all_reduce(sums)
             return sums, local
 
         sums, sums_local = stats(L - 1, dA) if spec[L - 1]["has_bn"] else (None, None)
@@ -215,7 +266,7 @@ class _ChainFunction(torch.autograd.Function):
                         sums = sums_local = prev_sums
                         if spec[l - 1]["sync"] and ctx.world > 1:
                             sums_local = prev_sums.clone()
-                            dist.all_reduce(prev_sums)             # SyncBatchNorm: dx uses the sums over the global batch
+                            sync_all_reduce(prev_sums)             # SyncBatchNorm: dx uses the sums over the global batch
                     else:
                         sums, sums_local = stats(l - 1, dA_prev)
                 else:
@@ -272,7 +323,7 @@ class _BnActFunction(torch.autograd.Function):
             if world > 1:
                 summed = torch.empty(2 * C, device=dev, dtype=F32)
                 check(lib().pcfb_sum_partials(ptr(ws), nblk.value, 2 * C, ptr(summed), stream_ptr()), "sum_partials")
-                dist.all_reduce(summed)
+                sync_all_reduce(summed)
                 part, nb = summed, 1
             scale = torch.empty(C, device=dev, dtype=F32); shift = torch.empty_like(scale)
             mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
@@ -310,7 +361,7 @@ class _BnActFunction(torch.autograd.Function):
             local = sums
             if cfg["training"] and ctx.world > 1:          # dx: sums over the global batch; dgamma / dbeta stay local
                 local = sums.clone()
-                dist.all_reduce(sums)
+                sync_all_reduce(sums)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x2)
