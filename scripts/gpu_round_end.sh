@@ -8,10 +8,11 @@ timeout 1500 python -m pytest tests -q -m gpu --no-header -p no:cacheprovider > 
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/summary.log
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks_$R.csv &
 SMI=$!
-timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference_$R.json 2> gpurun_out/bench_reference.err; echo "bench reference exit $?" >> gpurun_out/summary.log
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 --cpu-budget 60 > gpurun_out/bench_reference_$R.json 2> gpurun_out/bench_reference.err; echo "bench reference exit $?" >> gpurun_out/summary.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$R.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/summary.log
 kill $SMI
-timeout 600 python scripts/profile_step.py > gpurun_out/profile_step.log 2>&1 && cp gpurun_out/prof_table.txt gpurun_out/step_kernels_$R.txt
+timeout 600 python scripts/profile_step.py > gpurun_out/profile_step.log 2>&1 && cp gpurun_out/prof_table.txt gpurun_out/step_kernels_$R.txt && cp gpurun_out/prof_kernels_by_grid.txt gpurun_out/step_kernels_by_grid_$R.txt
+timeout 300 python bench.py --knn-sweep > gpurun_out/knn_sweep_$R.json 2> gpurun_out/knn_sweep.err; echo "knn sweep exit $?" >> gpurun_out/summary.log
 timeout 900 python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$R.csv \
     python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
