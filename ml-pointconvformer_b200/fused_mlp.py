@@ -62,6 +62,9 @@ def _peer_setup(device):
 
 def sync_all_reduce(t):
     """In-place sum of a small contiguous float32 CUDA tensor over all ranks (the BatchNorm sums)."""
+    if not t.is_cuda:                                         # gloo / CPU tensors (host-logic tests)
+        dist.all_reduce(t)
+        return t
     st = _PEER["state"]
     if st is None:
         if torch.cuda.is_current_stream_capturing():          # set-up needs host syncs: do it in the eager warm-up steps
@@ -88,7 +91,11 @@ _LOCAL_COUNTS = {}        # (counts, device) -> device tensor of the local count
 
 def register_levels(point_counts, device):
     """point_counts: local per-level point counts of this rank's packed batch.  No-op without an initialised
-    process group.  Levels whose local counts coincide are left unregistered (their global counts may differ)."""
+    process group.  The registry is keyed by the LOCAL count, so a rank on which two levels have the same count cannot
+    tell them apart; the decision has to be the same on every rank and must not need a host read (the step is captured
+    as a CUDA graph), so such a level gets a NaN count on ALL ranks -- the step then fails loudly (NaN loss) instead of
+    normalising with a wrong count or hanging in mismatched collectives.  (It takes a scene whose cloud stops shrinking
+    between two levels, i.e. <= 16 points, datasetCommon.py:413-414.)"""
     _LEVEL_ROWS.clear()
     _DERIVED_ROWS.clear()
     counts = [int(c) for c in point_counts]
@@ -99,12 +106,14 @@ def register_levels(point_counts, device):
     if local is None:                                 # H2D copy once per distinct packing, never inside a captured graph
         if len(_LOCAL_COUNTS) > 1024:
             _LOCAL_COUNTS.clear()
-        local = _LOCAL_COUNTS[key] = torch.tensor(counts, dtype=torch.float64).to(device)
+        ambiguous = [1.0 if counts.count(c) > 1 else 0.0 for c in counts]
+        local = _LOCAL_COUNTS[key] = torch.tensor(counts + ambiguous, dtype=torch.float64).to(device)
     g = local.clone()
     dist.all_reduce(g)
+    L = len(counts)
+    total = torch.where(g[L:] > 0, torch.full_like(g[:L], float("nan")), g[:L])
     for i, c in enumerate(counts):
-        if counts.count(c) == 1:
-            _LEVEL_ROWS[c] = g[i:i + 1]
+        _LEVEL_ROWS[c] = total[i:i + 1]
 
 
 def global_rows(lead_shape, rows, device):

@@ -94,6 +94,13 @@ def test_no_cpu_fallback():
         layer_utils.index_points(x, nei)
     with pytest.raises(RuntimeError):
         pcf_cuda.pconv_forward(x, nei, torch.randn(1, 5, 3, 2), None)
+    from pcf_b200 import fused_mlp
+    with pytest.raises(RuntimeError):
+        fused_mlp.bn_act(x, torch.nn.BatchNorm1d(4), fused_mlp.ACT_RELU)
+    with pytest.raises(RuntimeError):
+        fused_mlp.mlp_chain(x, [(torch.nn.Linear(4, 8), torch.nn.BatchNorm1d(8), fused_mlp.ACT_RELU)], True)
+    with pytest.raises(RuntimeError):
+        layer_utils.linear(x, torch.randn(3, 4))
     if not torch.cuda.is_available():
         from pcf_b200 import knn_post_dataloader_utils as KU
         with pytest.raises(RuntimeError):
