@@ -507,7 +507,7 @@ def cpu_step_factory(args):
         loss.backward()
         torch.nn.utils.clip_grad_norm_(leaves, 10.0)
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     n0 = pcs[0].shape[1]
     sample = ("1 synthetic scene of %d level-0 points (same generator, same PCF_Normal configPCF_Opt_10cm training step: C kNN x13 "
