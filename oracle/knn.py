@@ -12,6 +12,14 @@ not version-pinned and not installed here).  Pinned arithmetic of this restateme
     result  = the K references with the smallest (d, index) in lexicographic order, ascending
 which is KeOps' published formula ``((x_i - y_j)**2).sum(-1).argKmin(K)`` with ties resolved to
 the lowest reference index (what a sequential strict-< scan gives).
+
+What IS pinned: tests/golden/knn_packed.npz holds tables produced by the reference's own, unmodified
+compute_knn / compute_knn_packed / listToBatch / prepare with the kNN itself computed by the reference's
+sklearn KDTree option (``compute_knn(method='sklearn')``, lines 68-72) on tie-free clouds
+(tests/golden/make_golden.py::make_knn, oracle/ref_shim.load_knn_utils); this oracle reproduces them exactly
+(tests/test_oracle_golden.py::test_knn_packed_matches_reference) -- the scene x level loop, the offsets and
+the neighbour order wherever float32 and float64 distances order the candidates alike.  Tie order and
+float32 rounding of the KeOps reduction itself stay unpinned.
 """
 import ctypes
 import os

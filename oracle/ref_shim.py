@@ -61,3 +61,32 @@ def load():
     import layer_utils
     import model_architecture
     return layers, layer_utils, model_architecture
+
+
+def load_knn_utils():
+    """The reference's knn_post_dataloader_utils.py (unmodified) with its absent third-party imports stubbed
+    (pykeops, cuvs, cupy) and `knn_keops` -- whose arithmetic lives in pykeops -- routed to the reference's OWN
+    alternative, the sklearn KDTree of `compute_knn(method='sklearn')` (lines 68-72).  Everything else
+    (compute_knn's n_ref < K branch, compute_knn_packed's scene x level loop, listToBatch's offsets, tensorize)
+    is the reference's code.  KDTree works in float64 with unspecified tie order: use on tie-free clouds only."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    for name, attrs in (("pykeops", {}), ("pykeops.torch", {"LazyTensor": None}), ("cuvs", {}),
+                        ("cuvs.neighbors", {"brute_force": None}), ("cupy", {})):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import knn_post_dataloader_utils as KU
+
+    def knn_keops_via_kdtree(ref_points, query_points, K):
+        import numpy as np
+        ref = ref_points.numpy() if isinstance(ref_points, torch.Tensor) else np.asarray(ref_points)
+        qry = query_points.numpy() if isinstance(query_points, torch.Tensor) else np.asarray(query_points)
+        idx = KU.KDTree(ref).query(qry, k=K, return_distance=False)       # the body of the method == 'sklearn' branch
+        return torch.from_numpy(idx.astype(np.int64))                     # keops returns an int64 torch tensor
+    KU.knn_keops = knn_keops_via_kdtree
+    return KU

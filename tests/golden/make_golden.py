@@ -14,6 +14,8 @@ Files:
                         configPCF_2cm_PTF2 (use_level_1 False, mid_dim_back 3) and the guided_level / resblocks_back
                         branches (`python tests/golden/make_golden.py --model lite ptf2 routing`); they share
                         model_small.npz's pyramid and edges
+  knn_packed.npz        reference compute_knn_packed + prepare (knn_post_dataloader_utils.py:156-223) with its kNN on its
+                        own sklearn KDTree option (pykeops is absent), tie-free clouds (`--knn`)
   inverse.npz           reference create_inverse_python (test_kernels.py:177-213) on a kNN table
   grid_subsample.npz    reference C++ grid_subsampling (grid_subsampling.cpp:9-110) via oracle/_ref
   pconv_linear_seed42.npz  the reference's torch formulation (layers.py:713-719 + Linear) on the
@@ -338,8 +340,42 @@ def make_pconv_linear():
     print("pconv_linear_seed42: ok")
 
 
+def make_knn():
+    """Runs the reference's compute_knn_packed + prepare (knn_post_dataloader_utils.py:156-223, unmodified; its kNN
+    routed to its own sklearn KDTree option, see oracle/ref_shim.load_knn_utils) on a 3-level pyramid of 3 ragged
+    scenes.  KDTree orders by float64 distances, the path under test by float32 ones: seeds are retried until the
+    oracle's float32 tables equal the reference's exactly (no pair of candidates closer than float32 resolution)."""
+    KU = ref_shim.load_knn_utils()
+    Ks = [16, 16, 8]
+    for seed in range(500, 540):
+        stored = [[900, 400, 1500], [230, 100, 380], [60, 30, 90]]
+        rng = np.random.default_rng(seed)
+        pcs = [np.concatenate([surface_cloud(n, 1000 * seed + 10 * l + i)[0] + rng.random(3).astype(np.float32) for i, n in
+                               enumerate(stored[l])])[None] for l in range(3)]
+        es, ef, ep = KU.prepare(*KU.compute_knn_packed([t(p) for p in pcs], [list(x) for x in stored], Ks, Ks, Ks))
+        oes, oef, oep = oknn.compute_knn_packed(pcs, stored, Ks, Ks, Ks)
+        same = all(np.array_equal(a.numpy(), b) for a, b in zip(es + ef + ep, oes + oef + oep))
+        if not same:
+            print("knn_packed: seed %d has a float32 near-tie, retrying" % seed)
+            continue
+        out = {"stored": np.asarray(stored), "Ks": np.asarray(Ks)}
+        for l in range(3):
+            out["pc%d" % l] = pcs[l]
+            out["es%d" % l] = es[l].numpy()
+        for l in range(2):
+            out["ef%d" % l] = ef[l].numpy()
+            out["ep%d" % l] = ep[l].numpy()
+        np.savez_compressed(os.path.join(HERE, "knn_packed.npz"), **out)
+        print("knn_packed: ok (seed %d), dtypes %s, shapes %s" % (seed, es[0].dtype, [tuple(e.shape) for e in es + ef + ep]))
+        return
+    raise RuntimeError("no tie-free draw")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "--knn":
+        make_knn()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[1] == "--model":     # regenerate single model variants only
         for v in sys.argv[2:]:
             make_model(v)
@@ -347,6 +383,7 @@ if __name__ == "__main__":
     make_pconv_linear()
     make_inverse()
     make_grid_subsample()
+    make_knn()
     make_layers()
     for v in MODEL_VARIANTS:
         make_model(v)

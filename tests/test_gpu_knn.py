@@ -77,6 +77,21 @@ def test_knn_drop_in_interface():
         assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("method", ["grid", "brute"])
+def test_knn_drop_in_matches_reference_golden(golden_dir, method):
+    """compute_knn_packed() + prepare() against tables produced by the reference's OWN compute_knn_packed + prepare
+    (kNN on its sklearn KDTree option, tie-free clouds; tests/golden/knn_packed.npz)."""
+    from pcf_b200 import knn_post_dataloader_utils as KU
+    g = np.load(os.path.join(golden_dir, "knn_packed.npz"))
+    pcs = [torch.from_numpy(g["pc%d" % l]) for l in range(3)]
+    Ks = g["Ks"].tolist()
+    es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, g["stored"].tolist(), Ks, Ks, Ks, method=method))
+    want = [g["es%d" % l] for l in range(3)] + [g["ef%d" % l] for l in range(2)] + [g["ep%d" % l] for l in range(2)]
+    for got, w in zip(es + ef + ep, want):
+        assert got.dtype == torch.int64 and tuple(got.shape) == w.shape
+        assert np.array_equal(got.cpu().numpy(), w)
+
+
 def test_knn_full_size_properties():
     """BASELINE size (100k-point scene, K=16): size-independent properties + exact agreement with the oracle
     on a random subset of queries."""

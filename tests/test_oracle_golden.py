@@ -218,3 +218,22 @@ def test_knn_oracle_properties():
     # n_ref < K: deterministic cyclic fill
     c = OK.compute_knn(cloud[:5], cloud[:7], 8)
     assert c.shape == (7, 8) and np.array_equal(c[:, 5:], c[:, :3])
+
+
+def test_knn_packed_matches_reference(golden_dir):
+    """The oracle's packed kNN (scene x level loop, offsets, int64 tables) against tables produced by the reference's own
+    compute_knn_packed + prepare (knn_post_dataloader_utils.py:156-223), whose kNN ran on the reference's sklearn KDTree
+    option because pykeops is not installable here (tests/golden/make_golden.py::make_knn): pins rows a3 / a4 and, on
+    tie-free clouds, the neighbour order of a2."""
+    g = load(golden_dir, "knn_packed.npz")
+    pcs = [g["pc%d" % l] for l in range(3)]
+    Ks = g["Ks"].tolist()
+    es, ef, ep = OK.compute_knn_packed(pcs, g["stored"].tolist(), Ks, Ks, Ks)
+    for l in range(3):
+        assert es[l].dtype == np.int64 and np.array_equal(es[l], g["es%d" % l])
+    for l in range(2):
+        assert np.array_equal(ef[l], g["ef%d" % l]) and np.array_equal(ep[l], g["ep%d" % l])
+    # the C restatement agrees too
+    es2, ef2, ep2 = OK.compute_knn_packed(pcs, g["stored"].tolist(), Ks, Ks, Ks, use_c=True)
+    for a, b in zip(es + ef + ep, es2 + ef2 + ep2):
+        assert np.array_equal(a, b)
