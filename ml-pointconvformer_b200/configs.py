@@ -14,11 +14,11 @@ CONFIG_PCF_10CM_LITE = dict(         # configs/configPCF_10cm_lite.yaml
     CONFIG_PCF_OPT_10CM, PCONV_OPT=False, USE_CUDA_KERNEL=True, mid_dim=[4] * 5, resblocks=[0, 3, 3, 3, 3])
 
 CONFIG_PCF_5CM = dict(               # configs/configPCF_5cm.yaml:23-25 (K = 16 at every level)
-    CONFIG_PCF_OPT_10CM, PCONV_OPT=False, grid_size=[0.05, 0.1, 0.2, 0.4, 0.8])
+    CONFIG_PCF_OPT_10CM, PCONV_OPT=False, grid_size=[0.05, 0.1, 0.2, 0.4, 0.8], learning_rate=0.01, BATCH_SIZE=3)
 
 CONFIG_PCF_2CM_PTF2 = dict(          # configs/configPCF_2cm_PTF2.yaml
     CONFIG_PCF_OPT_10CM, PCONV_OPT=False, use_level_1=False, mid_dim_back=3,
-    grid_size=[0.02, 0.06, 0.15, 0.375, 0.9375], drop_path_rate=0.)
+    grid_size=[0.02, 0.06, 0.15, 0.375, 0.9375], drop_path_rate=0., learning_rate=0.01, BATCH_SIZE=2)
 
 
 def make_cfg(d):
