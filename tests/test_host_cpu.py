@@ -157,3 +157,53 @@ def test_restated_configs_match_reference_yaml(name, yaml_file):
     for k in ("num_level", "base_dim", "feat_dim", "mid_dim", "mid_dim_back", "num_heads", "resblocks", "grid_size", "K_self"):
         assert k in ours, k
     assert ours.get("use_level_1", True) == ref.get("use_level_1", True)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only in the build container")
+def test_prepare_matches_live_reference():
+    """Our listToBatch / tensorize / prepare against the reference's own functions (knn_post_dataloader_utils.py:89-167,
+    imported unmodified through oracle/ref_shim.load_knn_utils) on genuinely per-scene tables of three ragged scenes,
+    numpy and torch inputs, with -1 padding entries."""
+    from oracle import ref_shim
+    from pcf_b200 import knn_post_dataloader_utils as KU
+    RKU = ref_shim.load_knn_utils()
+    rng = np.random.default_rng(4)
+    sizes = [[40, 7, 23], [11, 3, 9], [5, 2, 4]]
+
+    def tables(as_numpy):
+        es, ef, ep = [], [], []
+        for s in range(3):
+            mk = lambda n_q, n_r: rng.integers(-1, n_r, (n_q, 4)).astype(np.int64)
+            a = [mk(sizes[l][s], sizes[l][s]) for l in range(3)]
+            b = [mk(sizes[l + 1][s], sizes[l][s]) for l in range(2)]
+            c = [mk(sizes[l][s], sizes[l + 1][s]) for l in range(2)]
+            conv = (lambda x: x) if as_numpy else torch.from_numpy
+            es.append([conv(x) for x in a]); ef.append([conv(x) for x in b]); ep.append([conv(x) for x in c])
+        return es, ef, ep
+    for as_numpy in (False, True):
+        es, ef, ep = tables(as_numpy)
+        clone = lambda lst: [[x.copy() if isinstance(x, np.ndarray) else x.clone() for x in scene] for scene in lst]
+        want = RKU.prepare(clone(es), clone(ef), clone(ep))
+        got = KU.prepare(es, ef, ep)
+        for w_list, g_list in zip(want, got):
+            assert len(w_list) == len(g_list)
+            for w, g in zip(w_list, g_list):
+                assert g.dtype == w.dtype and torch.equal(g, w)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only in the build container")
+def test_vi_transform_compat_entry_matches_live_reference():
+    """layer_utils.VI_coordinate_transform (the reference-signature compatibility entry, pure torch) against the reference's
+    function (layer_utils.py:176-231) on random edges; the fused edge_geometry kernel is checked against the same maths on
+    the GPU (tests/test_gpu_pconv.py::test_edge_geometry_vi)."""
+    from oracle import ref_shim
+    from pcf_b200 import layer_utils as LU
+    _, RLU, _ = ref_shim.load()
+    g = torch.Generator().manual_seed(0)
+    r = torch.randn(1, 50, 16, 3, generator=g) * 0.2
+    nj = torch.nn.functional.normalize(torch.randn(1, 50, 16, 3, generator=g), dim=-1)
+    ni = torch.nn.functional.normalize(torch.randn(1, 50, 3, generator=g), dim=-1)
+    want = RLU.VI_coordinate_transform(r, nj, ni, 16)
+    got = LU.VI_coordinate_transform(r, nj, ni, 16)
+    assert got.shape == want.shape == (1, 50, 16, 12)
+    torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
