@@ -207,3 +207,24 @@ def test_vi_transform_compat_entry_matches_live_reference():
     got = LU.VI_coordinate_transform(r, nj, ni, 16)
     assert got.shape == want.shape == (1, 50, 16, 12)
     torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only in the build container")
+@pytest.mark.parametrize("yaml_file,over", [("configPCF_10cm_lite.yaml", {}), ("configPCF_5cm.yaml", {}), ("configPCF_2cm_PTF2.yaml", {}),
+                                            ("configPCF_Opt_10cm.yaml", {"num_level": 6, "feat_dim": [64, 128, 192, 256, 384, 512],
+                                                                         "resblocks": [0, 2, 4, 6, 6, 2], "mid_dim": [16] * 6,
+                                                                         "resblocks_back": [0, 1, 0, 0, 0, 0], "guided_level": 1})])
+def test_every_shipped_config_builds_the_reference_state_dict(yaml_file, over):
+    """Constructor parity for every shipped YAML (and a 6-level PCF_Large-like variant with a StridePE encoder level and a
+    decoder res-block): same parameter names and shapes as the reference model, loadable with strict=True."""
+    import yaml
+    from oracle import ref_shim
+    from pcf_b200 import model_architecture as MA
+    _, _, RMA = ref_shim.load()
+    raw = dict(yaml.safe_load(open(os.path.join("/root/reference/configs", yaml_file))), **over)
+    raw.update(USE_CUDA_KERNEL=False, PCONV_OPT=False, drop_path_rate=0.)
+    c1 = RMA.get_default_configs(ref_shim.EasyDict(raw), raw["num_level"], raw["base_dim"])
+    c2 = MA.get_default_configs(MA.EasyDict(raw), raw["num_level"], raw["base_dim"])
+    r, m = RMA.PointConvFormer_Segmentation(c1), MA.PointConvFormer_Segmentation(c2)
+    assert {k: tuple(v.shape) for k, v in r.state_dict().items()} == {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(r.state_dict(), strict=True)
