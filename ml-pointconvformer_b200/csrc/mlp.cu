@@ -217,6 +217,54 @@ struct MlpBnCtx {            // BatchNorm + activation of one layer's output y (
 
 __device__ __forceinline__ float ctx_inv_count(const MlpBnCtx &B) { return B.d_count ? (float)(1.0 / *B.d_count) : B.inv_count; }
 
+// slope of act'(z) for z <= 0 (ReLU 0, LeakyReLU 0.1, none 1): act(z) = z > 0 ? z : slope*z, act'(z) = z > 0 ? 1 : slope
+__host__ __device__ inline float act_slope(int act) { return act == ACT_RELU ? 0.f : (act == ACT_LEAKY ? 0.1f : 1.f); }
+
+// Per-channel constants of one layer's BatchNorm + activation backward, filled into shared memory once per CTA so that the
+// row loops read broadcast LDS instead of six global loads per element:
+//   z = y*sc + sh ;  xhat = (y - mu)*is ;  dy = sc*dz + c1*(y - mu) + c0  with c1 = -sc*S2*is/E, c0 = -sc*S1/E
+// (no BatchNorm: sc = 1, the rest 0; padded channels: everything 0, so dy = 0 without a bounds test)
+template <int C>
+struct BnConst { float sc[C], sh[C], mu[C], is[C], c1[C], c0[C]; };
+
+template <int C>
+__device__ __forceinline__ void bn_const_fill(BnConst<C> &K, const MlpBnCtx &B, int c, float inv_count)
+{
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        float sc = 0.f, sh = 0.f, mu = 0.f, is = 0.f, c1 = 0.f, c0 = 0.f;
+        if (i < c) {
+            sc = 1.f;
+            if (B.scale) {
+                sc = B.scale[i]; sh = B.shift[i];
+                if (B.mean) { mu = B.mean[i]; is = B.invstd[i]; }
+                if (B.sums) { c1 = -sc * B.sums[c + i] * inv_count * is; c0 = -sc * B.sums[i] * inv_count; }
+            }
+        }
+        K.sc[i] = sc; K.sh[i] = sh; K.mu[i] = mu; K.is[i] = is; K.c1[i] = c1; K.c0[i] = c0;
+    }
+}
+
+// dz = dA * act'(z) for the C channels of one row (SIG: sigmoid, else slope form); returns dz in d[]
+template <int C, bool SIG>
+__device__ __forceinline__ void bn_row_dz(float *d, const float *yv, const BnConst<C> &K, float slope)
+{
+#pragma unroll
+    for (int o = 0; o < C; ++o) {
+        const float z = fmaf(yv[o], K.sc[o], K.sh[o]);
+        float gz;
+        if (SIG) { const float av = 1.f / (1.f + __expf(-z)); gz = av * (1.f - av); }
+        else gz = z > 0.f ? 1.f : slope;
+        d[o] *= gz;
+    }
+}
+// dy from dz (in place)
+template <int C>
+__device__ __forceinline__ void bn_row_dy(float *d, const float *yv, const BnConst<C> &K)
+{
+#pragma unroll
+    for (int o = 0; o < C; ++o) d[o] = fmaf(K.sc[o], d[o], fmaf(K.c1[o], yv[o] - K.mu[o], K.c0[o]));
+}
+
 // stats of one layer's output gradient: partial[block][2][C] = sum dz, sum dz*xhat  (thread = row)
 template <int COUT>
 __global__ void __launch_bounds__(ML_THREADS)
@@ -224,8 +272,13 @@ mlp_bwd_stats_kernel(const float *__restrict__ dA, int ldd, const float *__restr
                      MlpBnCtx B, float *__restrict__ partial, int rows_per_thread)
 {
     __shared__ float red[ML_WARPS][2 * COUT];
+    __shared__ BnConst<COUT> K;
+    bn_const_fill<COUT>(K, B, C, 0.f);
+    __syncthreads();
     const bool vec_d = ((ldd & 3) == 0) && ((C & 3) == 0) && ((uintptr_t)dA % 16 == 0);
     const bool vec_y = ((ldy & 3) == 0) && ((C & 3) == 0) && ((uintptr_t)y % 16 == 0);
+    const bool sig = B.act == ACT_SIGMOID;
+    const float slope = act_slope(B.act);
     float s1[COUT], s2[COUT];
 #pragma unroll
     for (int o = 0; o < COUT; ++o) { s1[o] = 0.f; s2[o] = 0.f; }
@@ -234,18 +287,11 @@ mlp_bwd_stats_kernel(const float *__restrict__ dA, int ldd, const float *__restr
         const int64_t row = block_row0 + (int64_t)r * ML_THREADS + threadIdx.x;
         if (row >= E) break;
         float d[COUT], yv[COUT];
-        load_row<COUT>(dA, ldd, row, C, vec_d, d);
+        load_row<COUT>(dA, ldd, row, C, vec_d, d);              // channels >= C load as 0
         load_row<COUT>(y, ldy, row, C, vec_y, yv);
+        if (sig) bn_row_dz<COUT, true>(d, yv, K, slope); else bn_row_dz<COUT, false>(d, yv, K, slope);
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            if (o < C) {
-                const float z = fmaf(yv[o], B.scale[o], B.shift[o]);
-                const float a = act_fwd(z, B.act);
-                const float dz = d[o] * act_bwd(z, a, B.act);
-                const float xhat = (yv[o] - B.mean[o]) * B.invstd[o];
-                s1[o] += dz; s2[o] = fmaf(dz, xhat, s2[o]);
-            }
-        }
+        for (int o = 0; o < COUT; ++o) { s1[o] += d[o]; s2[o] = fmaf(d[o], (yv[o] - K.mu[o]) * K.is[o], s2[o]); }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -296,16 +342,21 @@ mlp_bwd_input_kernel(const float *__restrict__ dA, int ldd, const float *__restr
 {
     __shared__ __align__(16) float Wt_s[CIN * COUT];          // transposed: [k][o]
     __shared__ float red[ML_WARPS][2 * CIN];
+    __shared__ BnConst<COUT> K;                                 // this layer
+    __shared__ BnConst<CIN> Kp;                                 // the layer below (only its sc / sh / mu / is are used)
     for (int i = threadIdx.x; i < CIN * COUT; i += ML_THREADS) {
         const int k = i / COUT, o = i - k * COUT;
         Wt_s[i] = (o < cout && k < cin) ? W[o * cin + k] : 0.f;
     }
+    bn_const_fill<COUT>(K, B, cout, ctx_inv_count(B));
+    if (FUSE_PREV && prev_partial) bn_const_fill<CIN>(Kp, Bp, cin, 0.f);
     __syncthreads();
     const bool vec_d = ((ldd & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)dA % 16 == 0);
     const bool vec_y = ((ldy & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
     const bool vec_p = ((ldp & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)dA_prev % 16 == 0);
     const bool vec_yp = y_prev && ((ldyp & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)y_prev % 16 == 0);
-    const float inv_count = ctx_inv_count(B);
+    const bool sig = B.act == ACT_SIGMOID;
+    const float slope = act_slope(B.act), pslope = act_slope(Bp.act);
     constexpr int SN = FUSE_PREV ? CIN : 1;
     float s1[SN], s2[SN];
 #pragma unroll
@@ -317,18 +368,8 @@ mlp_bwd_input_kernel(const float *__restrict__ dA, int ldd, const float *__restr
         float d[COUT], yv[COUT];
         load_row<COUT>(dA, ldd, row, cout, vec_d, d);
         load_row<COUT>(y, ldy, row, cout, vec_y, yv);
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) {
-            float dy = 0.f;
-            if (o < cout) {
-                float z = yv[o], xhat = 0.f;
-                if (B.scale) { z = fmaf(yv[o], B.scale[o], B.shift[o]); xhat = (yv[o] - B.mean[o]) * B.invstd[o]; }
-                const float a = act_fwd(z, B.act);
-                const float dz = d[o] * act_bwd(z, a, B.act);
-                dy = B.scale ? B.scale[o] * (dz - B.sums[o] * inv_count - xhat * B.sums[cout + o] * inv_count) : dz;
-            }
-            d[o] = dy;
-        }
+        if (sig) bn_row_dz<COUT, true>(d, yv, K, slope); else bn_row_dz<COUT, false>(d, yv, K, slope);
+        bn_row_dy<COUT>(d, yv, K);
         float g[CIN];
 #pragma unroll
         for (int k = 0; k < CIN; ++k) {
@@ -345,14 +386,10 @@ mlp_bwd_input_kernel(const float *__restrict__ dA, int ldd, const float *__restr
             float yp[CIN];
             load_row<CIN>(y_prev, ldyp, row, cin, vec_yp, yp);
 #pragma unroll
-            for (int k = 0; k < CIN; ++k) {
-                if (k < cin) {
-                    const float z = fmaf(yp[k], Bp.scale[k], Bp.shift[k]);
-                    const float a = act_fwd(z, Bp.act);
-                    const float dz = g[k] * act_bwd(z, a, Bp.act);
-                    const float xhat = (yp[k] - Bp.mean[k]) * Bp.invstd[k];
-                    s1[k % SN] += dz; s2[k % SN] = fmaf(dz, xhat, s2[k % SN]);
-                }
+            for (int k = 0; k < CIN; ++k) {                     // padded channels: W column 0 -> g 0 -> no contribution
+                const float z = fmaf(yp[k], Kp.sc[k], Kp.sh[k]);
+                const float dz = g[k] * (z > 0.f ? 1.f : pslope);
+                s1[k % SN] += dz; s2[k % SN] = fmaf(dz, (yp[k] - Kp.mu[k]) * Kp.is[k], s2[k % SN]);
             }
         }
     }
@@ -394,13 +431,21 @@ mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__rest
     static_assert(NPB <= ML_THREADS && ML_THREADS % NPB == 0, "bad tiling");
     __shared__ __align__(16) float dy_s[MW_TILE * DS];
     __shared__ __align__(16) float a_s[MW_TILE * AS];
+    __shared__ BnConst<COUT> K;                                 // this layer's BatchNorm / activation backward constants
+    __shared__ float ps_s[CIN], pt_s[CIN];                      // the layer below: a = act(x*ps + pt)
     const int t = threadIdx.x;
+    bn_const_fill<COUT>(K, B, cout, ctx_inv_count(B));
+    for (int i = t; i < CIN; i += ML_THREADS) {
+        ps_s[i] = i < cin ? (in_scale ? in_scale[i] : 1.f) : 0.f;
+        pt_s[i] = (i < cin && in_scale) ? in_shift[i] : 0.f;
+    }
+    const bool sig = B.act == ACT_SIGMOID, psig = in_act == ACT_SIGMOID;
+    const float slope = act_slope(B.act), pslope = act_slope(in_act);
     const int pb = t % NPB, slice = t / NPB;
     const int o4 = (pb / (CIN / 4)) * 4, k4 = (pb % (CIN / 4)) * 4;
     const bool vec_d = ((ldd & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)dA % 16 == 0);
     const bool vec_y = ((ldy & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
     const bool vec_x = ((ldx & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)x_prev % 16 == 0);
-    const float inv_count = ctx_inv_count(B);
     float acc[4][4], accb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { accb[i] = 0.f;
@@ -412,18 +457,13 @@ mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__rest
         __syncthreads();                                        // previous tile consumed
         if (t < MW_TILE) {
             float d[COUT], yv[COUT];
-            if (row < E) { load_row<COUT>(dA, ldd, row, cout, vec_d, d); load_row<COUT>(y, ldy, row, cout, vec_y, yv); }
+            if (row < E) {
+                load_row<COUT>(dA, ldd, row, cout, vec_d, d); load_row<COUT>(y, ldy, row, cout, vec_y, yv);
+                if (sig) bn_row_dz<COUT, true>(d, yv, K, slope); else bn_row_dz<COUT, false>(d, yv, K, slope);
+                bn_row_dy<COUT>(d, yv, K);
+            } else {
 #pragma unroll
-            for (int o = 0; o < COUT; ++o) {
-                float dy = 0.f;
-                if (row < E && o < cout) {
-                    float z = yv[o], xhat = 0.f;
-                    if (B.scale) { z = fmaf(yv[o], B.scale[o], B.shift[o]); xhat = (yv[o] - B.mean[o]) * B.invstd[o]; }
-                    const float av = act_fwd(z, B.act);
-                    const float dz = d[o] * act_bwd(z, av, B.act);
-                    dy = B.scale ? B.scale[o] * (dz - B.sums[o] * inv_count - xhat * B.sums[cout + o] * inv_count) : dz;
-                }
-                d[o] = dy;
+                for (int o = 0; o < COUT; ++o) d[o] = 0.f;
             }
 #pragma unroll
             for (int o = 0; o < COUT; o += 4)
@@ -431,15 +471,16 @@ mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__rest
         } else {
             const int r = t - MW_TILE;
             float a[CIN];
-            if (row < E) load_row<CIN>(x_prev, ldx, row, cin, vec_x, a);
+            if (row < E) {
+                load_row<CIN>(x_prev, ldx, row, cin, vec_x, a);
 #pragma unroll
-            for (int k = 0; k < CIN; ++k) {
-                float v = 0.f;
-                if (row < E && k < cin) {
-                    v = in_scale ? fmaf(a[k], in_scale[k], in_shift[k]) : a[k];
-                    v = act_fwd(v, in_act);
+                for (int k = 0; k < CIN; ++k) {                 // padded channels: ps = pt = 0 -> a = 0 (sigmoid: masked below)
+                    const float v = fmaf(a[k], ps_s[k], pt_s[k]);
+                    a[k] = psig ? (k < cin ? 1.f / (1.f + __expf(-v)) : 0.f) : (v > 0.f ? v : pslope * v);
                 }
-                a[k] = v;
+            } else {
+#pragma unroll
+                for (int k = 0; k < CIN; ++k) a[k] = 0.f;
             }
 #pragma unroll
             for (int k = 0; k < CIN; k += 4)
@@ -495,7 +536,12 @@ mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__rest
 //   then every lane: CIN/2 input-gradient channels of one row (+ lower-BN sums), and its 4x4 block of dW over 8 or 16 rows.
 // Block partials are combined once at the end in fixed order (no atomics).
 constexpr int MF_ROWS = 16;
-template <int CIN, int COUT>
+// SIG: this layer's activation is the sigmoid (last layer of the guidance MLP); the layer below never is (host checks).
+// Per-channel constants live in shared memory (ncu on the first version: 96 warp instructions per row, 6x the FMA minimum,
+// most of them per-element global loads of scale / shift / mean / invstd / sums and the run-time activation switch):
+//   this layer:  z = y*sc + sh,  dy = sc*dz + c1*(y - mu) + c0   with c1 = -sc*S2*invstd/E, c0 = -sc*S1/E  (no BN: sc 1, rest 0)
+//   layer below: a = act(x*psc + psh),  xhat = (x - pmu)*pis
+template <int CIN, int COUT, bool SIG>
 __global__ void __launch_bounds__(ML_THREADS, 3)
 mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restrict__ y, int ldy, int64_t E,
                      const float *__restrict__ W, int cin, int cout, MlpBnCtx B,
@@ -506,30 +552,56 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
     constexpr int NPB = (COUT / 4) * (CIN / 4);                 // 4x4 blocks of dW: 16 or 32
     constexpr int RH = 32 / NPB;                                // row halves per block (2 when NPB == 16, else 1)
     constexpr int RPL = MF_ROWS / RH;                           // rows each lane accumulates per iteration
-    constexpr int KH = CIN / 2;
+    constexpr int KH = CIN / 2, OH = COUT / 2;
     static_assert(NPB == 16 || NPB == 32, "warp tiling needs 16 or 32 blocks");
-    constexpr int SLICE = MF_ROWS * (DS + 2 * AS);              // floats of one warp's staging slice
+    constexpr int SLICE = MF_ROWS * (DS + AS);                  // floats of one warp's staging slice
     constexpr int STAGE_FLOATS = ML_WARPS * SLICE, RED_FLOATS = ML_WARPS * NPB * 20;
     __shared__ __align__(16) float stage_s[STAGE_FLOATS > RED_FLOATS ? STAGE_FLOATS : RED_FLOATS];   // staging, then the dW reduction scratch
     __shared__ __align__(16) float Wt_s[CIN * COUT];            // transposed: [k][o]
+    __shared__ __align__(16) float cst_s[5 * COUT + 4 * CIN];   // sc | sh | mu | c1 | c0 (this layer), psc | psh | pmu | pis (below)
     __shared__ float reds[ML_WARPS][2][2 * KH];
     float (*redw)[NPB * 20] = reinterpret_cast<float (*)[NPB * 20]>(stage_s);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const float inv_count = ctx_inv_count(B);
+    const bool prev_bn = prev_partial != nullptr;
     for (int i = t; i < CIN * COUT; i += ML_THREADS) {
         const int k = i / COUT, o = i - k * COUT;
         Wt_s[i] = (o < cout && k < cin) ? W[o * cin + k] : 0.f;
     }
+    for (int i = t; i < COUT; i += ML_THREADS) {
+        float sc = 0.f, sh = 0.f, mu = 0.f, c1 = 0.f, c0 = 0.f;
+        if (i < cout) {
+            sc = 1.f;
+            if (B.scale) {
+                sc = B.scale[i]; sh = B.shift[i]; mu = B.mean[i];
+                c1 = -sc * B.sums[cout + i] * inv_count * B.invstd[i];
+                c0 = -sc * B.sums[i] * inv_count;
+            }
+        }
+        cst_s[i] = sc; cst_s[COUT + i] = sh; cst_s[2 * COUT + i] = mu; cst_s[3 * COUT + i] = c1; cst_s[4 * COUT + i] = c0;
+    }
+    for (int i = t; i < CIN; i += ML_THREADS) {
+        float psc = 0.f, psh = 0.f, pmu = 0.f, pis = 0.f;
+        if (i < cin) {
+            psc = 1.f;
+            if (Bp.scale) { psc = Bp.scale[i]; psh = Bp.shift[i]; }
+            if (prev_bn) { pmu = Bp.mean[i]; pis = Bp.invstd[i]; }
+        }
+        float *pc = cst_s + 5 * COUT;
+        pc[i] = psc; pc[CIN + i] = psh; pc[2 * CIN + i] = pmu; pc[3 * CIN + i] = pis;
+    }
     __syncthreads();
+    const float slope = act_slope(B.act), pslope = act_slope(Bp.act);
     const int pb = lane % NPB, rh = lane / NPB;
     const int o4 = (pb / (CIN / 4)) * 4, k4 = (pb % (CIN / 4)) * 4;
-    const int r_in = lane & (MF_ROWS - 1), kh0 = (lane >> 4) * KH;
-    const bool vec_d = ((ldd & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)dA % 16 == 0);
-    const bool vec_y = ((ldy & 3) == 0) && ((cout & 3) == 0) && ((uintptr_t)y % 16 == 0);
-    const bool vec_x = ((ldx & 3) == 0) && ((cin & 3) == 0) && ((uintptr_t)x_prev % 16 == 0);
+    const int r_in = lane & (MF_ROWS - 1), kh0 = (lane >> 4) * KH, oh0 = (lane >> 4) * OH;
+    const bool vec_dy = ((ldd & 3) == 0) && ((ldy & 3) == 0) && cout == COUT && ((uintptr_t)dA % 16 == 0) && ((uintptr_t)y % 16 == 0);
+    const bool vec_x = ((ldx & 3) == 0) && cin == CIN && ((uintptr_t)x_prev % 16 == 0);
     const bool vec_p = ((ldp & 3) == 0) && ((uintptr_t)dA_prev % 16 == 0) && (KH % 4 == 0) && cin == CIN;
-    const float inv_count = ctx_inv_count(B);
-    const bool prev_bn = prev_partial != nullptr;
-    float *dyw = stage_s + warp * SLICE, *aw = dyw + MF_ROWS * DS, *xw = aw + MF_ROWS * AS;
+    const float *csc = cst_s + oh0, *csh = cst_s + COUT + oh0, *cmu = cst_s + 2 * COUT + oh0, *cc1 = cst_s + 3 * COUT + oh0,
+                *cc0 = cst_s + 4 * COUT + oh0;
+    const float *psc = cst_s + 5 * COUT + kh0, *psh = psc + CIN, *pmu = psc + 2 * CIN, *pis = psc + 3 * CIN;
+    float *dyw = stage_s + warp * SLICE, *aw = dyw + MF_ROWS * DS;
     float acc[4][4], accb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { accb[i] = 0.f;
@@ -541,77 +613,64 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
     const int64_t n_groups = (E + MF_ROWS - 1) / MF_ROWS;
     for (int64_t g = (int64_t)blockIdx.x * ML_WARPS + warp; g < n_groups; g += (int64_t)gridDim.x * ML_WARPS) {
         const int64_t row = g * MF_ROWS + r_in;
+        const bool live = row < E;
+        const size_t rc = (size_t)(live ? row : E - 1);        // rows past the end re-read the last row and are masked to zero
+        const float valid = live ? 1.f : 0.f;
         __syncwarp();                                           // the previous group's reads of the warp's slice are done
+        float xr[KH];                                           // my half of the stored input row: staging AND the lower-BN sums
         {   // staging, uniform over the warp: lane (row, half) handles half of the row's output and input channels
-            constexpr int OH = COUT / 2;
-            const int oh0 = (lane >> 4) * OH;
             float d[OH], yv[OH];
+            if (vec_dy) {
 #pragma unroll
-            for (int o = 0; o < OH; ++o) { d[o] = 0.f; yv[o] = 0.f; }
-            if (row < E) {
-                if (vec_d && vec_y && cout == COUT) {
-#pragma unroll
-                    for (int o = 0; o < OH; o += 4) {
-                        const float4 dv = __ldg(reinterpret_cast<const float4 *>(dA + (size_t)row * ldd + oh0 + o));
-                        const float4 yy = __ldg(reinterpret_cast<const float4 *>(y + (size_t)row * ldy + oh0 + o));
-                        d[o] = dv.x; d[o + 1] = dv.y; d[o + 2] = dv.z; d[o + 3] = dv.w;
-                        yv[o] = yy.x; yv[o + 1] = yy.y; yv[o + 2] = yy.z; yv[o + 3] = yy.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int o = 0; o < OH; ++o)
-                        if (oh0 + o < cout) { d[o] = __ldg(dA + (size_t)row * ldd + oh0 + o); yv[o] = __ldg(y + (size_t)row * ldy + oh0 + o); }
+                for (int o = 0; o < OH; o += 4) {
+                    const float4 dv = __ldg(reinterpret_cast<const float4 *>(dA + rc * ldd + oh0 + o));
+                    const float4 yy = __ldg(reinterpret_cast<const float4 *>(y + rc * ldy + oh0 + o));
+                    d[o] = dv.x; d[o + 1] = dv.y; d[o + 2] = dv.z; d[o + 3] = dv.w;
+                    yv[o] = yy.x; yv[o + 1] = yy.y; yv[o + 2] = yy.z; yv[o + 3] = yy.w;
                 }
+            } else {
+#pragma unroll
+                for (int o = 0; o < OH; ++o) {
+                    const bool ok = oh0 + o < cout;
+                    d[o] = ok ? __ldg(dA + rc * ldd + oh0 + o) : 0.f;
+                    yv[o] = ok ? __ldg(y + rc * ldy + oh0 + o) : 0.f;
+                }
+            }
+            if (vec_x) {
+#pragma unroll
+                for (int k = 0; k < KH; k += 4) {
+                    const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_prev + rc * ldx + kh0 + k));
+                    xr[k] = xv.x; xr[k + 1] = xv.y; xr[k + 2] = xv.z; xr[k + 3] = xv.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < KH; ++k) xr[k] = (kh0 + k < cin) ? __ldg(x_prev + rc * ldx + kh0 + k) : 0.f;
             }
 #pragma unroll
             for (int o = 0; o < OH; ++o) {
-                const int oo = oh0 + o;
-                float dy = 0.f;
-                if (row < E && oo < cout) {
-                    float z = yv[o], xhat = 0.f;
-                    if (B.scale) { z = fmaf(yv[o], B.scale[oo], B.shift[oo]); xhat = (yv[o] - B.mean[oo]) * B.invstd[oo]; }
-                    const float av = act_fwd(z, B.act);
-                    const float dz = d[o] * act_bwd(z, av, B.act);
-                    dy = B.scale ? B.scale[oo] * (dz - B.sums[oo] * inv_count - xhat * B.sums[cout + oo] * inv_count) : dz;
-                }
-                d[o] = dy;
+                const float sc = csc[o];
+                const float z = fmaf(yv[o], sc, csh[o]);
+                float gz;
+                if (SIG) { const float av = 1.f / (1.f + __expf(-z)); gz = av * (1.f - av); }
+                else gz = z > 0.f ? 1.f : slope;
+                const float dz = d[o] * gz;
+                d[o] = valid * fmaf(sc, dz, fmaf(cc1[o], yv[o] - cmu[o], cc0[o]));      // padded channels: all constants 0
             }
 #pragma unroll
             for (int o = 0; o < OH; o += 4)
                 *reinterpret_cast<float4 *>(&dyw[r_in * DS + oh0 + o]) = make_float4(d[o], d[o + 1], d[o + 2], d[o + 3]);
-            float xr[KH], a[KH];
-#pragma unroll
-            for (int k = 0; k < KH; ++k) xr[k] = 0.f;
-            if (row < E) {
-                if (vec_x && cin == CIN) {
-#pragma unroll
-                    for (int k = 0; k < KH; k += 4) {
-                        const float4 xv = __ldg(reinterpret_cast<const float4 *>(x_prev + (size_t)row * ldx + kh0 + k));
-                        xr[k] = xv.x; xr[k + 1] = xv.y; xr[k + 2] = xv.z; xr[k + 3] = xv.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < KH; ++k) if (kh0 + k < cin) xr[k] = __ldg(x_prev + (size_t)row * ldx + kh0 + k);
-                }
-            }
+            float a[KH];
 #pragma unroll
             for (int k = 0; k < KH; ++k) {
-                const int kk = kh0 + k;
-                float v = 0.f;
-                if (row < E && kk < cin) {
-                    v = Bp.scale ? fmaf(xr[k], Bp.scale[kk], Bp.shift[kk]) : xr[k];
-                    v = act_fwd(v, Bp.act);
-                }
-                a[k] = v;
+                const float v = fmaf(xr[k], psc[k], psh[k]);
+                a[k] = valid * (v > 0.f ? v : pslope * v);
             }
 #pragma unroll
-            for (int k = 0; k < KH; k += 4) {
+            for (int k = 0; k < KH; k += 4)
                 *reinterpret_cast<float4 *>(&aw[r_in * AS + kh0 + k]) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
-                *reinterpret_cast<float4 *>(&xw[r_in * AS + kh0 + k]) = make_float4(xr[k], xr[k + 1], xr[k + 2], xr[k + 3]);
-            }
         }
         __syncwarp();
-        if (row < E) {                                          // input gradient: KH channels of one row per lane
+        if (live && dA_prev) {                                  // input gradient: KH channels of one row per lane (skipped for a chain's first layer)
             float d[COUT];
 #pragma unroll
             for (int o = 0; o < COUT; o += 4) {
@@ -639,16 +698,10 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
             }
             if (prev_bn) {
 #pragma unroll
-                for (int k = 0; k < KH; ++k) {
-                    const int kk = kh0 + k;
-                    if (kk < cin) {
-                        const float xv = xw[r_in * AS + kk];
-                        const float z = fmaf(xv, Bp.scale[kk], Bp.shift[kk]);
-                        const float av = act_fwd(z, Bp.act);
-                        const float dz = gk[k] * act_bwd(z, av, Bp.act);
-                        const float xhat = (xv - Bp.mean[kk]) * Bp.invstd[kk];
-                        s1[k] += dz; s2[k] = fmaf(dz, xhat, s2[k]);
-                    }
+                for (int k = 0; k < KH; ++k) {                  // padded channels: W column 0 -> gk 0 -> no contribution
+                    const float z = fmaf(xr[k], psc[k], psh[k]);
+                    const float dz = gk[k] * (z > 0.f ? 1.f : pslope);
+                    s1[k] += dz; s2[k] = fmaf(dz, (xr[k] - pmu[k]) * pis[k], s2[k]);
                 }
             }
         }
@@ -757,7 +810,13 @@ __global__ void mlp_fused_finalize_kernel(const float *__restrict__ w_partial, c
     const float *src = is_w ? w_partial + i : p_partial + (i - n_w);
     const int stride = is_w ? n_w : n_p;
     double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += (double)src[(size_t)b * stride];
+    int b = lane;
+    for (; b + 96 < nblocks; b += 128) {                 // four independent loads in flight, same summation order
+        const float a0 = src[(size_t)b * stride], a1 = src[(size_t)(b + 32) * stride];
+        const float a2 = src[(size_t)(b + 64) * stride], a3 = src[(size_t)(b + 96) * stride];
+        s += (double)a0; s += (double)a1; s += (double)a2; s += (double)a3;
+    }
+    for (; b < nblocks; b += 32) s += (double)src[(size_t)b * stride];
 #pragma unroll
     for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
     if (lane != 0) return;
@@ -922,16 +981,21 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
     MlpBnCtx Bp{in_scale, in_shift, prev_mean, prev_invstd, nullptr, in_act, inv_count, d_count};
     const int ci = cmax_of(cin), co = cmax_of(cout);
     int rc;
-    if (dA_prev && (dW || db) && ci == 16 && co <= 32 && E > 0) {   // one sweep: input gradient + weight gradient (+ lower-BN sums)
+    if ((dW || db) && ci == 16 && co <= 32 && E > 0 && in_act != ACT_SIGMOID) {   // one sweep (dA_prev == NULL: weight gradient only): input gradient + weight gradient (+ lower-BN sums)
         int gpb;
         const int blocks = mlp_wblocks(E, &gpb);
         (void)gpb;
         float *w_part = partial;
         float *p_part = partial + (size_t)blocks * cout * (cin + 1);
 #define ML_FUSED_CASE(CI_, CO_)                                                                                   \
-        if (ci == CI_ && co == CO_)                                                                               \
-            mlp_bwd_fused_kernel<CI_, CO_><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, W, cin, cout, B, x_prev, ldx, Bp, \
-                                                                          dA_prev, ldp, prev_sums ? p_part : nullptr, w_part);
+        if (ci == CI_ && co == CO_) {                                                                             \
+            if (act == ACT_SIGMOID)                                                                               \
+                mlp_bwd_fused_kernel<CI_, CO_, true><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, W, cin, cout, B, x_prev, ldx, Bp, \
+                                                                                    dA_prev, ldp, prev_sums ? p_part : nullptr, w_part); \
+            else                                                                                                  \
+                mlp_bwd_fused_kernel<CI_, CO_, false><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, W, cin, cout, B, x_prev, ldx, Bp, \
+                                                                                     dA_prev, ldp, prev_sums ? p_part : nullptr, w_part); \
+        }
         ML_FUSED_CASE(16, 16) ML_FUSED_CASE(16, 32)
 #undef ML_FUSED_CASE
         if ((rc = check_launch("mlp_bwd_fused_kernel"))) return rc;

@@ -217,6 +217,9 @@ MODEL_VARIANTS = {
                   resblocks=[0, 1, 2, 1, 1, 1]), 220),
     # branches no shipped config takes: PointConvStridePE encoder level (guided_level=1) and decoder res-blocks
     "routing": (dict(guided_level=1, resblocks_back=[0, 1, 1, 0, 0], resblocks=[0, 1, 1, 1, 1]), 230),
+    # configPCF_Opt_10cm.yaml:27-43 at its REAL width (BASELINE configs[2], the model bench.py times): 5.4 M parameters,
+    # 22 PCFLayers; also evaluated in float64, with the reference's own fp32-vs-fp64 error stored per parameter
+    "normal": (dict(base_dim=64, feat_dim=[64, 128, 192, 256, 384], num_heads=8, resblocks=[0, 2, 4, 6, 6]), 240),
 }
 GRAD_KEY_PATTERNS = ["selfpointconv.linear.c.weight", "selfmlp.c.weight", "selfpointconv_res1.linear.c.weight",
                      "pointconv.0.linear.c.weight", "pointconv_res.1.0.guidance_weight.mlp.0.c.weight",
@@ -232,6 +235,11 @@ def make_model(variant="small"):
     torch.manual_seed(seed)
     model = MA.PointConvFormer_Segmentation(cfg)
     randomize_bn(model, seed + 1)
+    if variant == "normal":                       # parameters by name (tests/model_variants.synthetic_state_dict), not stored
+        sys.path.insert(0, os.path.dirname(HERE))
+        import model_variants
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        model.load_state_dict({k: t(v) for k, v in model_variants.synthetic_state_dict(shapes).items()}, strict=True)
     pcs, nrms, stored = small_pyramid()
     es, ef, ep = oknn.compute_knn_packed(pcs, stored, cfg.K_self, cfg.K_forward, cfg.K_propagate)
     rng = np.random.default_rng(seed + 2)
@@ -256,7 +264,9 @@ def make_model(variant="small"):
     # gradients: keep full tensors for a representative subset, norms for all
     out["grad_names"] = np.array(sorted(gn.keys()))
     out["grad_norms"] = np.array([float(gn[k].norm()) for k in sorted(gn.keys())], np.float32)
-    if variant == "small":
+    if variant == "normal":
+        keys = []                                # full-width model: fp64 gradient slices instead (fp64_targets)
+    elif variant == "small":
         keys = ["pcf_backbone.selfpointconv.linear.c.weight", "pcf_backbone.selfpointconv_res1.linear.c.weight",
                 "pcf_backbone.pointconv.0.linear.c.weight", "pcf_backbone.pointconv_res.1.1.guidance_weight.mlp.0.c.weight",
                 "pcf_backbone.pointconv_res.3.0.weightnet.mlp_convs.0.c.weight", "pointdeconv.3.linear.c.weight",
@@ -268,11 +278,45 @@ def make_model(variant="small"):
     model.eval()
     with torch.no_grad():
         out["logits_eval"] = model(t(feats), tt(pcs), tt(es), tt(ef), tt(ep), tt(nrms)).numpy()
-    for k, v in model.state_dict().items():
-        out["param." + k] = v.numpy()
+    if variant == "normal":
+        names = list(shapes)
+        out["param_names"] = np.array(names)
+        out["param_ndim"] = np.array([len(shapes[k]) for k in names])
+        out["param_shapes"] = np.array([list(shapes[k]) + [0] * (2 - len(shapes[k])) for k in names])
+    else:
+        for k, v in model.state_dict().items():
+            out["param." + k] = v.numpy()
+    if variant == "normal":
+        out.update(fp64_targets(MA, cfg, seed, model, gn, logits.detach(), feats, target, pcs, es, ef, ep, nrms))
     np.savez_compressed(os.path.join(HERE, "model_%s.npz" % variant), **out)
     print("model_%s: N per level" % variant, [p.shape[1] for p in pcs], "loss", loss.item(),
           "params", sum(p.numel() for p in model.parameters()), "full grads", len(keys))
+
+
+def fp64_targets(MA, cfg, seed, model32, grads32, logits32, feats, target, pcs, es, ef, ep, nrms):
+    """The same reference model evaluated in float64 (train mode, same parameters): logits, loss, and per parameter the
+    strided sample (model_variants.grad_sample) of the gradient, its max |.|, its norm and the reference's OWN fp32-vs-fp64 error
+    (max |g32 - g64| over the whole tensor) -- the yardstick the GPU gradients are held to (tests/test_gpu_layers.py)."""
+    import model_variants
+    torch.manual_seed(seed)
+    m64 = MA.PointConvFormer_Segmentation(cfg)
+    m64.load_state_dict(model32.state_dict())
+    m64 = m64.double().train()
+    tt = lambda lst: [t(x) for x in lst]
+    td = lambda lst: [t(x).double() for x in lst]
+    logits = m64(t(feats).double(), td(pcs), tt(es), tt(ef), tt(ep), td(nrms))
+    loss = torch.nn.functional.cross_entropy(logits[0], t(target), label_smoothing=0.2)
+    loss.backward()
+    out = {"logits_train64": logits.detach().float().numpy(), "loss64": np.float64(loss.item())}
+    names = sorted(grads32.keys())
+    g64 = {k: p.grad for k, p in m64.named_parameters()}
+    out["grad64_max"] = np.array([float(g64[k].abs().max()) for k in names])
+    out["grad64_norm"] = np.array([float(g64[k].norm()) for k in names])
+    out["grad32_err"] = np.array([float((grads32[k].double() - g64[k]).abs().max()) for k in names])
+    out["logits32_err"] = np.float64(float((logits32.double() - logits.detach()).abs().max()))
+    for k in names:
+        out["g64." + k] = model_variants.grad_sample(g64[k].flatten()).float().numpy()
+    return out
 
 
 def make_inverse():
