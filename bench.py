@@ -202,6 +202,15 @@ def run_ours(args):
     # replayed; inputs live in static device buffers that the per-step H2D copies overwrite.
     graph, static_in, static_loss = None, None, None
     launches_per_step = None
+    loss_check = None
+    selfcheck = syncbn_selfcheck(dev, rank, world) if sync_bn else None      # multi-GPU correctness before any timing
+    if selfcheck is not None:
+        note("syncbn_selfcheck: %s" % selfcheck)
+        if not selfcheck["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "syncbn_selfcheck failed", "syncbn_selfcheck": selfcheck}))
+            sys.stdout.flush()
+            os._exit(3)
     if use_graph:
         static_in = upload()
         side = torch.cuda.Stream()
@@ -221,6 +230,8 @@ def run_ours(args):
         launches_per_step = _lib.launch_count() - l_before
         torch.cuda.synchronize()
         note("graph captured (%d launches of ours per step)" % launches_per_step)
+        loss_check = check_graph_against_eager(model, opt, lambda: step(*static_in), graph, static_loss)
+        note("loss check: %s" % loss_check)
 
     def graph_step(fresh):
         if fresh is not None:                                            # new host data -> static buffers
@@ -310,7 +321,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.result(),
             "roofline": roof,
+            "loss_check": loss_check,
         }
+        if selfcheck is not None:
+            out["syncbn_selfcheck"] = selfcheck
         out.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args, steps=1, warmup=0)
@@ -328,6 +342,94 @@ def run_ours(args):
         dist.destroy_process_group()
         return None
     return out
+
+
+def check_graph_against_eager(model, opt, eager_step, graph, static_loss):
+    """One eager step and one graph replay from the SAME parameters / optimizer state / BatchNorm buffers must give the same
+    finite loss (every kernel of the step is deterministic).  State is snapshotted and restored in place, so the captured
+    graph keeps pointing at live tensors.  Raises on a non-finite or diverging loss -- a bench line is only printed for a
+    step that computes the right thing."""
+    state = [t for t in model.state_dict().values()]
+    for st in opt.state.values():
+        state += [v for v in st.values() if isinstance(v, torch.Tensor)]
+    snap = [t.clone() for t in state]
+
+    def restore():
+        with torch.no_grad():
+            for t, c in zip(state, snap):
+                t.copy_(c)
+    opt.zero_grad(set_to_none=True)
+    l_eager = float(eager_step().item())
+    restore()
+    opt.zero_grad(set_to_none=True)
+    graph.replay()
+    l_graph = float(static_loss.item())
+    restore()
+    ok = np.isfinite(l_eager) and np.isfinite(l_graph) and abs(l_eager - l_graph) <= 1e-6 * max(1.0, abs(l_eager))
+    res = {"eager": l_eager, "graph_replay": l_graph, "ok": bool(ok)}
+    if not ok:
+        raise RuntimeError("bench: loss check failed (eager vs graph replay, or non-finite): %s" % res)
+    return res
+
+
+def syncbn_selfcheck(dev, rank, world):
+    """SyncBatchNorm parity of this very process group before timing: a 3-layer fused chain (12->16->16->32, the fused MLP
+    kernels + the statistics exchange) and a wide BatchNorm+ReLU (pcfb_bn_*), every rank with a different row count, against
+    ONE float64 evaluation of the concatenated batch (computed redundantly on every rank from the same seeds).  Gradients of
+    parameters stay local (DDP sums them), so they are summed over ranks before the comparison.  -> dict(ok, errs)."""
+    import torch.distributed as dist
+    from pcf_b200 import fused_mlp
+    g = torch.Generator().manual_seed(11)
+    rows = [3000 - 411 * r for r in range(world)]
+    xs = [torch.randn(n, 12, generator=g) for n in rows]
+    gos = [torch.randn(n, 32, generator=g) for n in rows]
+    xw = [torch.randn(n, 96, generator=g) * 2 + 0.3 for n in rows]
+    gw = [torch.randn(n, 96, generator=g) for n in rows]
+
+    def build(dtype, sync):
+        torch.manual_seed(5)
+        dims = [12, 16, 16, 32]
+        lins = [torch.nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:])]
+        bns = [torch.nn.BatchNorm1d(b) for b in dims[1:]] + [torch.nn.BatchNorm1d(96)]
+        for bn in bns:
+            torch.nn.init.uniform_(bn.weight, 0.5, 1.5)
+            torch.nn.init.uniform_(bn.bias, -0.5, 0.5)
+        mods = torch.nn.ModuleList(lins + bns).to(device=dev, dtype=dtype)
+        if sync:
+            mods = torch.nn.SyncBatchNorm.convert_sync_batchnorm(mods)
+        return list(mods[:3]), list(mods[3:])
+    lins, bns = build(torch.float32, True)
+    x = xs[rank].to(dev).requires_grad_(True)
+    y = fused_mlp.mlp_chain(x, [(lins[i], bns[i], fused_mlp.ACT_RELU) for i in range(3)], training=True)
+    (y * gos[rank].to(dev)).sum().backward()
+    xw_r = xw[rank].to(dev)[None].requires_grad_(True)
+    yw = fused_mlp.bn_act(xw_r, bns[3], fused_mlp.ACT_RELU)
+    (yw * gw[rank].to(dev)[None]).sum().backward()
+    rl, rb = build(torch.float64, False)
+    X = torch.cat(xs).to(dev, torch.float64).requires_grad_(True)
+    h = X
+    for i in range(3):
+        h = torch.relu(rb[i](rl[i](h)))
+    (h * torch.cat(gos).to(dev, torch.float64)).sum().backward()
+    XW = torch.cat(xw).to(dev, torch.float64).requires_grad_(True)
+    hw = torch.relu(rb[3](XW))
+    (hw * torch.cat(gw).to(dev, torch.float64)).sum().backward()
+    lo, hi = sum(rows[:rank]), sum(rows[:rank + 1])
+    rel = lambda a, b: float((a.double() - b).abs().max() / b.abs().max())
+    errs = {"y": rel(y.detach(), h.detach()[lo:hi]), "gx": rel(x.grad, X.grad[lo:hi]),
+            "wide_y": rel(yw.detach()[0], hw.detach()[lo:hi]), "wide_gx": rel(xw_r.grad[0], XW.grad[lo:hi]),
+            "running_mean": rel(bns[3].running_mean, rb[3].running_mean), "running_var": rel(bns[3].running_var, rb[3].running_var)}
+    for name, mine, ref in (("gw0", lins[0].weight.grad, rl[0].weight.grad), ("gw2", lins[2].weight.grad, rl[2].weight.grad),
+                            ("ggamma1", bns[1].weight.grad, rb[1].weight.grad), ("gbeta2", bns[2].bias.grad, rb[2].bias.grad),
+                            ("wide_ggamma", bns[3].weight.grad, rb[3].weight.grad)):
+        tot = mine.detach().clone()
+        dist.all_reduce(tot)
+        errs[name] = rel(tot, ref)
+    tol = {"y": 2e-5, "gx": 2e-4, "wide_y": 1e-5, "wide_gx": 1e-4, "running_mean": 1e-5, "running_var": 1e-5}
+    ok = all(np.isfinite(v) and v < tol.get(k, 1e-3) for k, v in errs.items())
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)                          # every rank leaves the same way
+    return {"ok": bool(flag.item() > 0), "world": world, "errs": {k: float("%.3g" % v) for k, v in errs.items()}}
 
 
 def ncu_traffic(op, kernel_substr):
@@ -527,8 +629,8 @@ def choose_cpu_points(args, n_steps, budget_s):
     t0 = time.perf_counter(); step(); t_lin = (time.perf_counter() - t0) / n6
     pts = np.random.default_rng(0).random((20000, 3)).astype(np.float32)
     t0 = time.perf_counter(); OK.compute_knn(pts, pts, 16, use_c=True); pair_s = (time.perf_counter() - t0) / 4e8
-    for n in (100000, 50000, 25000, 12000):
-        if n_steps * (t_lin * n + 1.6 * pair_s * n * n) <= budget_s:
+    for n in (args.points, 50000, 25000, 12000):
+        if n <= args.points and n_steps * (t_lin * n + 1.6 * pair_s * n * n) <= budget_s:
             return n
     return 6000
 
@@ -546,22 +648,37 @@ def cpu_baseline(args, steps, warmup, budget_s=30.0):
         step()
     dt = time.perf_counter() - t0
     return {"value": n0 * steps / dt, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-            "s_per_step": dt / steps}
+            "s_per_step": dt / steps, "points": int(n0)}
 
 
 def run_reference(args):
+    """The CPU arm the driver times next to ours: the reference's PyTorch path restated in oracle/ (kind "port": the
+    reference's own Python cannot travel to the GPU box and its kNN dependencies are absent) on the host cores, same
+    generator / model / training step as our arm and -- whenever steps + warm-up fit the budget (300 s; 7.3 s per step on a
+    16-core box) -- the SAME ~100k-point scene (`same_config`); otherwise the largest sample of the ladder that fits, with
+    both sizes stated."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return None
-    base = cpu_baseline(args, steps=args.steps, warmup=min(args.warmup, 1), budget_s=150.0)
-    return {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": base["s_per_step"] * 1e3,
+    base = cpu_baseline(args, steps=args.steps, warmup=args.warmup, budget_s=300.0)
+    full = bench_points(args)
+    return {"impl": "reference", "arm": "cpu_port", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step on the host CPU (bounded sample)",
+            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step on the host CPU (oracle port of the reference's "
+                                   "PyTorch path + C kNN), same generator / model / step as the GPU arm",
+                       "sample_points": base["points"], "gpu_arm_points": full, "same_config": base["points"] == full,
                        "points_per_step": base["sample"]},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+
+
+def bench_points(args):
+    """Level-0 point count of the scene our arm runs at --points (the generator voxelises, so it is not --points exactly)."""
+    import pcf_b200  # noqa: F401
+    from pcf_b200 import configs, synthetic
+    return int(len(synthetic.make_scene(100, args.points, voxel=configs.CONFIG_PCF_OPT_10CM["grid_size"][0])[0]))
 
 
 def main():

@@ -3,6 +3,7 @@ replace_batchnorm (237-247), to_device (the reference's tensor mover)."""
 import torch
 
 from . import pcf_cuda
+from . import streams as S
 
 
 def to_device(inputs, non_blocking=True):
@@ -16,14 +17,25 @@ def compute_knn_inverse(pointclouds, edges_self, edges_forward, edges_propagate)
     [list_inv_neighbors, list_inv_k, list_inv_idx] (int32 [1,N*K], uint8 [1,N*K], int32 [1,total+1]).
     total_points = pointclouds[j].shape[1] for all three kinds, exactly as the reference does (for
     propagate edges that is the dense level: harmless padding, lines 303-306)."""
+    slot = [0]
+
     def run(edge_list):
-        out = ([], [], [])
+        # the 13 edge sets are independent: each inverse map (4 small launches) is built on a side stream
+        branches = []
         for j, e in enumerate(edge_list):
-            res = pcf_cuda.compute_knn_inverse(to_device(e).contiguous(), pointclouds[j].shape[1])
-            for lst, r in zip(out, res):
+            branches.append(S.fork(lambda e=e, j=j: pcf_cuda.compute_knn_inverse(to_device(e).contiguous(), pointclouds[j].shape[1]),
+                                   slot[0]))
+            slot[0] += 1
+        return branches
+
+    def collect(branches):
+        out = ([], [], [])
+        for b in branches:
+            for lst, r in zip(out, S.join(b)):
                 lst.append(r)
         return [out[0], out[1], out[2]]
-    return run(edges_self), run(edges_forward), run(edges_propagate)
+    bs, bf, bp = run(edges_self), run(edges_forward), run(edges_propagate)
+    return collect(bs), collect(bf), collect(bp)
 
 
 def replace_batchnorm(net):

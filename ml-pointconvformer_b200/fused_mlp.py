@@ -12,6 +12,7 @@ from ._lib import check, lib, ptr, stream_ptr, workspace
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
 F32 = torch.float32
+SYNC_CHANNELS = False       # True once the SyncBatchNorm exchange has one channel per stream (streams.side_index)
 
 
 def supported(dims):

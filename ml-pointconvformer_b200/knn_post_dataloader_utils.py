@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import pcf_cuda
+from . import streams as S
 
 
 def _as_cuda_xyz(x):
@@ -67,18 +68,28 @@ def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagat
     # search wins even when it is latency bound (measured per query set, grid vs brute force: 128 vs 232 us at 1 k
     # references, 185 vs 287 us at 5 k, 105 vs 84 us at 184) -- same table either way.
     small = [max(counts[j]) <= BRUTE_MAX_REFS for j in range(L)]
-    grids = [None if small[j] else pcf_cuda.KnnGrid(pcs[j], counts[j], 2.5 * float(grid_size[j]) if grid_size is not None else 0.0)
-             for j in range(L)]
+    hint = lambda j: 2.5 * float(grid_size[j]) if grid_size is not None else 0.0
 
-    def query(jr, jq, K):
-        if small[jr]:
-            return pcf_cuda.knn_packed(pcs[jr], counts[jr], pcs[jq], counts[jq], K)
-        return grids[jr].query(pcs[jq], counts[jq], K)
+    def against(jr):
+        """Everything that searches reference level jr: its grid build, then the self / propagate / forward queries.  The five
+        levels are independent of each other, so each runs on its own side stream (streams.fork): the step's 13 edge sets cost
+        the level-0 chain (build + two queries) instead of the sum of all of them."""
+        grid = None if small[jr] else pcf_cuda.KnnGrid(pcs[jr], counts[jr], hint(jr))
+
+        def query(jq, K):
+            if grid is None:
+                return pcf_cuda.knn_packed(pcs[jr], counts[jr], pcs[jq], counts[jq], K)
+            return grid.query(pcs[jq], counts[jq], K)
+        return (query(jr, K_self[jr]),                                        # self
+                query(jr - 1, K_propagate[jr]) if jr >= 1 else None,         # propagate: dense level jr-1 looks into jr
+                query(jr + 1, K_forward[jr + 1]) if jr + 1 < L else None)    # forward: level jr+1 looks into jr
+    branches = [S.fork(lambda j=j: against(j), j) for j in range(L)]
+    res = [S.join(b) for b in branches]
     for j in range(L):
-        e_self.append(query(j, j, K_self[j]))
+        e_self.append(res[j][0])
         if j >= 1:
-            e_fwd.append(query(j - 1, j, K_forward[j]))
-            e_prop.append(query(j, j - 1, K_propagate[j]))
+            e_fwd.append(res[j - 1][2])
+            e_prop.append(res[j][1])
     return [e_self], [e_fwd], [e_prop]
 
 

@@ -22,12 +22,15 @@ def resolve_inverse(nei_inds, total_points, inv_neighbors=None, inv_k=None, inv_
     if inv_neighbors is not None:
         return (inv_neighbors.to(torch.int32).contiguous(), inv_k.to(torch.uint8).contiguous(),
                 inv_idx.to(torch.int32).contiguous())
+    # the cache key carries the tensor's version counter and address: an index tensor that is overwritten in place (static
+    # input buffers, reused loader tensors) gets a fresh map instead of a stale one
+    key = (total_points, nei_inds._version, nei_inds.data_ptr())
     cached = getattr(nei_inds, "_pcfb_inverse", None)
-    if cached is not None and cached[0] == total_points:
+    if cached is not None and cached[0] == key:
         return cached[1]
     inv = pcf_cuda.compute_knn_inverse(nei_inds.contiguous(), total_points)
     try:
-        nei_inds._pcfb_inverse = (total_points, inv)
+        nei_inds._pcfb_inverse = (key, inv)
     except Exception:
         pass
     return inv

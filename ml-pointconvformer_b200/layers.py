@@ -16,6 +16,7 @@ from torch import nn
 import torch.nn.functional as F
 
 from . import fused_mlp
+from . import streams as S
 from .layer_utils import (FusedPConvFunction, PConvLinearOpt, Linear_BN, UnaryBlock, edge_geometry, gather_max,
                           index_points, linear, resolve_inverse)
 
@@ -191,11 +192,19 @@ class PCFLayer(_PointLayerBase):
         nei_inds = nei_inds.contiguous()
         inv = _inv_tuple(nei_inds, N, inv_neighbors, inv_k, inv_idx, torch.is_grad_enabled() and dense_feats.requires_grad)
 
-        feats_x = self.unary1(dense_feats)
         _, weightNetInput = self._geometry(dense_xyz, dense_xyz_norm, nei_inds, c_xyz, c_nrm, vi_features, self.cfg.USE_VI is True)
+        # three branches that only meet at the guidance / the contraction / the residual add run on side streams
+        par = _streams_ok(self)
+        br_w = S.fork(lambda: self.weightnet(weightNetInput), 0, par)
         spec = _chain_spec([self.mlp_conv], [fused_mlp.ACT_RELU])
-        feat_pe = fused_mlp.mlp_chain(weightNetInput, spec, self.training) if spec is not None else F.relu(self.mlp_conv(weightNetInput))
+        br_pe = S.fork(lambda: fused_mlp.mlp_chain(weightNetInput, spec, self.training) if spec is not None
+                       else F.relu(self.mlp_conv(weightNetInput)), 1, par)
+        has_sc = strided or not isinstance(self.unary_shortcut, nn.Identity)
+        br_sc = S.fork(lambda: self.unary_shortcut(gather_max(dense_feats, nei_inds, inv) if strided else dense_feats), 2,
+                       par and has_sc)
+        feats_x = self.unary1(dense_feats)
         guidance_x = self.guidance_unary(feats_x)
+        feat_pe = S.join(br_pe)
         guidance_feature = torch.cat([index_points(guidance_x, nei_inds, inv), feat_pe], dim=-1)
         if M == N:
             guidance_key = guidance_feature[:, :, :1, :]           # column 0 is the centre itself (T6)
@@ -203,7 +212,7 @@ class PCFLayer(_PointLayerBase):
             guidance_key = guidance_feature.max(dim=2, keepdim=True)[0]
         guidance_score = self.guidance_weight(guidance_feature, guidance_key.expand_as(guidance_feature)
                                               if self.cfg.attention_type != 'subtraction' else guidance_key)
-        weights = self.weightnet(weightNetInput)
+        weights = S.join(br_w)
 
         if isinstance(self.linear, Linear_BN):
             lin, post_bn = self.linear.c, self.linear
@@ -213,9 +222,19 @@ class PCFLayer(_PointLayerBase):
         new_feat = _bn_relu(post_bn.bn, new_feat, lin.bias) if post_bn is not None else F.relu(new_feat)
         new_feat = self.dropout(new_feat)
         new_feat = self.unary2(new_feat)
-        sparse_feats = gather_max(dense_feats, nei_inds, inv) if strided else dense_feats
-        shortcut = self.unary_shortcut(sparse_feats)
+        shortcut = S.join(br_sc)
         return self.leaky_relu(self.drop_path(new_feat) + shortcut), weightNetInput
+
+
+def _streams_ok(module):
+    """Side streams are used unless the module's BatchNorms exchange statistics across ranks without per-stream exchange
+    channels (fused_mlp.SYNC_CHANNELS)."""
+    if not S.ENABLED:
+        return False
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not fused_mlp.SYNC_CHANNELS:
+        return not any(isinstance(m, nn.SyncBatchNorm) for m in module.modules())
+    return True
 
 
 def _bn_relu(bn, x, pivot=None):
@@ -287,15 +306,20 @@ class PointConvStridePE(_PointLayerBase, _PConvLinearMixin):
         nei_inds = nei_inds.contiguous()
         inv = _inv_tuple(nei_inds, N, inv_neighbors, inv_k, inv_idx, torch.is_grad_enabled() and dense_feats.requires_grad)
 
-        feats_x = self.unary1(dense_feats)
         localized_xyz, weightNetInput = self._geometry(dense_xyz, dense_xyz_norm, nei_inds, c_xyz, c_nrm, vi_features,
                                                        self.cfg.USE_VI is True)
-        feat_pe = self.pe_convs(localized_xyz)
-        weights = self.weightnet(weightNetInput)
+        par = _streams_ok(self)
+        br_w = S.fork(lambda: self.weightnet(weightNetInput), 0, par)
+        br_pe = S.fork(lambda: self.pe_convs(localized_xyz), 1, par)
+        has_sc = strided or not isinstance(self.unary_shortcut, nn.Identity)
+        br_sc = S.fork(lambda: self.unary_shortcut(gather_max(dense_feats, nei_inds, inv) if strided else dense_feats), 2,
+                       par and has_sc)
+        feats_x = self.unary1(dense_feats)
+        feat_pe = S.join(br_pe)
+        weights = S.join(br_w)
         new_feat = self.dropout(self._contract_linear(feats_x, nei_inds, inv, weights, feat_pe))
         new_feat = self.unary2(new_feat)
-        sparse_feats = gather_max(dense_feats, nei_inds, inv) if strided else dense_feats
-        shortcut = self.unary_shortcut(sparse_feats)
+        shortcut = S.join(br_sc)
         return self.leaky_relu(self.drop_path(new_feat) + shortcut), weightNetInput
 
 
@@ -359,8 +383,10 @@ class PointConvTransposePE(_PointLayerBase, _PConvLinearMixin):
             inv = (inv[0], inv[1], inv[2][:, :n_in + 1].contiguous())
         localized_xyz, weightNetInput = self._geometry(sparse_xyz, sparse_xyz_norm, nei_inds, dense_xyz, dense_xyz_norm,
                                                        vi_features, self.cfg.USE_VI is True)
-        feat_pe = self.pe_convs(localized_xyz) if self.cfg.USE_PE else None
+        par = _streams_ok(self)
+        br_pe = S.fork(lambda: self.pe_convs(localized_xyz) if self.cfg.USE_PE else None, 1, par and self.cfg.USE_PE)
         weights = self.weightnet(weightNetInput)
+        feat_pe = S.join(br_pe)
         new_feat = self._contract_linear(sparse_feats, nei_inds, inv, weights, feat_pe)
         if dense_feats is not None:
             new_feat = new_feat + dense_feats

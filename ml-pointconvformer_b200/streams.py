@@ -1,0 +1,78 @@
+"""Fork / join of the independent branches of a layer onto side CUDA streams.
+
+Inside one PointConvFormer layer the WeightNet chain, the positional-encoding chain and the shortcut branch do not depend
+on each other until the contraction (/root/reference/layers.py:306-416: `weightnet`, `mlp_conv`, `unary_shortcut` are three
+sub-graphs hanging off the same inputs).  On the coarse levels of the pyramid (5 k / 1 k / 184 points: 19 of PCF_Normal's 25
+layers) every one of their kernels is a 2..65-CTA launch on a 148-SM GPU, so running the branches one after the other
+leaves the machine idle behind a chain of ~6 us launches.  fork() runs a branch on a side stream (ordered after everything
+already enqueued on the caller's stream), join() makes the caller's stream wait for it.  Autograd runs each backward node
+on the stream of its forward, so the backward passes of the branches overlap the same way; inside a captured CUDA graph
+the fork / join pairs become parallel branches of the graph.
+
+Memory safety with the caching allocator: every branch starts with side.wait_stream(main) and is joined into main before
+the caller goes on, results are record_stream()'ed on the consumer stream.
+"""
+import os
+
+import torch
+
+ENABLED = os.environ.get("PCFB_STREAMS", "1") != "0"
+N_SIDE = 3
+_POOL = {}
+
+
+def _side_streams(device):
+    key = (device.type, device.index)
+    pool = _POOL.get(key)
+    if pool is None:
+        pool = _POOL[key] = [torch.cuda.Stream(device=device) for _ in range(N_SIDE)]
+    return pool
+
+
+def side_index(stream=None):
+    """0 for the caller's main stream, 1..N_SIDE for the side streams (used as the exchange channel of SyncBatchNorm)."""
+    stream = stream or torch.cuda.current_stream()
+    pool = _POOL.get((stream.device.type, stream.device.index))
+    if pool:
+        for i, s in enumerate(pool):
+            if s == stream:
+                return i + 1
+    return 0
+
+
+class Branch:
+    __slots__ = ("result", "stream", "main")
+
+    def __init__(self, result, stream=None, main=None):
+        self.result, self.stream, self.main = result, stream, main
+
+
+def fork(fn, slot, enabled=True):
+    """Run fn() on side stream `slot` (inline when disabled, on the CPU, or when already on a side stream)."""
+    if not (ENABLED and enabled) or not torch.cuda.is_available():
+        return Branch(fn())
+    main = torch.cuda.current_stream()
+    if side_index(main) != 0:                       # no nested forks
+        return Branch(fn())
+    side = _side_streams(main.device)[slot % N_SIDE]
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        res = fn()
+    return Branch(res, side, main)
+
+
+def _record(x, stream):
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            x.record_stream(stream)
+    elif isinstance(x, (list, tuple)):
+        for y in x:
+            _record(y, stream)
+
+
+def join(branch):
+    """The caller's stream waits for the branch; returns the branch's result."""
+    if branch.stream is not None:
+        branch.main.wait_stream(branch.stream)
+        _record(branch.result, branch.main)
+    return branch.result

@@ -275,6 +275,8 @@ def make_model(variant="small"):
         keys = [k for pat in GRAD_KEY_PATTERNS for k in sorted(gn) if k.endswith(pat)]
     for k in keys:
         out["grad." + k] = gn[k].numpy()
+    if variant == "normal":                       # eval with the by-name buffers, not the running stats the train pass moved
+        model.load_state_dict({k: t(v) for k, v in model_variants.synthetic_state_dict(shapes).items()}, strict=True)
     model.eval()
     with torch.no_grad():
         out["logits_eval"] = model(t(feats), tt(pcs), tt(es), tt(ef), tt(ep), tt(nrms)).numpy()

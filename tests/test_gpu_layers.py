@@ -63,18 +63,22 @@ def test_layer_matches_reference_golden(golden_dir, name, use_kernel):
     torch.testing.assert_close(y.cpu(), torch.from_numpy(g["y_train64"]), rtol=2e-4, atol=2e-4)
     torch.testing.assert_close(y.cpu(), torch.from_numpy(g["y_train"]), rtol=2e-4, atol=2e-4)
     (y * cuda(g["gout"])).sum().backward()
-    assert max_err_scaled(a["feats"].grad, torch.from_numpy(g["g_feats64"])) < 2e-3
+    # gradients: held to the reference's OWN float32 evaluation of the same draw -- err_gpu(vs fp64) <= 2 * err_cpu_fp32(vs fp64)
+    # per tensor, or 1e-4 of the tensor's largest entry (the north-star tolerance) where the CPU happened to be luckier.
+    # A bias feeding a train-mode BatchNorm has zero true gradient (cancellation noise only): absolute floor.
+    def bound(got, ref64, ref32, what):
+        e32 = float((ref32.double() - ref64.double()).abs().max())
+        mx = float(ref64.abs().max())
+        err = float((got.cpu().double() - ref64.double()).abs().max())
+        tol = max(2 * e32, 1e-4 * mx, 2e-6)
+        assert err <= tol, (what, err, e32, mx)
+        return err / tol
+    worst = bound(a["feats"].grad, torch.from_numpy(g["g_feats64"]), torch.from_numpy(g["g_feats"]), "g_feats")
     for k in g.files:
         if k.startswith("grad64."):
             got = dict(layer.named_parameters())[k[7:]].grad
-            ref = torch.from_numpy(g[k])
-            # a bias feeding a train-mode BatchNorm has zero true gradient (only cancellation noise); weight
-            # gradients behind chains of train-mode BatchNorms are ill-conditioned in fp32 (two correct fp32
-            # evaluations differ by up to ~3e-3 of the largest entry, tests/test_oracle_golden.py) -- the tight
-            # 1e-4 bounds are carried by the op-level tests (test_gpu_pconv.py, test_gpu_gemm.py)
-            tol = 2e-2 if k.endswith(".c.bias") else 1e-2 * max(1.0, float(ref.abs().max()))
-            err = float((got.cpu() - ref).abs().max())
-            assert err <= tol, (k, err, tol)
+            worst = max(worst, bound(got, torch.from_numpy(g[k]), torch.from_numpy(g["grad." + k[7:]]), k))
+    print("layer_%s use_kernel=%s: worst gradient err / tol = %.2f" % (name, use_kernel, worst))
     layer.load_state_dict(sd, strict=True)
     layer.eval()
     with torch.no_grad():
@@ -145,6 +149,47 @@ def test_model_matches_reference_golden(golden_dir, variant, pconv_opt):
     with torch.no_grad():
         le = model(cuda(g["feats"]), pcs, es, ef, ep, nrm)
     torch.testing.assert_close(le.cpu(), torch.from_numpy(g["logits_eval"]), rtol=2e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("pconv_opt", [False, True])
+def test_model_normal_full_width_vs_float64(golden_dir, pconv_opt):
+    """BASELINE configs[2]'s own model -- PCF_Normal configPCF_Opt_10cm at its real width (feat_dim 64..384, 8 heads,
+    resblocks [0,2,4,6,6], 5.4 M parameters; configs/configPCF_Opt_10cm.yaml:27-43, model_architecture.py:406-502) --
+    against the UNMODIFIED reference evaluated in float64 on the same two-scene pyramid (tests/golden/make_golden.py
+    --model normal), in both PCONV_OPT spellings.  Yardstick for every gradient: the reference's OWN float32 CPU
+    evaluation of the same draw, whose max error against float64 is stored per parameter (grad32_err):
+        err_gpu <= 2 * err_cpu_fp32   (or 1e-4 of the largest entry, the north-star tolerance, whichever is larger)
+    Parameters whose true gradient is zero (a bias in front of a train-mode BatchNorm) carry only rounding noise on
+    both sides and are held to an absolute floor."""
+    import model_variants
+    g = model_variants.load(golden_dir, "normal")
+    model, sd = _build_model(g, "normal", pconv_opt)
+    pcs, nrm, es, ef, ep = _model_inputs(g)
+    from pcf_b200 import common_util as CU
+    inv = CU.compute_knn_inverse(pcs, es, ef, ep) if pconv_opt else (None, None, None)
+    model.train()
+    logits = model(cuda(g["feats"]), pcs, es, ef, ep, nrm, *inv)
+    ref = torch.from_numpy(g["logits_train64"])
+    err_logits = float((logits.cpu() - ref).abs().max())
+    assert err_logits <= max(2 * float(g["logits32_err"]), 1e-4 * float(ref.abs().max())), (err_logits, float(g["logits32_err"]))
+    loss = torch.nn.functional.cross_entropy(logits[0], cuda(g["target"]), label_smoothing=0.2)
+    assert abs(loss.item() - float(g["loss64"])) < 2e-5
+    loss.backward()
+    params = dict(model.named_parameters())
+    bad, worst = [], 0.0
+    for k, mx, e32 in zip(g["grad_names"].tolist(), g["grad64_max"].tolist(), g["grad32_err"].tolist()):
+        k2 = k
+        if pconv_opt and k not in params:
+            k2 = k.replace(".linear.c.", ".pconv_linear_opt.linear.").replace(".linear.bn.", ".bn.")
+        got = model_variants.grad_sample(params[k2].grad.flatten()).cpu().double()
+        err = float((got - torch.from_numpy(g["g64." + k]).double()).abs().max())
+        tol = max(2 * e32, 1e-4 * mx, 2e-7)
+        worst = max(worst, err / tol)
+        if err > tol:
+            bad.append((k, err, e32, mx))
+    print("model_normal pconv_opt=%s: logits err %.2e (cpu fp32 %.2e), worst gradient err / tol %.2f" %
+          (pconv_opt, err_logits, float(g["logits32_err"]), worst))
+    assert not bad, (len(bad), bad[:8])
 
 
 @pytest.mark.parametrize("variant", ["small", "ptf2"])

@@ -115,7 +115,7 @@ def model_inputs(g):
     return t(g["feats"]), pcs, es, ef, ep, nrms
 
 
-@pytest.mark.parametrize("variant", ["small", "lite", "ptf2", "routing"])
+@pytest.mark.parametrize("variant", ["small", "lite", "ptf2", "routing", "normal"])
 def test_model_matches_reference(golden_dir, variant):
     """Whole-model oracle vs the unmodified reference for the structures of every shipped config family
     (tests/model_variants.py) plus the guided_level / resblocks_back branches."""
