@@ -126,7 +126,7 @@ class ClockSampler(threading.Thread):
 def run_ours(args):
     import torch.distributed as dist
     import pcf_b200  # noqa: F401
-    from pcf_b200 import _lib, pcf_cuda, configs, sharding
+    from pcf_b200 import _lib, pcf_cuda, configs, sharding, losses
     from pcf_b200 import model_architecture as MA, knn_post_dataloader_utils as KU, common_util as CU
 
     rank = int(os.environ.get("RANK", 0))
@@ -148,6 +148,7 @@ def run_ours(args):
         # SyncBatchNorm makes ~450 all-reduces of a few hundred bytes per step: latency, not bandwidth.  The NVLink-SHARP
         # (NVLS) path costs more per tiny message than the LL ring/tree (measured at N=2: 55.4 -> 53.7 ms/step).
         os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        os.environ.setdefault("PCFB_PEER_REDUCE", "1")                 # SyncBatchNorm statistics over NVLink peer memory (opt-in)
         dist.init_process_group("nccl", device_id=dev)
     pcf_cuda.FORWARD_VARIANT = args.variant
     note("process group ready")
@@ -162,7 +163,8 @@ def run_ours(args):
     model.train()
     use_graph = not args.no_graph
     flat = sharding.FlatParameters(model)                              # one buffer: optimizer / clip / all-reduce see one tensor
-    opt = torch.optim.AdamW([flat.flat], lr=1e-3, weight_decay=cfgd["adamw_decay"], fused=True, capturable=use_graph)
+    # clip_grad_norm_(10) + AdamW (train_ScanNet_DDP_WarmUP.py:421-424) as two launches of ours on the flat buffer
+    opt = sharding.FlatAdamW(flat, lr=1e-3, weight_decay=cfgd["adamw_decay"], max_norm=10.0)
 
     host = host_pyramid(1 + rank, args.points, cfgd["grid_size"], args.scenes)
     L = cfgd["num_level"]
@@ -186,12 +188,9 @@ def run_ours(args):
                                                        grid_size=cfgd["grid_size"]))
         inv_s, inv_f, inv_p = CU.compute_knn_inverse(pcs, es, ef, ep)
         logits = model(col.unsqueeze(0), pcs, es, ef, ep, nrms, inv_s, inv_f, inv_p)
-        loss = torch.nn.functional.cross_entropy(logits[0], lab, ignore_index=cfgd["ignore_label"],
-                                                 label_smoothing=cfgd["label_smoothing"])
+        loss = losses.cross_entropy(logits[0], lab, ignore_index=cfgd["ignore_label"], label_smoothing=cfgd["label_smoothing"])
         loss.backward()
-        flat.gather_grads(world)                                       # flat gradient (+ the DDP all-reduce, mean over ranks)
-        torch.nn.utils.clip_grad_norm_([flat.flat], 10.0)
-        opt.step()
+        opt.step(flat.gather_grads(world))                             # flat gradient (+ the DDP all-reduce, mean over ranks), clip, AdamW
         return loss
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
@@ -222,7 +221,6 @@ def run_ours(args):
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         note("eager warm-up done, capturing")
-        opt.zero_grad(set_to_none=True)
         l_before = _lib.launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -349,19 +347,15 @@ def check_graph_against_eager(model, opt, eager_step, graph, static_loss):
     finite loss (every kernel of the step is deterministic).  State is snapshotted and restored in place, so the captured
     graph keeps pointing at live tensors.  Raises on a non-finite or diverging loss -- a bench line is only printed for a
     step that computes the right thing."""
-    state = [t for t in model.state_dict().values()]
-    for st in opt.state.values():
-        state += [v for v in st.values() if isinstance(v, torch.Tensor)]
+    state = [t for t in model.state_dict().values()] + opt.state_tensors()
     snap = [t.clone() for t in state]
 
     def restore():
         with torch.no_grad():
             for t, c in zip(state, snap):
                 t.copy_(c)
-    opt.zero_grad(set_to_none=True)
     l_eager = float(eager_step().item())
     restore()
-    opt.zero_grad(set_to_none=True)
     graph.replay()
     l_graph = float(static_loss.item())
     restore()

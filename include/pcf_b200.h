@@ -196,15 +196,12 @@ size_t pcfb_mlp_workspace(int64_t E, int cin, int cout);
 int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int cout, const float *W, const float *b,
                      const float *in_scale, const float *in_shift, int in_act, float *y, int ldy,
                      float *stat_partial, int *h_nblocks, void *stream);
-int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, const double *d_count, const float *pivot,
-                     const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
-                     float *running_var, float *scale, float *shift, float *mean, float *invstd,
-                     int64_t *batches_tracked /* BatchNorm.num_batches_tracked, incremented; may be NULL */, void *stream);
 int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
                 void *stream);
 int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y, int ldy, int64_t E, int C, const float *scale,
-                            const float *shift, const float *mean, const float *invstd, int act, float *sums,
-                            void *workspace, size_t workspace_bytes, void *stream);
+                            const float *shift, const float *mean, const float *invstd, int act,
+                            float *sums /* NULL: leave the block partials [*h_nblocks][2][C] in the workspace for pcfb_bn_reduce_sums */,
+                            int *h_nblocks, void *workspace, size_t workspace_bytes, void *stream);
 int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int ldy, int64_t E, int cin, int cout,
                       const float *W, const float *scale, const float *shift, const float *mean,
                       const float *invstd, const float *sums, int act,
@@ -215,18 +212,33 @@ int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int ldy, int64_t
 int pcfb_sum_partials(const float *partial, int nblocks, int n, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Small all-reduce (sum, <= pcfb_peer_max_floats() floats) over NVLink / NVSwitch peer memory: the SyncBatchNorm
- * statistics exchange (torch.nn.SyncBatchNorm after convert_sync_batchnorm, train_ScanNet_DDP_WarmUP.py:190-195;
- * sync_bn: True in configs/configPCF_Opt_10cm.yaml) as ONE single-CTA kernel instead of an NCCL call: every rank
- * stores its values into its slot of every peer's buffer, publishes an epoch flag (st.release.sys), waits for the
- * peers' flags (ld.acquire.sys) and sums the slots in rank order (bit-identical on all ranks).
- * peer_bases: device array of `world` pointers, entry r = rank r's symmetric buffer of pcfb_peer_buffer_bytes(world)
- * bytes as mapped into THIS process (all-zero before the first call).  Every rank must make the same sequence of
- * calls; in/out may alias; the kernel traps after 20 s if a peer never arrives.
+ * BatchNorm statistics: block partials -> per-channel sums -> [SyncBatchNorm exchange] -> scale / shift / running
+ * statistics in ONE kernel (csrc/peer_reduce.cu).  Replaces torch.nn.BatchNorm's finalize and, across ranks,
+ * torch.nn.SyncBatchNorm's all_gather / all_reduce of per-channel statistics (convert_sync_batchnorm,
+ * train_ScanNet_DDP_WarmUP.py:190-195; sync_bn: True in configs/configPCF_Opt_10cm.yaml): ~540 latency-bound messages
+ * per step.  partial: [nblocks][2][C] (sum, sum of squares -- pivoted by `pivot` -- or sum dz, sum dz*xhat).
+ * peer_bases (NULL = single process): device array of `world` pointers, entry r = rank r's symmetric buffer of
+ * pcfb_syncbn_buffer_bytes(world) bytes as mapped into THIS process (all-zero before the first call).  One CTA per 8
+ * channels pushes its sums + the local row count into its slot of every rank's buffer, publishes an epoch flag
+ * (st.release.sys), waits for the peers' flags (ld.acquire.sys) and adds the slots in rank order (bit-identical on all
+ * ranks).  Every rank must issue the same sequence of calls per `channel` (< pcfb_syncbn_channels()); calls of one channel
+ * must be stream ordered.  timeout_s > 0: a CTA that waited that long sets the buffer's error word (byte 0), writes NaN
+ * and returns (no trap); 0 = wait forever.
+ *   pcfb_bn_finalize: (scale, shift) = (gamma*invstd, beta - mean*gamma*invstd), mean / invstd saved, running statistics
+ *     updated with the GLOBAL count (momentum < 0: cumulative average 1/num_batches_tracked, counter not touched; else
+ *     batches_tracked += 1), count_out (optional) = global row count (device double, consumed by the backward kernels).
+ *     d_count (optional) = global count already on the device (NCCL fallback: partial then holds the all-reduced sums).
+ *   pcfb_bn_reduce_sums: sums_local[2][C] (dgamma / dbeta stay local, like torch.nn.SyncBatchNorm) and sums_global[2][C].
  * ------------------------------------------------------------------------------------------- */
-size_t pcfb_peer_buffer_bytes(int world);
-int pcfb_peer_max_floats(void);
-int pcfb_peer_allreduce(const float *in, float *out, int n, const void *peer_bases, int rank, int world, void *stream);
+size_t pcfb_syncbn_buffer_bytes(int world);
+int pcfb_syncbn_channels(void);
+int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, const double *d_count, const float *pivot,
+                     const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                     float *running_var, float *scale, float *shift, float *mean, float *invstd,
+                     int64_t *batches_tracked, double *count_out, const void *peer_bases, int rank, int world, int channel,
+                     double timeout_s, void *stream);
+int pcfb_bn_reduce_sums(const float *partial, int nblocks, int C, float *sums_local, float *sums_global,
+                        const void *peer_bases, int rank, int world, int channel, double timeout_s, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm (+ activation) over a contiguous [rows, C] tensor, C % 4 == 0, C <= 1024: the BatchNorm + ReLU that
@@ -246,8 +258,8 @@ size_t pcfb_bn_workspace(int64_t rows, int C);
 int pcfb_bn_stats(const float *x, int64_t rows, int C, const float *pivot, float *partial, size_t partial_bytes,
                   int *h_nblocks, void *stream);
 int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
-                           const float *mean, const float *invstd, int act, float *sums, void *workspace,
-                           size_t workspace_bytes, void *stream);
+                           const float *mean, const float *invstd, int act, float *sums /* NULL: partials stay in the workspace */,
+                           int *h_nblocks, void *workspace, size_t workspace_bytes, void *stream);
 int pcfb_bn_backward(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
                      const float *mean, const float *invstd, const float *sums, int act, const double *d_count,
                      float *dX, void *stream);
@@ -282,6 +294,39 @@ int pcfb_gridsub_count(const float *xyz, const int32_t *seg_off, int n_seg, int 
 int pcfb_gridsub_emit(const float *xyz, const float *feats, int n_seg, int n_pts, int F,
                       int64_t total_cells, float *out_xyz, float *out_feats, void *workspace,
                       size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layer glue the reference leaves to chains of torch elementwise ops.
+ *
+ * Guidance input of the PointConvFormer layer (layers.py:372-382):
+ *   q = cat(index_points(guidance_x, nei), feat_pe);  key = q[:, :, :1] if M == N else max_k q;  out = q - key
+ * gx [n_in, G], pe [n_out, K, P], nei [n_out, K] -> out [n_out, K, G+P]; arg [n_out, G+P] (use_max only: the k
+ * attaining the maximum, first on ties).  G, P multiples of 4.  -1 / out-of-range neighbours gather zeros.
+ * Backward: d_gq [n_out, K, G] is the per-edge gradient of the gathered half (sum it per input point with
+ * pcfb_gather_backward: the index_put_(accumulate) of the reference's autograd, without atomics), d_pe [n_out, K, P].
+ * ------------------------------------------------------------------------------------------- */
+int pcfb_guidance_input(const float *gx, const float *pe, const int64_t *nei, int n_in, int n_out, int K, int G, int P,
+                        int use_max, float *out, uint8_t *arg, void *stream);
+int pcfb_guidance_input_backward(const float *ds, const uint8_t *arg, int n_out, int K, int G, int P, int use_max,
+                                 float *d_gq, float *d_pe, void *stream);
+
+/* clip_grad_norm_(max_norm) + AdamW step on ONE flat fp32 buffer (train_ScanNet_DDP_WarmUP.py:421-424; torch.optim.AdamW
+ * semantics: step += 1; p *= 1 - lr*wd; m, v moments; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)).  lr and step are DEVICE
+ * scalars (float) so a captured step can be replayed under a learning-rate schedule; max_norm <= 0 disables clipping;
+ * norm_out (optional) receives the gradient norm before clipping.  Two launches, fixed-order reductions. */
+size_t pcfb_adamw_workspace(void);
+int pcfb_adamw_clip_step(float *p, const float *g, float *m, float *v, int64_t n, const float *lr, float *step,
+                         float beta1, float beta2, float eps, float weight_decay, float max_norm, float *norm_out,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
+/* Cross entropy over logits [N, C] (C <= 64) with torch.nn.CrossEntropyLoss semantics (train_ScanNet_DDP_WarmUP.py:417:
+ * class weights, ignore_index, label_smoothing, mean reduction = sum / sum of the target-class weights of the valid rows).
+ * forward -> loss[1], den[1]; backward recomputes the softmax from the logits: dlogits = grad_scale[0] * dL/dlogits. */
+size_t pcfb_ce_workspace(int64_t N);
+int pcfb_ce_forward(const float *logits, const int64_t *labels, const float *weight, int64_t N, int C, int64_t ignore_index,
+                    float smoothing, float *loss, float *den, void *workspace, size_t workspace_bytes, void *stream);
+int pcfb_ce_backward(const float *logits, const int64_t *labels, const float *weight, int64_t N, int C, int64_t ignore_index,
+                     float smoothing, const float *den, const float *grad_scale, float *dlogits, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Hardware self-test of the tcgen05 (UMMA) operand / accumulator conventions used by the fused

@@ -567,15 +567,21 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 struct NtSetup { int Nblk, n_blocks, Npad, n_chunks, resident; size_t block_bytes, prep_bytes; GemmNtPlan plan; };
 
 // One column block when the tile (A double buffer + B ring or resident B) fits for the whole width, else column
-// blocks of 128 (64 for very long K) handled by blockIdx.y of the same launch.
-static NtSetup nt_setup(int N, int K) {
+// blocks of 128 (64 for very long K) handled by blockIdx.y of the same launch.  Few rows (M <= 0: unknown / many): the
+// 184- and 1 k-point levels gave 2 .. 8 row tiles, i.e. 2 .. 8 CTAs each streaming the whole weight matrix (31 us for a
+// 184 x 1536 x 192 product, profiles/step_kernels_by_grid_r01.txt); narrower column blocks spread the weight stream over
+// ~NT_TARGET_CTAS CTAs instead.
+constexpr int NT_TARGET_CTAS = 24;
+static NtSetup nt_setup(int N, int K, int M = 0) {
     NtSetup s;
     s.n_chunks = ceil_div(K, GT_KC);
+    const int tiles = M > 0 ? ceil_div(M, GT_M) : (1 << 20);
     const int widths[] = {N, 128, 64, 32, 16};
     for (int wi = 0; wi < 5; ++wi) {
         const int nb = widths[wi];
         if (wi > 0 && nb >= N) continue;
         if (nb > 256) continue;
+        if (wi < 4 && nb > 16 && tiles * ceil_div(N, nb) < NT_TARGET_CTAS && N > 16) continue;   // too few CTAs: try narrower blocks
         s.Nblk = nb;
         s.n_blocks = ceil_div(N, nb);
         s.Npad = round_up(nb < 16 ? 16 : nb, 16);
@@ -593,7 +599,8 @@ static NtSetup nt_setup(int N, int K) {
 
 extern "C" size_t pcfb_gemm_nt_workspace(int N, int K)
 {
-    return pcfb::nt_setup(N, K).prep_bytes;
+    const size_t a = pcfb::nt_setup(N, K).prep_bytes, b = pcfb::nt_setup(N, K, 1).prep_bytes;      // any M: wide or narrow column blocks
+    return a > b ? a : b;
 }
 
 extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,
@@ -603,7 +610,7 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     PCFB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "pcfb_gemm_nt: need N >= 1, K >= 1 (N=%d K=%d)", N, K);
     PCFB_REQUIRE(A && W && C && workspace, "pcfb_gemm_nt: null pointer");
     PCFB_REQUIRE(lda >= K && ldc >= N, "pcfb_gemm_nt: bad leading dimensions");
-    NtSetup s = nt_setup(N, K);
+    NtSetup s = nt_setup(N, K, M);
     PCFB_REQUIRE(s.plan.total <= 225 * 1024, "pcfb_gemm_nt: tile does not fit in shared memory (N=%d K=%d)", N, K);
     PCFB_REQUIRE(s.n_blocks <= 65535, "pcfb_gemm_nt: too many column blocks");
     if (workspace_bytes < s.prep_bytes) { set_error("pcfb_gemm_nt: workspace %zu < %zu", workspace_bytes, s.prep_bytes); return PCFB_ERR_WORKSPACE; }

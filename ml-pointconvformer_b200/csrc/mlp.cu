@@ -142,52 +142,7 @@ mlp_fwd_kernel(const float *__restrict__ x, int ldx, int64_t E, MlpLayer L, floa
     }
 }
 
-// BN finalize: mean/var from pivoted partial sums (double), scale/shift, running-stat update, saved mean/invstd
-__global__ void bn_finalize_kernel(const float *__restrict__ partial, int nblocks, int C, double count_host,
-                                   const double *__restrict__ d_count, const float *__restrict__ pivot, const float *__restrict__ gamma,
-                                   const float *__restrict__ beta, float eps, float momentum, float *__restrict__ running_mean,
-                                   float *__restrict__ running_var, float *__restrict__ scale, float *__restrict__ shift,
-                                   float *__restrict__ mean_out, float *__restrict__ invstd_out, long long *__restrict__ batches_tracked)
-{
-    // one warp per channel: lanes stride over the block partials, then a fixed shuffle tree (deterministic)
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= C) return;
-    const double count = d_count ? *d_count : count_host;
-    double s1 = 0.0, s2 = 0.0;
-    int b = lane;
-    for (; b + 96 < nblocks; b += 128) {                 // four independent loads per sum in flight (the loop is pure latency)
-        const float a0 = partial[((size_t)b * 2 + 0) * C + c], a1 = partial[((size_t)(b + 32) * 2 + 0) * C + c];
-        const float a2 = partial[((size_t)(b + 64) * 2 + 0) * C + c], a3 = partial[((size_t)(b + 96) * 2 + 0) * C + c];
-        const float q0 = partial[((size_t)b * 2 + 1) * C + c], q1 = partial[((size_t)(b + 32) * 2 + 1) * C + c];
-        const float q2 = partial[((size_t)(b + 64) * 2 + 1) * C + c], q3 = partial[((size_t)(b + 96) * 2 + 1) * C + c];
-        s1 += (double)a0; s1 += (double)a1; s1 += (double)a2; s1 += (double)a3;
-        s2 += (double)q0; s2 += (double)q1; s2 += (double)q2; s2 += (double)q3;
-    }
-    for (; b < nblocks; b += 32) {
-        s1 += (double)partial[((size_t)b * 2 + 0) * C + c];
-        s2 += (double)partial[((size_t)b * 2 + 1) * C + c];
-    }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, sft); s2 += __shfl_xor_sync(0xffffffffu, s2, sft); }
-    if (lane != 0) return;
-    if (c == 0 && batches_tracked) *batches_tracked += 1;          // BatchNorm.num_batches_tracked (int64), one writer
-    const double m_p = s1 / count;                       // mean of (y - pivot)
-    double var = s2 / count - m_p * m_p;
-    if (var < 0.0) var = 0.0;
-    const double mean = m_p + (pivot ? (double)pivot[c] : 0.0);
-    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
-    scale[c] = g * invstd;
-    shift[c] = bt - (float)mean * g * invstd;
-    if (mean_out) mean_out[c] = (float)mean;
-    if (invstd_out) invstd_out[c] = invstd;
-    if (running_mean) {
-        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
-    }
-}
+// (BatchNorm finalize: bn_reduce_kernel in peer_reduce.cu -- partial sums -> [SyncBatchNorm exchange] -> scale / shift / running stats)
 
 // a = act(y*scale+shift), elementwise (the chain's last BatchNorm + activation, materialised for its consumer)
 __global__ void bn_act_kernel(const float *__restrict__ y, int64_t n, int C, const float *__restrict__ scale,
@@ -900,18 +855,6 @@ extern "C" int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int
     return check_launch("mlp_fwd_kernel");
 }
 
-extern "C" int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, const double *d_count, const float *pivot,
-                                const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
-                                float *running_var, float *scale, float *shift, float *mean, float *invstd,
-                                int64_t *batches_tracked, void *stream)
-{
-    PCFB_REQUIRE(partial && scale && shift && C >= 1, "pcfb_bn_finalize: null pointer");
-    bn_finalize_kernel<<<ceil_div(C * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        partial, nblocks, C, (double)count, d_count, pivot, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean, invstd,
-        reinterpret_cast<long long *>(batches_tracked));
-    return check_launch("bn_finalize_kernel");
-}
-
 extern "C" int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
                            void *stream)
 {
@@ -935,10 +878,11 @@ extern "C" int pcfb_bn_act(const float *y, int64_t rows, int C, const float *sca
 // BN-backward sums of one layer: sums[2][C] = (sum dz, sum dz*xhat) for dz = dA * act'(y*scale+shift)
 extern "C" int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y, int ldy, int64_t E, int C, const float *scale,
                                        const float *shift, const float *mean, const float *invstd, int act, float *sums,
-                                       void *workspace, size_t workspace_bytes, void *stream)
+                                       int *nblocks, void *workspace, size_t workspace_bytes, void *stream)
 {
-    PCFB_REQUIRE(C >= 1 && C <= 64 && dA && y && scale && shift && mean && invstd && sums && workspace, "pcfb_mlp_backward_stats: bad arguments");
+    PCFB_REQUIRE(C >= 1 && C <= 64 && dA && y && scale && shift && mean && invstd && workspace, "pcfb_mlp_backward_stats: bad arguments");
     const int blocks = mlp_blocks(E);
+    if (nblocks) *nblocks = E > 0 ? blocks : 0;
     PCFB_REQUIRE(workspace_bytes >= (size_t)blocks * 2 * C * sizeof(float), "pcfb_mlp_backward_stats: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *partial = static_cast<float *>(workspace);
@@ -951,6 +895,7 @@ extern "C" int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y,
         else mlp_bwd_stats_kernel<64><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
         if ((rc = check_launch("mlp_bwd_stats_kernel"))) return rc;
     }
+    if (!sums) return PCFB_OK;                                   // the caller reduces the partials itself (pcfb_bn_reduce_sums)
     sum_partials_kernel<<<ceil_div(2 * C * 32, 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * C, sums);
     return check_launch("sum_partials_kernel");
 }
@@ -1222,13 +1167,14 @@ extern "C" int pcfb_bn_stats(const float *x, int64_t rows, int C, const float *p
 }
 
 extern "C" int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
-                                      const float *mean, const float *invstd, int act, float *sums, void *workspace,
+                                      const float *mean, const float *invstd, int act, float *sums, int *nblocks, void *workspace,
                                       size_t workspace_bytes, void *stream)
 {
     PCFB_REQUIRE(pcfb_bn_supported(C), "pcfb_bn_backward_stats: C = %d unsupported (multiple of 4, <= 1024)", C);
-    PCFB_REQUIRE(dA && y && scale && shift && mean && invstd && sums && workspace && ((uintptr_t)dA % 16 == 0) &&
+    PCFB_REQUIRE(dA && y && scale && shift && mean && invstd && workspace && ((uintptr_t)dA % 16 == 0) &&
                  ((uintptr_t)y % 16 == 0), "pcfb_bn_backward_stats: null or misaligned pointer");
     const BaGeom g = ba_geom(rows, C);
+    if (nblocks) *nblocks = g.blocks;
     PCFB_REQUIRE(workspace_bytes >= (size_t)g.blocks * 2 * C * sizeof(float), "pcfb_bn_backward_stats: workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     float *partial = static_cast<float *>(workspace);
@@ -1238,6 +1184,7 @@ extern "C" int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t r
             dA, y, rows, C, scale, shift, mean, invstd, act, partial, g.c4, g.ry, g.rows_per_block);
         if ((rc = check_launch("bn_bwd_stats_kernel"))) return rc;
     }
+    if (!sums) return PCFB_OK;                                   // the caller reduces the partials itself (pcfb_bn_reduce_sums)
     sum_partials_kernel<<<ceil_div(2 * C * 32, 128), 128, 0, st>>>(partial, g.blocks, 2 * C, sums);
     return check_launch("sum_partials_kernel");
 }

@@ -94,7 +94,7 @@ __device__ __forceinline__ void ffma2(float &a0, float &a1, float x, float y0, f
 // multi-instruction cvt.rna.tf32 sequence
 __device__ __forceinline__ void split(float x, float &hi, float &lo) {
     hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
-    lo = x - hi;
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);      // rounded, not truncated by the tensor core (umma.cuh)
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(umma::smem_u32(bar)) : "memory");

@@ -103,12 +103,16 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     return false;
 }
 
-// ---- 3xTF32 operand split: x = hi + lo, hi = rna_tf32(x), lo = fp32(x - hi) (exact) ----
+// ---- 3xTF32 operand split: x ~ hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi) ----
+// The tensor core reads only the upper 19 bits of an operand (it truncates): left as the exact fp32 remainder, lo would
+// lose up to 2^-10 of itself = 2^-21 |x|; rounded to nearest here the split carries 22 mantissa bits (unit round-off
+// 2^-22 |x|, fp32 itself: 2^-24) -- measured on the full-width model golden: logits error vs float64 1.5e-4 -> see DESIGN.md 4.
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    uint32_t h;
+    uint32_t h, l;
     asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(x));
     hi = __uint_as_float(h);
-    lo = x - hi;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
 }
 
 }  // namespace umma

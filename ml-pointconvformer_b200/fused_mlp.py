@@ -3,16 +3,18 @@ pcfb_mlp_* (csrc/mlp.cu): one streaming kernel pass per layer in the forward, tw
 statistics accumulated on the fly, every reduction deterministic.  Mirrors what the reference computes with
 Linear_BN + activation sequences (/root/reference/layers.py:127-191, 38-68; layer_utils.py:241-319)."""
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
 
 from . import _lib
+from . import streams as S
 from ._lib import check, lib, ptr, stream_ptr, workspace
 
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_SIGMOID = 0, 1, 2, 3
 F32 = torch.float32
-SYNC_CHANNELS = False       # True once the SyncBatchNorm exchange has one channel per stream (streams.side_index)
+SYNC_CHANNELS = True        # SyncBatchNorm exchanges are serialised on one stream (_on_exchange_stream): side streams are safe
 
 
 def supported(dims):
@@ -27,22 +29,23 @@ def _sync_group(bn):
 
 
 # ---- the SyncBatchNorm statistics exchange --------------------------------------------------------------------------
-# ~540 all-reduces of <= 2 x 384 floats per training step: latency only.  When the ranks share an NVLink / NVSwitch domain
-# the exchange runs as one single-CTA kernel over symmetric peer memory (csrc/peer_reduce.cu, ~1/3 of the latency of an
-# NCCL call inside the captured step); otherwise -- other backend, no peer access, PCFB_PEER_REDUCE=0 -- it is
+# ~540 exchanges of <= 3 KB per training step: latency only.  When the ranks share an NVLink / NVSwitch domain and
+# PCFB_PEER_REDUCE=1 (bench.py sets it; opt-in elsewhere: the exchange spins on the GPU until every rank arrives, for at
+# most PCFB_PEER_TIMEOUT_S seconds, default 600) the partial sums -> exchange -> finalize sequence is ONE kernel over
+# symmetric peer memory (csrc/peer_reduce.cu); otherwise -- other backend, no peer access -- the sums go through
 # dist.all_reduce.  torch.distributed._symmetric_memory only provides the allocation + address exchange (plumbing).
+# The global row count travels inside the message: nothing has to know the pyramid's level sizes.
 _PEER = {"state": None}       # None = not tried, False = unavailable, dict = ready
 
 
 def _peer_setup(device):
-    import os
     st = {"ok": False}
     try:
-        if os.environ.get("PCFB_PEER_REDUCE", "1") == "0" or dist.get_backend() != "nccl":
+        if os.environ.get("PCFB_PEER_REDUCE", "0") != "1" or dist.get_backend() != "nccl":
             raise RuntimeError("disabled")
         import torch.distributed._symmetric_memory as symm_mem
         world, rank = dist.get_world_size(), dist.get_rank()
-        nbytes = int(lib().pcfb_peer_buffer_bytes(world))
+        nbytes = int(lib().pcfb_syncbn_buffer_bytes(world))
         if nbytes == 0:
             raise RuntimeError("world size not supported")
         buf = symm_mem.empty(nbytes // 4, dtype=F32, device=device)
@@ -51,7 +54,7 @@ def _peer_setup(device):
         bases = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64).to(device)
         torch.cuda.synchronize(device)
         st = {"ok": True, "buf": buf, "hdl": hdl, "bases": bases, "rank": rank, "world": world,
-              "maxn": int(lib().pcfb_peer_max_floats())}
+              "timeout": float(os.environ.get("PCFB_PEER_TIMEOUT_S", "600"))}
     except Exception as e:                                    # every rank must agree: vote below
         st = {"ok": False, "why": "%s: %s" % (type(e).__name__, e)}
     vote = torch.tensor([1.0 if st["ok"] else 0.0], device=device)
@@ -61,128 +64,146 @@ def _peer_setup(device):
     return st
 
 
-def sync_all_reduce(t):
-    """In-place sum of a small contiguous float32 CUDA tensor over all ranks (the BatchNorm sums)."""
-    if not t.is_cuda:                                         # gloo / CPU tensors (host-logic tests)
-        dist.all_reduce(t)
-        return t
+def _peer(device):
+    """The peer-memory exchange state, False if unavailable.  Set up in the eager warm-up steps (needs host syncs)."""
     st = _PEER["state"]
     if st is None:
-        if torch.cuda.is_current_stream_capturing():          # set-up needs host syncs: do it in the eager warm-up steps
-            st = False
-        else:
-            st = _PEER["state"] = _peer_setup(t.device)
-    if st and t.dtype == F32 and t.is_contiguous() and t.numel() <= st["maxn"]:
-        check(lib().pcfb_peer_allreduce(ptr(t), ptr(t), t.numel(), ptr(st["bases"]), st["rank"], st["world"], stream_ptr()),
-              "peer_allreduce")
-        return t
+        if device.type != "cuda" or torch.cuda.is_current_stream_capturing():
+            return False
+        st = _PEER["state"] = _peer_setup(device)
+    return st
+
+
+def peer_error():
+    """True if an exchange on this rank gave up waiting for a peer (the kernel then wrote NaN statistics)."""
+    st = _PEER["state"]
+    return bool(st) and bool(st["buf"][0].view(torch.int32).item() != 0)
+
+
+_XSTREAM = {}
+
+
+def _on_exchange_stream(launch, device):
+    """Run `launch()` (one exchange kernel) on the rank's single exchange stream.  When the branches of a layer run on side
+    streams (streams.py), their SyncBatchNorm exchanges must still execute in ONE order that is the same on every rank: two
+    spinning exchange kernels that the hardware happens to serialise in opposite orders on two GPUs would wait for each other
+    forever (CUDA does not guarantee that independent streams / graph branches run concurrently).  Python program order is
+    the same on every rank (same model, autograd replays nodes by sequence number), so enqueueing every exchange on one
+    stream gives that order; the compute branches around them still overlap."""
+    if not S.ENABLED:
+        return launch()
+    cur = torch.cuda.current_stream()
+    key = (device.type, device.index)
+    xs = _XSTREAM.get(key)
+    if xs is None:
+        xs = _XSTREAM[key] = torch.cuda.Stream(device=device)
+    xs.wait_stream(cur)
+    with torch.cuda.stream(xs):
+        launch()
+    cur.wait_stream(xs)
+
+
+def sync_all_reduce(t):
+    """In-place sum of a small tensor over all ranks through torch.distributed (gloo / CPU tensors, NCCL fallback)."""
     dist.all_reduce(t)
     return t
 
 
-# ---- global row counts for SyncBatchNorm -------------------------------------------------------------------------
-# A BatchNorm over [1, N_l, (K,) C] needs the row count summed over all ranks.  Every tensor of the model has N_l rows
-# of some pyramid level l, so ONE all-reduce of the per-level point counts at the start of a forward
-# (register_levels, called by PointConvFormer_Segmentation.forward) serves all ~190 BatchNorms of the step; a chain
-# whose leading shape is not a registered level falls back to its own all-reduce.
-_LEVEL_ROWS = {}          # local N_l -> (1-element double tensor with the global N_l)
-_DERIVED_ROWS = {}        # (local N_l, factor) -> global N_l * factor
-_LOCAL_COUNTS = {}        # (counts, device) -> device tensor of the local counts
+def bn_finalize(part, nb, C, rows, pivot, gamma, beta, eps, momentum, rm, rv, nbt, sync, dev):
+    """Block partials [nb][2][C] -> (scale, shift, mean, invstd, d_count): one launch (csrc/peer_reduce.cu), including the
+    cross-rank exchange when `sync`.  d_count: 1-element device double with the global row count (None without sync)."""
+    scale = torch.empty(C, device=dev, dtype=F32); shift = torch.empty_like(scale)
+    mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
+    if momentum is None:                                       # cumulative moving average: 1 / num_batches_tracked
+        if nbt is not None:
+            nbt.add_(1)
+        momentum = -1.0
+    world = dist.get_world_size() if sync else 1
+    d_count = torch.empty(1, device=dev, dtype=torch.float64) if world > 1 else None
+
+    def launch(partial, nblocks, d_count_in, bases, rank, wld, timeout):
+        check(lib().pcfb_bn_finalize(ptr(partial), nblocks, C, rows, ptr(d_count_in), ptr(pivot), ptr(gamma), ptr(beta), float(eps),
+                                     float(momentum), ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(nbt),
+                                     ptr(d_count) if d_count_in is None else 0, bases, rank, wld, 0, timeout, stream_ptr()), "bn_finalize")
+    if world == 1:
+        launch(part, nb, None, 0, 0, 1, 0.0)
+        return scale, shift, mean, invstd, None
+    st = _peer(dev)
+    if st:
+        _on_exchange_stream(lambda: launch(part, nb, None, ptr(st["bases"]), st["rank"], st["world"], st["timeout"]), dev)
+        return scale, shift, mean, invstd, d_count
+    # torch.distributed fallback: local sums -> all_reduce of (sums, count) in double -> finalize from the reduced sums
+    local = torch.empty(2 * C, device=dev, dtype=F32)
+    check(lib().pcfb_bn_reduce_sums(ptr(part), nb, C, ptr(local), 0, 0, 0, 1, 0, 0.0, stream_ptr()), "bn_reduce_sums")
+    msg = torch.cat([local.double(), torch.full((1,), float(rows), device=dev, dtype=torch.float64)])
+    sync_all_reduce(msg)
+    summed = msg[:2 * C].float()
+    d_count = msg[2 * C:].contiguous()
+    launch(summed, 1, d_count, 0, 0, 1, 0.0)
+    return scale, shift, mean, invstd, d_count
 
 
-def register_levels(point_counts, device):
-    """point_counts: local per-level point counts of this rank's packed batch.  No-op without an initialised
-    process group.  The registry is keyed by the LOCAL count, so a rank on which two levels have the same count cannot
-    tell them apart; the decision has to be the same on every rank and must not need a host read (the step is captured
-    as a CUDA graph), so such a level gets a NaN count on ALL ranks -- the step then fails loudly (NaN loss) instead of
-    normalising with a wrong count or hanging in mismatched collectives.  (It takes a scene whose cloud stops shrinking
-    between two levels, i.e. <= 16 points, datasetCommon.py:413-414.)"""
-    _LEVEL_ROWS.clear()
-    _DERIVED_ROWS.clear()
-    counts = [int(c) for c in point_counts]
-    if not counts or not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-        return
-    key = (tuple(counts), str(device))
-    local = _LOCAL_COUNTS.get(key)
-    if local is None:                                 # H2D copy once per distinct packing, never inside a captured graph
-        if len(_LOCAL_COUNTS) > 1024:
-            _LOCAL_COUNTS.clear()
-        ambiguous = [1.0 if counts.count(c) > 1 else 0.0 for c in counts]
-        local = _LOCAL_COUNTS[key] = torch.tensor(counts + ambiguous, dtype=torch.float64).to(device)
-    g = local.clone()
-    dist.all_reduce(g)
-    L = len(counts)
-    total = torch.where(g[L:] > 0, torch.full_like(g[:L], float("nan")), g[:L])
-    for i, c in enumerate(counts):
-        _LEVEL_ROWS[c] = total[i:i + 1]
-
-
-def global_rows(lead_shape, rows, device):
-    """1-element device double with the number of rows summed over all ranks (stays on the device: no host sync)."""
-    m = int(lead_shape[1]) if len(lead_shape) >= 2 else -1
-    if m > 0 and m in _LEVEL_ROWS and rows % m == 0:
-        key = (m, rows // m)
-        if key not in _DERIVED_ROWS:
-            _DERIVED_ROWS[key] = _LEVEL_ROWS[m] * float(rows // m)
-        return _DERIVED_ROWS[key]
-    d = torch.full((1,), float(rows), device=device, dtype=torch.float64)
-    dist.all_reduce(d)
-    return d
+def bn_reduce_sums(part, nb, C, sync, dev):
+    """Block partials [nb][2][C] of (sum dz, sum dz*xhat) -> (sums over the global batch, local sums).  dx needs the global
+    sums; dgamma / dbeta stay local (the DDP gradient all-reduce adds the ranks up, exactly as torch.nn.SyncBatchNorm does)."""
+    local = torch.empty(2 * C, device=dev, dtype=F32)
+    world = dist.get_world_size() if sync else 1
+    if world == 1:
+        check(lib().pcfb_bn_reduce_sums(ptr(part), nb, C, ptr(local), 0, 0, 0, 1, 0, 0.0, stream_ptr()), "bn_reduce_sums")
+        return local, local
+    st = _peer(dev)
+    if st:
+        glob = torch.empty(2 * C, device=dev, dtype=F32)
+        _on_exchange_stream(lambda: check(lib().pcfb_bn_reduce_sums(ptr(part), nb, C, ptr(local), ptr(glob), ptr(st["bases"]), st["rank"],
+                                                                    st["world"], 0, st["timeout"], stream_ptr()), "bn_reduce_sums"), dev)
+        return glob, local
+    check(lib().pcfb_bn_reduce_sums(ptr(part), nb, C, ptr(local), 0, 0, 0, 1, 0, 0.0, stream_ptr()), "bn_reduce_sums")
+    glob = local.clone()
+    sync_all_reduce(glob)
+    return glob, local
 
 
 class _ChainFunction(torch.autograd.Function):
-    """args: x2 [E, cin] (rows contiguous), spec (python: list of dict(act, has_bn, eps, momentum, sync)), training,
-    then per layer (W, b, gamma, beta) tensors (gamma/beta None without BN); running stats are passed through `buffers`."""
+    """args: x2 [E, cin] (rows contiguous), spec (python: list of dict(act, has_bn, train, eps, momentum, sync)), then per
+    layer (W, b, gamma, beta) tensors (gamma/beta None without BN); running stats are passed through `buffers`."""
 
     @staticmethod
-    def forward(ctx, x2, spec, training, buffers, lead, *params):
+    def forward(ctx, x2, spec, buffers, *params):
         E = x2.shape[0]
         dev = x2.device
         L = len(spec)
         cur, ld = x2, x2.stride(0)
         in_scale = in_shift = None
         in_act = ACT_NONE
-        ys, ctxs = [], []
-        world = dist.get_world_size() if any(s["sync"] for s in spec) else 1
-        count, d_count = E, None
-        if world > 1 and training:                       # global row count stays on the device (no host sync)
-            d_count = global_rows(lead, E, dev)
+        ys, ctxs, counts = [], [], []
         for l, s in enumerate(spec):
             W, b, gamma, beta = params[4 * l: 4 * l + 4]
             cout, cin = W.shape
             y = torch.empty(E, cout, device=dev, dtype=F32)
-            want_stats = s["has_bn"] and training
+            want_stats = s["has_bn"] and s["train"]
             nblk = ctypes.c_int(0)
             ws = workspace(lib().pcfb_mlp_workspace(E, cin, cout), dev) if want_stats else None
             check(lib().pcfb_mlp_forward(ptr(cur), ld, E, cin, cout, ptr(W), ptr(b), ptr(in_scale), ptr(in_shift), in_act,
                                          ptr(y), cout, ptr(ws), ctypes.addressof(nblk), stream_ptr()), "mlp_forward")
-            scale = shift = mean = invstd = None
+            scale = shift = mean = invstd = d_count = None
             if s["has_bn"]:
                 rm, rv, nbt = buffers[l]
-                if training:
-                    scale = torch.empty(cout, device=dev, dtype=F32); shift = torch.empty_like(scale)
-                    mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
-                    part, nb = ws, nblk.value
-                    if s["sync"] and world > 1:
-                        summed = torch.empty(2 * cout, device=dev, dtype=F32)
-                        check(lib().pcfb_sum_partials(ptr(ws), nblk.value, 2 * cout, ptr(summed), stream_ptr()), "sum_partials")
-                        sync_all_reduce(summed)
-                        part, nb = summed, 1
-                    check(lib().pcfb_bn_finalize(ptr(part), nb, cout, count, ptr(d_count) if s["sync"] else 0, ptr(b), ptr(gamma), ptr(beta), float(s["eps"]),
-                                                 float(s["momentum"]), ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean),
-                                                 ptr(invstd), ptr(nbt), stream_ptr()), "bn_finalize")
-                else:
+                if want_stats:
+                    scale, shift, mean, invstd, d_count = bn_finalize(ws, nblk.value, cout, E, b, gamma, beta, s["eps"], s["momentum"],
+                                                                      rm, rv, nbt, s["sync"], dev)
+                else:                                        # eval-mode BatchNorm: a fixed affine map
                     invstd = torch.rsqrt(rv + s["eps"])
-                    scale = (gamma * invstd).contiguous()
-                    shift = (beta - rm * scale).contiguous()
+                    scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
+                    shift = ((beta if beta is not None else 0.) - rm * scale).contiguous()
                     mean = rm
             ys.append(y)
             ctxs.append((scale, shift, mean, invstd))
+            counts.append(d_count)
             cur, ld = y, cout
             in_scale, in_shift, in_act = scale, shift, s["act"]
         out = torch.empty_like(ys[-1])
         check(lib().pcfb_bn_act(ptr(ys[-1]), E, ys[-1].shape[1], ptr(in_scale), ptr(in_shift), in_act, ptr(out), stream_ptr()), "bn_act")
-        ctx.spec, ctx.training, ctx.d_count, ctx.world = spec, training, d_count, world
+        ctx.spec, ctx.counts = spec, counts
         ctx.n_layers = L
         saved = [x2] + ys + list(params)
         for c in ctxs:
@@ -204,39 +225,33 @@ class _ChainFunction(torch.autograd.Function):
         if dA.stride(-1) != 1 or dA.stride(0) != dA.shape[1]:
             dA = dA.contiguous()
         grads = [None] * (4 * L)
-        train_bn = ctx.training
-        zeros_cache = {}
-
-        def bn_ctx(l):
-            """(scale, shift, mean, invstd) usable by the kernels; eval-mode BN = fixed affine (mean terms vanish)."""
-            scale, shift, mean, invstd = ctxs[l]
-            return scale, shift, mean, invstd
 
         def stats(l, dA_l):
+            """-> (global sums, local sums) of (dz, dz*xhat) for layer l's BatchNorm (running statistics in eval mode)."""
             C = ys[l].shape[1]
-            scale, shift, mean, invstd = bn_ctx(l)
-            sums = torch.empty(2 * C, device=dev, dtype=F32)
-            if not train_bn:
-                sums.zero_()
-                return sums, sums
+            scale, shift, mean, invstd = ctxs[l]
             ws = workspace(lib().pcfb_mlp_workspace(E, C, C), dev)
+            nblk = ctypes.c_int(0)
             check(lib().pcfb_mlp_backward_stats(ptr(dA_l), dA_l.stride(0), ptr(ys[l]), C, E, C, ptr(scale), ptr(shift), ptr(mean),
-                                                ptr(invstd), spec[l]["act"], ptr(sums), ptr(ws), ws.numel(), stream_ptr()), "mlp_backward_stats")
-            local = sums
-            if spec[l]["sync"] and ctx.world > 1:
-                # dx needs the sums over the GLOBAL batch; dgamma / dbeta stay LOCAL (the DDP gradient all-reduce adds the
-                # ranks up, exactly as torch.nn.SyncBatchNorm does)
-                local = sums.clone()
-                sync_all_reduce(sums)
-            return sums, local
+                                                ptr(invstd), spec[l]["act"], 0, ctypes.addressof(nblk), ptr(ws), ws.numel(),
+                                                stream_ptr()), "mlp_backward_stats")
+            return bn_reduce_sums(ws, nblk.value, C, spec[l]["sync"] and spec[l]["train"], dev)
 
-        sums, sums_local = stats(L - 1, dA) if spec[L - 1]["has_bn"] else (None, None)
+        def affine_needed(l):
+            gamma, beta = params[4 * l + 2], params[4 * l + 3]
+            return (gamma is not None and gamma.requires_grad) or (beta is not None and beta.requires_grad)
+
+        top = spec[L - 1]
+        sums = sums_local = None
+        if top["has_bn"] and (top["train"] or affine_needed(L - 1)):
+            sums, sums_local = stats(L - 1, dA)
         need_x_grad = ctx.needs_input_grad[0]
+        zeros = {}
         for l in range(L - 1, -1, -1):
             W, b, gamma, beta = params[4 * l: 4 * l + 4]
             cout, cin = W.shape
             scale, shift, mean, invstd = ctxs[l]
-            has_bn = spec[l]["has_bn"]
+            has_bn, train_l = spec[l]["has_bn"], spec[l]["train"]
             if l > 0:
                 x_prev, ldx = ys[l - 1], ys[l - 1].shape[1]
                 p_scale, p_shift, p_mean, p_invstd = ctxs[l - 1]
@@ -248,47 +263,51 @@ class _ChainFunction(torch.autograd.Function):
             want_prev = l > 0 or need_x_grad
             dA_prev = torch.empty(E, cin, device=dev, dtype=F32) if want_prev else None
             prev_has_bn = l > 0 and spec[l - 1]["has_bn"]
-            fuse_prev = prev_has_bn and train_bn and cin <= 32
+            fuse_prev = prev_has_bn and spec[l - 1]["train"] and cin <= 32
             prev_sums = torch.empty(2 * cin, device=dev, dtype=F32) if fuse_prev else None
             dW = torch.empty_like(W)
             db = torch.empty(cout, device=dev, dtype=F32) if b is not None else None
             ws = workspace(lib().pcfb_mlp_workspace(E, cin, cout), dev)
-            inv_scale = 1.0
+            sums_dx = None
+            if has_bn:
+                if train_l:
+                    sums_dx = sums
+                else:                                        # eval-mode BatchNorm: dy = scale * dz, the batch terms vanish
+                    sums_dx = zeros.get(cout)
+                    if sums_dx is None:
+                        sums_dx = zeros[cout] = torch.zeros(2 * cout, device=dev, dtype=F32)
+            d_count = ctx.counts[l] if (has_bn and train_l) else None
             check(lib().pcfb_mlp_backward(
                 ptr(dA), dA.stride(0), ptr(ys[l]), cout, E, cin, cout, ptr(W),
                 ptr(scale) if has_bn else 0, ptr(shift) if has_bn else 0, ptr(mean) if has_bn else 0,
-                ptr(invstd) if has_bn else 0, ptr(sums) if has_bn else 0, spec[l]["act"],
+                ptr(invstd) if has_bn else 0, ptr(sums_dx) if has_bn else 0, spec[l]["act"],
                 ptr(x_prev), ldx, ptr(p_scale), ptr(p_shift), in_act, ptr(p_mean), ptr(p_invstd),
-                ptr(dA_prev), cin, ptr(prev_sums), ptr(dW), ptr(db), ptr(ctx.d_count) if (has_bn and spec[l]["sync"]) else 0,
+                ptr(dA_prev), cin, ptr(prev_sums), ptr(dW), ptr(db), ptr(d_count),
                 ptr(ws), ws.numel(), stream_ptr()), "mlp_backward")
             grads[4 * l] = dW
             grads[4 * l + 1] = db
-            if has_bn and gamma is not None:
-                # dgamma = sum dz * xhat, dbeta = sum dz  (train mode); eval mode: recompute from dA is not needed
-                # because the affine is constant w.r.t. the batch -- dgamma/dbeta then come from the same sums
-                C = cout
-                if train_bn:
-                    grads[4 * l + 2] = sums_local[C:]    # views: AccumulateGrad takes them as they are (no copy kernels)
-                    grads[4 * l + 3] = sums_local[:C]
+            if has_bn and gamma is not None and sums_local is not None:
+                grads[4 * l + 2] = sums_local[cout:]          # dgamma = sum dz * xhat, dbeta = sum dz: views, no copy kernels
+                grads[4 * l + 3] = sums_local[:cout]
             if l > 0:
+                sums = sums_local = None
                 if prev_has_bn:
                     if fuse_prev:
                         sums = sums_local = prev_sums
-                        if spec[l - 1]["sync"] and ctx.world > 1:
-                            sums_local = prev_sums.clone()
-                            sync_all_reduce(prev_sums)             # SyncBatchNorm: dx uses the sums over the global batch
-                    else:
+                        if spec[l - 1]["sync"] and dist.get_world_size() > 1:     # SyncBatchNorm: dx uses the sums over the global batch
+                            sums, sums_local = bn_reduce_sums(prev_sums, 1, cin, True, dev)
+                    elif spec[l - 1]["train"] or affine_needed(l - 1):
                         sums, sums_local = stats(l - 1, dA_prev)
-                else:
-                    sums = sums_local = None
                 dA = dA_prev
         gx = dA_prev if need_x_grad else None
-        return (gx, None, None, None, None) + tuple(grads)
+        return (gx, None, None) + tuple(grads)
 
 
-def mlp_chain(x, layers, training):
+def mlp_chain(x, layers, training=None):
     """x [..., cin]; layers: list of (linear_module, bn_module_or_None, act_code).  Returns act_L(BN_L(...)) with the
-    same leading shape.  Raises if a layer size is not supported (callers check `supported`)."""
+    same leading shape.  Every BatchNorm follows its OWN mode (bn.training or not bn.track_running_stats, as torch does):
+    freezing only the BatchNorm modules (bn.eval()) freezes their statistics in the fused chains too; `training` is accepted
+    for compatibility and ignored.  Raises if a layer size is not supported (callers check `supported`)."""
     if not x.is_cuda:
         raise RuntimeError("pcf_b200 fused MLP needs CUDA tensors (no CPU path)")
     lead = x.shape[:-1]
@@ -299,12 +318,14 @@ def mlp_chain(x, layers, training):
     for lin, bn, act in layers:
         has_bn = bn is not None
         spec.append(dict(act=act, has_bn=has_bn, eps=bn.eps if has_bn else 1e-5,
-                         momentum=(bn.momentum if bn.momentum is not None else 0.1) if has_bn else 0.1,
+                         train=has_bn and (bn.training or not bn.track_running_stats),
+                         momentum=bn.momentum if has_bn else 0.1,            # None = cumulative moving average (torch semantics)
                          sync=_sync_group(bn) if has_bn else False))
         params += [lin.weight, lin.bias, bn.weight if has_bn else None, bn.bias if has_bn else None]
         # num_batches_tracked is incremented by the finalize kernel (one tiny torch add_ per BatchNorm was 273 launches a step)
-        buffers.append((bn.running_mean, bn.running_var, bn.num_batches_tracked) if has_bn else (None, None, None))
-    out = _ChainFunction.apply(x2, spec, training, buffers, tuple(lead), *params)
+        tracked = has_bn and bn.track_running_stats
+        buffers.append((bn.running_mean, bn.running_var, bn.num_batches_tracked) if tracked else (None, None, None))
+    out = _ChainFunction.apply(x2, spec, buffers, *params)
     return out.reshape(*lead, out.shape[-1])
 
 
@@ -314,32 +335,20 @@ def bn_supported(C):
 
 
 class _BnActFunction(torch.autograd.Function):
-    """out = act(BatchNorm(x2)) for contiguous x2 [rows, C]; cfg = dict(act, training, eps, momentum, sync, lead)."""
+    """out = act(BatchNorm(x2)) for contiguous x2 [rows, C]; cfg = dict(act, training, eps, momentum, sync, nbt)."""
 
     @staticmethod
     def forward(ctx, x2, gamma, beta, pivot, running_mean, running_var, cfg):
         rows, C = x2.shape
         dev = x2.device
         act, training = cfg["act"], cfg["training"]
-        world = dist.get_world_size() if cfg["sync"] else 1
         d_count = None
         if training:
-            if world > 1:
-                d_count = global_rows(cfg["lead"], rows, dev)
             ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
             nblk = ctypes.c_int(0)
             check(lib().pcfb_bn_stats(ptr(x2), rows, C, ptr(pivot), ptr(ws), ws.numel(), ctypes.addressof(nblk), stream_ptr()), "bn_stats")
-            part, nb = ws, nblk.value
-            if world > 1:
-                summed = torch.empty(2 * C, device=dev, dtype=F32)
-                check(lib().pcfb_sum_partials(ptr(ws), nblk.value, 2 * C, ptr(summed), stream_ptr()), "sum_partials")
-                sync_all_reduce(summed)
-                part, nb = summed, 1
-            scale = torch.empty(C, device=dev, dtype=F32); shift = torch.empty_like(scale)
-            mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
-            check(lib().pcfb_bn_finalize(ptr(part), nb, C, rows, ptr(d_count), ptr(pivot), ptr(gamma), ptr(beta), float(cfg["eps"]),
-                                         float(cfg["momentum"]), ptr(running_mean), ptr(running_var), ptr(scale), ptr(shift),
-                                         ptr(mean), ptr(invstd), ptr(cfg["nbt"]), stream_ptr()), "bn_finalize")
+            scale, shift, mean, invstd, d_count = bn_finalize(ws, nblk.value, C, rows, pivot, gamma, beta, cfg["eps"], cfg["momentum"],
+                                                              running_mean, running_var, cfg["nbt"], cfg["sync"], dev)
         else:
             invstd = torch.rsqrt(running_var + cfg["eps"])
             scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
@@ -347,7 +356,7 @@ class _BnActFunction(torch.autograd.Function):
             mean = running_mean
         out = torch.empty_like(x2)
         check(lib().pcfb_bn_act(ptr(x2), rows, C, ptr(scale), ptr(shift), act, ptr(out), stream_ptr()), "bn_act")
-        ctx.cfg, ctx.d_count, ctx.world = cfg, d_count, world
+        ctx.cfg, ctx.d_count = cfg, d_count
         ctx.has_affine = gamma is not None
         ctx.save_for_backward(x2, scale, shift, mean, invstd)
         return out
@@ -364,14 +373,12 @@ class _BnActFunction(torch.autograd.Function):
         need_affine = ctx.has_affine and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         sums = local = None
         if cfg["training"] or need_affine:
-            sums = torch.empty(2 * C, device=dev, dtype=F32)
             ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
+            nblk = ctypes.c_int(0)
             check(lib().pcfb_bn_backward_stats(ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cfg["act"],
-                                               ptr(sums), ptr(ws), ws.numel(), stream_ptr()), "bn_backward_stats")
-            local = sums
-            if cfg["training"] and ctx.world > 1:          # dx: sums over the global batch; dgamma / dbeta stay local
-                local = sums.clone()
-                sync_all_reduce(sums)
+                                               0, ctypes.addressof(nblk), ptr(ws), ws.numel(), stream_ptr()), "bn_backward_stats")
+            # dx: sums over the global batch; dgamma / dbeta stay local
+            sums, local = bn_reduce_sums(ws, nblk.value, C, cfg["sync"] and cfg["training"], dev)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x2)
@@ -393,8 +400,8 @@ def bn_act(x, bn, act, pivot=None):
     if not x2.is_contiguous():
         x2 = x2.contiguous()
     training = bn.training or not bn.track_running_stats
-    cfg = dict(act=act, training=training, eps=bn.eps, momentum=0.1 if bn.momentum is None else bn.momentum,
-               sync=_sync_group(bn), lead=lead,
+    cfg = dict(act=act, training=training, eps=bn.eps, momentum=bn.momentum,      # None = cumulative moving average
+               sync=_sync_group(bn),
                nbt=bn.num_batches_tracked if bn.track_running_stats else None)      # incremented by the finalize kernel
     rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
     out = _BnActFunction.apply(x2, bn.weight, bn.bias, pivot.detach() if pivot is not None else None, rm, rv, cfg)

@@ -92,6 +92,43 @@ def gather_max(points, idx, inv=None):
     return _GatherMaxFunction.apply(points.contiguous(), idx.contiguous(), inv)
 
 
+class _GuidanceInputFunction(torch.autograd.Function):
+    """q - key with q = cat(index_points(guidance_x, nei), feat_pe), key = q[:, :, :1] (M == N) or max_k q
+    (layers.py:372-382) in one kernel; the backward emits d feat_pe and the per-edge gradient of the gathered half, which
+    the kNN inverse map sums per input point (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, guidance_x, feat_pe, nei, inv, use_max):
+        outs, args = zip(*[pcf_cuda.guidance_input(guidance_x[b], feat_pe[b], nei[b], use_max) for b in range(nei.shape[0])])
+        ctx.inv, ctx.nei, ctx.use_max = inv, nei, use_max
+        ctx.n_in, ctx.G, ctx.P = guidance_x.shape[1], guidance_x.shape[2], feat_pe.shape[3]
+        ctx.save_for_backward(*[a for a in args if a is not None])
+        return torch.stack(outs) if len(outs) > 1 else outs[0].unsqueeze(0)
+
+    @staticmethod
+    def backward(ctx, grad):
+        grad = grad.contiguous()
+        args = ctx.saved_tensors
+        want_gx, want_pe = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_gx, g_pe = [], []
+        inv = None
+        if want_gx:
+            inv = ctx.inv if ctx.inv is not None else resolve_inverse(ctx.nei, ctx.n_in)
+        for b in range(grad.shape[0]):
+            d_gq, d_pe = pcf_cuda.guidance_input_backward(grad[b], args[b] if ctx.use_max else None, ctx.G, ctx.P, ctx.use_max,
+                                                          want_gx, want_pe)
+            if want_gx:
+                g_gx.append(pcf_cuda.gather_backward(d_gq, (inv[0][b], inv[1][b], inv[2][b]), ctx.n_in))
+            g_pe.append(d_pe)
+        stack = lambda lst: torch.stack(lst) if len(lst) > 1 else lst[0].unsqueeze(0)
+        return (stack(g_gx) if want_gx else None), (stack(g_pe) if want_pe else None), None, None, None
+
+
+def guidance_input(guidance_x, feat_pe, nei_inds, inv, use_max):
+    """[B,N,G], [B,M,K,P], [B,M,K] -> [B,M,K,G+P] = cat(gather, pe) - key."""
+    return _GuidanceInputFunction.apply(guidance_x.contiguous(), feat_pe.contiguous(), nei_inds, inv, bool(use_max))
+
+
 # ------------------------------------------------------------------------------------------------
 # fused contraction (+guidance) + Linear
 # ------------------------------------------------------------------------------------------------

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 from . import fused_mlp
 from . import streams as S
 from .layer_utils import (FusedPConvFunction, PConvLinearOpt, Linear_BN, UnaryBlock, edge_geometry, gather_max,
-                          index_points, linear, resolve_inverse)
+                          guidance_input, index_points, linear, resolve_inverse)
 
 
 def _chain_spec(mods, acts):
@@ -95,7 +95,8 @@ class MultiHeadGuidance(nn.Module):
             self.mlp.append(Linear_BN(cin, cout) if cfg.BATCH_NORM else nn.Linear(cin, cout))
 
     def forward(self, guidance_query, guidance_key):
-        s = self.layer_norm_q(guidance_query) - self.layer_norm_k(guidance_key)
+        """guidance_key None: guidance_query already is query - key (layer_utils.guidance_input)."""
+        s = guidance_query if guidance_key is None else self.layer_norm_q(guidance_query) - self.layer_norm_k(guidance_key)
         last = len(self.mlp) - 1
         spec = _chain_spec(list(self.mlp), [fused_mlp.ACT_RELU] * last + [fused_mlp.ACT_SIGMOID])
         if spec is not None:                       # one fused pass per layer (csrc/mlp.cu)
@@ -205,13 +206,20 @@ class PCFLayer(_PointLayerBase):
         feats_x = self.unary1(dense_feats)
         guidance_x = self.guidance_unary(feats_x)
         feat_pe = S.join(br_pe)
-        guidance_feature = torch.cat([index_points(guidance_x, nei_inds, inv), feat_pe], dim=-1)
-        if M == N:
-            guidance_key = guidance_feature[:, :, :1, :]           # column 0 is the centre itself (T6)
+        fused_qk = (self.cfg.attention_type == 'subtraction' and not self.cfg.layer_norm_guidance
+                    and guidance_x.shape[-1] % 4 == 0 and feat_pe.shape[-1] % 4 == 0)
+        if fused_qk:
+            # gather + cat + key (column 0 = the centre itself when M == N, T6; else max over the neighbours) + subtraction:
+            # one kernel (csrc/glue.cu) instead of five passes over a [M, K, 64] tensor
+            guidance_score = self.guidance_weight(guidance_input(guidance_x, feat_pe, nei_inds, inv, M != N), None)
         else:
-            guidance_key = guidance_feature.max(dim=2, keepdim=True)[0]
-        guidance_score = self.guidance_weight(guidance_feature, guidance_key.expand_as(guidance_feature)
-                                              if self.cfg.attention_type != 'subtraction' else guidance_key)
+            guidance_feature = torch.cat([index_points(guidance_x, nei_inds, inv), feat_pe], dim=-1)
+            if M == N:
+                guidance_key = guidance_feature[:, :, :1, :]
+            else:
+                guidance_key = guidance_feature.max(dim=2, keepdim=True)[0]
+            guidance_score = self.guidance_weight(guidance_feature, guidance_key.expand_as(guidance_feature)
+                                                  if self.cfg.attention_type != 'subtraction' else guidance_key)
         weights = S.join(br_w)
 
         if isinstance(self.linear, Linear_BN):

@@ -178,17 +178,7 @@ class PointConvFormer_Segmentation(nn.Module):
 
     def forward(self, features, pointclouds, edges_self, edges_forward, edges_propagate, norms,
                 inv_self=None, inv_forward=None, inv_propagate=None):
-        # SyncBatchNorm needs the row counts summed over ranks: one all-reduce of the per-level point counts here
-        # serves every BatchNorm of the step (no-op on one GPU); cleared again so nothing stale outlives the forward
-        fused_mlp.register_levels([p.shape[1] for p in pointclouds], features.device)
-        try:
-            return self._forward(features, pointclouds, edges_self, edges_forward, edges_propagate, norms,
-                                 inv_self, inv_forward, inv_propagate)
-        finally:
-            fused_mlp.register_levels([], features.device)
-
-    def _forward(self, features, pointclouds, edges_self, edges_forward, edges_propagate, norms,
-                 inv_self=None, inv_forward=None, inv_propagate=None):
+        # (SyncBatchNorm row counts travel inside each statistics message, fused_mlp.bn_finalize: nothing to set up here)
         opt = bool(self.cfg.PCONV_OPT)
         ins, iks, iis = inv_self if (opt and inv_self is not None) else (None, None, None)
         inf, ikf, iif = inv_forward if (opt and inv_forward is not None) else (None, None, None)

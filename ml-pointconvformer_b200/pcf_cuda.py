@@ -378,6 +378,30 @@ def gather_max_backward(grad_out, arg, inv, n_in, K):
     return g
 
 
+def guidance_input(gx, pe, nei, use_max):
+    """gx [N,G], pe [M,K,P], nei [M,K] -> (cat(gx[nei], pe) - key [M,K,G+P], arg [M,G+P] uint8 or None)
+    with key = column 0 (use_max False) or max over the K neighbours (layers.py:372-382)."""
+    require(gx, F32, "guidance_x"); require(pe, F32, "feat_pe"); require(nei, I64, "nei")
+    M, K = nei.shape
+    G, P = gx.shape[1], pe.shape[2]
+    out = torch.empty(M, K, G + P, device=gx.device, dtype=F32)
+    arg = torch.empty(M, G + P, device=gx.device, dtype=U8) if use_max else None
+    check(lib().pcfb_guidance_input(ptr(gx), ptr(pe), ptr(nei), gx.shape[0], M, K, G, P, 1 if use_max else 0, ptr(out), ptr(arg),
+                                    stream_ptr()), "guidance_input")
+    return out, arg
+
+
+def guidance_input_backward(ds, arg, G, P, use_max, want_gq=True, want_pe=True):
+    """ds [M,K,G+P] -> (d_gq [M,K,G] per-edge gradient of the gathered half, d_pe [M,K,P])."""
+    require(ds, F32, "grad")
+    M, K, _ = ds.shape
+    d_gq = torch.empty(M, K, G, device=ds.device, dtype=F32) if want_gq else None
+    d_pe = torch.empty(M, K, P, device=ds.device, dtype=F32) if want_pe else None
+    check(lib().pcfb_guidance_input_backward(ptr(ds), ptr(arg), M, K, G, P, 1 if use_max else 0, ptr(d_gq), ptr(d_pe), stream_ptr()),
+          "guidance_input_backward")
+    return d_gq, d_pe
+
+
 def edge_geometry(xyz_in, nrm_in, xyz_out, nrm_out, nei, want_r=True, want_vi=True):
     """-> (localized_xyz [M,K,3] or None, vi_features [M,K,12] or None)."""
     require(xyz_in, F32, "xyz_in"); require(xyz_out, F32, "xyz_out"); require(nei, I64, "nei")

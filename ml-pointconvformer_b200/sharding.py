@@ -69,3 +69,47 @@ class FlatParameters:
         for p in self.params:
             p.grad = None
         return g
+
+
+class FlatAdamW:
+    """clip_grad_norm_(max_norm) + torch.optim.AdamW.step() (train_ScanNet_DDP_WarmUP.py:421-424) on the ONE flat buffer of
+    FlatParameters as two kernel launches (csrc/glue.cu: gradient norm partials, then clip + moments + update), replacing
+    torch's norm / clamp / mul / fused-Adam / step-increment sequence.  The learning rate and the step counter are device
+    scalars, so a step captured in a CUDA graph follows a learning-rate schedule: set_lr() between replays."""
+
+    def __init__(self, flat, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_norm=0.0):
+        from ._lib import lib
+        self.flat = flat.flat
+        p = self.flat.data
+        if not p.is_cuda or p.dtype != torch.float32:
+            raise RuntimeError("FlatAdamW needs a CUDA float32 parameter buffer (no CPU path)")
+        self.exp_avg = torch.zeros_like(p)
+        self.exp_avg_sq = torch.zeros_like(p)
+        self.step_t = torch.zeros((), device=p.device, dtype=torch.float32)
+        self.lr_t = torch.full((), float(lr), device=p.device, dtype=torch.float32)
+        self.norm_t = torch.zeros((), device=p.device, dtype=torch.float32)
+        self.betas, self.eps, self.weight_decay, self.max_norm = betas, eps, weight_decay, max_norm
+        self._ws = torch.empty(int(lib().pcfb_adamw_workspace()), dtype=torch.uint8, device=p.device)
+
+    def set_lr(self, lr):
+        self.lr_t.fill_(float(lr))
+
+    def state_tensors(self):
+        return [self.exp_avg, self.exp_avg_sq, self.step_t, self.lr_t]
+
+    def zero_grad(self, set_to_none=True):
+        self.flat.grad = None
+
+    @torch.no_grad()
+    def step(self, grad=None):
+        from ._lib import check, lib, ptr, stream_ptr
+        g = self.flat.grad if grad is None else grad
+        if g is None:
+            raise RuntimeError("FlatAdamW.step: no gradient (call FlatParameters.gather_grads first)")
+        g = g.contiguous()
+        p = self.flat.data
+        check(lib().pcfb_adamw_clip_step(ptr(p), ptr(g), ptr(self.exp_avg), ptr(self.exp_avg_sq), p.numel(), ptr(self.lr_t),
+                                         ptr(self.step_t), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                                         float(self.weight_decay), float(self.max_norm), ptr(self.norm_t), ptr(self._ws),
+                                         self._ws.numel(), stream_ptr()), "adamw_clip_step")
+        return self.norm_t

@@ -19,7 +19,8 @@ def main():
     model = MA.PointConvFormer_Segmentation(configs.make_cfg(cfgd)).to(dev).train()
     from pcf_b200 import sharding
     flat = sharding.FlatParameters(model)
-    opt = torch.optim.AdamW([flat.flat], lr=1e-3, weight_decay=0.05, fused=True)
+    opt = sharding.FlatAdamW(flat, lr=1e-3, weight_decay=0.05, max_norm=10.0)
+    from pcf_b200 import losses
     host = bench.host_pyramid(1, args.points, cfgd["grid_size"], args.scenes)
     pts = [torch.from_numpy(p).to(dev) for p in host["points"]]
     nrm = [torch.from_numpy(p).to(dev) for p in host["normals"]]
@@ -32,18 +33,27 @@ def main():
             inv = CU.compute_knn_inverse(pcs, es, ef, ep)
         with torch.profiler.record_function("forward"):
             logits = model(col.unsqueeze(0), pcs, es, ef, ep, nrms, *inv)
-            loss = torch.nn.functional.cross_entropy(logits[0], lab, label_smoothing=0.2)
+            loss = losses.cross_entropy(logits[0], lab, label_smoothing=0.2)
         with torch.profiler.record_function("backward"):
             loss.backward()
         with torch.profiler.record_function("optimizer"):
-            flat.gather_grads()
-            torch.nn.utils.clip_grad_norm_([flat.flat], 10.0)
-            opt.step()
-    for _ in range(2):
-        step()
+            opt.step(flat.gather_grads())
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    use_graph = "eager" not in os.environ.get("PROFILE_STEP_FLAGS", "")
+    if use_graph:                                   # profile one REPLAY of the captured step: the timeline the bench times
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        graph.replay()
+        torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=stacks) as prof:
-        step()
+        graph.replay() if use_graph else step()
         torch.cuda.synchronize()
     out = os.path.join(ROOT, "gpurun_out", "prof_table.txt")
     with open(out, "w") as f:
@@ -54,11 +64,41 @@ def main():
     trace = os.path.join(ROOT, "gpurun_out", "prof_trace.json")
     prof.export_chrome_trace(trace)
     agg = collections.defaultdict(list)
+    spans = []
     for ev in json.load(open(trace))["traceEvents"]:
         if ev.get("cat") == "kernel":
             name = re.sub(r"\(.*$", "", ev["name"]).replace("void ", "").replace("pcfb::", "")
-            agg[(name[:60], str(ev.get("args", {}).get("grid")))].append(ev["dur"])
+            grid = ev.get("args", {}).get("grid")
+            agg[(name[:60], str(grid))].append(ev["dur"])
+            ctas = 1
+            for gdim in (grid or [1]):
+                ctas *= int(gdim)
+            spans.append((ev["ts"], ev["ts"] + ev["dur"], ev["dur"], ctas, ev.get("args", {}).get("stream")))
     os.remove(trace)
+    # timeline summary: is the step bound by work or by dependent-launch latency?
+    spans.sort()
+    wall = max(e for _, e, _, _, _ in spans) - spans[0][0]
+    busy, cur_s, cur_e = 0.0, None, None
+    for s0, e0, _, _, _ in spans:
+        if cur_e is None or s0 > cur_e:
+            if cur_e is not None:
+                busy += cur_e - cur_s
+            cur_s, cur_e = s0, e0
+        else:
+            cur_e = max(cur_e, e0)
+    busy += cur_e - cur_s
+    total = sum(d for _, _, d, _, _ in spans)
+    sub = sum(d for _, _, d, c, _ in spans if c < 148)
+    with open(os.path.join(ROOT, "gpurun_out", "prof_timeline.txt"), "w") as f:
+        f.write("kernels %d  wall %.1f us  GPU busy (union of kernel spans) %.1f us  idle %.1f us  sum of kernel durations %.1f us "
+                "(avg concurrency %.2f)  sub-wave (<148 CTAs) kernels: %d launches, %.1f us\n"
+                % (len(spans), wall, busy, wall - busy, total, total / max(busy, 1e-9), sum(1 for x in spans if x[3] < 148), sub))
+        per_stream = collections.defaultdict(float)
+        for _, _, d, _, st in spans:
+            per_stream[st] += d
+        for st, d in sorted(per_stream.items(), key=lambda kv: -kv[1]):
+            f.write("  stream %s: %.1f us of kernels\n" % (st, d))
+    print(open(os.path.join(ROOT, "gpurun_out", "prof_timeline.txt")).read())
     with open(os.path.join(ROOT, "gpurun_out", "prof_kernels_by_grid.txt"), "w") as f:
         f.write("# one training step, CUPTI kernel durations grouped by (kernel, grid): calls, mean us, total us\n")
         for (name, grid), d in sorted(agg.items(), key=lambda kv: -sum(kv[1])):

@@ -35,8 +35,8 @@ def _build(dtype, device, sync):
     return list(mods[:3]), list(mods[3:])
 
 
-def _worker(rank, world, port, ret):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, ret, peer):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PCFB_PEER_REDUCE=peer)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
@@ -51,16 +51,14 @@ def _worker(rank, world, port, ret):
     (y * gos[rank].to(dev)).sum().backward()
     out = {"y": y.detach().cpu(), "gx": x.grad.cpu(), "gw0": lins[0].weight.grad.cpu(), "gw2": lins[2].weight.grad.cpu(),
            "gg1": bns[1].weight.grad.cpu(), "gb2": bns[2].bias.grad.cpu()}
-    # the wide BatchNorm + ReLU (pcfb_bn_*) under SyncBatchNorm, with the row counts coming from register_levels
+    # the wide BatchNorm + ReLU (pcfb_bn_*) under SyncBatchNorm (the global row count travels inside the statistics message)
     torch.manual_seed(7)
     wbn = torch.nn.SyncBatchNorm.convert_sync_batchnorm(torch.nn.BatchNorm1d(96)).to(dev)
     torch.nn.init.uniform_(wbn.weight, 0.5, 1.5)
     xw_all = [torch.randn(1, n, 96, generator=g) * 2 + 0.3 for n in rows]
     gw_all = [torch.randn(1, n, 96, generator=g) for n in rows]
-    fused_mlp.register_levels([rows[rank]], dev)
     xw = xw_all[rank].to(dev).requires_grad_(True)
     yw = fused_mlp.bn_act(xw, wbn, fused_mlp.ACT_RELU)
-    fused_mlp.register_levels([], dev)
     (yw * gw_all[rank].to(dev)).sum().backward()
     out.update(wy=yw.detach().cpu()[0], wgx=xw.grad.cpu()[0], wgg=wbn.weight.grad.cpu(), wgb=wbn.bias.grad.cpu(),
                wrm=wbn.running_mean.cpu(), wrv=wbn.running_var.cpu())
@@ -99,18 +97,22 @@ def _worker(rank, world, port, ret):
         errs["wrm"] = rel(gathered[1]["wrm"], rbn.running_mean)
         errs["wrv"] = rel(gathered[1]["wrv"], rbn.running_var)
         ret["errs"] = errs
+        ret["peer_active"] = bool(fused_mlp._PEER["state"])
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_fused_chain_syncbn_two_ranks_match_single_process():
+@pytest.mark.parametrize("peer", ["1", "0"])
+def test_fused_chain_syncbn_two_ranks_match_single_process(peer):
+    """peer "1": statistics exchanged by the one-kernel peer-memory path; "0": the torch.distributed fallback."""
     world, port = 2, _free_port()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ret, peer), nprocs=world, join=True)
     errs = dict(ret["errs"])
-    print(errs)
+    print(errs, "peer path active:", ret["peer_active"])
+    assert ret["peer_active"] == (peer == "1")
     assert errs["y"] < 2e-5 and errs["gx"] < 2e-4, errs
     for k in ("gw0", "gw2", "gg1", "gb2"):
         assert errs[k] < 1e-3, errs                                # fp32 sums behind three train-mode BatchNorms (see DESIGN.md §4)

@@ -80,11 +80,36 @@ def test_chain_matches_float64(name, training):
         if not (norm is not None and training):           # bias before a train-mode BN has zero gradient (noise only)
             assert max_err_scaled(lin.bias.grad, rl.bias.grad) < 2e-4
         if norm is not None:
-            if training:
-                assert max_err_scaled(norm.weight.grad, rn.weight.grad) < 2e-4
-                assert max_err_scaled(norm.bias.grad, rn.bias.grad) < 2e-4
+            # eval mode too: a frozen BatchNorm's affine parameters keep training (dgamma = sum dz*xhat with the running statistics)
+            assert max_err_scaled(norm.weight.grad, rn.weight.grad) < 2e-4
+            assert max_err_scaled(norm.bias.grad, rn.bias.grad) < 2e-4
             assert max_err_scaled(norm.running_mean, rn.running_mean) < 1e-5
             assert max_err_scaled(norm.running_var, rn.running_var) < 1e-5
+
+
+def test_chain_follows_each_batchnorm_mode():
+    """torch semantics per BatchNorm module: a chain whose BatchNorms alone are put in eval mode (frozen-BN fine-tuning) must
+    use the running statistics and leave them untouched, whatever the parent module's mode; momentum=None is the cumulative
+    moving average 1 / num_batches_tracked."""
+    import copy
+    from pcf_b200 import fused_mlp
+    mods = build([12, 8, 16], True, 11)
+    mods[1][1].momentum = None
+    ref = copy.deepcopy(mods)
+    x = torch.randn(5000, 12, generator=torch.Generator().manual_seed(2))
+    mods[0][1].eval()                                           # layer 0 frozen, layer 1 training with a cumulative average
+    ref[0][1].eval()
+    for lin, norm in mods:
+        lin.cuda(); norm.cuda()
+    for rep in range(2):
+        h = x.double()
+        for lin, norm in ref:
+            h = torch.relu(norm.double()(lin.double()(h)))
+        out = fused_mlp.mlp_chain(x.cuda(), [(lin, norm, 1) for lin, norm in mods], True)
+        assert max_err_scaled(out, h) < 2e-5
+    for (lin, norm), (rl, rn) in zip(mods, ref):
+        assert max_err_scaled(norm.running_mean, rn.running_mean) < 1e-5 and max_err_scaled(norm.running_var, rn.running_var) < 1e-5
+        assert int(norm.num_batches_tracked) == int(rn.num_batches_tracked)
 
 
 def test_chain_strided_input_and_determinism():
