@@ -162,7 +162,8 @@ def run_ours(args):
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
     model.train()
     use_graph = not args.no_graph
-    flat = sharding.FlatParameters(model)                              # one buffer: optimizer / clip / all-reduce see one tensor
+    # one buffer: optimizer / clip / all-reduce see one tensor; weight-gradient GEMMs run off the backward's critical path
+    flat = sharding.FlatParameters(model, async_weight_grads=True)
     # clip_grad_norm_(10) + AdamW (train_ScanNet_DDP_WarmUP.py:421-424) as two launches of ours on the flat buffer
     opt = sharding.FlatAdamW(flat, lr=1e-3, weight_decay=cfgd["adamw_decay"], max_norm=10.0)
 

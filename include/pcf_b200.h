@@ -296,6 +296,31 @@ int pcfb_gridsub_emit(const float *xyz, const float *feats, int n_seg, int n_pts
                       size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Device-resident pyramid construction: raw scene -> voxelised level 0 -> grid-subsampled levels without a
+ * host read per level.
+ *   pcfb_voxelize: voxelize(coord, voxel_size, hash_type='ravel', mode='deterministic') of util/voxelize.py:44-70 on packed
+ *     scenes: discrete = floor(coord / voxel) (float64, as numpy promotes it), key = Fortran-style ravel of discrete - per-scene min
+ *     (ravel_hash_vec, voxelize.py:26-41); one point per occupied voxel -- the SMALLEST input index (the reference takes
+ *     the first of an unstable argsort: implementation defined) -- emitted in ascending (scene, key) order, which is the
+ *     reference's idx_sort order.  out_idx [<= n_pts] int32 packed point indices, out_seg_off [n_seg+1] device prefix of the
+ *     per-scene output counts.
+ *   pcfb_pyramid_level: one grid_subsampling() level (grid_subsampling.cpp:9-110, bit-identical sums, see pcfb_gridsub_*)
+ *     whose INPUT size is only known on the device: seg_off [n_seg+1] is the device prefix array of the previous level
+ *     (its last entry the point count, <= n_pts_max, the host's upper bound = the size of the buffers); out_seg_off feeds
+ *     the next level.  The host reads all counts once, after the last level (datasetCommon.py:384-420 reads per level).
+ * cells_max: host upper bound of the dense voxel table (from the level-0 bounding box); *status |= 1 if the data needs
+ * more (nothing is emitted for that call).
+ * ------------------------------------------------------------------------------------------- */
+size_t pcfb_voxelize_workspace(int n_seg, int n_pts, int64_t cells_max);
+int pcfb_voxelize(const float *xyz, const int32_t *seg_off, int n_seg, int n_pts, double voxel, int64_t cells_max,
+                  int32_t *out_idx, int32_t *out_seg_off, int32_t *status, void *workspace, size_t workspace_bytes,
+                  void *stream);
+size_t pcfb_pyramid_level_workspace(int n_seg, int n_pts_max, int64_t cells_max);
+int pcfb_pyramid_level(const float *xyz, const float *feats, int F, const int32_t *seg_off, int n_seg, int n_pts_max,
+                       float dl, int64_t cells_max, float *out_xyz, float *out_feats, int32_t *out_seg_off,
+                       int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Layer glue the reference leaves to chains of torch elementwise ops.
  *
  * Guidance input of the PointConvFormer layer (layers.py:372-382):

@@ -599,8 +599,19 @@ static NtSetup nt_setup(int N, int K, int M = 0) {
 
 extern "C" size_t pcfb_gemm_nt_workspace(int N, int K)
 {
-    const size_t a = pcfb::nt_setup(N, K).prep_bytes, b = pcfb::nt_setup(N, K, 1).prep_bytes;      // any M: wide or narrow column blocks
-    return a > b ? a : b;
+    // any M: the widest prepared-B footprint over all column-block widths nt_setup may pick
+    using namespace pcfb;
+    size_t best = nt_setup(N, K).prep_bytes;
+    const int n_chunks = ceil_div(K, GT_KC);
+    const int widths[] = {N, 128, 64, 32, 16};
+    for (int wi = 0; wi < 5; ++wi) {
+        const int nb = widths[wi];
+        if ((wi > 0 && nb >= N) || nb > 256) continue;
+        const int npad = round_up(nb < 16 ? 16 : nb, 16);
+        const size_t bytes = align_up((size_t)n_chunks * 2 * npad * GT_KC * sizeof(float), 256) * (size_t)ceil_div(N, nb);
+        if (bytes > best) best = bytes;
+    }
+    return best;
 }
 
 extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,

@@ -124,6 +124,129 @@ __global__ void gs_emit_kernel(const float *__restrict__ xyz, const float *__res
     }
 }
 
+
+// ---- device-sized variants: the whole pyramid without per-level host reads ---------------------------------------------
+// The input size of level l is only known on the device (it is the output count of level l-1): kernels run over the host's
+// upper bound n_pts_max and guard with the device total seg_off[n_seg]; points past it get cell id -1, which the CSR
+// transpose ignores.  The dense cell table is sized by a host upper bound (cells_max, from the level-0 bounding box).
+__global__ void gs_bounds_dev_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ seg_off, int n_seg,
+                                     int n_pts_max, int *__restrict__ mm)
+{
+    const int n_pts = min(seg_off[n_seg], n_pts_max);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
+        const int s = find_seg(seg_off, n_seg, i);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int o = float_to_ordered(xyz[3 * (size_t)i + d]);
+            atomicMin(&mm[s * 6 + d], o);
+            atomicMax(&mm[s * 6 + 3 + d], o);
+        }
+    }
+}
+
+// cell_off = exclusive prefix of the per-scene cell counts; status |= 1 (and an empty grid) if they exceed cells_max
+__global__ void gs_cell_off_kernel(int32_t *__restrict__ dims, int n_seg, long long cells_max, int32_t *__restrict__ cell_off,
+                                   int32_t *__restrict__ status)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    long long tot = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        cell_off[s] = (int32_t)tot;
+        tot += (long long)dims[3 * s] * dims[3 * s + 1] * dims[3 * s + 2];
+        if (tot > cells_max) break;
+    }
+    if (tot > cells_max) {
+        if (status) atomicOr(status, 1);
+        for (int s = 0; s < n_seg; ++s) { cell_off[s] = 0; dims[3 * s] = dims[3 * s + 1] = dims[3 * s + 2] = 0; }
+        tot = 0;
+    }
+    cell_off[n_seg] = (int32_t)tot;
+}
+
+__global__ void gs_cell_dev_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ seg_off, int n_seg,
+                                   int n_pts_max, float dl, const float *__restrict__ origin, const int32_t *__restrict__ dims,
+                                   const int32_t *__restrict__ cell_off, int64_t *__restrict__ cell)
+{
+    const int n_pts = min(seg_off[n_seg], n_pts_max);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts_max; i += gridDim.x * blockDim.x) {
+        if (i >= n_pts) { cell[i] = -1; continue; }
+        const int s = find_seg(seg_off, n_seg, i);
+        const int64_t nx = dims[3 * s], ny = dims[3 * s + 1], nz = dims[3 * s + 2];
+        if (nx * ny * nz == 0) { cell[i] = -1; continue; }
+        const int ix = (int)floorf(__fdiv_rn(__fsub_rn(xyz[3 * (size_t)i], origin[3 * s]), dl));
+        const int iy = (int)floorf(__fdiv_rn(__fsub_rn(xyz[3 * (size_t)i + 1], origin[3 * s + 1]), dl));
+        const int iz = (int)floorf(__fdiv_rn(__fsub_rn(xyz[3 * (size_t)i + 2], origin[3 * s + 2]), dl));
+        cell[i] = (int64_t)cell_off[s] + ix + nx * iy + nx * ny * iz;
+    }
+}
+
+// per-scene output counts -> the next level's scene offsets
+__global__ void gs_out_off_kernel(const int32_t *__restrict__ rank, const int32_t *__restrict__ cell_off, int n_seg,
+                                  int32_t *__restrict__ out_seg_off)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    int tot = 0;
+    out_seg_off[0] = 0;
+    for (int s = 0; s < n_seg; ++s) {
+        tot += rank[cell_off[s + 1]] - rank[cell_off[s]];
+        out_seg_off[s + 1] = tot;
+    }
+}
+
+// ---- voxelisation: one point per occupied voxel (the smallest input index), util/voxelize.py:44-70 'deterministic' -----
+// discrete = floor(coord / voxel) in float64 (numpy promotes float32 coordinates / np.array(voxel_size) to float64, NEP 50);
+// key = ravel of (discrete - per-scene min) -- ravel_hash_vec, voxelize.py:26-41
+__global__ void vx_cell_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ seg_off, int n_seg, int n_pts,
+                               double voxel, const int *__restrict__ mm, const int32_t *__restrict__ dims,
+                               const int32_t *__restrict__ cell_off, int32_t *__restrict__ first)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
+        const int s = find_seg(seg_off, n_seg, i);
+        const int64_t nx = dims[3 * s], ny = dims[3 * s + 1], nz = dims[3 * s + 2];
+        if (nx * ny * nz == 0) continue;
+        int d[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double lo = floor((double)ordered_to_float(mm[s * 6 + a]) / voxel);
+            d[a] = (int)(floor((double)xyz[3 * (size_t)i + a] / voxel) - lo);
+        }
+        // Fortran-style ravel of voxelize.py:36-40: ((x * ny + y) * nz + z): ascending key = the reference's sorted order
+        const int64_t key = ((int64_t)d[0] * ny + d[1]) * nz + d[2];
+        atomicMin(&first[cell_off[s] + key], i);                   // integer min: deterministic
+    }
+}
+
+__global__ void vx_dims_kernel(const int *__restrict__ mm, const int32_t *__restrict__ seg_off, int n_seg, double voxel,
+                               int32_t *__restrict__ dims)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const bool empty = seg_off[s + 1] <= seg_off[s];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (empty) { dims[3 * s + a] = 0; continue; }
+        const double lo = floor((double)ordered_to_float(mm[s * 6 + a]) / voxel);
+        const double hi = floor((double)ordered_to_float(mm[s * 6 + 3 + a]) / voxel);
+        dims[3 * s + a] = (int)(hi - lo) + 1;
+    }
+}
+
+__global__ void vx_fill_kernel(int32_t *__restrict__ first, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) first[i] = 0x7fffffff;
+}
+__global__ void vx_flag_kernel(const int32_t *__restrict__ first, const int32_t *__restrict__ cell_off, int n_seg, int cells_max,
+                               int32_t *__restrict__ flag) {
+    const int total = cell_off[n_seg];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= cells_max; i += gridDim.x * blockDim.x)
+        flag[i] = (i < total && first[i] != 0x7fffffff) ? 1 : 0;
+}
+__global__ void vx_emit_kernel(const int32_t *__restrict__ first, const int32_t *__restrict__ rank, const int32_t *__restrict__ cell_off,
+                               int n_seg, int32_t *__restrict__ out_idx) {
+    const int total = cell_off[n_seg];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        if (first[i] != 0x7fffffff) out_idx[rank[i]] = first[i];
+}
+
 struct GsWorkspace {
     int *mm;             // [n_seg*6] ordered-int min/max
     int64_t *cell;       // [n_pts]
@@ -234,4 +357,125 @@ extern "C" int pcfb_gridsub_emit(const float *xyz, const float *feats, int n_seg
     gs_emit_kernel<<<blocks_for(total_cells), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         xyz, feats, F, w.cell_ptr, w.pts, w.rank, (int)total_cells, out_xyz, out_feats);
     return check_launch("gs_emit_kernel");
+}
+
+
+// ---- one pyramid level with device-side sizes (no host read) -----------------------------------------------------------
+namespace pcfb {
+struct GsDevExtra { float *origin; int32_t *dims, *cell_off; size_t bytes; };
+static GsDevExtra carve_gs_dev(void *ws, size_t base_bytes, int n_seg) {
+    Carver c(ws);
+    c.off = base_bytes;
+    GsDevExtra e{};
+    e.origin = c.take<float>((size_t)n_seg * 3 + 1);
+    e.dims = c.take<int32_t>((size_t)n_seg * 3 + 1);
+    e.cell_off = c.take<int32_t>((size_t)n_seg + 2);
+    e.bytes = align_up(c.off, 256);
+    return e;
+}
+}  // namespace pcfb
+
+extern "C" size_t pcfb_pyramid_level_workspace(int n_seg, int n_pts_max, int64_t cells_max)
+{
+    using namespace pcfb;
+    return carve_gs_dev(nullptr, carve_gs(nullptr, n_seg, n_pts_max, cells_max).bytes, n_seg).bytes;
+}
+
+extern "C" int pcfb_pyramid_level(const float *xyz, const float *feats, int F, const int32_t *seg_off, int n_seg, int n_pts_max,
+                                  float dl, int64_t cells_max, float *out_xyz, float *out_feats, int32_t *out_seg_off,
+                                  int32_t *status, void *workspace, size_t workspace_bytes, void *stream)
+{
+    using namespace pcfb;
+    PCFB_REQUIRE(n_seg >= 1 && n_pts_max >= 0 && dl > 0.f && F >= 0, "pcfb_pyramid_level: bad arguments");
+    PCFB_REQUIRE(cells_max >= 1 && cells_max < (1ll << 30), "pcfb_pyramid_level: cells_max = %lld outside [1, 2^30)", (long long)cells_max);
+    PCFB_REQUIRE(xyz && seg_off && out_xyz && out_seg_off && workspace && (F == 0 || (feats && out_feats)), "pcfb_pyramid_level: null pointer");
+    GsWorkspace w = carve_gs(workspace, n_seg, n_pts_max, cells_max);
+    GsDevExtra e = carve_gs_dev(workspace, w.bytes, n_seg);
+    if (workspace_bytes < e.bytes) { set_error("pcfb_pyramid_level: workspace %zu < %zu", workspace_bytes, e.bytes); return PCFB_ERR_WORKSPACE; }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    gs_init_bounds_kernel<<<ceil_div(n_seg * 6, 256), 256, 0, st>>>(w.mm, n_seg);
+    if ((rc = check_launch("gs_init_bounds_kernel"))) return rc;
+    gs_bounds_dev_kernel<<<blocks_for(n_pts_max), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts_max, w.mm);
+    if ((rc = check_launch("gs_bounds_dev_kernel"))) return rc;
+    gs_finish_bounds_kernel<<<ceil_div(n_seg, 128), 128, 0, st>>>(w.mm, seg_off, n_seg, dl, e.origin, e.dims);
+    if ((rc = check_launch("gs_finish_bounds_kernel"))) return rc;
+    gs_cell_off_kernel<<<1, 32, 0, st>>>(e.dims, n_seg, (long long)cells_max, e.cell_off, status);
+    if ((rc = check_launch("gs_cell_off_kernel"))) return rc;
+    gs_cell_dev_kernel<<<blocks_for(n_pts_max), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts_max, dl, e.origin, e.dims, e.cell_off, w.cell);
+    if ((rc = check_launch("gs_cell_dev_kernel"))) return rc;
+    if ((rc = pcfb_knn_inverse(w.cell, n_pts_max, 1, (int)cells_max, w.pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream))) return rc;
+    PCFB_CUDA(cudaMemsetAsync(w.state, 0, (size_t)((char *)w.inv_ws - (char *)w.state), st));
+    PCFB_CUDA(cudaMemsetAsync(w.flag + cells_max, 0, sizeof(int32_t), st));
+    gs_flag_kernel<<<blocks_for(cells_max), 256, 0, st>>>(w.cell_ptr, (int)cells_max, w.flag);
+    if ((rc = check_launch("gs_flag_kernel"))) return rc;
+    inv_scan_kernel<<<ceil_div((int)cells_max + 1, SCAN_TILE), SCAN_THREADS, 0, st>>>(w.flag, (int)cells_max, w.rank, w.state, w.ticket);
+    if ((rc = check_launch("inv_scan_kernel"))) return rc;
+    gs_out_off_kernel<<<1, 32, 0, st>>>(w.rank, e.cell_off, n_seg, out_seg_off);
+    if ((rc = check_launch("gs_out_off_kernel"))) return rc;
+    gs_emit_kernel<<<blocks_for(cells_max), 256, 0, st>>>(xyz, feats, F, w.cell_ptr, w.pts, w.rank, (int)cells_max, out_xyz, out_feats);
+    return check_launch("gs_emit_kernel");
+}
+
+extern "C" size_t pcfb_voxelize_workspace(int n_seg, int n_pts, int64_t cells_max)
+{
+    using namespace pcfb;
+    Carver c(nullptr);
+    c.take<int>((size_t)n_seg * 6 + 1);
+    c.take<int32_t>((size_t)n_seg * 3 + 1);
+    c.take<int32_t>((size_t)n_seg + 2);
+    c.take<int32_t>((size_t)cells_max + 2);
+    c.take<int32_t>((size_t)cells_max + 2);
+    c.take<int32_t>((size_t)cells_max + 2);
+    c.take<unsigned long long>((size_t)(cells_max + 1) / SCAN_TILE + 2);
+    c.take<unsigned int>(4);
+    (void)n_pts;
+    return align_up(c.off, 256);
+}
+
+extern "C" int pcfb_voxelize(const float *xyz, const int32_t *seg_off, int n_seg, int n_pts, double voxel, int64_t cells_max,
+                             int32_t *out_idx, int32_t *out_seg_off, int32_t *status, void *workspace, size_t workspace_bytes,
+                             void *stream)
+{
+    using namespace pcfb;
+    PCFB_REQUIRE(n_seg >= 1 && n_pts >= 0 && voxel > 0.0, "pcfb_voxelize: bad arguments");
+    PCFB_REQUIRE(cells_max >= 1 && cells_max < (1ll << 30), "pcfb_voxelize: cells_max = %lld outside [1, 2^30)", (long long)cells_max);
+    PCFB_REQUIRE(xyz && seg_off && out_idx && out_seg_off && workspace, "pcfb_voxelize: null pointer");
+    if (workspace_bytes < pcfb_voxelize_workspace(n_seg, n_pts, cells_max)) { set_error("pcfb_voxelize: workspace too small"); return PCFB_ERR_WORKSPACE; }
+    Carver c(workspace);
+    int *mm = c.take<int>((size_t)n_seg * 6 + 1);
+    int32_t *dims = c.take<int32_t>((size_t)n_seg * 3 + 1);
+    int32_t *cell_off = c.take<int32_t>((size_t)n_seg + 2);
+    int32_t *first = c.take<int32_t>((size_t)cells_max + 2);
+    int32_t *flag = c.take<int32_t>((size_t)cells_max + 2);
+    int32_t *rank = c.take<int32_t>((size_t)cells_max + 2);
+    unsigned long long *state = c.take<unsigned long long>((size_t)(cells_max + 1) / SCAN_TILE + 2);
+    unsigned int *ticket = c.take<unsigned int>(4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc;
+    gs_init_bounds_kernel<<<ceil_div(n_seg * 6, 256), 256, 0, st>>>(mm, n_seg);
+    if ((rc = check_launch("gs_init_bounds_kernel"))) return rc;
+    if (n_pts > 0) {
+        gs_bounds_kernel<<<blocks_for(n_pts), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts, mm);
+        if ((rc = check_launch("gs_bounds_kernel"))) return rc;
+    }
+    vx_dims_kernel<<<ceil_div(n_seg, 128), 128, 0, st>>>(mm, seg_off, n_seg, voxel, dims);
+    if ((rc = check_launch("vx_dims_kernel"))) return rc;
+    gs_cell_off_kernel<<<1, 32, 0, st>>>(dims, n_seg, (long long)cells_max, cell_off, status);
+    if ((rc = check_launch("gs_cell_off_kernel"))) return rc;
+    vx_fill_kernel<<<blocks_for(cells_max + 1), 256, 0, st>>>(first, (long long)cells_max + 1);
+    if ((rc = check_launch("vx_fill_kernel"))) return rc;
+    if (n_pts > 0) {
+        vx_cell_kernel<<<blocks_for(n_pts), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts, voxel, mm, dims, cell_off, first);
+        if ((rc = check_launch("vx_cell_kernel"))) return rc;
+    }
+    PCFB_CUDA(cudaMemsetAsync(state, 0, (size_t)((char *)ticket + 4 * sizeof(unsigned int) - (char *)state), st));
+    vx_flag_kernel<<<blocks_for(cells_max + 1), 256, 0, st>>>(first, cell_off, n_seg, (int)cells_max, flag);
+    if ((rc = check_launch("vx_flag_kernel"))) return rc;
+    inv_scan_kernel<<<ceil_div((int)cells_max + 1, SCAN_TILE), SCAN_THREADS, 0, st>>>(flag, (int)cells_max, rank, state, ticket);
+    if ((rc = check_launch("inv_scan_kernel"))) return rc;
+    gs_out_off_kernel<<<1, 32, 0, st>>>(rank, cell_off, n_seg, out_seg_off);
+    if ((rc = check_launch("gs_out_off_kernel"))) return rc;
+    vx_emit_kernel<<<blocks_for(cells_max), 256, 0, st>>>(first, rank, cell_off, n_seg, out_idx);
+    return check_launch("vx_emit_kernel");
 }

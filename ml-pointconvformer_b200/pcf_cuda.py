@@ -14,6 +14,7 @@ import os
 import torch
 
 from . import _lib
+from . import streams as S
 from ._lib import PconvShape, check, lib, ptr, require, stream_ptr, workspace
 
 F32, I64, I32, U8 = torch.float32, torch.int64, torch.int32, torch.uint8
@@ -112,9 +113,12 @@ def _pconv_bwd(grad_y, grad_p, inp, inv, nei, weights, additional, guidance, lin
     ws_bytes = lib().pcfb_pconv_backward_workspace(ctypes.byref(sh), 0)
     ws = workspace(ws_bytes, dev)
     g_lw_acc, g_lb_acc = None, None
+    # dW = dY^T P / db are leaves of the backward graph: with streams.LEAF_ASYNC they run as a separate product on the leaf
+    # stream (joined by streams.join_leaves()) instead of inside the composed backward call
+    leaf = (S.ENABLED and S.LEAF_ASYNC and (n_lw or n_lb) and grad_y is not None and pconv_out is not None and 0 < C_out <= 256)
     for b in range(B):
-        g_lw = torch.empty_like(lin_w) if n_lw else None
-        g_lb = torch.empty(C_out, device=dev, dtype=F32) if n_lb else None
+        g_lw = torch.empty_like(lin_w) if (n_lw and not leaf) else None
+        g_lb = torch.empty(C_out, device=dev, dtype=F32) if (n_lb and not leaf) else None
         inv_n, inv_k, inv_idx = (None, None, None) if inv is None else (inv[0][b], inv[1][b], inv[2][b])
         check(lib().pcfb_pconv_backward(
             ctypes.byref(sh), ptr(grad_y[b]) if grad_y is not None else 0, ptr(grad_p[b]) if grad_p is not None else 0,
@@ -123,6 +127,8 @@ def _pconv_bwd(grad_y, grad_p, inp, inv, nei, weights, additional, guidance, lin
             ptr(pconv_out[b]) if pconv_out is not None else 0,
             ptr(g_in[b]) if n_in else 0, ptr(g_w[b]) if n_w else 0, ptr(g_add[b]) if n_add else 0,
             ptr(g_gd[b]) if n_gd else 0, ptr(g_lw), ptr(g_lb), ptr(ws), ws_bytes, 0, stream_ptr()), "pconv_backward")
+        if leaf:
+            g_lw, g_lb = S.fork_leaf(lambda: gemm_tn(grad_y[b], pconv_out[b], want_rowsum=True))
         if n_lw:
             g_lw_acc = g_lw if g_lw_acc is None else g_lw_acc + g_lw
         if n_lb:
@@ -451,3 +457,64 @@ def grid_subsample(xyz, feats, counts, dl):
     check(lib().pcfb_gridsub_emit(ptr(xyz), ptr(feats), n_seg, n_pts, F, total_cells, ptr(out_xyz), ptr(out_f), ptr(ws),
                                   ws_bytes, stream_ptr()), "gridsub_emit")
     return out_xyz, out_f, sub_counts
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident pyramid construction (voxelisation + grid subsampling without a host read per level)
+# ------------------------------------------------------------------------------------------------
+def _cells_upper_bound(xyz, counts, cell, margin=2):
+    """Host upper bound of the dense voxel table for cell edge `cell`, from the per-scene bounding boxes (ONE device->host
+    read of 6 floats per scene).  Barycentres of coarser levels stay inside the box of level 0, so the same boxes bound
+    every level of the pyramid."""
+    dev = xyz.device
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + int(c))
+    boxes = []
+    for s in range(len(counts)):
+        seg = xyz[off[s]:off[s + 1]]
+        boxes.append(torch.cat([seg.min(0).values, seg.max(0).values]) if seg.shape[0] else torch.zeros(6, device=dev))
+    return torch.stack(boxes).cpu().double()                            # [n_seg, 6] (min xyz, max xyz)
+
+
+def cells_for(boxes, cell, margin=2):
+    ext = (boxes[:, 3:] - boxes[:, :3]).clamp(min=0) / float(cell)
+    dims = ext.floor().to(torch.int64) + 1 + margin
+    return int(dims.prod(1).sum().item())
+
+
+def voxelize(xyz, counts, voxel, boxes=None):
+    """voxelize(coord, voxel, hash_type='ravel', mode='deterministic') (util/voxelize.py:44-70) on packed scenes.
+    -> (idx int32 [<= N] upper-bound sized, seg_off int32 device [n_seg+1], status device int32, boxes)."""
+    require(xyz, F32, "xyz")
+    dev = xyz.device
+    n_seg, n_pts = len(counts), xyz.shape[0]
+    if boxes is None:
+        boxes = _cells_upper_bound(xyz, counts, voxel)
+    cells_max = max(cells_for(boxes, voxel), 1)
+    seg_off = _offsets(counts, dev)
+    out_idx = torch.empty(max(n_pts, 1), device=dev, dtype=I32)
+    out_off = torch.empty(n_seg + 1, device=dev, dtype=I32)
+    status = torch.zeros(1, device=dev, dtype=I32)
+    ws_bytes = lib().pcfb_voxelize_workspace(n_seg, n_pts, cells_max)
+    ws = workspace(ws_bytes, dev)
+    check(lib().pcfb_voxelize(ptr(xyz), ptr(seg_off), n_seg, n_pts, float(voxel), cells_max, ptr(out_idx), ptr(out_off),
+                              ptr(status), ptr(ws), ws_bytes, stream_ptr()), "voxelize")
+    return out_idx, out_off, status, boxes
+
+
+def pyramid_level(xyz, feats, seg_off, n_seg, dl, boxes, status):
+    """One grid-subsampling level whose input size lives on the device (seg_off[-1]).  Buffers are upper-bound sized.
+    -> (sub_xyz, sub_feats, sub_seg_off)."""
+    dev = xyz.device
+    n_max = xyz.shape[0]
+    F = 0 if feats is None else feats.shape[1]
+    cells_max = max(cells_for(boxes, dl), 1)
+    out_xyz = torch.empty(n_max, 3, device=dev, dtype=F32)
+    out_f = torch.empty(n_max, F, device=dev, dtype=F32) if F else None
+    out_off = torch.empty(n_seg + 1, device=dev, dtype=I32)
+    ws_bytes = lib().pcfb_pyramid_level_workspace(n_seg, n_max, cells_max)
+    ws = workspace(ws_bytes, dev)
+    check(lib().pcfb_pyramid_level(ptr(xyz), ptr(feats), F, ptr(seg_off), n_seg, n_max, float(dl), cells_max, ptr(out_xyz),
+                                   ptr(out_f), ptr(out_off), ptr(status), ptr(ws), ws_bytes, stream_ptr()), "pyramid_level")
+    return out_xyz, out_f, out_off

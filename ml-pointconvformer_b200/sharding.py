@@ -41,7 +41,12 @@ class FlatParameters:
     optimizer bookkeeping alone was ~3 ms of a 48 ms training step).  The module keeps using its own parameter
     objects; only their storage moves.  Call after any module surgery (e.g. SyncBatchNorm conversion)."""
 
-    def __init__(self, module):
+    def __init__(self, module, async_weight_grads=False):
+        """async_weight_grads: let the weight-gradient GEMMs of the backward run on their own stream (streams.LEAF_ASYNC);
+        gather_grads() joins them.  Only for loops that read gradients through gather_grads()."""
+        if async_weight_grads:
+            from . import streams
+            streams.LEAF_ASYNC = True
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
@@ -60,6 +65,8 @@ class FlatParameters:
     def gather_grads(self, world_size=1, group=None):
         """Concatenate the per-parameter gradients into the flat gradient (mean over ranks when world_size > 1), attach
         it to the flat parameter and drop the per-parameter ones."""
+        from . import streams
+        streams.join_leaves()                           # weight gradients that ran on the leaf stream (streams.fork_leaf)
         pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
         g = torch.cat(pieces)
         if world_size > 1:

@@ -19,6 +19,12 @@ import torch
 ENABLED = os.environ.get("PCFB_STREAMS", "1") != "0"
 N_SIDE = 3
 _POOL = {}
+# Weight-gradient products (dW = dY^T X of every Linear, dW of the fused contraction's Linear) are LEAVES of the backward
+# graph: nothing downstream waits for them except the optimizer.  With LEAF_ASYNC they run on their own stream and are only
+# joined by join_leaves() (called by sharding.FlatParameters.gather_grads before the flat gradient is assembled), taking
+# ~120 small GEMM launches off the backward's critical path.  Opt-in: whoever reads .grad must call join_leaves() first.
+LEAF_ASYNC = False
+_LEAF = {}
 
 
 def _side_streams(device):
@@ -76,3 +82,29 @@ def join(branch):
         branch.main.wait_stream(branch.stream)
         _record(branch.result, branch.main)
     return branch.result
+
+
+def fork_leaf(fn):
+    """Run fn() (a leaf of the backward graph: a weight gradient) on the leaf stream; NOT joined until join_leaves()."""
+    if not (ENABLED and LEAF_ASYNC) or not torch.cuda.is_available():
+        return fn()
+    cur = torch.cuda.current_stream()
+    key = (cur.device.type, cur.device.index)
+    leaf = _LEAF.get(key)
+    if leaf is None:
+        leaf = _LEAF[key] = torch.cuda.Stream(device=cur.device)
+    if leaf == cur:
+        return fn()
+    leaf.wait_stream(cur)
+    with torch.cuda.stream(leaf):
+        return fn()
+
+
+def join_leaves():
+    """The current stream waits for every weight-gradient product enqueued by fork_leaf()."""
+    if not torch.cuda.is_available():
+        return
+    cur = torch.cuda.current_stream()
+    leaf = _LEAF.get((cur.device.type, cur.device.index))
+    if leaf is not None and leaf != cur:
+        cur.wait_stream(leaf)

@@ -18,7 +18,7 @@ def main():
     cfgd = configs.CONFIG_PCF_OPT_10CM
     model = MA.PointConvFormer_Segmentation(configs.make_cfg(cfgd)).to(dev).train()
     from pcf_b200 import sharding
-    flat = sharding.FlatParameters(model)
+    flat = sharding.FlatParameters(model, async_weight_grads=True)
     opt = sharding.FlatAdamW(flat, lr=1e-3, weight_decay=0.05, max_norm=10.0)
     from pcf_b200 import losses
     host = bench.host_pyramid(1, args.points, cfgd["grid_size"], args.scenes)

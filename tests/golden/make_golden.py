@@ -417,8 +417,29 @@ def make_knn():
     raise RuntimeError("no tie-free draw")
 
 
+def make_voxelize():
+    """The reference's own voxelize(coord, voxel, hash_type='ravel', mode='deterministic') (util/voxelize.py:44-70, imported
+    unmodified) on two clouds with negative coordinates; stores its idx_unique and the ravel keys of the selected points."""
+    sys.path.insert(0, REF)
+    from util import voxelize as RV
+    out = {}
+    for i, (n, voxel, seed) in enumerate([(6000, 0.1, 600), (4000, 0.05, 601)]):
+        p, _ = surface_cloud(n, seed, extent=(5.2, 4.1, 2.6))
+        p -= np.array([1.3, 0.7, -0.2], np.float32)
+        idx = RV.voxelize(p, voxel, hash_type='ravel', mode='deterministic')
+        d = np.floor(p / np.array(voxel))
+        keys = RV.ravel_hash_vec(d)
+        out.update({"p%d" % i: p, "voxel%d" % i: np.float64(voxel), "idx%d" % i: idx.astype(np.int64),
+                    "keys%d" % i: keys[idx].astype(np.uint64)})
+    np.savez_compressed(os.path.join(HERE, "voxelize.npz"), **out)
+    print("voxelize: ok", [len(out["idx%d" % i]) for i in range(2)])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "--voxelize":
+        make_voxelize()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "--knn":
         make_knn()
         sys.exit(0)
@@ -430,6 +451,7 @@ if __name__ == "__main__":
     make_inverse()
     make_grid_subsample()
     make_knn()
+    make_voxelize()
     make_layers()
     for v in MODEL_VARIANTS:
         make_model(v)

@@ -255,3 +255,46 @@ def test_subsample_drop_in():
     wp, wn = OG.subsample(p, n, [0.1, 0.2, 0.4, 0.8, 1.6])
     for a, b in zip(pts + nrm, wp + wn):
         assert np.array_equal(a.cpu().numpy(), b)
+
+
+def test_voxelize_matches_oracle_and_reference(golden_dir):
+    """GPU voxelisation (pcfb_voxelize) = the oracle exactly (index for index), on the reference's golden clouds -- whose
+    occupied voxels / order it therefore reproduces (tests/test_oracle_golden.py::test_voxelize_matches_reference) -- and
+    on a packed batch of three ragged scenes."""
+    from oracle import voxelize as OV
+    from pcf_b200 import grid_subsampling as GS
+    g = np.load(os.path.join(golden_dir, "voxelize.npz"))
+    for i in range(2):
+        p, voxel = g["p%d" % i], float(g["voxel%d" % i])
+        idx, cnt = GS.voxelize_packed(p, [len(p)], voxel)
+        assert cnt == [len(g["idx%d" % i])]
+        assert np.array_equal(idx.cpu().numpy(), OV.voxelize(p, voxel))
+        assert np.array_equal(OV.ravel_keys(p, voxel)[idx.cpu().numpy()], g["keys%d" % i])
+    rng = np.random.default_rng(4)
+    counts = [3000, 1, 4500]
+    clouds = [(rng.random((n, 3)) * [4, 3, 2.5] - [1.0, 2.0, 0.5]).astype(np.float32) for n in counts]
+    packed = np.concatenate(clouds)
+    idx, cnt = GS.voxelize_packed(packed, counts, 0.1)
+    ref_idx, ref_cnt = OV.voxelize_packed(packed, counts, 0.1)
+    assert cnt == ref_cnt and np.array_equal(idx.cpu().numpy(), ref_idx)
+
+
+def test_build_pyramid_equals_per_level_subsampling():
+    """The device-sized pyramid (one host read for all levels) must give exactly the per-level grid subsampling (two host
+    reads per level), which is bit-exact against the reference C++ (test_grid_subsample_golden); a second call with the
+    counts / boxes of the first reads nothing back."""
+    from pcf_b200 import grid_subsampling as GS
+    from gpu_util import surface_cloud
+    grid = [0.1, 0.2, 0.4, 0.8, 1.6]
+    clouds = [surface_cloud(9000, 31, extent=(7.0, 5.0, 2.6)), surface_cloud(5000, 32, extent=(4.0, 6.0, 2.6))]
+    p = np.concatenate([c[0] for c in clouds]); n = np.concatenate([c[1] for c in clouds])
+    counts = [len(c[0]) for c in clouds]
+    pts, nrm, cnt, info = GS.build_pyramid(p, n, counts, grid)
+    rp, rn, rc = GS.subsample_packed(p, n, counts, grid)
+    assert cnt == [list(map(int, c)) for c in rc]
+    for a, b in zip(pts + nrm, rp + rn):
+        assert torch.equal(a, b)
+    pts2, nrm2, cnt2, info2 = GS.build_pyramid(p, n, counts, grid, expect=cnt, boxes=info["boxes"])
+    assert int(info2["status"].item()) == 0 and cnt2 == cnt
+    for a, b in zip(pts2 + nrm2, pts + nrm):
+        assert torch.equal(a, b)

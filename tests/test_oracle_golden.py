@@ -237,3 +237,18 @@ def test_knn_packed_matches_reference(golden_dir):
     es2, ef2, ep2 = OK.compute_knn_packed(pcs, g["stored"].tolist(), Ks, Ks, Ks, use_c=True)
     for a, b in zip(es + ef + ep, es2 + ef2 + ep2):
         assert np.array_equal(a, b)
+
+
+def test_voxelize_matches_reference(golden_dir):
+    """oracle/voxelize.py against the reference's own voxelize(hash_type='ravel', mode='deterministic')
+    (util/voxelize.py:44-70): same occupied voxels in the same (ascending key) order; the representative of a voxel is a
+    point of that voxel (the reference's choice among them is an unstable argsort: implementation defined)."""
+    from oracle import voxelize as OV
+    g = load(golden_dir, "voxelize.npz")
+    for i in range(2):
+        p, voxel = g["p%d" % i], float(g["voxel%d" % i])
+        idx = OV.voxelize(p, voxel)
+        keys = OV.ravel_keys(p, voxel)
+        assert np.array_equal(keys[idx], g["keys%d" % i])             # same voxels, same order
+        assert np.array_equal(keys[g["idx%d" % i]], g["keys%d" % i])  # the reference's picks lie in those voxels
+        assert np.all(idx <= g["idx%d" % i])                          # ours is the smallest index of each voxel
