@@ -57,36 +57,36 @@ def parse():
 # ---------------------------------------------------------------------------------------------------
 # synthetic workload (host side)
 # ---------------------------------------------------------------------------------------------------
-def host_pyramid(seed, n_points, grid_size, n_scenes=1):
-    """Level-0 clouds from the synthetic room generator; coarser levels by the oracle-free numpy voxel
-    barycentre below (host data preparation, like the reference's DataLoader workers)."""
+def host_scenes(seed, n_points, grid_size, n_scenes=1):
+    """Level-0 clouds (voxelised at grid_size[0]) from the synthetic room generator: what the reference's dataset hands to
+    subsample() (scannet_data_loader_color_DDP.py:167-278 -> datasetCommon.py:384-420).  The coarser levels are NOT built
+    here: our arm builds them on the GPU inside the step, the CPU arm with the reference-pinned oracle."""
     from pcf_b200 import synthetic
-    pts, nrm, col, lab = [[] for _ in grid_size], [[] for _ in grid_size], [], []
-    stored = [[] for _ in grid_size]
+    pts, nrm, col, lab, stored = [], [], [], [], []
     rng = np.random.default_rng(seed + 999)
     for s in range(n_scenes):
         xyz, n, c = synthetic.make_scene(seed * 100 + s, n_points, voxel=grid_size[0])
-        p_l, n_l = xyz, n
-        for l, g in enumerate(grid_size):
-            if l > 0:
-                p_l, n_l = voxel_barycentre(p_l, n_l, g)
-            pts[l].append(p_l); nrm[l].append(n_l); stored[l].append(len(p_l))
-        col.append(c)
+        pts.append(xyz); nrm.append(n); col.append(c); stored.append(len(xyz))
         lab.append(rng.integers(0, 20, len(xyz)))
     cat = lambda lst: np.ascontiguousarray(np.concatenate(lst))
-    return dict(points=[cat(p) for p in pts], normals=[cat(n) for n in nrm], colors=cat(col),
-                labels=cat(lab).astype(np.int64), stored=stored)
+    return dict(points0=cat(pts), normals0=cat(nrm), colors=cat(col), labels=cat(lab).astype(np.int64), stored0=stored)
 
 
-def voxel_barycentre(p, f, dl):
-    key = np.floor((p - p.min(0)) / np.float32(dl)).astype(np.int64)
-    mx = key.max(0) + 1
-    flat = (key[:, 2] * mx[1] + key[:, 1]) * mx[0] + key[:, 0]
-    order = np.argsort(flat, kind="stable")
-    uniq, start, cnt = np.unique(flat[order], return_index=True, return_counts=True)
-    sp = np.add.reduceat(p[order], start) / cnt[:, None]
-    sf = np.add.reduceat(f[order], start) / cnt[:, None]
-    return sp.astype(np.float32), sf.astype(np.float32)
+def host_pyramid(seed, n_points, grid_size, n_scenes=1):
+    """host_scenes + the pyramid by the oracle's grid subsampling (bit-exact against the reference C++,
+    tests/test_oracle_golden.py) -- the CPU arm's data preparation, like the reference's DataLoader workers."""
+    from oracle import grid_subsample as OG
+    h = host_scenes(seed, n_points, grid_size, n_scenes)
+    L = len(grid_size)
+    pts, nrm, stored = [[] for _ in range(L)], [[] for _ in range(L)], [[] for _ in range(L)]
+    off = 0
+    for c in h["stored0"]:
+        p_l, n_l = OG.subsample(h["points0"][off:off + c], h["normals0"][off:off + c], grid_size)
+        off += c
+        for l in range(L):
+            pts[l].append(p_l[l]); nrm[l].append(n_l[l]); stored[l].append(len(p_l[l]))
+    cat = lambda lst: np.ascontiguousarray(np.concatenate(lst))
+    return dict(points=[cat(p) for p in pts], normals=[cat(n) for n in nrm], colors=h["colors"], labels=h["labels"], stored=stored)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -167,22 +167,26 @@ def run_ours(args):
     # clip_grad_norm_(10) + AdamW (train_ScanNet_DDP_WarmUP.py:421-424) as two launches of ours on the flat buffer
     opt = sharding.FlatAdamW(flat, lr=1e-3, weight_decay=cfgd["adamw_decay"], max_norm=10.0)
 
-    host = host_pyramid(1 + rank, args.points, cfgd["grid_size"], args.scenes)
+    host = host_scenes(1 + rank, args.points, cfgd["grid_size"], args.scenes)
     L = cfgd["num_level"]
     pin = lambda a: torch.from_numpy(a).pin_memory()
-    h_pts = [pin(p) for p in host["points"]]
-    h_nrm = [pin(p) for p in host["normals"]]
+    h_pts0, h_nrm0 = pin(host["points0"]), pin(host["normals0"])
     h_col, h_lab = pin(host["colors"]), pin(host["labels"])
-    stored = host["stored"]
-    n0 = h_pts[0].shape[0]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in h_pts + h_nrm + [h_col, h_lab])
+    n0 = h_pts0.shape[0]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in (h_pts0, h_nrm0, h_col, h_lab))
 
     def upload():
-        pts = [t.to(dev, non_blocking=True) for t in h_pts]
-        nrm = [t.to(dev, non_blocking=True) for t in h_nrm]
-        return pts, nrm, h_col.to(dev, non_blocking=True), h_lab.to(dev, non_blocking=True)
+        return [t.to(dev, non_blocking=True) for t in (h_pts0, h_nrm0, h_col, h_lab)]
 
-    def step(pts, nrm, col, lab):
+    # The pyramid is built on the device inside the step (grid_subsampling.build_pyramid: every level enqueued with
+    # device-side sizes).  Its per-level counts are read back ONCE here; the step then runs without any host read, which
+    # is what lets it be captured (the captured step is tied to this batch: same scenes, same sizes).
+    from pcf_b200 import grid_subsampling as GS
+    _, _, stored, pyr_info = GS.build_pyramid(h_pts0.to(dev), h_nrm0.to(dev), host["stored0"], cfgd["grid_size"])
+    level_sizes = [int(sum(c)) for c in stored]
+
+    def step(pts0, nrm0, col, lab):
+        pts, nrm, _, info = GS.build_pyramid(pts0, nrm0, host["stored0"], cfgd["grid_size"], expect=stored, boxes=pyr_info["boxes"])
         pcs = [p.unsqueeze(0) for p in pts]
         nrms = [p.unsqueeze(0) for p in nrm]
         es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, stored, cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"],
@@ -234,8 +238,7 @@ def run_ours(args):
 
     def graph_step(fresh):
         if fresh is not None:                                            # new host data -> static buffers
-            for dst, src in zip(static_in[0] + static_in[1] + [static_in[2], static_in[3]],
-                                fresh[0] + fresh[1] + [fresh[2], fresh[3]]):
+            for dst, src in zip(static_in, fresh):
                 dst.copy_(src, non_blocking=True)
         graph.replay()
         return static_loss
@@ -253,7 +256,7 @@ def run_ours(args):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             if e2e:
-                loss = graph_step((h_pts, h_nrm, h_col, h_lab)) if use_graph else step(*upload())
+                loss = graph_step((h_pts0, h_nrm0, h_col, h_lab)) if use_graph else step(*upload())
                 _ = loss.item()                                          # D2H read of the step's result
             else:
                 loss = graph_step(None) if use_graph else step(*resident)
@@ -301,17 +304,38 @@ def run_ours(args):
     e2e_value = total_points * args.steps / (ms_e2e / 1e3)
 
     roof, extra = (None, {})
+    # what the step is made of: algorithmic work (one eager step with the wrappers' accounting on) and the kernel profile of
+    # one replay -- on every rank (the step holds collectives when world > 1); then, on rank 0, the hot kernels timed alone
+    _lib.ACCOUNT = {"bytes": 0.0, "flops": 0.0}
+    step(*(static_in if use_graph else upload()))
+    torch.cuda.synchronize()
+    work, _lib.ACCOUNT = _lib.ACCOUNT, None
+    prof = None
+    if use_graph:
+        try:
+            prof = step_profile(graph.replay)
+        except Exception as e:                                          # CUPTI unavailable: keep the bench line
+            prof = {"error": "%s: %s" % (type(e).__name__, str(e)[:80])}
     if rank == 0:
-        roof, extra = kernel_rooflines(dev, host, cfgd, args)
+        res, models, peaks = kernel_rooflines(dev, host, cfgd, args)
+        shares = prof.pop("shares", None) if prof else None
+        roof = make_roofline(res, models, peaks, shares)
+        step_info = {"alg_bytes_op_boundary": work["bytes"], "alg_flops": work["flops"],
+                     "launches": launches_per_step if use_graph else None}
+        step_info.update(prof or {})
+        extra = {"step": step_info, "kernels": res, "knn_mpts_per_s": res["knn_grid_self_level0"]["Mqueries_per_s"],
+                 "knn_bruteforce_mpts_per_s": res["knn_self_level0"]["Mqueries_per_s"]}
+    if world > 1:
+        dist.barrier()                                                  # the other ranks wait for rank 0's extra measurements
     out = None
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step (kNN x13 + inverse maps x13 + fwd + CE + bwd "
-                                   "+ grad-clip + AdamW), %d synthetic scene(s) of ~%d level-0 points per GPU, K=16" % (args.scenes, args.points),
-                       "points_per_gpu": int(n0), "levels": [int(t.shape[0]) for t in h_pts], "parallelism": "dp%d" % world,
+            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step (grid-subsampled pyramid x4 + kNN x13 + inverse maps x13 "
+                                   "+ fwd + CE + bwd + grad-clip + AdamW), %d synthetic scene(s) of ~%d level-0 points per GPU, K=16" % (args.scenes, args.points),
+                       "points_per_gpu": int(n0), "levels": level_sizes, "parallelism": "dp%d" % world,
                        "sync_bn": bool(sync_bn), "cuda_graph": bool(use_graph), "forward_variant": {0: "auto(tcgen05)", 1: "simt_fp32", 2: "tcgen05 pipelined", 3: "tcgen05 simple", 4: "tcgen05 warp-specialised"}[args.variant],
                        "l2": "256 MiB buffer written between timed steps; per-step working set >> 126 MB L2"},
             "scenes_per_s": total_scenes * args.steps / (ms_dev / 1e3),
@@ -470,9 +494,9 @@ def kernel_rooflines(dev, host, cfgd, args):
             ts.append(a.elapsed_time(b))
         return float(np.mean(ts))
 
-    xyz = torch.from_numpy(host["points"][0]).to(dev)
+    xyz = torch.from_numpy(host["points0"]).to(dev)
     n = xyz.shape[0]
-    counts = host["stored"][0]
+    counts = host["stored0"]
     K, C_in, C_add, C_mid, C_out = 16, 16, 16, 16, 32
     g = torch.Generator(device="cpu").manual_seed(0)
     nei = pcf_cuda.knn_packed(xyz, counts, xyz, counts, K)
@@ -513,18 +537,122 @@ def kernel_rooflines(dev, host, cfgd, args):
     inv_bytes = n * K * (8 + 4 + 1) + 4 * (n + 1)
     res["knn_inverse_level0"] = {"ms": ms, "alg_bytes": inv_bytes, "GBps": inv_bytes / ms / 1e6, "frac_hbm": inv_bytes / ms / 1e6 / peaks["hbm_gbs"]}
 
-    key = "fused_fwd_saveP" if "ms" in res.get("fused_fwd_saveP", {}) else "fused_fwd_simt"
-    traffic = ncu_traffic("fwdp", "pconv_fwd_ws") if args.variant in (0, 4) else None
-    r = res[key]
+    res.update(chain_kernels(dev, n * K, time_op, peaks))
+    fwd_key = "fused_fwd_saveP" if "ms" in res.get("fused_fwd_saveP", {}) else "fused_fwd_simt"
     kname = {0: "pconv_fwd_ws_kernel<4,0>", 4: "pconv_fwd_ws_kernel<4,0>", 2: "pconv_fwd_umma2_kernel<16,false>",
              3: "pconv_fwd_umma_kernel<16,4>", 1: "pconv_fwd_simt_kernel<16>"}[args.variant]
-    roof = {"kernel": kname if key != "fused_fwd_simt" else "pconv_fwd_simt_kernel<16>",
-            "shape": "level-0 PointConvStridePE contraction: N=%d K=16 C_in=16 C_add=16 C_mid=16 C_out=32, P saved" % n,
-            "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": r["frac_hbm"],
-            "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
-            "peak_source": peaks["src"], "ms": r["ms"], "alg_bytes_per_launch": r["alg_bytes"]}
-    return roof, {"kernels": res, "knn_mpts_per_s": res["knn_grid_self_level0"]["Mqueries_per_s"],
-                  "knn_bruteforce_mpts_per_s": res["knn_self_level0"]["Mqueries_per_s"]}
+    # the kernels with a single-launch HBM model, keyed by the kernel family they stand for in the step profile
+    models = {
+        "mlp_bwd_fused_kernel": ("chain_bwd_8x16", "mlp_bwd_fused_kernel<8,16,false>",
+                                 "WeightNet layer 8->16 backward (dA, y, x_prev read; dA_prev written; dW, db, lower BatchNorm sums) at the "
+                                 "level-0 edge count E=%d" % (n * K), "chain", "mlp_bwd_fused_kernel<8, 16"),
+        "mlp_fwd_kernel": ("chain_fwd_8x16", "mlp_fwd_kernel<8,16>", "WeightNet layer 8->16 forward + BatchNorm partial sums, E=%d" % (n * K),
+                           "chain", "mlp_fwd_kernel<8, 16"),
+        "pconv_fwd_ws_kernel": (fwd_key, kname if fwd_key != "fused_fwd_simt" else "pconv_fwd_simt_kernel<16>",
+                                "level-0 PointConvStridePE contraction: N=%d K=16 C_in=16 C_add=16 C_mid=16 C_out=32, P saved" % n,
+                                "fwdp", "pconv_fwd_ws"),
+    }
+    return res, models, peaks
+
+
+def make_roofline(res, models, peaks, shares):
+    """`roofline` = the modelled kernel family with the largest share of the step (shares: family -> fraction of the summed
+    kernel time of one replayed step, None when no profile is available: then the chain backward, round 1's dominant group)."""
+    fam = "mlp_bwd_fused_kernel"
+    if shares:
+        fam = max(models, key=lambda f: shares.get(f, 0.0))
+    key, kname, shape, ncu_op, ncu_sub = models[fam]
+    r = res[key]
+    traffic = ncu_traffic(ncu_op, ncu_sub)
+    return {"kernel": kname, "shape": shape, "bound": "hbm", "achieved": r["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": r["frac_hbm"], "traffic": traffic["bytes"] if traffic else None,
+            "traffic_source": traffic["source"] if traffic else None, "peak_source": peaks["src"], "ms": r["ms"],
+            "alg_bytes_per_launch": r["alg_bytes"], "step_share": (shares or {}).get(fam),
+            "why": "largest share of the step's kernel time among the kernels with a single-launch HBM model "
+                   "(the other groups are listed under step.top_kernels and kernels)"}
+
+
+def chain_kernels(dev, E, time_op, peaks):
+    """The per-edge MLP chain kernels (csrc/mlp.cu) timed alone at the level-0 edge count: forward and fused backward of the
+    WeightNet's widest layer (8 -> 16), straight through the C ABI."""
+    import ctypes
+    from pcf_b200._lib import lib, ptr, check, stream_ptr
+    cin, cout = 8, 16
+    g = torch.Generator(device="cpu").manual_seed(1)
+    mk = lambda *shape: torch.randn(*shape, generator=g).to(dev)
+    x, dA, W, b = mk(E, cin), mk(E, cout), mk(cout, cin) * 0.3, mk(cout) * 0.1
+    y = torch.empty(E, cout, device=dev)
+    vec = lambda c, lo=0.5: (lo + torch.rand(c, generator=g)).to(dev)
+    scale, shift, mean, invstd, sums = vec(cout), vec(cout, -0.5), vec(cout, -0.5), vec(cout), mk(2 * cout)
+    p_scale, p_shift, p_mean, p_invstd = vec(cin), vec(cin, -0.5), vec(cin, -0.5), vec(cin)
+    dA_prev, prev_sums = torch.empty(E, cin, device=dev), torch.empty(2 * cin, device=dev)
+    dW, db = torch.empty(cout, cin, device=dev), torch.empty(cout, device=dev)
+    ws_bytes = lib().pcfb_mlp_workspace(E, cin, cout)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    nblk = ctypes.c_int(0)
+
+    def fwd():
+        check(lib().pcfb_mlp_forward(ptr(x), cin, E, cin, cout, ptr(W), ptr(b), ptr(p_scale), ptr(p_shift), 1, ptr(y), cout, ptr(ws),
+                                     ctypes.addressof(nblk), stream_ptr()), "mlp_forward")
+
+    def bwd():
+        check(lib().pcfb_mlp_backward(ptr(dA), cout, ptr(y), cout, E, cin, cout, ptr(W), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                                      ptr(sums), 1, ptr(x), cin, ptr(p_scale), ptr(p_shift), 1, ptr(p_mean), ptr(p_invstd), ptr(dA_prev),
+                                      cin, ptr(prev_sums), ptr(dW), ptr(db), 0, ptr(ws), ws_bytes, stream_ptr()), "mlp_backward")
+    out = {}
+    ms = time_op(fwd)
+    byts = 4.0 * E * (cin + cout)
+    out["chain_fwd_8x16"] = {"ms": ms, "alg_bytes": byts, "GBps": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"]}
+    ms = time_op(bwd)
+    byts = 4.0 * E * (2 * cout + 2 * cin)
+    out["chain_bwd_8x16"] = {"ms": ms, "alg_bytes": byts, "GBps": byts / ms / 1e6, "frac_hbm": byts / ms / 1e6 / peaks["hbm_gbs"],
+                             "note": "mlp_bwd_fused_kernel<8,16> + its 4 us finalize launch"}
+    return out
+
+
+def step_profile(replay):
+    """CUPTI kernel records of ONE replay of the captured step (torch.profiler): per kernel family launches / time / share of
+    the summed kernel time, the time spent in sub-wave launches (< 148 CTAs), wall vs busy time and the mean concurrency."""
+    import collections
+    import re
+    import tempfile
+    from torch.profiler import profile, ProfilerActivity
+    replay(); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        replay()
+        torch.cuda.synchronize()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "trace.json")
+        prof.export_chrome_trace(path)
+        events = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]
+    fam = collections.defaultdict(lambda: [0, 0.0])
+    spans, sub_us, sub_n = [], 0.0, 0
+    for e in events:
+        name = re.sub(r"[<(].*$", "", e["name"]).replace("void ", "").replace("pcfb::", "")
+        fam[name][0] += 1
+        fam[name][1] += e["dur"]
+        ctas = 1
+        for gdim in (e.get("args", {}).get("grid") or [1]):
+            ctas *= int(gdim)
+        if ctas < 148:
+            sub_us += e["dur"]; sub_n += 1
+        spans.append((e["ts"], e["ts"] + e["dur"]))
+    spans.sort()
+    busy, cs, ce = 0.0, None, None
+    for a, b in spans:
+        if ce is None or a > ce:
+            busy += (ce - cs) if ce is not None else 0.0
+            cs, ce = a, b
+        else:
+            ce = max(ce, b)
+    busy += ce - cs
+    total = sum(v[1] for v in fam.values())
+    top = sorted(fam.items(), key=lambda kv: -kv[1][1])[:12]
+    return {"launches": len(events), "wall_ms": (max(b for _, b in spans) - spans[0][0]) / 1e3, "busy_ms": busy / 1e3,
+            "kernel_ms_sum": total / 1e3, "mean_concurrency": total / max(busy, 1e-9),
+            "ms_subwave": sub_us / 1e3, "launches_subwave": sub_n,
+            "top_kernels": [{"kernel": k, "launches": v[0], "ms": v[1] / 1e3, "share": v[1] / total} for k, v in top],
+            "shares": {k: v[1] / total for k, v in fam.items()}}
 
 
 def knn_sweep(args):

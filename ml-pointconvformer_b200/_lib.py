@@ -131,5 +131,16 @@ def workspace(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
+# Algorithmic work of the step at the op boundary (compulsory reads + writes, useful FLOPs), accumulated by the Python wrappers
+# while bench.py runs one eager step with ACCOUNT = {"bytes": 0.0, "flops": 0.0} (None = off, the default).
+ACCOUNT = None
+
+
+def account(nbytes, flops=0.0):
+    if ACCOUNT is not None:
+        ACCOUNT["bytes"] += float(nbytes)
+        ACCOUNT["flops"] += float(flops)
+
+
 def launch_count():
     return int(lib().pcfb_launch_count())

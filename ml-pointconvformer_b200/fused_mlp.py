@@ -185,6 +185,7 @@ class _ChainFunction(torch.autograd.Function):
             ws = workspace(lib().pcfb_mlp_workspace(E, cin, cout), dev) if want_stats else None
             check(lib().pcfb_mlp_forward(ptr(cur), ld, E, cin, cout, ptr(W), ptr(b), ptr(in_scale), ptr(in_shift), in_act,
                                          ptr(y), cout, ptr(ws), ctypes.addressof(nblk), stream_ptr()), "mlp_forward")
+            _lib.account(4.0 * E * (cin + cout), 2.0 * E * cin * cout)
             scale = shift = mean = invstd = d_count = None
             if s["has_bn"]:
                 rm, rv, nbt = buffers[l]
@@ -203,6 +204,7 @@ class _ChainFunction(torch.autograd.Function):
             in_scale, in_shift, in_act = scale, shift, s["act"]
         out = torch.empty_like(ys[-1])
         check(lib().pcfb_bn_act(ptr(ys[-1]), E, ys[-1].shape[1], ptr(in_scale), ptr(in_shift), in_act, ptr(out), stream_ptr()), "bn_act")
+        _lib.account(8.0 * E * ys[-1].shape[1])
         ctx.spec, ctx.counts = spec, counts
         ctx.n_layers = L
         saved = [x2] + ys + list(params)
@@ -235,6 +237,7 @@ class _ChainFunction(torch.autograd.Function):
             check(lib().pcfb_mlp_backward_stats(ptr(dA_l), dA_l.stride(0), ptr(ys[l]), C, E, C, ptr(scale), ptr(shift), ptr(mean),
                                                 ptr(invstd), spec[l]["act"], 0, ctypes.addressof(nblk), ptr(ws), ws.numel(),
                                                 stream_ptr()), "mlp_backward_stats")
+            _lib.account(8.0 * E * C)
             return bn_reduce_sums(ws, nblk.value, C, spec[l]["sync"] and spec[l]["train"], dev)
 
         def affine_needed(l):
@@ -284,6 +287,7 @@ class _ChainFunction(torch.autograd.Function):
                 ptr(x_prev), ldx, ptr(p_scale), ptr(p_shift), in_act, ptr(p_mean), ptr(p_invstd),
                 ptr(dA_prev), cin, ptr(prev_sums), ptr(dW), ptr(db), ptr(d_count),
                 ptr(ws), ws.numel(), stream_ptr()), "mlp_backward")
+            _lib.account(4.0 * E * (2 * cout + cin + (cin if want_prev else 0)), (4.0 if want_prev else 2.0) * E * cin * cout)
             grads[4 * l] = dW
             grads[4 * l + 1] = db
             if has_bn and gamma is not None and sums_local is not None:
@@ -347,6 +351,7 @@ class _BnActFunction(torch.autograd.Function):
             ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
             nblk = ctypes.c_int(0)
             check(lib().pcfb_bn_stats(ptr(x2), rows, C, ptr(pivot), ptr(ws), ws.numel(), ctypes.addressof(nblk), stream_ptr()), "bn_stats")
+            _lib.account(4.0 * rows * C)
             scale, shift, mean, invstd, d_count = bn_finalize(ws, nblk.value, C, rows, pivot, gamma, beta, cfg["eps"], cfg["momentum"],
                                                               running_mean, running_var, cfg["nbt"], cfg["sync"], dev)
         else:
@@ -356,6 +361,7 @@ class _BnActFunction(torch.autograd.Function):
             mean = running_mean
         out = torch.empty_like(x2)
         check(lib().pcfb_bn_act(ptr(x2), rows, C, ptr(scale), ptr(shift), act, ptr(out), stream_ptr()), "bn_act")
+        _lib.account(8.0 * rows * C)
         ctx.cfg, ctx.d_count = cfg, d_count
         ctx.has_affine = gamma is not None
         ctx.save_for_backward(x2, scale, shift, mean, invstd)
@@ -377,6 +383,7 @@ class _BnActFunction(torch.autograd.Function):
             nblk = ctypes.c_int(0)
             check(lib().pcfb_bn_backward_stats(ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cfg["act"],
                                                0, ctypes.addressof(nblk), ptr(ws), ws.numel(), stream_ptr()), "bn_backward_stats")
+            _lib.account(8.0 * rows * C)
             # dx: sums over the global batch; dgamma / dbeta stay local
             sums, local = bn_reduce_sums(ws, nblk.value, C, cfg["sync"] and cfg["training"], dev)
         dx = None
@@ -384,6 +391,7 @@ class _BnActFunction(torch.autograd.Function):
             dx = torch.empty_like(x2)
             check(lib().pcfb_bn_backward(ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
                                          ptr(sums) if cfg["training"] else 0, cfg["act"], ptr(ctx.d_count), ptr(dx), stream_ptr()), "bn_backward")
+            _lib.account(12.0 * rows * C)
         dgamma = local[C:] if need_affine else None
         dbeta = local[:C] if need_affine else None
         return dx, dgamma, dbeta, None, None, None, None

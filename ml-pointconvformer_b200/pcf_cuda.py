@@ -83,6 +83,8 @@ def _pconv_fwd(inp, nei, weights, additional, guidance, lin_w, lin_b, want_p, va
             ptr(additional[b]) if C_add else 0, ptr(guidance[b]) if H else 0,
             ptr(lin_w), ptr(lin_b), ptr(out_y[b]) if out_y is not None else 0,
             ptr(out_p[b]) if out_p is not None else 0, ptr(ws), ws_bytes, v, stream_ptr()), "pconv_forward")
+    _lib.account(B * (M * (8.0 * K + 4.0 * K * (C_mid + C_add + H) + 4.0 * C_out + (4.0 * KK if out_p is not None else 0.0)) + 4.0 * N_in * C_in),
+                 B * M * (2.0 * K * (C_in + C_add) * C_mid + 2.0 * KK * C_out))
     return out_y, out_p
 
 
@@ -127,6 +129,9 @@ def _pconv_bwd(grad_y, grad_p, inp, inv, nei, weights, additional, guidance, lin
             ptr(pconv_out[b]) if pconv_out is not None else 0,
             ptr(g_in[b]) if n_in else 0, ptr(g_w[b]) if n_w else 0, ptr(g_add[b]) if n_add else 0,
             ptr(g_gd[b]) if n_gd else 0, ptr(g_lw), ptr(g_lb), ptr(ws), ws_bytes, 0, stream_ptr()), "pconv_backward")
+        KK = (C_in + C_add) * C_mid
+        _lib.account(M * (8.0 * K + 5.0 * K + 4.0 * C_out + 4.0 * KK + 8.0 * K * (C_mid + C_add + H)) + 8.0 * N_in * C_in + 4.0 * C_out * KK,
+                     2.0 * M * (2.0 * K * (C_in + C_add) * C_mid + 2.0 * KK * C_out))
         if leaf:
             g_lw, g_lb = S.fork_leaf(lambda: gemm_tn(grad_y[b], pconv_out[b], want_rowsum=True))
         if n_lw:
@@ -227,6 +232,7 @@ def compute_knn_inverse(neighbor_inds, total_points):
     for b in range(B):
         check(lib().pcfb_knn_inverse(ptr(neighbor_inds[b]), N, K, total, ptr(inv_n[b]), ptr(inv_k[b]), ptr(inv_idx[b]),
                                      ptr(ws), ws_bytes, stream_ptr()), "compute_knn_inverse")
+        _lib.account(13.0 * N * K + 4.0 * (total + 1))
     return inv_n, inv_k, inv_idx
 
 
@@ -283,6 +289,7 @@ def gemm_nt(x, w, bias=None, w_is_kn=False, act=0):
     ws = workspace(ws_bytes, x.device)
     check(lib().pcfb_gemm_nt(ptr(x), x.stride(0), ptr(w), w.stride(0), 1 if w_is_kn else 0, ptr(bias), ptr(out), N, M, N, K, int(act),
                              ptr(ws), ws_bytes, stream_ptr()), "gemm_nt")
+    _lib.account(4.0 * (M * K + N * K + M * N), 2.0 * M * N * K)
     return out
 
 
@@ -301,6 +308,7 @@ def gemm_tn(a, b, want_rowsum=False):
     ws = workspace(ws_bytes, a.device)
     check(lib().pcfb_gemm_tn(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), N2, ptr(rs), M, N1, N2, ptr(ws), ws_bytes,
                              stream_ptr()), "gemm_tn")
+    _lib.account(4.0 * (M * N1 + M * N2 + N1 * N2), 2.0 * M * N1 * N2)
     return out, rs
 
 
@@ -344,6 +352,7 @@ class KnnGrid:
         out = torch.empty(qry_xyz.shape[0], K, device=qry_xyz.device, dtype=I64)
         check(lib().pcfb_knn_grid_query(ptr(self.ref), self.n_seg, self.ref.shape[0], ptr(qry_xyz), ptr(qo), qry_xyz.shape[0],
                                         int(K), ptr(out), ptr(self.ws), self.ws_bytes, stream_ptr()), "knn_grid_query")
+        _lib.account(12.0 * (self.ref.shape[0] + qry_xyz.shape[0]) + 8.0 * K * qry_xyz.shape[0])
         return out
 
 
@@ -353,6 +362,7 @@ def gather(feats, nei):
     M, K = nei.shape
     out = torch.empty(M, K, feats.shape[1], device=feats.device, dtype=F32)
     check(lib().pcfb_gather(ptr(feats), ptr(nei), feats.shape[0], M, K, feats.shape[1], ptr(out), stream_ptr()), "gather")
+    _lib.account(8.0 * M * K + 4.0 * feats.numel() + 4.0 * out.numel())
     return out
 
 
@@ -362,6 +372,7 @@ def gather_backward(grad_out, inv, n_in):
     g = torch.empty(n_in, C, device=grad_out.device, dtype=F32)
     check(lib().pcfb_gather_backward(ptr(grad_out), ptr(inv[0]), ptr(inv[1]), ptr(inv[2]), n_in, M, K, C, ptr(g),
                                      stream_ptr()), "gather_backward")
+    _lib.account(4.0 * grad_out.numel() + 5.0 * M * K + 4.0 * (n_in + 1) + 4.0 * g.numel())
     return g
 
 
@@ -372,6 +383,7 @@ def gather_max(feats, nei):
     out = torch.empty(M, C, device=feats.device, dtype=F32)
     arg = torch.empty(M, C, device=feats.device, dtype=U8)
     check(lib().pcfb_gather_max(ptr(feats), ptr(nei), feats.shape[0], M, K, C, ptr(out), ptr(arg), stream_ptr()), "gather_max")
+    _lib.account(8.0 * M * K + 4.0 * feats.numel() + 5.0 * out.numel())
     return out, arg
 
 
@@ -381,6 +393,7 @@ def gather_max_backward(grad_out, arg, inv, n_in, K):
     g = torch.empty(n_in, C, device=grad_out.device, dtype=F32)
     check(lib().pcfb_gather_max_backward(ptr(grad_out), ptr(arg), ptr(inv[0]), ptr(inv[1]), ptr(inv[2]), n_in, M, K, C,
                                          ptr(g), stream_ptr()), "gather_max_backward")
+    _lib.account(5.0 * grad_out.numel() + 5.0 * M * K + 4.0 * (n_in + 1) + 4.0 * g.numel())
     return g
 
 
@@ -394,6 +407,7 @@ def guidance_input(gx, pe, nei, use_max):
     arg = torch.empty(M, G + P, device=gx.device, dtype=U8) if use_max else None
     check(lib().pcfb_guidance_input(ptr(gx), ptr(pe), ptr(nei), gx.shape[0], M, K, G, P, 1 if use_max else 0, ptr(out), ptr(arg),
                                     stream_ptr()), "guidance_input")
+    _lib.account(8.0 * M * K + 4.0 * gx.numel() + 4.0 * pe.numel() + 4.0 * out.numel())
     return out, arg
 
 
@@ -405,6 +419,7 @@ def guidance_input_backward(ds, arg, G, P, use_max, want_gq=True, want_pe=True):
     d_pe = torch.empty(M, K, P, device=ds.device, dtype=F32) if want_pe else None
     check(lib().pcfb_guidance_input_backward(ptr(ds), ptr(arg), M, K, G, P, 1 if use_max else 0, ptr(d_gq), ptr(d_pe), stream_ptr()),
           "guidance_input_backward")
+    _lib.account(8.0 * ds.numel())
     return d_gq, d_pe
 
 
@@ -420,6 +435,7 @@ def edge_geometry(xyz_in, nrm_in, xyz_out, nrm_out, nei, want_r=True, want_vi=Tr
         vi = torch.empty(M, K, 12, device=dev, dtype=F32)
     check(lib().pcfb_edge_geometry(ptr(xyz_in), ptr(nrm_in), ptr(xyz_out), ptr(nrm_out), ptr(nei), xyz_in.shape[0], M, K,
                                    ptr(r), ptr(vi), stream_ptr()), "edge_geometry")
+    _lib.account(8.0 * M * K + 24.0 * (xyz_in.shape[0] + M) + (12.0 * M * K if want_r else 0.0) + (48.0 * M * K if want_vi else 0.0))
     return r, vi
 
 
@@ -517,4 +533,5 @@ def pyramid_level(xyz, feats, seg_off, n_seg, dl, boxes, status):
     ws = workspace(ws_bytes, dev)
     check(lib().pcfb_pyramid_level(ptr(xyz), ptr(feats), F, ptr(seg_off), n_seg, n_max, float(dl), cells_max, ptr(out_xyz),
                                    ptr(out_f), ptr(out_off), ptr(status), ptr(ws), ws_bytes, stream_ptr()), "pyramid_level")
+    _lib.account(n_max * (12.0 * 3 + 4.0 * F * 2 + 8.0) + 12.0 * cells_max)
     return out_xyz, out_f, out_off

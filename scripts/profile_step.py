@@ -21,11 +21,15 @@ def main():
     flat = sharding.FlatParameters(model, async_weight_grads=True)
     opt = sharding.FlatAdamW(flat, lr=1e-3, weight_decay=0.05, max_norm=10.0)
     from pcf_b200 import losses
-    host = bench.host_pyramid(1, args.points, cfgd["grid_size"], args.scenes)
-    pts = [torch.from_numpy(p).to(dev) for p in host["points"]]
-    nrm = [torch.from_numpy(p).to(dev) for p in host["normals"]]
+    host = bench.host_scenes(1, args.points, cfgd["grid_size"], args.scenes)
+    from pcf_b200 import grid_subsampling as GS
+    p0, n0 = torch.from_numpy(host["points0"]).to(dev), torch.from_numpy(host["normals0"]).to(dev)
     col, lab = torch.from_numpy(host["colors"]).to(dev), torch.from_numpy(host["labels"]).to(dev)
+    _, _, stored, pyr = GS.build_pyramid(p0, n0, host["stored0"], cfgd["grid_size"])
+    host["stored"] = stored
     def step():
+        with torch.profiler.record_function("pyramid"):
+            pts, nrm, _, _ = GS.build_pyramid(p0, n0, host["stored0"], cfgd["grid_size"], expect=stored, boxes=pyr["boxes"])
         pcs = [p.unsqueeze(0) for p in pts]; nrms = [p.unsqueeze(0) for p in nrm]
         with torch.profiler.record_function("edges_knn"):
             es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, host["stored"], cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"], grid_size=cfgd["grid_size"]))
