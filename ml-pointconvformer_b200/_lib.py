@@ -68,6 +68,7 @@ SIGNATURES = {
     "pcfb_gridsub_bounds": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "pcfb_gridsub_count": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_int64, _P, _P, c_size_t, _P]),
     "pcfb_gridsub_emit": (c_int, [_P, _P, c_int, c_int, c_int, c_int64, _P, _P, _P, c_size_t, _P]),
+    "pcfb_set_point_kernel_max": (c_int, [c_int]),
     "pcfb_voxelize_workspace": (c_size_t, [c_int, c_int, c_int64]),
     "pcfb_voxelize": (c_int, [_P, _P, c_int, c_int, ctypes.c_double, c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "pcfb_pyramid_level_workspace": (c_size_t, [c_int, c_int, c_int64]),

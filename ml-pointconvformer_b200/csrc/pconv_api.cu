@@ -48,7 +48,28 @@ bool pconv_bwd2_supported(const pcfb_pconv_shape *s);
 int pconv_bwd2(const pcfb_pconv_shape *s, const float *dP, const float *feats, const int64_t *nei, const float *weights,
                const float *additional, const float *guidance, float *grad_weights, float *grad_additional,
                float *grad_guidance, float *grad_edge, cudaStream_t st);
+// pconv_point.cu (one CTA per output point: the coarse levels of the pyramid)
+bool pconv_point_supported(const pcfb_pconv_shape *s);
+int pconv_point_max_points();
+int pconv_point_bwd(const pcfb_pconv_shape *s, const float *dP, const float *feats, const int64_t *nei, const float *weights,
+                    const float *additional, const float *guidance, float *grad_weights, float *grad_additional,
+                    float *grad_guidance, float *grad_edge, cudaStream_t st);
+int pconv_point_fwd_p(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
+                      const float *additional, const float *guidance, float *P, cudaStream_t st);
 }  // namespace pcfb
+
+// coarse levels: per-point CTAs (pconv_point.cu) instead of the tiled kernels
+static bool point_path(const pcfb_pconv_shape *s) {
+    return s->n_out > 0 && s->n_out <= pcfb::pconv_point_max_points() && pcfb::pconv_point_supported(s);
+}
+// the contraction backward on dP: per-point kernel on the coarse levels, the pipelined tiled kernel otherwise
+static int contraction_backward(const pcfb_pconv_shape *s, const float *dP, const float *feats, const int64_t *nei,
+                                const float *weights, const float *additional, const float *guidance, float *grad_weights,
+                                float *grad_additional, float *grad_guidance, float *grad_edge, cudaStream_t st) {
+    if (point_path(s))
+        return pcfb::pconv_point_bwd(s, dP, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance, grad_edge, st);
+    return pcfb::pconv_bwd2(s, dP, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance, grad_edge, st);
+}
 
 static bool mid1_path(const pcfb_pconv_shape *s, int variant) {
     return variant != 1 && variant != 3 && variant != 4 && s->C_out >= 1 && s->C_out <= 256 && pcfb::pconv_mid1_supported(s);
@@ -58,6 +79,7 @@ static bool mid1_path(const pcfb_pconv_shape *s, int variant) {
 // P by the CUDA-core contraction kernel, Y = P W^T + b as a column-block tensor-core GEMM.  The simple tcgen05 kernel
 // these shapes used before keeps 2-3 CTAs busy for ~0.4 ms.
 static bool compose_path(const pcfb_pconv_shape *s) {
+    if (s->C_out > 0 && s->C_mid > 1 && point_path(s) && s->n_out <= pcfb::pconv_point_max_points() / 2) return true;
     return s->C_out > 0 && s->C_mid > 1 && !pcfb::pconv_forward_ws_supported(s, true) && !pcfb::pconv_forward_umma2_supported(s, true);
 }
 
@@ -78,7 +100,13 @@ extern "C" size_t pcfb_pconv_forward_workspace(const pcfb_pconv_shape *s, int va
     if (mid1_path(s, variant))
         return pcfb::align_up((size_t)s->n_out * (s->C_in + s->C_add) * sizeof(float), 256) + pcfb_gemm_nt_workspace(s->C_out, s->C_in + s->C_add);
     size_t ws = 0;                                      // auto may fall from one tcgen05 kernel to the next: size for all
-    if ((variant == 0 || variant == 4) && pcfb::pconv_forward_ws_supported(s, s->C_out > 0)) ws = pcfb::pconv_forward_ws_workspace(s);
+    if (variant == 0 && compose_path(s))
+        ws = pcfb::align_up((size_t)s->n_out * (s->C_in + s->C_add) * s->C_mid * sizeof(float), 256) +
+             pcfb_gemm_nt_workspace(s->C_out, (s->C_in + s->C_add) * s->C_mid);
+    if ((variant == 0 || variant == 4) && pcfb::pconv_forward_ws_supported(s, s->C_out > 0)) {
+        const size_t w1 = pcfb::pconv_forward_ws_workspace(s);
+        ws = w1 > ws ? w1 : ws;
+    }
     if (variant == 4) return ws;
     if (variant != 3 && pcfb::pconv_forward_umma2_supported(s, s->C_out > 0)) {
         const size_t w2 = pcfb::pconv_forward_umma2_workspace(s);
@@ -118,7 +146,8 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
         return pcfb_gemm_nt(P, C_cat, lin_w, C_cat, 0, lin_b, out_y, s->C_out, s->n_out, s->C_out, C_cat, 0,
                             static_cast<char *>(workspace) + p_bytes, nt_bytes, stream);
     }
-    if (variant == 0 || variant == 4) {
+    const bool small_compose = variant == 0 && lin_w && compose_path(s) && point_path(s);
+    if (!small_compose && (variant == 0 || variant == 4)) {
         const bool aligned = ((uintptr_t)feats % 16 == 0) && (s->C_add == 0 || (uintptr_t)additional % 16 == 0) &&
                              (s->H == 0 || (uintptr_t)guidance % 16 == 0);
         if (lin_w && (variant == 4 || aligned) && pconv_forward_ws_supported(s, true))
@@ -136,7 +165,8 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
         PCFB_REQUIRE(workspace && workspace_bytes >= p_bytes + nt_bytes, "pcfb_pconv_forward: workspace too small");
         float *P = out_p ? out_p : static_cast<float *>(workspace);
         int rc;
-        if (s->n_out <= 16384 && pconv_p_small_supported(s, weights, P)) rc = pconv_p_small(s, feats, nei, weights, additional, guidance, P, st);
+        if (point_path(s)) rc = pconv_point_fwd_p(s, feats, nei, weights, additional, guidance, P, st);
+        else if (s->n_out <= 16384 && pconv_p_small_supported(s, weights, P)) rc = pconv_p_small(s, feats, nei, weights, additional, guidance, P, st);
         else rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, P, st);
         if (rc) return rc;
         return pcfb_gemm_nt(P, KK, lin_w, KK, 0, lin_b, out_y, s->C_out, s->n_out, s->C_out, KK, 0,
@@ -216,8 +246,8 @@ extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_
         PCFB_REQUIRE(!grad_feats || (workspace && workspace_bytes >= need), "pcfb_pconv_backward: workspace too small");
         PCFB_REQUIRE(!grad_feats || (inv_neighbors && inv_k && inv_idx), "pcfb_pconv_backward: grad_feats needs the inverse map");
         float *grad_edge = grad_feats ? static_cast<float *>(workspace) : nullptr;
-        int rc0 = pconv_bwd2(s, grad_p, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance,
-                             grad_edge, st);
+        int rc0 = contraction_backward(s, grad_p, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance,
+                                       grad_edge, st);
         if (rc0 || !grad_feats) return rc0;
         return pcfb_gather_backward(grad_edge, inv_neighbors, inv_k, inv_idx, s->n_in, s->n_out, s->K, s->C_in, grad_feats, stream);
     }
@@ -254,8 +284,8 @@ extern "C" int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_
     if (pconv_bwd2_supported(s)) {
         float *grad_edge = grad_feats ? static_cast<float *>(w.simt_ws) : nullptr;     // [n_out, K, C_in] scratch
         PCFB_REQUIRE(!grad_feats || (inv_neighbors && inv_k && inv_idx), "pcfb_pconv_backward: grad_feats needs the inverse map");
-        if ((rc = pconv_bwd2(s, w.dP, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance,
-                             grad_edge, st))) return rc;
+        if ((rc = contraction_backward(s, w.dP, feats, nei, weights, additional, guidance, grad_weights, grad_additional, grad_guidance,
+                                       grad_edge, st))) return rc;
         if (grad_feats)
             return pcfb_gather_backward(grad_edge, inv_neighbors, inv_k, inv_idx, s->n_in, s->n_out, s->K, s->C_in, grad_feats, stream);
         return PCFB_OK;

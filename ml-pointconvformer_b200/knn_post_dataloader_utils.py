@@ -70,27 +70,28 @@ def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagat
     small = [max(counts[j]) <= BRUTE_MAX_REFS for j in range(L)]
     hint = lambda j: 2.5 * float(grid_size[j]) if grid_size is not None else 0.0
 
-    def against(jr):
-        """Everything that searches reference level jr: its grid build, then the self / propagate / forward queries.  The five
-        levels are independent of each other, so each runs on its own side stream (streams.fork): the step's 13 edge sets cost
-        the level-0 chain (build + two queries) instead of the sum of all of them."""
-        grid = None if small[jr] else pcf_cuda.KnnGrid(pcs[jr], counts[jr], hint(jr))
-
-        def query(jq, K):
-            if grid is None:
-                return pcf_cuda.knn_packed(pcs[jr], counts[jr], pcs[jq], counts[jq], K)
-            return grid.query(pcs[jq], counts[jq], K)
-        return (query(jr, K_self[jr]),                                        # self
-                query(jr - 1, K_propagate[jr]) if jr >= 1 else None,         # propagate: dense level jr-1 looks into jr
-                query(jr + 1, K_forward[jr + 1]) if jr + 1 < L else None)    # forward: level jr+1 looks into jr
-    branches = [S.fork(lambda j=j: against(j), j) for j in range(L)]
-    res = [S.join(b) for b in branches]
+    # Two fork / join stages over the side streams (streams.fork): the five grid builds, then the 13 queries -- the heaviest
+    # first, so that the two 100k-query sets (level-0 self, level-0 -> level-1 propagate) land on different streams.  The
+    # step's edge construction then costs one large query instead of the sum of all of them.
+    builds = [S.fork(lambda j=j: None if small[j] else pcf_cuda.KnnGrid(pcs[j], counts[j], hint(j)), j) for j in range(L)]
+    grids = [S.join(b) for b in builds]
+    jobs = []                                                        # (kind, level index in the output list, jr, jq, K)
     for j in range(L):
-        e_self.append(res[j][0])
+        jobs.append(("self", j, j, j, K_self[j]))
         if j >= 1:
-            e_fwd.append(res[j - 1][2])
-            e_prop.append(res[j][1])
-    return [e_self], [e_fwd], [e_prop]
+            jobs.append(("fwd", j - 1, j - 1, j, K_forward[j]))      # level j looks into level j-1
+            jobs.append(("prop", j - 1, j, j - 1, K_propagate[j]))   # dense level j-1 looks into level j
+    jobs.sort(key=lambda t: -pcs[t[3]].shape[0])
+
+    def query(jr, jq, K):
+        if grids[jr] is None:
+            return pcf_cuda.knn_packed(pcs[jr], counts[jr], pcs[jq], counts[jq], K)
+        return grids[jr].query(pcs[jq], counts[jq], K)
+    running = [(job, S.fork(lambda job=job: query(job[2], job[3], job[4]), i)) for i, job in enumerate(jobs)]
+    out = {"self": [None] * L, "fwd": [None] * (L - 1), "prop": [None] * (L - 1)}
+    for job, br in running:
+        out[job[0]][job[1]] = S.join(br)
+    return [out["self"]], [out["fwd"]], [out["prop"]]
 
 
 def tensorizeTensorList(tensor_list):

@@ -17,7 +17,7 @@ import os
 import torch
 
 ENABLED = os.environ.get("PCFB_STREAMS", "1") != "0"
-N_SIDE = 3
+N_SIDE = 4
 _POOL = {}
 # Weight-gradient products (dW = dY^T X of every Linear, dW of the fused contraction's Linear) are LEAVES of the backward
 # graph: nothing downstream waits for them except the optimizer.  With LEAF_ASYNC they run on their own stream and are only

@@ -77,13 +77,13 @@ def main():
             ctas = 1
             for gdim in (grid or [1]):
                 ctas *= int(gdim)
-            spans.append((ev["ts"], ev["ts"] + ev["dur"], ev["dur"], ctas, ev.get("args", {}).get("stream")))
+            spans.append((ev["ts"], ev["ts"] + ev["dur"], ev["dur"], ctas, ev.get("args", {}).get("stream"), name[:44]))
     os.remove(trace)
     # timeline summary: is the step bound by work or by dependent-launch latency?
     spans.sort()
-    wall = max(e for _, e, _, _, _ in spans) - spans[0][0]
+    wall = max(x[1] for x in spans) - spans[0][0]
     busy, cur_s, cur_e = 0.0, None, None
-    for s0, e0, _, _, _ in spans:
+    for s0, e0, _, _, _, _ in spans:
         if cur_e is None or s0 > cur_e:
             if cur_e is not None:
                 busy += cur_e - cur_s
@@ -91,17 +91,32 @@ def main():
         else:
             cur_e = max(cur_e, e0)
     busy += cur_e - cur_s
-    total = sum(d for _, _, d, _, _ in spans)
-    sub = sum(d for _, _, d, c, _ in spans if c < 148)
+    total = sum(x[2] for x in spans)
+    sub = sum(x[2] for x in spans if x[3] < 148)
+    # approximate critical path: from the last kernel walk back to the kernel that finished latest before it started
+    import bisect
+    by_end = sorted(spans, key=lambda x: x[1])
+    ends = [x[1] for x in by_end]
+    cur = by_end[-1]
+    crit = collections.defaultdict(lambda: [0, 0.0])
+    gap_total, n_crit = 0.0, 0
+    while True:
+        crit[cur[5]][0] += 1; crit[cur[5]][1] += cur[2]; n_crit += 1
+        i = bisect.bisect_right(ends, cur[0] + 0.5) - 1
+        while i >= 0 and by_end[i] is cur:
+            i -= 1
+        if i < 0:
+            break
+        gap_total += max(0.0, cur[0] - by_end[i][1])
+        cur = by_end[i]
     with open(os.path.join(ROOT, "gpurun_out", "prof_timeline.txt"), "w") as f:
         f.write("kernels %d  wall %.1f us  GPU busy (union of kernel spans) %.1f us  idle %.1f us  sum of kernel durations %.1f us "
                 "(avg concurrency %.2f)  sub-wave (<148 CTAs) kernels: %d launches, %.1f us\n"
                 % (len(spans), wall, busy, wall - busy, total, total / max(busy, 1e-9), sum(1 for x in spans if x[3] < 148), sub))
-        per_stream = collections.defaultdict(float)
-        for _, _, d, _, st in spans:
-            per_stream[st] += d
-        for st, d in sorted(per_stream.items(), key=lambda kv: -kv[1]):
-            f.write("  stream %s: %.1f us of kernels\n" % (st, d))
+        f.write("approximate critical path: %d kernels, %.1f us of kernels + %.1f us of gaps; by kernel:\n"
+                % (n_crit, sum(v[1] for v in crit.values()), gap_total))
+        for k, v in sorted(crit.items(), key=lambda kv: -kv[1][1])[:40]:
+            f.write("  %-46s %4d launches %9.1f us\n" % (k, v[0], v[1]))
     print(open(os.path.join(ROOT, "gpurun_out", "prof_timeline.txt")).read())
     with open(os.path.join(ROOT, "gpurun_out", "prof_kernels_by_grid.txt"), "w") as f:
         f.write("# one training step, CUPTI kernel durations grouped by (kernel, grid): calls, mean us, total us\n")

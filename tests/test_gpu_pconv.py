@@ -21,6 +21,16 @@ def _pc():
     return pcf_cuda
 
 
+@pytest.fixture(params=[12000, 0], ids=["point_kernels", "tiled_kernels"], autouse=True)
+def point_kernel_threshold(request):
+    """Every case runs twice: with the per-point CTA kernels of the coarse levels (csrc/pconv_point.cu, taken below 12000
+    output points) and with the tiled kernels only -- same results either way."""
+    from pcf_b200 import _lib
+    old = _lib.lib().pcfb_set_point_kernel_max(request.param)
+    yield
+    _lib.lib().pcfb_set_point_kernel_max(old)
+
+
 def make_case(seed, n_in, n_out, K, C_in, C_add, C_mid, C_out, H, pad=False):
     g = torch.Generator().manual_seed(seed)
     d = dict(
