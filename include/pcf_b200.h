@@ -197,7 +197,7 @@ int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int cout, cons
                      const float *in_scale, const float *in_shift, int in_act, float *y, int ldy,
                      float *stat_partial, int *h_nblocks, void *stream);
 int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
-                void *stream);
+                const float *residual /* optional [rows, C] */, int residual_after_act, void *stream);
 int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y, int ldy, int64_t E, int C, const float *scale,
                             const float *shift, const float *mean, const float *invstd, int act,
                             float *sums /* NULL: leave the block partials [*h_nblocks][2][C] in the workspace for pcfb_bn_reduce_sums */,
@@ -251,6 +251,10 @@ int pcfb_bn_reduce_sums(const float *partial, int nblocks, int C, float *sums_lo
  *   backward: pcfb_bn_backward_stats -> sums[2][C] = (sum dz, sum dz*xhat) = (dbeta, dgamma), dz = dA*act'(z);
  *     pcfb_bn_backward: dX = scale*(dz - S1/E - xhat*S2/E) (sums == NULL: eval mode, dX = scale*dz).
  *     d_count (device double, may be NULL) = global row count for SyncBatchNorm.
+ *   residual (optional, [rows, C]): pcfb_bn_act computes act(x*scale + shift + r) (residual_after_act == 0: the tail of a
+ *     PointConvFormer / PointConvStridePE block, leaky_relu(unary2(h) + shortcut), layers.py:413-415, 737-739) or
+ *     act(x*scale + shift) + r (the decoder's skip connection, layers.py:1096-1097) in the same pass; for the first form the
+ *     backward kernels take r to evaluate act' and pcfb_bn_backward also writes d_residual = dz.
  * Every reduction is block partials summed in fixed order (deterministic).
  * ------------------------------------------------------------------------------------------- */
 int pcfb_bn_supported(int C);
@@ -258,11 +262,12 @@ size_t pcfb_bn_workspace(int64_t rows, int C);
 int pcfb_bn_stats(const float *x, int64_t rows, int C, const float *pivot, float *partial, size_t partial_bytes,
                   int *h_nblocks, void *stream);
 int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
-                           const float *mean, const float *invstd, int act, float *sums /* NULL: partials stay in the workspace */,
-                           int *h_nblocks, void *workspace, size_t workspace_bytes, void *stream);
+                           const float *mean, const float *invstd, int act, const float *residual,
+                           float *sums /* NULL: partials stay in the workspace */, int *h_nblocks, void *workspace,
+                           size_t workspace_bytes, void *stream);
 int pcfb_bn_backward(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
                      const float *mean, const float *invstd, const float *sums, int act, const double *d_count,
-                     float *dX, void *stream);
+                     const float *residual, float *dX, float *d_residual, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Grid (voxel) subsampling with barycentres on packed scenes.  Replaces grid_subsampling()

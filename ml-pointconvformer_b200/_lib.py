@@ -54,7 +54,7 @@ SIGNATURES = {
     "pcfb_bn_reduce_sums": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, ctypes.c_double, _P]),
     "pcfb_syncbn_buffer_bytes": (c_size_t, [c_int]),
     "pcfb_syncbn_channels": (c_int, []),
-    "pcfb_bn_act": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P]),
+    "pcfb_bn_act": (c_int, [_P, c_int64, c_int, _P, _P, c_int, _P, _P, c_int, _P]),
     "pcfb_mlp_backward_stats": (c_int, [_P, c_int, _P, c_int, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "pcfb_mlp_backward": (c_int, [_P, c_int, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int,
                                   _P, c_int, _P, _P, c_int, _P, _P, _P, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
@@ -62,8 +62,8 @@ SIGNATURES = {
     "pcfb_bn_supported": (c_int, [c_int]),
     "pcfb_bn_workspace": (c_size_t, [c_int64, c_int]),
     "pcfb_bn_stats": (c_int, [_P, c_int64, c_int, _P, _P, c_size_t, _P, _P]),
-    "pcfb_bn_backward_stats": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, c_size_t, _P]),
-    "pcfb_bn_backward": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "pcfb_bn_backward_stats": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "pcfb_bn_backward": (c_int, [_P, _P, c_int64, c_int, _P, _P, _P, _P, _P, c_int, _P, _P, _P, _P, _P]),
     "pcfb_gridsub_workspace": (c_size_t, [c_int, c_int, c_int64]),
     "pcfb_gridsub_bounds": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_size_t, _P]),
     "pcfb_gridsub_count": (c_int, [_P, _P, c_int, c_int, c_float, _P, _P, _P, c_int64, _P, _P, c_size_t, _P]),

@@ -145,19 +145,25 @@ mlp_fwd_kernel(const float *__restrict__ x, int ldx, int64_t E, MlpLayer L, floa
 // (BatchNorm finalize: bn_reduce_kernel in peer_reduce.cu -- partial sums -> [SyncBatchNorm exchange] -> scale / shift / running stats)
 
 // a = act(y*scale+shift), elementwise (the chain's last BatchNorm + activation, materialised for its consumer)
+// res (optional): a residual added before the activation (res_after == 0: act(bn(y) + r), the tail of a PointConvFormer
+// block, layers.py:415) or after it (act(bn(y)) + r, the decoder's skip connection, layers.py:1096-1097)
 __global__ void bn_act_kernel(const float *__restrict__ y, int64_t n, int C, const float *__restrict__ scale,
-                              const float *__restrict__ shift, int act, float *__restrict__ out)
+                              const float *__restrict__ shift, int act, float *__restrict__ out,
+                              const float *__restrict__ res, int res_after)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
-        const float z = scale ? fmaf(y[i], scale[c], shift[c]) : y[i];
-        out[i] = act_fwd(z, act);
+        float z = scale ? fmaf(y[i], scale[c], shift[c]) : y[i];
+        if (res && !res_after) z += res[i];
+        float o = act_fwd(z, act);
+        if (res && res_after) o += res[i];
+        out[i] = o;
     }
 }
 
 __global__ void __launch_bounds__(256)
 bn_act4_kernel(const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale, const float *__restrict__ shift,
-               int act, float *__restrict__ out, int c4, int ry);                          // float4 form, defined below
+               int act, float *__restrict__ out, int c4, int ry, const float *__restrict__ res, int res_after);   // float4 form, defined below
 
 // ------------------------------------------------------------------------------------------------------------
 // backward
@@ -869,22 +875,23 @@ extern "C" int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int
 }
 
 extern "C" int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
-                           void *stream)
+                           const float *residual, int residual_after_act, void *stream)
 {
     PCFB_REQUIRE(y && out, "pcfb_bn_act: null pointer");
     const int64_t n = rows * C;
     if (n == 0) return PCFB_OK;
     int64_t blocks = (n + 255) / 256;
     if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-    if ((C & 3) == 0 && C <= 1024 && ((uintptr_t)y % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+    if ((C & 3) == 0 && C <= 1024 && ((uintptr_t)y % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)residual % 16 == 0) &&
         (!scale || (((uintptr_t)scale % 16 == 0) && ((uintptr_t)shift % 16 == 0)))) {
         const int c4 = C >> 2, ry = 256 / c4;
         int64_t b4 = (rows + ry - 1) / ry;
         if (b4 > (int64_t)kNumSMs * 8) b4 = (int64_t)kNumSMs * 8;
-        bn_act4_kernel<<<(int)b4, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, rows, C, scale, shift, act, out, c4, ry);
+        bn_act4_kernel<<<(int)b4, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, rows, C, scale, shift, act, out, c4, ry, residual,
+                                                                               residual_after_act);
         return check_launch("bn_act4_kernel");
     }
-    bn_act_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, n, C, scale, shift, act, out);
+    bn_act_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, n, C, scale, shift, act, out, residual, residual_after_act);
     return check_launch("bn_act_kernel");
 }
 
@@ -1071,7 +1078,7 @@ bn_stats_kernel(const float *__restrict__ x, int64_t rows, int C, const float *_
 // out = act(y * scale + shift), float4 columns (the vector form of bn_act_kernel)
 __global__ void __launch_bounds__(BA_THREADS)
 bn_act4_kernel(const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale, const float *__restrict__ shift,
-               int act, float *__restrict__ out, int c4, int ry)
+               int act, float *__restrict__ out, int c4, int ry, const float *__restrict__ res, int res_after)
 {
     const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
     if (ty >= ry) return;
@@ -1079,15 +1086,18 @@ bn_act4_kernel(const float *__restrict__ y, int64_t rows, int C, const float *__
     const float4 sh = scale ? __ldg(reinterpret_cast<const float4 *>(shift) + tx) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t r = (int64_t)blockIdx.x * ry + ty; r < rows; r += (int64_t)gridDim.x * ry) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * C) + tx);
+        float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (res) rr = __ldg(reinterpret_cast<const float4 *>(res + r * C) + tx);
+        const float4 pre = res_after ? make_float4(0.f, 0.f, 0.f, 0.f) : rr, post = res_after ? rr : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 o;
-        o.x = act_fwd(fmaf(v.x, sc.x, sh.x), act); o.y = act_fwd(fmaf(v.y, sc.y, sh.y), act);
-        o.z = act_fwd(fmaf(v.z, sc.z, sh.z), act); o.w = act_fwd(fmaf(v.w, sc.w, sh.w), act);
+        o.x = act_fwd(fmaf(v.x, sc.x, sh.x) + pre.x, act) + post.x; o.y = act_fwd(fmaf(v.y, sc.y, sh.y) + pre.y, act) + post.y;
+        o.z = act_fwd(fmaf(v.z, sc.z, sh.z) + pre.z, act) + post.z; o.w = act_fwd(fmaf(v.w, sc.w, sh.w) + pre.w, act) + post.w;
         *(reinterpret_cast<float4 *>(out + r * C) + tx) = o;
     }
 }
 
-__device__ __forceinline__ float ba_dz(float d, float yv, float sc, float sh, int act) {
-    const float z = fmaf(yv, sc, sh);
+__device__ __forceinline__ float ba_dz(float d, float yv, float sc, float sh, int act, float r = 0.f) {
+    const float z = fmaf(yv, sc, sh) + r;                 // r: the residual added before the activation (0 otherwise)
     return d * act_bwd(z, act_fwd(z, act), act);
 }
 
@@ -1095,7 +1105,7 @@ __device__ __forceinline__ float ba_dz(float d, float yv, float sc, float sh, in
 __global__ void __launch_bounds__(BA_THREADS)
 bn_bwd_stats_kernel(const float *__restrict__ dA, const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale,
                     const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd, int act,
-                    float *__restrict__ partial, int c4, int ry, int rows_per_block)
+                    float *__restrict__ partial, int c4, int ry, int rows_per_block, const float *__restrict__ res)
 {
     extern __shared__ float4 ba_sm[];
     const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
@@ -1109,8 +1119,10 @@ bn_bwd_stats_kernel(const float *__restrict__ dA, const float *__restrict__ y, i
         for (int64_t r = r0 + ty; r < r1; r += ry) {
             const float4 d = __ldg(reinterpret_cast<const float4 *>(dA + r * C) + tx);
             const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * C) + tx);
-            const float dx_ = ba_dz(d.x, v.x, sc.x, sh.x, act), dy_ = ba_dz(d.y, v.y, sc.y, sh.y, act);
-            const float dz_ = ba_dz(d.z, v.z, sc.z, sh.z, act), dw_ = ba_dz(d.w, v.w, sc.w, sh.w, act);
+            float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (res) rr = __ldg(reinterpret_cast<const float4 *>(res + r * C) + tx);
+            const float dx_ = ba_dz(d.x, v.x, sc.x, sh.x, act, rr.x), dy_ = ba_dz(d.y, v.y, sc.y, sh.y, act, rr.y);
+            const float dz_ = ba_dz(d.z, v.z, sc.z, sh.z, act, rr.z), dw_ = ba_dz(d.w, v.w, sc.w, sh.w, act, rr.w);
             s1.x += dx_; s1.y += dy_; s1.z += dz_; s1.w += dw_;
             s2.x = fmaf(dx_, (v.x - mu.x) * is.x, s2.x); s2.y = fmaf(dy_, (v.y - mu.y) * is.y, s2.y);
             s2.z = fmaf(dz_, (v.z - mu.z) * is.z, s2.z); s2.w = fmaf(dw_, (v.w - mu.w) * is.w, s2.w);
@@ -1124,7 +1136,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 bn_bwd_kernel(const float *__restrict__ dA, const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale,
               const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd,
               const float *__restrict__ sums, int act, float inv_count, const double *__restrict__ d_count,
-              float *__restrict__ dX, int c4, int ry)
+              float *__restrict__ dX, int c4, int ry, const float *__restrict__ res, float *__restrict__ dR)
 {
     const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
     if (ty >= ry) return;
@@ -1140,12 +1152,17 @@ bn_bwd_kernel(const float *__restrict__ dA, const float *__restrict__ y, int64_t
     for (int64_t r = (int64_t)blockIdx.x * ry + ty; r < rows; r += (int64_t)gridDim.x * ry) {
         const float4 d = __ldg(reinterpret_cast<const float4 *>(dA + r * C) + tx);
         const float4 v = __ldg(reinterpret_cast<const float4 *>(y + r * C) + tx);
+        float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (res) rr = __ldg(reinterpret_cast<const float4 *>(res + r * C) + tx);
+        const float4 dz = make_float4(ba_dz(d.x, v.x, sc.x, sh.x, act, rr.x), ba_dz(d.y, v.y, sc.y, sh.y, act, rr.y),
+                                      ba_dz(d.z, v.z, sc.z, sh.z, act, rr.z), ba_dz(d.w, v.w, sc.w, sh.w, act, rr.w));
+        if (dR) *(reinterpret_cast<float4 *>(dR + r * C) + tx) = dz;        // gradient of the pre-activation residual
         float4 o;
-        o.x = sc.x * (ba_dz(d.x, v.x, sc.x, sh.x, act) - m1.x - (v.x - mu.x) * is.x * m2.x);
-        o.y = sc.y * (ba_dz(d.y, v.y, sc.y, sh.y, act) - m1.y - (v.y - mu.y) * is.y * m2.y);
-        o.z = sc.z * (ba_dz(d.z, v.z, sc.z, sh.z, act) - m1.z - (v.z - mu.z) * is.z * m2.z);
-        o.w = sc.w * (ba_dz(d.w, v.w, sc.w, sh.w, act) - m1.w - (v.w - mu.w) * is.w * m2.w);
-        *(reinterpret_cast<float4 *>(dX + r * C) + tx) = o;
+        o.x = sc.x * (dz.x - m1.x - (v.x - mu.x) * is.x * m2.x);
+        o.y = sc.y * (dz.y - m1.y - (v.y - mu.y) * is.y * m2.y);
+        o.z = sc.z * (dz.z - m1.z - (v.z - mu.z) * is.z * m2.z);
+        o.w = sc.w * (dz.w - m1.w - (v.w - mu.w) * is.w * m2.w);
+        if (dX) *(reinterpret_cast<float4 *>(dX + r * C) + tx) = o;
     }
 }
 
@@ -1183,8 +1200,8 @@ extern "C" int pcfb_bn_stats(const float *x, int64_t rows, int C, const float *p
 }
 
 extern "C" int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
-                                      const float *mean, const float *invstd, int act, float *sums, int *nblocks, void *workspace,
-                                      size_t workspace_bytes, void *stream)
+                                      const float *mean, const float *invstd, int act, const float *residual, float *sums, int *nblocks,
+                                      void *workspace, size_t workspace_bytes, void *stream)
 {
     PCFB_REQUIRE(pcfb_bn_supported(C), "pcfb_bn_backward_stats: C = %d unsupported (multiple of 4, <= 1024)", C);
     PCFB_REQUIRE(dA && y && scale && shift && mean && invstd && workspace && ((uintptr_t)dA % 16 == 0) &&
@@ -1197,7 +1214,7 @@ extern "C" int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t r
     int rc;
     if (g.blocks > 0) {
         bn_bwd_stats_kernel<<<g.blocks, BA_THREADS, (size_t)2 * g.ry * g.c4 * sizeof(float4), st>>>(
-            dA, y, rows, C, scale, shift, mean, invstd, act, partial, g.c4, g.ry, g.rows_per_block);
+            dA, y, rows, C, scale, shift, mean, invstd, act, partial, g.c4, g.ry, g.rows_per_block, residual);
         if ((rc = check_launch("bn_bwd_stats_kernel"))) return rc;
     }
     if (!sums) return PCFB_OK;                                   // the caller reduces the partials itself (pcfb_bn_reduce_sums)
@@ -1207,14 +1224,15 @@ extern "C" int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t r
 
 extern "C" int pcfb_bn_backward(const float *dA, const float *y, int64_t rows, int C, const float *scale, const float *shift,
                                 const float *mean, const float *invstd, const float *sums, int act, const double *d_count,
-                                float *dX, void *stream)
+                                const float *residual, float *dX, float *d_residual, void *stream)
 {
     PCFB_REQUIRE(pcfb_bn_supported(C), "pcfb_bn_backward: C = %d unsupported (multiple of 4, <= 1024)", C);
-    PCFB_REQUIRE(dA && y && scale && shift && dX && (!sums || (mean && invstd)) && ((uintptr_t)dA % 16 == 0) &&
-                 ((uintptr_t)y % 16 == 0) && ((uintptr_t)dX % 16 == 0), "pcfb_bn_backward: null or misaligned pointer");
+    PCFB_REQUIRE(dA && y && scale && shift && (dX || d_residual) && (!sums || (mean && invstd)) && ((uintptr_t)dA % 16 == 0) &&
+                 ((uintptr_t)y % 16 == 0) && ((uintptr_t)dX % 16 == 0) && ((uintptr_t)residual % 16 == 0) &&
+                 ((uintptr_t)d_residual % 16 == 0), "pcfb_bn_backward: null or misaligned pointer");
     if (rows == 0) return PCFB_OK;
     const int c4 = C >> 2, ry = BA_THREADS / c4;
     bn_bwd_kernel<<<ba_stream_blocks(rows, ry), BA_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        dA, y, rows, C, scale, shift, mean, invstd, sums, act, (float)(1.0 / (double)rows), d_count, dX, c4, ry);
+        dA, y, rows, C, scale, shift, mean, invstd, sums, act, (float)(1.0 / (double)rows), d_count, dX, c4, ry, residual, d_residual);
     return check_launch("bn_bwd_kernel");
 }

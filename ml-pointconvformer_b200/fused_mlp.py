@@ -203,7 +203,7 @@ class _ChainFunction(torch.autograd.Function):
             cur, ld = y, cout
             in_scale, in_shift, in_act = scale, shift, s["act"]
         out = torch.empty_like(ys[-1])
-        check(lib().pcfb_bn_act(ptr(ys[-1]), E, ys[-1].shape[1], ptr(in_scale), ptr(in_shift), in_act, ptr(out), stream_ptr()), "bn_act")
+        check(lib().pcfb_bn_act(ptr(ys[-1]), E, ys[-1].shape[1], ptr(in_scale), ptr(in_shift), in_act, ptr(out), 0, 0, stream_ptr()), "bn_act")
         _lib.account(8.0 * E * ys[-1].shape[1])
         ctx.spec, ctx.counts = spec, counts
         ctx.n_layers = L
@@ -342,7 +342,7 @@ class _BnActFunction(torch.autograd.Function):
     """out = act(BatchNorm(x2)) for contiguous x2 [rows, C]; cfg = dict(act, training, eps, momentum, sync, nbt)."""
 
     @staticmethod
-    def forward(ctx, x2, gamma, beta, pivot, running_mean, running_var, cfg):
+    def forward(ctx, x2, gamma, beta, pivot, running_mean, running_var, cfg, residual):
         rows, C = x2.shape
         dev = x2.device
         act, training = cfg["act"], cfg["training"]
@@ -360,47 +360,57 @@ class _BnActFunction(torch.autograd.Function):
             shift = ((beta if beta is not None else 0.) - running_mean * scale).contiguous()
             mean = running_mean
         out = torch.empty_like(x2)
-        check(lib().pcfb_bn_act(ptr(x2), rows, C, ptr(scale), ptr(shift), act, ptr(out), stream_ptr()), "bn_act")
-        _lib.account(8.0 * rows * C)
+        after = 1 if cfg.get("res_after") else 0
+        check(lib().pcfb_bn_act(ptr(x2), rows, C, ptr(scale), ptr(shift), act, ptr(out), ptr(residual), after, stream_ptr()), "bn_act")
+        _lib.account((8.0 if residual is None else 12.0) * rows * C)
         ctx.cfg, ctx.d_count = cfg, d_count
         ctx.has_affine = gamma is not None
-        ctx.save_for_backward(x2, scale, shift, mean, invstd)
+        # only a residual added BEFORE the activation enters the backward kernels (act' is evaluated at z + r)
+        ctx.pre_res = residual is not None and not after
+        ctx.save_for_backward(x2, scale, shift, mean, invstd, residual if ctx.pre_res else None)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
-        x2, scale, shift, mean, invstd = ctx.saved_tensors
+        x2, scale, shift, mean, invstd, res = ctx.saved_tensors
         rows, C = x2.shape
         dev = x2.device
         cfg = ctx.cfg
         dA = grad_out.reshape(rows, C)
         if not dA.is_contiguous():
             dA = dA.contiguous()
+        need_res = ctx.needs_input_grad[7]
         need_affine = ctx.has_affine and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         sums = local = None
         if cfg["training"] or need_affine:
             ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
             nblk = ctypes.c_int(0)
             check(lib().pcfb_bn_backward_stats(ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cfg["act"],
-                                               0, ctypes.addressof(nblk), ptr(ws), ws.numel(), stream_ptr()), "bn_backward_stats")
+                                               ptr(res), 0, ctypes.addressof(nblk), ptr(ws), ws.numel(), stream_ptr()), "bn_backward_stats")
             _lib.account(8.0 * rows * C)
             # dx: sums over the global batch; dgamma / dbeta stay local
             sums, local = bn_reduce_sums(ws, nblk.value, C, cfg["sync"] and cfg["training"], dev)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x2)
+        dx = d_res = None
+        want_dres = need_res and ctx.pre_res
+        if ctx.needs_input_grad[0] or want_dres:
+            dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+            d_res = torch.empty_like(x2) if want_dres else None
             check(lib().pcfb_bn_backward(ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
-                                         ptr(sums) if cfg["training"] else 0, cfg["act"], ptr(ctx.d_count), ptr(dx), stream_ptr()), "bn_backward")
-            _lib.account(12.0 * rows * C)
+                                         ptr(sums) if cfg["training"] else 0, cfg["act"], ptr(ctx.d_count), ptr(res), ptr(dx), ptr(d_res),
+                                         stream_ptr()), "bn_backward")
+            _lib.account((12.0 + (4.0 if res is not None else 0.0) + (4.0 if want_dres else 0.0)) * rows * C)
+        if need_res and not ctx.pre_res:
+            d_res = dA                                        # added after the activation: the gradient passes through
         dgamma = local[C:] if need_affine else None
         dbeta = local[:C] if need_affine else None
-        return dx, dgamma, dbeta, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, d_res
 
 
-def bn_act(x, bn, act, pivot=None):
+def bn_act(x, bn, act, pivot=None, residual=None, residual_after_act=False):
     """act(bn(x)) over the last dim of x [..., C] with a BatchNorm1d/2d/SyncBatchNorm-like module `bn` (batch statistics
     over all leading dims when bn.training, running statistics otherwise; running stats / num_batches_tracked updated
-    like torch).  pivot: optional per-channel offset near the mean (the bias of the Linear that produced x)."""
+    like torch).  pivot: optional per-channel offset near the mean (the bias of the Linear that produced x).
+    residual (same shape as x): act(bn(x) + residual), or act(bn(x)) + residual with residual_after_act, in the same pass."""
     if not x.is_cuda:
         raise RuntimeError("pcf_b200 BatchNorm needs CUDA tensors (no CPU path)")
     lead = tuple(x.shape[:-1])
@@ -409,8 +419,13 @@ def bn_act(x, bn, act, pivot=None):
         x2 = x2.contiguous()
     training = bn.training or not bn.track_running_stats
     cfg = dict(act=act, training=training, eps=bn.eps, momentum=bn.momentum,      # None = cumulative moving average
-               sync=_sync_group(bn),
+               sync=_sync_group(bn), res_after=bool(residual_after_act),
                nbt=bn.num_batches_tracked if bn.track_running_stats else None)      # incremented by the finalize kernel
     rm, rv = (bn.running_mean, bn.running_var) if bn.track_running_stats else (None, None)
-    out = _BnActFunction.apply(x2, bn.weight, bn.bias, pivot.detach() if pivot is not None else None, rm, rv, cfg)
+    r2 = None
+    if residual is not None:
+        r2 = residual.reshape(-1, x.shape[-1])
+        if not r2.is_contiguous():
+            r2 = r2.contiguous()
+    out = _BnActFunction.apply(x2, bn.weight, bn.bias, pivot.detach() if pivot is not None else None, rm, rv, cfg, r2)
     return out.reshape(*lead, out.shape[-1])

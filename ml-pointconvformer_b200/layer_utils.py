@@ -346,15 +346,18 @@ class Linear_BN(nn.Module):
         fused.bias.copy_(self.bn.bias + (self.c.bias - self.bn.running_mean) * scale)
         return fused
 
-    def forward(self, x, act=0):
+    def forward(self, x, act=0, residual=None):
         """act (fused_mlp.ACT_*): activation applied after the BatchNorm in the same kernel pass (0 = none, the
-        reference's module; callers that follow the block with ReLU / LeakyReLU pass it here)."""
+        reference's module; callers that follow the block with ReLU / LeakyReLU pass it here).  residual: added to the
+        BatchNorm output before the activation, in the same pass (the `+ shortcut` of a block's tail)."""
         from . import fused_mlp
         x = linear(x, self.c.weight, self.c.bias)
         if fused_mlp.bn_supported(x.shape[-1]):
             # BatchNorm over the last dim == the reference's permute(0,3,2,1) -> BN2d -> permute back / BN1d over a
             # [rows, C] view (layer_utils.py:272-277): statistics + apply(+activation) as two passes of pcfb_bn_*
-            return fused_mlp.bn_act(x, self.bn, act, pivot=self.c.bias)
+            return fused_mlp.bn_act(x, self.bn, act, pivot=self.c.bias, residual=residual)
+        if residual is not None:
+            raise RuntimeError("Linear_BN: a fused residual needs the pcfb_bn_* path (C % 4 == 0, C <= 1024)")
         shape = x.shape
         if isinstance(self.bn, nn.SyncBatchNorm):          # after convert_sync_batchnorm (DDP, sync_bn: True)
             y = self.bn(x.reshape(-1, shape[-1])).reshape(shape)
@@ -391,9 +394,19 @@ class UnaryBlock(nn.Module):
         self.mlp = Linear_BN(in_dim, out_dim, bn_momentum=bn_momentum, bn_ver='1d') if use_bn else nn.Linear(in_dim, out_dim)
         self.leaky_relu = nn.Identity() if no_relu else nn.LeakyReLU(0.1)
 
-    def forward(self, x):
+    def can_fuse_tail(self):
+        """True if forward(x, residual=..., act=...) can add a residual and apply an activation inside the BatchNorm pass."""
+        from . import fused_mlp
+        return (isinstance(self.mlp, Linear_BN) and self.no_relu and fused_mlp.bn_supported(self.out_dim)
+                and not fused_mlp.supported([(self.in_dim, self.out_dim)]))
+
+    def forward(self, x, residual=None, act=None):
+        """residual / act (only when can_fuse_tail()): returns act(block(x) + residual) in the block's own BatchNorm pass --
+        the `leaky_relu(unary2(h) + shortcut)` tail of the PointConvFormer / PointConvStridePE blocks (layers.py:413-415)."""
         from . import fused_mlp
         lin, bn = (self.mlp.c, self.mlp.bn) if isinstance(self.mlp, Linear_BN) else (self.mlp, None)
+        if residual is not None:
+            return self.mlp(x, act=act, residual=residual)
         if fused_mlp.supported([(lin.in_features, lin.out_features)]):
             act = fused_mlp.ACT_NONE if self.no_relu else fused_mlp.ACT_LEAKY
             return fused_mlp.mlp_chain(x, [(lin, bn, act)], self.training)

@@ -229,9 +229,16 @@ class PCFLayer(_PointLayerBase):
         new_feat = _contract(self.cfg, feats_x, nei_inds, inv, weights, None, guidance_score, lin.weight, lin.bias)
         new_feat = _bn_relu(post_bn.bn, new_feat, lin.bias) if post_bn is not None else F.relu(new_feat)
         new_feat = self.dropout(new_feat)
-        new_feat = self.unary2(new_feat)
         shortcut = S.join(br_sc)
-        return self.leaky_relu(self.drop_path(new_feat) + shortcut), weightNetInput
+        return _block_tail(self, new_feat, shortcut), weightNetInput
+
+
+def _block_tail(block, new_feat, shortcut):
+    """leaky_relu(drop_path(unary2(new_feat)) + shortcut) (layers.py:413-415, 737-739): with drop_path off and a wide unary2
+    the residual add and the LeakyReLU ride in unary2's BatchNorm apply pass (fused_mlp.bn_act)."""
+    if isinstance(block.drop_path, nn.Identity) and block.unary2.can_fuse_tail() and shortcut.shape == new_feat.shape[:-1] + (block.unary2.out_dim,):
+        return block.unary2(new_feat, residual=shortcut, act=fused_mlp.ACT_LEAKY)
+    return block.leaky_relu(block.drop_path(block.unary2(new_feat)) + shortcut)
 
 
 def _streams_ok(module):
@@ -245,11 +252,14 @@ def _streams_ok(module):
     return True
 
 
-def _bn_relu(bn, x, pivot=None):
-    """ReLU(BatchNorm(x)) over the last dim of [B,N,C] with a BatchNorm1d-like module `bn` (batch statistics over all
-    points of the packed batch when training, layer_utils.py:276-277; layers.py:708-709,721): two passes of pcfb_bn_*."""
+def _bn_relu(bn, x, pivot=None, skip=None):
+    """ReLU(BatchNorm(x)) [+ skip] over the last dim of [B,N,C] with a BatchNorm1d-like module `bn` (batch statistics over all
+    points of the packed batch when training, layer_utils.py:276-277; layers.py:708-709,721): two passes of pcfb_bn_*;
+    skip (the decoder's `new_feat + dense_feats`, layers.py:1096-1097) is added after the ReLU in the same pass."""
     if fused_mlp.bn_supported(x.shape[-1]):
-        return fused_mlp.bn_act(x, bn, fused_mlp.ACT_RELU, pivot=pivot)
+        return fused_mlp.bn_act(x, bn, fused_mlp.ACT_RELU, pivot=pivot, residual=skip, residual_after_act=True)
+    if skip is not None:
+        return _bn_relu(bn, x, pivot) + skip
     shape = x.shape
     if isinstance(bn, nn.SyncBatchNorm):
         return F.relu(bn(x.reshape(-1, shape[-1])).reshape(shape))
@@ -272,8 +282,8 @@ class _PConvLinearMixin:
         else:
             self.linear = Linear_BN(lin_in, lin_out, bn_ver='1d') if cfg.BATCH_NORM else nn.Linear(lin_in, lin_out)
 
-    def _contract_linear(self, feats, nei_inds, inv, weights, additional):
-        """-> ReLU(BN(Linear(contraction))): every caller in the reference applies ReLU right after the BatchNorm
+    def _contract_linear(self, feats, nei_inds, inv, weights, additional, skip=None):
+        """-> ReLU(BN(Linear(contraction))) [+ skip]: every caller in the reference applies ReLU right after the BatchNorm
         (layers.py:709,721, 898, 1092), so the activation rides in the BatchNorm's apply pass."""
         cfg = self.cfg
         if cfg.PCONV_OPT:
@@ -283,7 +293,9 @@ class _PConvLinearMixin:
         else:
             lin, bn = self.linear, None
         y = _contract(cfg, feats, nei_inds, inv, weights, additional, None, lin.weight, lin.bias)
-        return F.relu(y) if bn is None else _bn_relu(bn, y, lin.bias)
+        if bn is None:
+            return F.relu(y) if skip is None else F.relu(y) + skip
+        return _bn_relu(bn, y, lin.bias, skip)
 
 
 class PointConvStridePE(_PointLayerBase, _PConvLinearMixin):
@@ -326,9 +338,8 @@ class PointConvStridePE(_PointLayerBase, _PConvLinearMixin):
         feat_pe = S.join(br_pe)
         weights = S.join(br_w)
         new_feat = self.dropout(self._contract_linear(feats_x, nei_inds, inv, weights, feat_pe))
-        new_feat = self.unary2(new_feat)
         shortcut = S.join(br_sc)
-        return self.leaky_relu(self.drop_path(new_feat) + shortcut), weightNetInput
+        return _block_tail(self, new_feat, shortcut), weightNetInput
 
 
 class PointConv(_PointLayerBase, _PConvLinearMixin):
@@ -395,9 +406,7 @@ class PointConvTransposePE(_PointLayerBase, _PConvLinearMixin):
         br_pe = S.fork(lambda: self.pe_convs(localized_xyz) if self.cfg.USE_PE else None, 1, par and self.cfg.USE_PE)
         weights = self.weightnet(weightNetInput)
         feat_pe = S.join(br_pe)
-        new_feat = self._contract_linear(sparse_feats, nei_inds, inv, weights, feat_pe)
-        if dense_feats is not None:
-            new_feat = new_feat + dense_feats
+        new_feat = self._contract_linear(sparse_feats, nei_inds, inv, weights, feat_pe, skip=dense_feats)
         new_feat = self.dropout(new_feat)
         for conv in self.mlp2_convs:
             new_feat = conv(new_feat, act=fused_mlp.ACT_RELU) if isinstance(conv, Linear_BN) else \

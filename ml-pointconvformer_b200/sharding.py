@@ -62,14 +62,18 @@ class FlatParameters:
                 off += n
         self.flat = torch.nn.Parameter(flat)
 
-    def gather_grads(self, world_size=1, group=None):
+    def gather_grads(self, world_size=1, group=None, sync=True, accumulate=False):
         """Concatenate the per-parameter gradients into the flat gradient (mean over ranks when world_size > 1), attach
-        it to the flat parameter and drop the per-parameter ones."""
+        it to the flat parameter and drop the per-parameter ones.  Gradient accumulation: accumulate=True adds to the flat
+        gradient of the previous micro-steps, sync=False skips the all-reduce (DDP's no_sync; the reference all-reduces on
+        every micro-step, train_ScanNet_DDP_WarmUP.py:418-424) -- all-reduce once, on the last micro-step."""
         from . import streams
         streams.join_leaves()                           # weight gradients that ran on the leaf stream (streams.fork_leaf)
         pieces = [(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self.params]
         g = torch.cat(pieces)
-        if world_size > 1:
+        if accumulate and self.flat.grad is not None:
+            g += self.flat.grad
+        if world_size > 1 and sync:
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
             g.div_(world_size)
         self.flat.grad = g

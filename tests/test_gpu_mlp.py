@@ -170,3 +170,30 @@ def test_bn_act_deterministic_and_rejects_cpu():
     assert torch.equal(a, b)
     with pytest.raises(RuntimeError):
         fused_mlp.bn_act(x.cpu(), bn, 1)
+
+
+@pytest.mark.parametrize("after", [False, True])
+def test_bn_act_with_fused_residual_matches_float64(after):
+    """act(bn(x) + r) (the tail of a PointConvFormer block, /root/reference/layers.py:413-415) and act(bn(x)) + r (the
+    decoder's skip connection, layers.py:1096-1097) in the BatchNorm apply pass, forward and backward, against float64."""
+    import copy
+    from pcf_b200 import fused_mlp
+    g = torch.Generator().manual_seed(9)
+    rows, C = 3001, 96
+    x = torch.randn(1, rows, C, generator=g) * 1.5 + 0.2
+    r = torch.randn(1, rows, C, generator=g)
+    go = torch.randn(1, rows, C, generator=g)
+    bn = torch.nn.BatchNorm1d(C)
+    torch.nn.init.uniform_(bn.weight, 0.5, 1.5); torch.nn.init.uniform_(bn.bias, -0.5, 0.5)
+    ref = copy.deepcopy(bn).double()
+    xr, rr = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    z = ref(xr.reshape(rows, C)).reshape(1, rows, C)
+    yr = torch.nn.functional.leaky_relu(z, 0.1) + rr if after else torch.nn.functional.leaky_relu(z + rr, 0.1)
+    (yr * go.double()).sum().backward()
+    bn.cuda()
+    xc, rc = x.cuda().requires_grad_(True), r.cuda().requires_grad_(True)
+    y = fused_mlp.bn_act(xc, bn, fused_mlp.ACT_LEAKY, residual=rc, residual_after_act=after)
+    (y * go.cuda()).sum().backward()
+    assert max_err_scaled(y, yr) < 1e-5
+    assert max_err_scaled(xc.grad, xr.grad) < 1e-4 and max_err_scaled(rc.grad, rr.grad) < 1e-5
+    assert max_err_scaled(bn.weight.grad, ref.weight.grad) < 1e-4 and max_err_scaled(bn.bias.grad, ref.bias.grad) < 1e-4
