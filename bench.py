@@ -29,6 +29,16 @@ if ROOT not in sys.path:
 
 METRIC = "points_per_sec_fwd_bwd_PCF_Normal_10cm"
 UNIT = "points/s"
+# --config: the training-step workloads (BASELINE.json configs[2] = the default, configs[3]) share run_ours / the CPU arm;
+# the forward / inference workloads (configs[0], [1], [4]) have their own runners below (run_extra_config)
+TRAIN_CONFIGS = {"10cm": ("CONFIG_PCF_OPT_10CM", "points_per_sec_fwd_bwd_PCF_Normal_10cm", "PCF_Normal configPCF_Opt_10cm"),
+                 "5cm": ("CONFIG_PCF_5CM", "points_per_sec_fwd_bwd_PCF_Normal_5cm", "PCF_Normal configPCF_5cm")}
+
+
+def train_config(args):
+    from pcf_b200 import configs
+    name, metric, label = TRAIN_CONFIGS[args.config]
+    return getattr(configs, name), metric, label
 
 
 def parse():
@@ -37,7 +47,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--points", type=int, default=100000, help="level-0 points per scene")
+    ap.add_argument("--config", default="10cm", choices=["10cm", "5cm", "single", "tiny", "ptf2_infer"],
+                    help="10cm (default, BASELINE configs[2]) / 5cm (configs[3]): training step; single (configs[0]), tiny (configs[1]), "
+                         "ptf2_infer (configs[4]): forward / inference workloads with their own JSON line")
+    ap.add_argument("--points", type=int, default=0, help="level-0 points per scene (0 = the config's default: 100000; 5cm: 80000)")
     ap.add_argument("--scenes", type=int, default=1, help="scenes per GPU (packed)")
     ap.add_argument("--cpu-points", type=int, default=0,
                     help="level-0 points of the bounded CPU sample (0 = the largest of 100k/50k/25k/12k/6k that fits --cpu-budget)")
@@ -153,7 +166,7 @@ def run_ours(args):
     pcf_cuda.FORWARD_VARIANT = args.variant
     note("process group ready")
 
-    cfgd = configs.CONFIG_PCF_OPT_10CM
+    cfgd, metric, cfg_label = train_config(args)
     cfg = configs.make_cfg(cfgd)
     torch.manual_seed(1)                                            # same init on every rank (DDP broadcast equivalent)
     model = MA.PointConvFormer_Segmentation(cfg).to(dev)
@@ -212,7 +225,7 @@ def run_ours(args):
         note("syncbn_selfcheck: %s" % selfcheck)
         if not selfcheck["ok"]:
             if rank == 0:
-                print(json.dumps({"metric": METRIC, "error": "syncbn_selfcheck failed", "syncbn_selfcheck": selfcheck}))
+                print(json.dumps({"metric": metric, "error": "syncbn_selfcheck failed", "syncbn_selfcheck": selfcheck}))
             sys.stdout.flush()
             os._exit(3)
     if use_graph:
@@ -330,11 +343,11 @@ def run_ours(args):
     out = None
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step (grid-subsampled pyramid x4 + kNN x13 + inverse maps x13 "
-                                   "+ fwd + CE + bwd + grad-clip + AdamW), %d synthetic scene(s) of ~%d level-0 points per GPU, K=16" % (args.scenes, args.points),
+            "config": {"workload": "%s training step (grid-subsampled pyramid x4 + kNN x13 + inverse maps x13 "
+                                   "+ fwd + CE + bwd + grad-clip + AdamW), %d synthetic scene(s) of ~%d level-0 points per GPU, K=16" % (cfg_label, args.scenes, args.points),
                        "points_per_gpu": int(n0), "levels": level_sizes, "parallelism": "dp%d" % world,
                        "sync_bn": bool(sync_bn), "cuda_graph": bool(use_graph), "forward_variant": {0: "auto(tcgen05)", 1: "simt_fp32", 2: "tcgen05 pipelined", 3: "tcgen05 simple", 4: "tcgen05 warp-specialised"}[args.variant],
                        "l2": "256 MiB buffer written between timed steps; per-step working set >> 126 MB L2"},
@@ -705,7 +718,7 @@ def cpu_step_factory(args):
     import pcf_b200  # noqa: F401
     from pcf_b200 import configs, model_architecture as MA
     from oracle import knn as OK, inverse as OI, layers as OL
-    cfgd = configs.CONFIG_PCF_OPT_10CM
+    cfgd, _, cfg_label = train_config(args)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     host = host_pyramid(1, args.cpu_points, cfgd["grid_size"], 1)
@@ -735,8 +748,8 @@ def cpu_step_factory(args):
         return float(loss.detach())
 
     n0 = pcs[0].shape[1]
-    sample = ("1 synthetic scene of %d level-0 points (same generator, same PCF_Normal configPCF_Opt_10cm training step: C kNN x13 "
-              "+ inverse maps + torch-CPU fwd/bwd of the oracle port + AdamW); fp32, %d threads" % (n0, cores))
+    sample = ("1 synthetic scene of %d level-0 points (same generator, same %s training step: C kNN x13 "
+              "+ inverse maps + torch-CPU fwd/bwd of the oracle port + AdamW); fp32, %d threads" % (n0, cfg_label, cores))
     return step, n0, cores, sample
 
 
@@ -785,11 +798,11 @@ def run_reference(args):
         return None
     base = cpu_baseline(args, steps=args.steps, warmup=args.warmup, budget_s=300.0)
     full = bench_points(args)
-    return {"impl": "reference", "arm": "cpu_port", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+    return {"impl": "reference", "arm": "cpu_port", "metric": train_config(args)[1], "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["s_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PCF_Normal configPCF_Opt_10cm training step on the host CPU (oracle port of the reference's "
-                                   "PyTorch path + C kNN), same generator / model / step as the GPU arm",
+            "config": {"workload": "%s training step on the host CPU (oracle port of the reference's "
+                                   "PyTorch path + C kNN), same generator / model / step as the GPU arm" % train_config(args)[2],
                        "sample_points": base["points"], "gpu_arm_points": full, "same_config": base["points"] == full,
                        "points_per_step": base["sample"]},
             "cpu_baseline": base,
@@ -801,13 +814,186 @@ def bench_points(args):
     """Level-0 point count of the scene our arm runs at --points (the generator voxelises, so it is not --points exactly)."""
     import pcf_b200  # noqa: F401
     from pcf_b200 import configs, synthetic
-    return int(len(synthetic.make_scene(100, args.points, voxel=configs.CONFIG_PCF_OPT_10CM["grid_size"][0])[0]))
+    return int(len(synthetic.make_scene(100, args.points, voxel=train_config(args)[0]["grid_size"][0])[0]))
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0], [1], [4]: forward / inference workloads (each prints its own JSON line)
+# ---------------------------------------------------------------------------------------------------
+def _gpu_time(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.mean(ts))
+
+
+def _oracle_cfg(cfgd):
+    return dict(USE_VI=True, USE_PE=cfgd.get("USE_PE", False), USE_XYZ=True, use_level_1=cfgd.get("use_level_1", True),
+                num_level=cfgd["num_level"], guided_level=cfgd.get("guided_level", 0), resblocks=cfgd["resblocks"],
+                resblocks_back=cfgd.get("resblocks_back", [0] * cfgd["num_level"]))
+
+
+def run_extra_config(args):
+    import pcf_b200  # noqa: F401
+    from pcf_b200 import configs, layers as L, model_architecture as MA, pcf_cuda, synthetic, eval_utils as EU, _lib
+    from pcf_b200 import knn_post_dataloader_utils as KU
+    from oracle import layers as OL, knn as OK
+    if int(os.environ.get("RANK", 0)) != 0:
+        return None
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    base = {"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "unit": UNIT}
+    l0 = _lib.launch_count()
+    if args.config == "single":
+        # configs[0]: one PointConv(3 -> 32) of test_configs/pointconv_single.yaml (no VI / PE / BatchNorm, weightnet [3, 16]) on a
+        # randn cloud, K = 16 (tests_pointconv/test_pointconv_single.py:17-48), plus one PCFLayer(64 -> 128) (SURVEY D6)
+        cfg = MA.EasyDict(USE_VI=False, USE_PE=False, BATCH_NORM=False, USE_CUDA_KERNEL=True, PCONV_OPT=False, drop_path_rate=0.,
+                          dropout_rate=0., attention_type="subtraction", layer_norm_guidance=False)
+        cfg_pcf = MA.EasyDict(dict(cfg, USE_VI=True, USE_PE=True, BATCH_NORM=True))
+        torch.manual_seed(0)
+        layer = L.PointConv(3, 32, cfg, [3, 16]).to(dev).eval()
+        pcf = L.PCFLayer(64, 128, cfg_pcf, [12, 16], 8).to(dev).eval()
+        rows = []
+        for n in (8192, args.points):
+            g = torch.Generator().manual_seed(0)
+            xyz, feats = torch.randn(1, n, 3, generator=g), torch.randn(1, n, 3, generator=g)
+            nrm = torch.nn.functional.normalize(torch.randn(1, n, 3, generator=g), dim=-1)
+            f64 = torch.randn(1, n, 64, generator=g)
+            xyz_d, feats_d, nrm_d, f64_d = xyz.to(dev), feats.to(dev), nrm.to(dev), f64.to(dev)
+            nei = KU.compute_knn(xyz_d[0], xyz_d[0], 16)[None]
+            with torch.no_grad():
+                ms_knn = _gpu_time(lambda: KU.compute_knn(xyz_d[0], xyz_d[0], 16), args.steps)
+                ms_pc = _gpu_time(lambda: layer(xyz_d, feats_d, nei), args.steps)
+                ms_pcf = _gpu_time(lambda: pcf(xyz_d, f64_d, nei, nrm_d), args.steps)
+                y, _ = layer(xyz_d, feats_d, nei)
+                z, _ = pcf(xyz_d, f64_d, nei, nrm_d)
+            row = {"N": n, "knn_ms": ms_knn, "pointconv_fwd_ms": ms_pc, "pcf_layer_fwd_ms": ms_pcf,
+                   "pointconv_Mpts_per_s": n / ms_pc / 1e3, "pcf_layer_Mpts_per_s": n / ms_pcf / 1e3}
+            if n <= 8192:                                            # parity + CPU baseline at the CPU-runnable size
+                P = {"." + k: v.detach().cpu() for k, v in layer.state_dict().items()}
+                Q = {"." + k: v.detach().cpu() for k, v in pcf.state_dict().items()}
+                nei_c = nei.cpu()
+                with torch.no_grad():
+                    t0 = time.perf_counter()
+                    yo, _ = OL.point_conv(P, "", dict(USE_VI=False, USE_PE=False), xyz, feats, nei_c, training=False)
+                    t_pc = time.perf_counter() - t0
+                    t0 = time.perf_counter()
+                    zo, _ = OL.pcf_layer(Q, "", dict(USE_VI=True, USE_PE=True), xyz, f64, nei_c, nrm, training=False)
+                    t_pcf = time.perf_counter() - t0
+                row.update(parity_pointconv_max_abs=float((y.cpu() - yo).abs().max()), parity_pcf_max_abs=float((z.cpu() - zo).abs().max()),
+                           cpu_pointconv_fwd_ms=t_pc * 1e3, cpu_pcf_layer_fwd_ms=t_pcf * 1e3)
+                assert row["parity_pointconv_max_abs"] < 1e-3 and row["parity_pcf_max_abs"] < 1e-3, row
+            rows.append(row)
+        big = rows[-1]
+        return dict(base, metric="points_per_sec_fwd_single_PointConv", value=big["N"] / big["pointconv_fwd_ms"] * 1e3,
+                    ms_per_step=big["pointconv_fwd_ms"], gpu_launches=int(_lib.launch_count() - l0),
+                    config={"workload": "single PointConv(3->32) forward (test_configs/pointconv_single.yaml) and one PCFLayer(64->128), randn cloud, K=16",
+                            "points": big["N"]}, rows=rows,
+                    cpu_baseline={"value": 8192 / rows[0]["cpu_pointconv_fwd_ms"] * 1e3, "unit": UNIT, "cores": cores, "kind": "port",
+                                  "sample": "oracle PointConv forward on the 8192-point cloud"})
+    if args.config == "tiny":
+        # configs[1]: configPCF_10cm_lite segmentation model and the PCF_Tiny backbone preset, eval-mode forward with post_knn
+        # edges, on a packed batch of 16 ScanNet-sized rooms (~19 k points each)
+        cfgd = configs.CONFIG_PCF_10CM_LITE
+        cfg = configs.make_cfg(cfgd)
+        torch.manual_seed(1)
+        model = MA.PointConvFormer_Segmentation(cfg).to(dev).eval()
+        tiny, tcfg = MA.PCF_Tiny(0.1)
+        tcfg.USE_CUDA_KERNEL = True
+        tcfg.PCONV_OPT = False
+        tiny = tiny.to(dev).eval()
+
+        def batch(n_scenes, seed):
+            h = host_scenes(seed, args.points, cfgd["grid_size"], n_scenes)
+            p0, n0 = torch.from_numpy(h["points0"]).to(dev), torch.from_numpy(h["normals0"]).to(dev)
+            return h, p0, n0, torch.from_numpy(h["colors"]).to(dev)[None]
+        h, p0, n0, col = batch(16, 3)
+        from pcf_b200 import grid_subsampling as GS
+
+        def edges():
+            pts, nrm, stored, _ = GS.build_pyramid(p0, n0, h["stored0"], cfgd["grid_size"])
+            pcs = [p[None] for p in pts]
+            es, ef, ep = KU.prepare(*KU.compute_knn_packed(pcs, stored, cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"],
+                                                           grid_size=cfgd["grid_size"]))
+            return pcs, [x[None] for x in nrm], es, ef, ep
+        pcs, nrms, es, ef, ep = edges()
+        with torch.no_grad():
+            ms_edges = _gpu_time(edges, max(args.steps // 2, 2))
+            ms_lite = _gpu_time(lambda: model(col, pcs, es, ef, ep, nrms), args.steps)
+            ms_tiny = _gpu_time(lambda: tiny(col, pcs, es, ef, nrms), args.steps)
+        n_total = int(p0.shape[0])
+        # parity + CPU baseline on a 2-room batch through the oracle port
+        h2, q0, m0, col2 = batch(2, 5)
+        pts2, nrm2, st2, _ = GS.build_pyramid(q0, m0, h2["stored0"], cfgd["grid_size"])
+        pcs2 = [p[None] for p in pts2]
+        e2 = KU.prepare(*KU.compute_knn_packed(pcs2, st2, cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"], grid_size=cfgd["grid_size"]))
+        with torch.no_grad():
+            out = model(col2, pcs2, *e2, [x[None] for x in nrm2])
+            params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            cpu = lambda lst: [t.cpu() for t in lst]
+            t0 = time.perf_counter()
+            ref = OL.segmentation_model(params, _oracle_cfg(cfgd), col2.cpu(), cpu(pcs2), cpu(e2[0]), cpu(e2[1]), cpu(e2[2]),
+                                        [x[None].cpu() for x in nrm2], training=False)
+            t_cpu = time.perf_counter() - t0
+        err = float((out.cpu() - ref).abs().max())
+        assert err < 2e-3, err
+        ms = ms_edges + ms_lite
+        return dict(base, metric="points_per_sec_fwd_PCF_10cm_lite", value=n_total / ms * 1e3, ms_per_step=ms,
+                    gpu_launches=int(_lib.launch_count() - l0),
+                    config={"workload": "configPCF_10cm_lite segmentation model, eval forward incl. post_knn edge construction (pyramid + 13 kNN sets), "
+                                        "16 packed synthetic rooms", "points": n_total, "levels": [int(p.shape[1]) for p in pcs]},
+                    parts={"edges_ms": ms_edges, "lite_forward_ms": ms_lite, "pcf_tiny_backbone_forward_ms": ms_tiny},
+                    parity={"max_abs_logit_err_vs_oracle_2_rooms": err},
+                    cpu_baseline={"value": int(q0.shape[0]) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                                  "sample": "oracle forward (no edges) on a 2-room batch of %d points" % int(q0.shape[0])})
+    # configs[4]: configPCF_2cm_PTF2 inference on a ~250 k-point scene with the reference's protocol (test_ScanNet_simple.py:
+    # 139-174: BatchNorm folded, batch 1, model forward only between two synchronisations, mean over scenes)
+    cfgd = configs.CONFIG_PCF_2CM_PTF2
+    cfg = configs.make_cfg(cfgd)
+    torch.manual_seed(1)
+    model = MA.PointConvFormer_Segmentation(cfg).to(dev)
+    model.eval()
+    # parity of the folded model on a small scene against the oracle's eval-mode forward (BatchNorm with running statistics)
+    xyz, nrm, col = synthetic.make_scene(11, 6000, voxel=cfgd["grid_size"][0])
+    pcs, nrms, es, ef, ep = EU.prepare_scene(xyz, nrm, cfg)
+    params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    cpu = lambda lst: [t.cpu() for t in lst]
+    with torch.no_grad():
+        ref = OL.segmentation_model(params, _oracle_cfg(cfgd), torch.from_numpy(col)[None], cpu(pcs), cpu(es), cpu(ef), cpu(ep), cpu(nrms),
+                                    training=False)
+    scenes = [synthetic.make_scene(20 + i, args.points, voxel=cfgd["grid_size"][0]) for i in range(3)]
+    probs, times, mean_s = EU.timed_inference(model, scenes, cfg, fold_bn=True, warmup=2)
+    with torch.no_grad():
+        out = model(torch.from_numpy(col).to(dev)[None], pcs, es, ef, ep, nrms)             # folded model, small scene
+    err = float((out.cpu() - ref).abs().max())
+    assert err < 2e-3, err
+    n_mean = float(np.mean([len(s[0]) for s in scenes]))
+    return dict(base, metric="ms_per_scene_inference_PCF_2cm_PTF2", unit="ms", higher_is_better=False, value=mean_s * 1e3,
+                ms_per_step=mean_s * 1e3, gpu_launches=int(_lib.launch_count() - l0), points_per_s=n_mean / mean_s,
+                config={"workload": "configPCF_2cm_PTF2 inference, BatchNorm folded, batch 1, model forward only (test_ScanNet_simple.py protocol), "
+                                    "3 synthetic scenes", "points_per_scene": [len(s[0]) for s in scenes]},
+                parity={"max_abs_logit_err_vs_oracle_small_scene": err, "scene_times_ms": [t * 1e3 for t in times]})
 
 
 def main():
     args = parse()
+    if args.points <= 0:
+        args.points = {"5cm": 80000, "ptf2_infer": 250000, "tiny": 19000, "single": 60000}.get(args.config, 100000)
     if args.knn_sweep:
         out = knn_sweep(args)
+    elif args.config not in TRAIN_CONFIGS:
+        out = run_extra_config(args)
     else:
         out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
