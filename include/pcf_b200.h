@@ -44,6 +44,10 @@ const char *pcfb_last_error(void);
 const char *pcfb_version(void);
 /* Number of kernel launches enqueued by this library since load (for bench.py's gpu_launches). */
 uint64_t pcfb_launch_count(void);
+/* Programmatic dependent launch for every kernel of the library (default on; env PCFB_PDL=0): each kernel starts with
+ * griddepcontrol.wait and is launched with programmaticStreamSerializationAllowed, hiding the launch latency between the
+ * ~1800 dependent kernels of a training step.  Returns the previous setting. */
+int pcfb_set_pdl(int on);
 
 /* ---------------------------------------------------------------------------------------------
  * kNN on packed scenes.  Replaces knn_keops (knn_post_dataloader_utils.py:22-41) + the per-scene loop

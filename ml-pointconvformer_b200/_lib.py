@@ -26,6 +26,7 @@ SIGNATURES = {
     "pcfb_last_error": (ctypes.c_char_p, []),
     "pcfb_version": (ctypes.c_char_p, []),
     "pcfb_launch_count": (c_uint64, []),
+    "pcfb_set_pdl": (c_int, [c_int]),
     "pcfb_knn_packed": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "pcfb_knn_grid_workspace": (c_size_t, [c_int, c_int]),
     "pcfb_knn_grid_build": (c_int, [_P, _P, c_int, c_int, c_float, _P, c_size_t, _P]),

@@ -42,6 +42,29 @@ inline int check_launch(const char *what) {
 
 constexpr int kNumSMs = 148;   // B200
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------
+// A training step is a chain of ~1800 DEPENDENT kernels, most of them sub-wave; between two of them the GPU idled ~1.7 us
+// (profiles/step_timeline_r02.txt: 3.6 ms of gaps on the critical path).  Every kernel of this library starts with
+// pdl_wait() (griddepcontrol.wait: returns once all prerequisite grids have completed and their memory is visible) and is
+// launched with programmaticStreamSerializationAllowed, so that its CTAs are already resident, waiting, when its stream
+// predecessor drains -- the launch latency is paid while the predecessor runs.  Nothing is read or written before the
+// wait, so the semantics are exactly those of an ordinary stream-ordered launch.  PCFB_PDL=0 turns the attribute off.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through check_launch()
+}
+
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

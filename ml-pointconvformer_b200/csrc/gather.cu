@@ -11,6 +11,7 @@ template <typename VT>
 __global__ void gather_kernel(const VT *__restrict__ feats, const int64_t *__restrict__ nei,
                               int n_in, int64_t n_edges, int CV, VT *__restrict__ out)
 {
+    pdl_wait();
     const int64_t total = n_edges * CV;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -34,6 +35,7 @@ __global__ void gather_bwd_kernel(const VT *__restrict__ grad_out, const int32_t
                                   const uint8_t *__restrict__ inv_k, const int32_t *__restrict__ inv_idx,
                                   int n_in, int K, int CV, VT *__restrict__ grad_feats)
 {
+    pdl_wait();
     const int64_t total = (int64_t)n_in * CV;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -53,6 +55,7 @@ __global__ void gather_max_kernel(const float *__restrict__ feats, const int64_t
                                   int n_in, int n_out, int K, int C, float *__restrict__ out,
                                   uint8_t *__restrict__ arg)
 {
+    pdl_wait();
     const int64_t total = (int64_t)n_out * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -76,6 +79,7 @@ __global__ void gather_max_bwd_kernel(const float *__restrict__ grad_out, const 
                                       const int32_t *__restrict__ inv_idx, int n_in, int C,
                                       float *__restrict__ grad_feats)
 {
+    pdl_wait();
     const int64_t total = (int64_t)n_in * C;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -108,10 +112,9 @@ extern "C" int pcfb_gather(const float *feats, const int64_t *nei, int n_in, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t E = (int64_t)n_out * K;
     if (C % 4 == 0 && ((uintptr_t)feats % 16 == 0) && ((uintptr_t)out % 16 == 0))
-        gather_kernel<float4><<<grid_for(E * (C / 4), 256), 256, 0, st>>>(
-            reinterpret_cast<const float4 *>(feats), nei, n_in, E, C / 4, reinterpret_cast<float4 *>(out));
+        launch_k(gather_kernel<float4>, grid_for(E * (C / 4), 256), 256, 0, st, reinterpret_cast<const float4 *>(feats), nei, n_in, E, C / 4, reinterpret_cast<float4 *>(out));
     else
-        gather_kernel<float><<<grid_for(E * C, 256), 256, 0, st>>>(feats, nei, n_in, E, C, out);
+        launch_k(gather_kernel<float>, grid_for(E * C, 256), 256, 0, st, feats, nei, n_in, E, C, out);
     return check_launch("pcfb_gather");
 }
 
@@ -125,12 +128,10 @@ extern "C" int pcfb_gather_backward(const float *grad_out, const int32_t *inv_ne
     PCFB_REQUIRE(grad_out && inv_neighbors && inv_k && inv_idx && grad_feats, "pcfb_gather_backward: null pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (C % 4 == 0 && ((uintptr_t)grad_out % 16 == 0) && ((uintptr_t)grad_feats % 16 == 0))
-        gather_bwd_kernel<float4><<<grid_for((int64_t)n_in * (C / 4), 256), 256, 0, st>>>(
-            reinterpret_cast<const float4 *>(grad_out), inv_neighbors, inv_k, inv_idx, n_in, K, C / 4,
+        launch_k(gather_bwd_kernel<float4>, grid_for((int64_t)n_in * (C / 4), 256), 256, 0, st, reinterpret_cast<const float4 *>(grad_out), inv_neighbors, inv_k, inv_idx, n_in, K, C / 4,
             reinterpret_cast<float4 *>(grad_feats));
     else
-        gather_bwd_kernel<float><<<grid_for((int64_t)n_in * C, 256), 256, 0, st>>>(
-            grad_out, inv_neighbors, inv_k, inv_idx, n_in, K, C, grad_feats);
+        launch_k(gather_bwd_kernel<float>, grid_for((int64_t)n_in * C, 256), 256, 0, st, grad_out, inv_neighbors, inv_k, inv_idx, n_in, K, C, grad_feats);
     return check_launch("pcfb_gather_backward");
 }
 
@@ -141,8 +142,7 @@ extern "C" int pcfb_gather_max(const float *feats, const int64_t *nei, int n_in,
     PCFB_REQUIRE(n_in >= 0 && n_out >= 0 && K >= 1 && K <= 255 && C >= 1, "pcfb_gather_max: bad sizes");
     if ((int64_t)n_out * C == 0) return PCFB_OK;
     PCFB_REQUIRE(feats && nei && out, "pcfb_gather_max: null pointer");
-    gather_max_kernel<<<grid_for((int64_t)n_out * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        feats, nei, n_in, n_out, K, C, out, arg);
+    launch_k(gather_max_kernel, grid_for((int64_t)n_out * C, 256), 256, 0, static_cast<cudaStream_t>(stream), feats, nei, n_in, n_out, K, C, out, arg);
     return check_launch("pcfb_gather_max");
 }
 
@@ -155,7 +155,6 @@ extern "C" int pcfb_gather_max_backward(const float *grad_out, const uint8_t *ar
     PCFB_REQUIRE(n_in >= 0 && C >= 1, "pcfb_gather_max_backward: bad sizes");
     if ((int64_t)n_in * C == 0) return PCFB_OK;
     PCFB_REQUIRE(grad_out && arg && inv_neighbors && inv_k && inv_idx && grad_feats, "pcfb_gather_max_backward: null pointer");
-    gather_max_bwd_kernel<<<grid_for((int64_t)n_in * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        grad_out, arg, inv_neighbors, inv_k, inv_idx, n_in, C, grad_feats);
+    launch_k(gather_max_bwd_kernel, grid_for((int64_t)n_in * C, 256), 256, 0, static_cast<cudaStream_t>(stream), grad_out, arg, inv_neighbors, inv_k, inv_idx, n_in, C, grad_feats);
     return check_launch("pcfb_gather_max_backward");
 }

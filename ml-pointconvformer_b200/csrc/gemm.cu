@@ -41,6 +41,7 @@ __device__ __forceinline__ void g_cp_wait() { asm volatile("cp.async.wait_group 
 __global__ void gemm_prep_b_kernel(const float *__restrict__ W, int ldw, int trans, int N_total, int Nblk, int Npad, int K, int n_chunks,
                                    size_t block_floats, float *__restrict__ out)
 {
+    pdl_wait();
     const int n_col0 = blockIdx.y * Nblk;
     const int N = min(Nblk, N_total - n_col0);
     W += trans ? (size_t)n_col0 : (size_t)n_col0 * ldw;
@@ -99,6 +100,7 @@ __host__ __device__ inline GemmNtPlan gemm_nt_plan(int Npad, int n_chunks, bool 
 
 __global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
 {
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GemmNtPlan pl = gemm_nt_plan(a.Npad, a.n_chunks, a.b_resident != 0);
     unsigned char *A_base = smem_raw + pl.off_A;
@@ -315,6 +317,7 @@ __host__ __device__ inline GemmTnPlan gemm_tn_plan(int N1pad, int n2_tile, int R
 
 __global__ void __launch_bounds__(G_NT, 2) gemm_tn_kernel(GemmTnArgs a)
 {
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const GemmTnPlan pl = gemm_tn_plan(a.N1pad, a.n2_tile, a.RC);
     const int RC = a.RC;
@@ -525,6 +528,7 @@ __global__ void __launch_bounds__(G_NT, 2) gemm_tn_kernel(GemmTnArgs a)
 __global__ void gemm_tn_reduce_kernel(const float *__restrict__ partial, int S, int N1, int N2, int ldp,
                                       float *__restrict__ C, int ldc, float *__restrict__ rowsum, int transposed)
 {
+    pdl_wait();
     const int total = N1 * ldp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -538,6 +542,7 @@ __global__ void gemm_tn_reduce_kernel(const float *__restrict__ partial, int S, 
 // column sums of a row-major [M x N] matrix (N <= 256), two deterministic stages: partial[slice][n], then out[n]
 __global__ void gemm_colsum_kernel(const float *__restrict__ A, int lda, int M, int N, int slice_rows, float *__restrict__ partial)
 {
+    pdl_wait();
     __shared__ float red[256];
     const int n = threadIdx.x % N, sub = threadIdx.x / N, nsub = blockDim.x / N;
     const int m_begin = blockIdx.x * slice_rows, m_end = min(M, m_begin + slice_rows);
@@ -554,6 +559,7 @@ __global__ void gemm_colsum_kernel(const float *__restrict__ A, int lda, int M, 
 }
 __global__ void gemm_colsum_reduce_kernel(const float *__restrict__ partial, int S, int N, float *__restrict__ out)
 {
+    pdl_wait();
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
     float s = 0.f;
@@ -631,7 +637,7 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     {
         const int64_t total = (int64_t)s.n_chunks * (GT_KC / 4) * s.Npad;
         const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
-        gemm_prep_b_kernel<<<dim3(blocks < 1 ? 1 : blocks, s.n_blocks), 256, 0, st>>>(W, ldw, w_is_kn, N, s.Nblk, s.Npad, K, s.n_chunks,
+        launch_k(gemm_prep_b_kernel, dim3(blocks < 1 ? 1 : blocks, s.n_blocks), 256, 0, st, W, ldw, w_is_kn, N, s.Nblk, s.Npad, K, s.n_chunks,
                                                                               s.block_bytes / sizeof(float), static_cast<float *>(workspace));
         if ((rc = check_launch("gemm_prep_b_kernel"))) return rc;
     }
@@ -651,7 +657,7 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     int gx = ceil_div(kNumSMs * per_sm, s.n_blocks);               // CTAs per column block: the whole grid is about one wave
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;
-    gemm_nt_kernel<<<dim3(gx, s.n_blocks), G_NT, s.plan.total, st>>>(a);
+    launch_k(gemm_nt_kernel, dim3(gx, s.n_blocks), G_NT, s.plan.total, st, a);
     return check_launch("gemm_nt_kernel");
 }
 
@@ -724,17 +730,17 @@ extern "C" int pcfb_gemm_tn(const float *A, int lda, const float *B, int ldb, fl
     if (!attr) { PCFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr = true; }
     int rc;
     dim3 grid(s.n2_tiles, s.S, s.n1_blocks);
-    gemm_tn_kernel<<<grid, G_NT, s.plan.total, st>>>(a);
+    launch_k(gemm_tn_kernel, grid, G_NT, s.plan.total, st, a);
     if ((rc = check_launch("gemm_tn_kernel"))) return rc;
     const int total = s.n1 * s.ldp;
-    gemm_tn_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st>>>(a.partial, s.S, s.n1, s.n2, s.ldp, C, ldc,
+    launch_k(gemm_tn_reduce_kernel, min(ceil_div(total, 256), kNumSMs * 4), 256, 0, st, a.partial, s.S, s.n1, s.n2, s.ldp, C, ldc,
                                                                             s.swap ? nullptr : rowsum, s.swap);
     if ((rc = check_launch("gemm_tn_reduce_kernel"))) return rc;
     if (rowsum && s.swap) {
         float *cpart = reinterpret_cast<float *>(static_cast<char *>(workspace) + s.colsum_off);
-        gemm_colsum_kernel<<<s.S, 256, 0, st>>>(A, lda, M, N1, s.slice_rows, cpart);
+        launch_k(gemm_colsum_kernel, s.S, 256, 0, st, A, lda, M, N1, s.slice_rows, cpart);
         if ((rc = check_launch("gemm_colsum_kernel"))) return rc;
-        gemm_colsum_reduce_kernel<<<ceil_div(N1, 128), 128, 0, st>>>(cpart, s.S, N1, rowsum);
+        launch_k(gemm_colsum_reduce_kernel, ceil_div(N1, 128), 128, 0, st, cpart, s.S, N1, rowsum);
         if ((rc = check_launch("gemm_colsum_reduce_kernel"))) return rc;
     }
     return PCFB_OK;

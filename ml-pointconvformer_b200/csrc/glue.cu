@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(256)
 guidance_input_kernel(const float4 *__restrict__ gx, const float4 *__restrict__ pe, const int64_t *__restrict__ nei, int n_in,
                       int64_t M, int K, int G4, int P4, int use_max, float4 *__restrict__ out, uchar4 *__restrict__ arg)
 {
+    pdl_wait();
     const int C4 = G4 + P4;
     const int64_t total = M * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256)
 guidance_input_bwd_kernel(const float4 *__restrict__ ds, const uchar4 *__restrict__ arg, int64_t M, int K, int G4, int P4,
                           int use_max, float4 *__restrict__ d_gq, float4 *__restrict__ d_pe)
 {
+    pdl_wait();
     const int C4 = G4 + P4;
     const int64_t total = M * C4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -94,6 +96,7 @@ constexpr int OPT_MAX_BLOCKS = 2 * kNumSMs;
 __global__ void __launch_bounds__(OPT_THREADS)
 sqnorm_partials_kernel(const float *__restrict__ g, int64_t n, double *__restrict__ partial, float *__restrict__ step)
 {
+    pdl_wait();
     __shared__ double red[OPT_THREADS / 32];
     double s = 0.0;
     const int64_t n4 = n >> 2;
@@ -137,6 +140,7 @@ __device__ __forceinline__ void adam_one(float &p, float g, float &m, float &v, 
 __global__ void __launch_bounds__(OPT_THREADS)
 adamw_clip_kernel(AdamArgs a)
 {
+    pdl_wait();
     __shared__ double tot_s;
     if (threadIdx.x < 32) {                     // every block sums the same partials in the same order: same coefficient
         double t = 0.0;
@@ -184,6 +188,7 @@ ce_kernel(const float *__restrict__ logits, const int64_t *__restrict__ labels, 
           const float *__restrict__ den /* bwd: sum of weights of the valid rows */, const float *__restrict__ gscale,
           float *__restrict__ dlogits)
 {
+    pdl_wait();
     __shared__ float w_s[CE_MAXC];
     __shared__ float wsum_s;
     __shared__ double red[CE_THREADS / 32][2];
@@ -240,6 +245,7 @@ ce_kernel(const float *__restrict__ logits, const int64_t *__restrict__ labels, 
 
 __global__ void ce_finalize_kernel(const double *__restrict__ partial, int nblocks, float *__restrict__ loss, float *__restrict__ den)
 {
+    pdl_wait();
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < nblocks; i += 32) { a += partial[2 * i]; b += partial[2 * i + 1]; }
 #pragma unroll
@@ -260,8 +266,7 @@ extern "C" int pcfb_guidance_input(const float *gx, const float *pe, const int64
     PCFB_REQUIRE((G == 0 || gx) && (P == 0 || pe) && nei && out && (!use_max || arg), "pcfb_guidance_input: null pointer");
     PCFB_REQUIRE(((uintptr_t)gx % 16 == 0) && ((uintptr_t)pe % 16 == 0) && ((uintptr_t)out % 16 == 0), "pcfb_guidance_input: misaligned pointer");
     const int64_t work = (int64_t)n_out * ((G + P) / 4);
-    guidance_input_kernel<<<glue_grid(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4 *>(gx), reinterpret_cast<const float4 *>(pe), nei, n_in, n_out, K, G / 4, P / 4, use_max,
+    launch_k(guidance_input_kernel, glue_grid(work, 256), 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4 *>(gx), reinterpret_cast<const float4 *>(pe), nei, n_in, n_out, K, G / 4, P / 4, use_max,
         reinterpret_cast<float4 *>(out), reinterpret_cast<uchar4 *>(arg));
     return check_launch("guidance_input_kernel");
 }
@@ -274,8 +279,7 @@ extern "C" int pcfb_guidance_input_backward(const float *ds, const uint8_t *arg,
     PCFB_REQUIRE(ds && (!use_max || arg), "pcfb_guidance_input_backward: null pointer");
     PCFB_REQUIRE(((uintptr_t)ds % 16 == 0) && ((uintptr_t)d_gq % 16 == 0) && ((uintptr_t)d_pe % 16 == 0), "pcfb_guidance_input_backward: misaligned pointer");
     const int64_t work = (int64_t)n_out * ((G + P) / 4);
-    guidance_input_bwd_kernel<<<glue_grid(work, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4 *>(ds), reinterpret_cast<const uchar4 *>(arg), n_out, K, G / 4, P / 4, use_max,
+    launch_k(guidance_input_bwd_kernel, glue_grid(work, 256), 256, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const float4 *>(ds), reinterpret_cast<const uchar4 *>(arg), n_out, K, G / 4, P / 4, use_max,
         reinterpret_cast<float4 *>(d_gq), reinterpret_cast<float4 *>(d_pe));
     return check_launch("guidance_input_bwd_kernel");
 }
@@ -295,11 +299,11 @@ extern "C" int pcfb_adamw_clip_step(float *p, const float *g, float *m, float *v
     int64_t b = ((n >> 2) + OPT_THREADS - 1) / OPT_THREADS;
     const int blocks = (int)(b < 1 ? 1 : (b > OPT_MAX_BLOCKS ? OPT_MAX_BLOCKS : b));
     double *partial = static_cast<double *>(workspace);
-    sqnorm_partials_kernel<<<blocks, OPT_THREADS, 0, st>>>(g, n, partial, step);
+    launch_k(sqnorm_partials_kernel, blocks, OPT_THREADS, 0, st, g, n, partial, step);
     int rc = check_launch("sqnorm_partials_kernel");
     if (rc) return rc;
     AdamArgs a{p, g, m, v, n, partial, blocks, lr, step, beta1, beta2, eps, weight_decay, max_norm, norm_out};
-    adamw_clip_kernel<<<blocks, OPT_THREADS, 0, st>>>(a);
+    launch_k(adamw_clip_kernel, blocks, OPT_THREADS, 0, st, a);
     return check_launch("adamw_clip_kernel");
 }
 
@@ -325,10 +329,10 @@ extern "C" int pcfb_ce_forward(const float *logits, const int64_t *labels, const
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int blocks = ce_blocks(N);
     double *partial = static_cast<double *>(workspace);
-    ce_kernel<false><<<blocks, CE_THREADS, 0, st>>>(logits, labels, weight, N, C, ignore_index, smoothing, partial, nullptr, nullptr, nullptr);
+    launch_k(ce_kernel<false>, blocks, CE_THREADS, 0, st, logits, labels, weight, N, C, ignore_index, smoothing, partial, nullptr, nullptr, nullptr);
     int rc = check_launch("ce_kernel<fwd>");
     if (rc) return rc;
-    ce_finalize_kernel<<<1, 32, 0, st>>>(partial, blocks, loss, den);
+    launch_k(ce_finalize_kernel, 1, 32, 0, st, partial, blocks, loss, den);
     return check_launch("ce_finalize_kernel");
 }
 
@@ -337,7 +341,7 @@ extern "C" int pcfb_ce_backward(const float *logits, const int64_t *labels, cons
 {
     PCFB_REQUIRE(logits && labels && den && dlogits && N >= 0 && C >= 1 && C <= CE_MAXC, "pcfb_ce_backward: bad arguments");
     if (N == 0) return PCFB_OK;
-    ce_kernel<true><<<ce_blocks(N), CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, weight, N, C, ignore_index, smoothing,
+    launch_k(ce_kernel<true>, ce_blocks(N), CE_THREADS, 0, static_cast<cudaStream_t>(stream), logits, labels, weight, N, C, ignore_index, smoothing,
                                                                                        nullptr, den, grad_scale, dlogits);
     return check_launch("ce_kernel<bwd>");
 }

@@ -35,6 +35,7 @@ __device__ __forceinline__ int find_seg(const int32_t *__restrict__ off, int n_s
 }
 
 __global__ void gs_init_bounds_kernel(int *__restrict__ mm, int n_seg) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_seg * 6) mm[i] = (i % 6 < 3) ? 0x7fffffff : (int)0x80000000;
 }
@@ -42,6 +43,7 @@ __global__ void gs_init_bounds_kernel(int *__restrict__ mm, int n_seg) {
 __global__ void gs_bounds_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ seg_off, int n_seg,
                                  int n_pts, int *__restrict__ mm)
 {
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
         const int s = find_seg(seg_off, n_seg, i);
 #pragma unroll
@@ -57,6 +59,7 @@ __global__ void gs_bounds_kernel(const float *__restrict__ xyz, const int32_t *_
 __global__ void gs_finish_bounds_kernel(const int *__restrict__ mm, const int32_t *__restrict__ seg_off, int n_seg,
                                         float dl, float *__restrict__ origin, int32_t *__restrict__ dims)
 {
+    pdl_wait();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const bool empty = seg_off[s + 1] <= seg_off[s];
@@ -75,6 +78,7 @@ __global__ void gs_cell_kernel(const float *__restrict__ xyz, const int32_t *__r
                                int n_pts, float dl, const float *__restrict__ origin, const int32_t *__restrict__ dims,
                                const int32_t *__restrict__ cell_off, int64_t *__restrict__ cell)
 {
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
         const int s = find_seg(seg_off, n_seg, i);
         const int ix = (int)floorf(__fdiv_rn(__fsub_rn(xyz[3 * (size_t)i], origin[3 * s]), dl));
@@ -86,12 +90,14 @@ __global__ void gs_cell_kernel(const float *__restrict__ xyz, const int32_t *__r
 }
 
 __global__ void gs_flag_kernel(const int32_t *__restrict__ cell_ptr, int total_cells, int32_t *__restrict__ flag) {
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_cells; i += gridDim.x * blockDim.x)
         flag[i] = (cell_ptr[i + 1] > cell_ptr[i]) ? 1 : 0;
 }
 
 __global__ void gs_counts_kernel(const int32_t *__restrict__ rank, const int32_t *__restrict__ cell_off, int n_seg,
                                  int32_t *__restrict__ out_counts) {
+    pdl_wait();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n_seg) out_counts[s] = rank[cell_off[s + 1]] - rank[cell_off[s]];
 }
@@ -101,6 +107,7 @@ __global__ void gs_emit_kernel(const float *__restrict__ xyz, const float *__res
                                const int32_t *__restrict__ rank, int total_cells,
                                float *__restrict__ out_xyz, float *__restrict__ out_feats)
 {
+    pdl_wait();
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < total_cells; c += gridDim.x * blockDim.x) {
         const int beg = cell_ptr[c], end = cell_ptr[c + 1];
         if (end <= beg) continue;
@@ -132,6 +139,7 @@ __global__ void gs_emit_kernel(const float *__restrict__ xyz, const float *__res
 __global__ void gs_bounds_dev_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ seg_off, int n_seg,
                                      int n_pts_max, int *__restrict__ mm)
 {
+    pdl_wait();
     const int n_pts = min(seg_off[n_seg], n_pts_max);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
         const int s = find_seg(seg_off, n_seg, i);
@@ -148,6 +156,7 @@ __global__ void gs_bounds_dev_kernel(const float *__restrict__ xyz, const int32_
 __global__ void gs_cell_off_kernel(int32_t *__restrict__ dims, int n_seg, long long cells_max, int32_t *__restrict__ cell_off,
                                    int32_t *__restrict__ status)
 {
+    pdl_wait();
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     long long tot = 0;
     for (int s = 0; s < n_seg; ++s) {
@@ -167,6 +176,7 @@ __global__ void gs_cell_dev_kernel(const float *__restrict__ xyz, const int32_t 
                                    int n_pts_max, float dl, const float *__restrict__ origin, const int32_t *__restrict__ dims,
                                    const int32_t *__restrict__ cell_off, int64_t *__restrict__ cell)
 {
+    pdl_wait();
     const int n_pts = min(seg_off[n_seg], n_pts_max);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts_max; i += gridDim.x * blockDim.x) {
         if (i >= n_pts) { cell[i] = -1; continue; }
@@ -184,6 +194,7 @@ __global__ void gs_cell_dev_kernel(const float *__restrict__ xyz, const int32_t 
 __global__ void gs_out_off_kernel(const int32_t *__restrict__ rank, const int32_t *__restrict__ cell_off, int n_seg,
                                   int32_t *__restrict__ out_seg_off)
 {
+    pdl_wait();
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     int tot = 0;
     out_seg_off[0] = 0;
@@ -200,6 +211,7 @@ __global__ void vx_cell_kernel(const float *__restrict__ xyz, const int32_t *__r
                                double voxel, const int *__restrict__ mm, const int32_t *__restrict__ dims,
                                const int32_t *__restrict__ cell_off, int32_t *__restrict__ first)
 {
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
         const int s = find_seg(seg_off, n_seg, i);
         const int64_t nx = dims[3 * s], ny = dims[3 * s + 1], nz = dims[3 * s + 2];
@@ -219,6 +231,7 @@ __global__ void vx_cell_kernel(const float *__restrict__ xyz, const int32_t *__r
 __global__ void vx_dims_kernel(const int *__restrict__ mm, const int32_t *__restrict__ seg_off, int n_seg, double voxel,
                                int32_t *__restrict__ dims)
 {
+    pdl_wait();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const bool empty = seg_off[s + 1] <= seg_off[s];
@@ -232,16 +245,19 @@ __global__ void vx_dims_kernel(const int *__restrict__ mm, const int32_t *__rest
 }
 
 __global__ void vx_fill_kernel(int32_t *__restrict__ first, long long n) {
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) first[i] = 0x7fffffff;
 }
 __global__ void vx_flag_kernel(const int32_t *__restrict__ first, const int32_t *__restrict__ cell_off, int n_seg, int cells_max,
                                int32_t *__restrict__ flag) {
+    pdl_wait();
     const int total = cell_off[n_seg];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= cells_max; i += gridDim.x * blockDim.x)
         flag[i] = (i < total && first[i] != 0x7fffffff) ? 1 : 0;
 }
 __global__ void vx_emit_kernel(const int32_t *__restrict__ first, const int32_t *__restrict__ rank, const int32_t *__restrict__ cell_off,
                                int n_seg, int32_t *__restrict__ out_idx) {
+    pdl_wait();
     const int total = cell_off[n_seg];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
         if (first[i] != 0x7fffffff) out_idx[rank[i]] = first[i];
@@ -303,13 +319,13 @@ extern "C" int pcfb_gridsub_bounds(const float *xyz, const int32_t *seg_off, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int *mm = static_cast<int *>(workspace);
     int rc;
-    gs_init_bounds_kernel<<<ceil_div(n_seg * 6, 256), 256, 0, st>>>(mm, n_seg);
+    launch_k(gs_init_bounds_kernel, ceil_div(n_seg * 6, 256), 256, 0, st, mm, n_seg);
     if ((rc = check_launch("gs_init_bounds_kernel"))) return rc;
     if (n_pts > 0) {
-        gs_bounds_kernel<<<blocks_for(n_pts), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts, mm);
+        launch_k(gs_bounds_kernel, blocks_for(n_pts), 256, 0, st, xyz, seg_off, n_seg, n_pts, mm);
         if ((rc = check_launch("gs_bounds_kernel"))) return rc;
     }
-    gs_finish_bounds_kernel<<<ceil_div(n_seg, 128), 128, 0, st>>>(mm, seg_off, n_seg, dl, out_origin, out_dims);
+    launch_k(gs_finish_bounds_kernel, ceil_div(n_seg, 128), 128, 0, st, mm, seg_off, n_seg, dl, out_origin, out_dims);
     return check_launch("gs_finish_bounds_kernel");
 }
 
@@ -327,7 +343,7 @@ extern "C" int pcfb_gridsub_count(const float *xyz, const int32_t *seg_off, int 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
     if (n_pts > 0) {
-        gs_cell_kernel<<<blocks_for(n_pts), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts, dl, origin, dims, cell_off, w.cell);
+        launch_k(gs_cell_kernel, blocks_for(n_pts), 256, 0, st, xyz, seg_off, n_seg, n_pts, dl, origin, dims, cell_off, w.cell);
         if ((rc = check_launch("gs_cell_kernel"))) return rc;
     }
     if ((rc = pcfb_knn_inverse(w.cell, n_pts, 1, (int)total_cells, w.pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream))) return rc;
@@ -335,12 +351,12 @@ extern "C" int pcfb_gridsub_count(const float *xyz, const int32_t *seg_off, int 
     PCFB_CUDA(cudaMemsetAsync(w.state, 0, (size_t)((char *)w.inv_ws - (char *)w.state), st));
     PCFB_CUDA(cudaMemsetAsync(w.flag + total_cells, 0, sizeof(int32_t), st));
     if (total_cells > 0) {
-        gs_flag_kernel<<<blocks_for(total_cells), 256, 0, st>>>(w.cell_ptr, (int)total_cells, w.flag);
+        launch_k(gs_flag_kernel, blocks_for(total_cells), 256, 0, st, w.cell_ptr, (int)total_cells, w.flag);
         if ((rc = check_launch("gs_flag_kernel"))) return rc;
     }
-    inv_scan_kernel<<<ceil_div((int)total_cells + 1, SCAN_TILE), SCAN_THREADS, 0, st>>>(w.flag, (int)total_cells, w.rank, w.state, w.ticket);
+    launch_k(inv_scan_kernel, ceil_div((int)total_cells + 1, SCAN_TILE), SCAN_THREADS, 0, st, w.flag, (int)total_cells, w.rank, w.state, w.ticket);
     if ((rc = check_launch("inv_scan_kernel"))) return rc;
-    gs_counts_kernel<<<ceil_div(n_seg, 128), 128, 0, st>>>(w.rank, cell_off, n_seg, out_counts);
+    launch_k(gs_counts_kernel, ceil_div(n_seg, 128), 128, 0, st, w.rank, cell_off, n_seg, out_counts);
     return check_launch("gs_counts_kernel");
 }
 
@@ -354,8 +370,7 @@ extern "C" int pcfb_gridsub_emit(const float *xyz, const float *feats, int n_seg
     GsWorkspace w = carve_gs(workspace, n_seg, n_pts, total_cells);
     if (workspace_bytes < w.bytes) { set_error("pcfb_gridsub_emit: workspace %zu < %zu", workspace_bytes, w.bytes); return PCFB_ERR_WORKSPACE; }
     if (total_cells == 0) return PCFB_OK;
-    gs_emit_kernel<<<blocks_for(total_cells), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        xyz, feats, F, w.cell_ptr, w.pts, w.rank, (int)total_cells, out_xyz, out_feats);
+    launch_k(gs_emit_kernel, blocks_for(total_cells), 256, 0, static_cast<cudaStream_t>(stream), xyz, feats, F, w.cell_ptr, w.pts, w.rank, (int)total_cells, out_xyz, out_feats);
     return check_launch("gs_emit_kernel");
 }
 
@@ -394,26 +409,26 @@ extern "C" int pcfb_pyramid_level(const float *xyz, const float *feats, int F, c
     if (workspace_bytes < e.bytes) { set_error("pcfb_pyramid_level: workspace %zu < %zu", workspace_bytes, e.bytes); return PCFB_ERR_WORKSPACE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    gs_init_bounds_kernel<<<ceil_div(n_seg * 6, 256), 256, 0, st>>>(w.mm, n_seg);
+    launch_k(gs_init_bounds_kernel, ceil_div(n_seg * 6, 256), 256, 0, st, w.mm, n_seg);
     if ((rc = check_launch("gs_init_bounds_kernel"))) return rc;
-    gs_bounds_dev_kernel<<<blocks_for(n_pts_max), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts_max, w.mm);
+    launch_k(gs_bounds_dev_kernel, blocks_for(n_pts_max), 256, 0, st, xyz, seg_off, n_seg, n_pts_max, w.mm);
     if ((rc = check_launch("gs_bounds_dev_kernel"))) return rc;
-    gs_finish_bounds_kernel<<<ceil_div(n_seg, 128), 128, 0, st>>>(w.mm, seg_off, n_seg, dl, e.origin, e.dims);
+    launch_k(gs_finish_bounds_kernel, ceil_div(n_seg, 128), 128, 0, st, w.mm, seg_off, n_seg, dl, e.origin, e.dims);
     if ((rc = check_launch("gs_finish_bounds_kernel"))) return rc;
-    gs_cell_off_kernel<<<1, 32, 0, st>>>(e.dims, n_seg, (long long)cells_max, e.cell_off, status);
+    launch_k(gs_cell_off_kernel, 1, 32, 0, st, e.dims, n_seg, (long long)cells_max, e.cell_off, status);
     if ((rc = check_launch("gs_cell_off_kernel"))) return rc;
-    gs_cell_dev_kernel<<<blocks_for(n_pts_max), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts_max, dl, e.origin, e.dims, e.cell_off, w.cell);
+    launch_k(gs_cell_dev_kernel, blocks_for(n_pts_max), 256, 0, st, xyz, seg_off, n_seg, n_pts_max, dl, e.origin, e.dims, e.cell_off, w.cell);
     if ((rc = check_launch("gs_cell_dev_kernel"))) return rc;
     if ((rc = pcfb_knn_inverse(w.cell, n_pts_max, 1, (int)cells_max, w.pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream))) return rc;
     PCFB_CUDA(cudaMemsetAsync(w.state, 0, (size_t)((char *)w.inv_ws - (char *)w.state), st));
     PCFB_CUDA(cudaMemsetAsync(w.flag + cells_max, 0, sizeof(int32_t), st));
-    gs_flag_kernel<<<blocks_for(cells_max), 256, 0, st>>>(w.cell_ptr, (int)cells_max, w.flag);
+    launch_k(gs_flag_kernel, blocks_for(cells_max), 256, 0, st, w.cell_ptr, (int)cells_max, w.flag);
     if ((rc = check_launch("gs_flag_kernel"))) return rc;
-    inv_scan_kernel<<<ceil_div((int)cells_max + 1, SCAN_TILE), SCAN_THREADS, 0, st>>>(w.flag, (int)cells_max, w.rank, w.state, w.ticket);
+    launch_k(inv_scan_kernel, ceil_div((int)cells_max + 1, SCAN_TILE), SCAN_THREADS, 0, st, w.flag, (int)cells_max, w.rank, w.state, w.ticket);
     if ((rc = check_launch("inv_scan_kernel"))) return rc;
-    gs_out_off_kernel<<<1, 32, 0, st>>>(w.rank, e.cell_off, n_seg, out_seg_off);
+    launch_k(gs_out_off_kernel, 1, 32, 0, st, w.rank, e.cell_off, n_seg, out_seg_off);
     if ((rc = check_launch("gs_out_off_kernel"))) return rc;
-    gs_emit_kernel<<<blocks_for(cells_max), 256, 0, st>>>(xyz, feats, F, w.cell_ptr, w.pts, w.rank, (int)cells_max, out_xyz, out_feats);
+    launch_k(gs_emit_kernel, blocks_for(cells_max), 256, 0, st, xyz, feats, F, w.cell_ptr, w.pts, w.rank, (int)cells_max, out_xyz, out_feats);
     return check_launch("gs_emit_kernel");
 }
 
@@ -453,29 +468,29 @@ extern "C" int pcfb_voxelize(const float *xyz, const int32_t *seg_off, int n_seg
     unsigned int *ticket = c.take<unsigned int>(4);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    gs_init_bounds_kernel<<<ceil_div(n_seg * 6, 256), 256, 0, st>>>(mm, n_seg);
+    launch_k(gs_init_bounds_kernel, ceil_div(n_seg * 6, 256), 256, 0, st, mm, n_seg);
     if ((rc = check_launch("gs_init_bounds_kernel"))) return rc;
     if (n_pts > 0) {
-        gs_bounds_kernel<<<blocks_for(n_pts), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts, mm);
+        launch_k(gs_bounds_kernel, blocks_for(n_pts), 256, 0, st, xyz, seg_off, n_seg, n_pts, mm);
         if ((rc = check_launch("gs_bounds_kernel"))) return rc;
     }
-    vx_dims_kernel<<<ceil_div(n_seg, 128), 128, 0, st>>>(mm, seg_off, n_seg, voxel, dims);
+    launch_k(vx_dims_kernel, ceil_div(n_seg, 128), 128, 0, st, mm, seg_off, n_seg, voxel, dims);
     if ((rc = check_launch("vx_dims_kernel"))) return rc;
-    gs_cell_off_kernel<<<1, 32, 0, st>>>(dims, n_seg, (long long)cells_max, cell_off, status);
+    launch_k(gs_cell_off_kernel, 1, 32, 0, st, dims, n_seg, (long long)cells_max, cell_off, status);
     if ((rc = check_launch("gs_cell_off_kernel"))) return rc;
-    vx_fill_kernel<<<blocks_for(cells_max + 1), 256, 0, st>>>(first, (long long)cells_max + 1);
+    launch_k(vx_fill_kernel, blocks_for(cells_max + 1), 256, 0, st, first, (long long)cells_max + 1);
     if ((rc = check_launch("vx_fill_kernel"))) return rc;
     if (n_pts > 0) {
-        vx_cell_kernel<<<blocks_for(n_pts), 256, 0, st>>>(xyz, seg_off, n_seg, n_pts, voxel, mm, dims, cell_off, first);
+        launch_k(vx_cell_kernel, blocks_for(n_pts), 256, 0, st, xyz, seg_off, n_seg, n_pts, voxel, mm, dims, cell_off, first);
         if ((rc = check_launch("vx_cell_kernel"))) return rc;
     }
     PCFB_CUDA(cudaMemsetAsync(state, 0, (size_t)((char *)ticket + 4 * sizeof(unsigned int) - (char *)state), st));
-    vx_flag_kernel<<<blocks_for(cells_max + 1), 256, 0, st>>>(first, cell_off, n_seg, (int)cells_max, flag);
+    launch_k(vx_flag_kernel, blocks_for(cells_max + 1), 256, 0, st, first, cell_off, n_seg, (int)cells_max, flag);
     if ((rc = check_launch("vx_flag_kernel"))) return rc;
-    inv_scan_kernel<<<ceil_div((int)cells_max + 1, SCAN_TILE), SCAN_THREADS, 0, st>>>(flag, (int)cells_max, rank, state, ticket);
+    launch_k(inv_scan_kernel, ceil_div((int)cells_max + 1, SCAN_TILE), SCAN_THREADS, 0, st, flag, (int)cells_max, rank, state, ticket);
     if ((rc = check_launch("inv_scan_kernel"))) return rc;
-    gs_out_off_kernel<<<1, 32, 0, st>>>(rank, cell_off, n_seg, out_seg_off);
+    launch_k(gs_out_off_kernel, 1, 32, 0, st, rank, cell_off, n_seg, out_seg_off);
     if ((rc = check_launch("gs_out_off_kernel"))) return rc;
-    vx_emit_kernel<<<blocks_for(cells_max), 256, 0, st>>>(first, rank, cell_off, n_seg, out_idx);
+    launch_k(vx_emit_kernel, blocks_for(cells_max), 256, 0, st, first, rank, cell_off, n_seg, out_idx);
     return check_launch("vx_emit_kernel");
 }

@@ -16,6 +16,7 @@ namespace pcfb {
 __global__ void inv_count_kernel(const int64_t *__restrict__ nei, int64_t n_edges, int total,
                                  int32_t *__restrict__ counts)
 {
+    pdl_wait();
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = nei[e];
@@ -27,6 +28,7 @@ __global__ void inv_fill_kernel(const int64_t *__restrict__ nei, int64_t n_edges
                                 const int32_t *__restrict__ inv_idx, int32_t *__restrict__ cursor,
                                 int32_t *__restrict__ scratch)
 {
+    pdl_wait();
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t p = nei[e];
@@ -42,6 +44,7 @@ __global__ void inv_sort_kernel(const int32_t *__restrict__ scratch, const int32
                                 int total, int K, int32_t *__restrict__ inv_neighbors,
                                 uint8_t *__restrict__ inv_k)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     for (int p = blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < total; p += gridDim.x * warps_per_block) {
@@ -121,19 +124,19 @@ extern "C" int pcfb_knn_inverse(const int64_t *nei, int n_out, int K, int total,
     const int64_t eb64 = (E + 255) / 256;
     const int eb = (int)(eb64 < (int64_t)kNumSMs * 16 ? eb64 : (int64_t)kNumSMs * 16);
     if (E > 0) {
-        inv_count_kernel<<<eb, 256, 0, st>>>(nei, E, total, w.counts);
+        launch_k(inv_count_kernel, eb, 256, 0, st, nei, E, total, w.counts);
         if ((rc = check_launch("inv_count_kernel"))) return rc;
     }
     const int tiles = ceil_div(total + 1, SCAN_TILE);
     // scan over total+1 entries (the extra trailing zero yields inv_idx[total] = grand total)
-    inv_scan_kernel<<<tiles, SCAN_THREADS, 0, st>>>(w.counts, total, inv_idx, w.state, w.ticket);
+    launch_k(inv_scan_kernel, tiles, SCAN_THREADS, 0, st, w.counts, total, inv_idx, w.state, w.ticket);
     if ((rc = check_launch("inv_scan_kernel"))) return rc;
     if (E > 0) {
         PCFB_CUDA(cudaMemsetAsync(w.counts, 0, sizeof(int32_t) * (size_t)total, st));
-        inv_fill_kernel<<<eb, 256, 0, st>>>(nei, E, total, inv_idx, w.counts, w.scratch);
+        launch_k(inv_fill_kernel, eb, 256, 0, st, nei, E, total, inv_idx, w.counts, w.scratch);
         if ((rc = check_launch("inv_fill_kernel"))) return rc;
         const int sb = min(ceil_div(total, 8), kNumSMs * 8);
-        inv_sort_kernel<<<max(sb, 1), 256, 0, st>>>(w.scratch, inv_idx, total, K, inv_neighbors, inv_k);
+        launch_k(inv_sort_kernel, max(sb, 1), 256, 0, st, w.scratch, inv_idx, total, K, inv_neighbors, inv_k);
         if ((rc = check_launch("inv_sort_kernel"))) return rc;
     }
     return PCFB_OK;

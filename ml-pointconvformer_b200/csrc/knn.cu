@@ -60,6 +60,7 @@ knn_packed_kernel(const float *__restrict__ ref, const int32_t *__restrict__ ref
                   const float *__restrict__ qry, const int32_t *__restrict__ qry_off,
                   int n_seg, int n_qry, int K, int64_t *__restrict__ out)
 {
+    pdl_wait();
     __shared__ __align__(16) float sx[KNN_TILE], sy[KNN_TILE], sz[KNN_TILE];
     __shared__ int s_lo, s_hi;
 
@@ -149,6 +150,7 @@ knn_packed_generic_kernel(const float *__restrict__ ref, const int32_t *__restri
                           const float *__restrict__ qry, const int32_t *__restrict__ qry_off,
                           int n_seg, int n_qry, int K, int64_t *__restrict__ out)
 {
+    pdl_wait();
     extern __shared__ float smem[];
     float *ld = smem;                                              // [K][T]
     int *li = reinterpret_cast<int *>(smem + (size_t)K * KNN_GEN_THREADS);  // [K][T]
@@ -194,11 +196,11 @@ extern "C" int pcfb_knn_packed(const float *ref_xyz, const int32_t *ref_off, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = ceil_div(n_qry, KNN_THREADS);
     if (K <= 16)
-        knn_packed_kernel<16><<<grid, KNN_THREADS, 0, st>>>(ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_packed_kernel<16>, grid, KNN_THREADS, 0, st, ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else if (K <= 32)
-        knn_packed_kernel<32><<<grid, KNN_THREADS, 0, st>>>(ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_packed_kernel<32>, grid, KNN_THREADS, 0, st, ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else if (K <= 64)
-        knn_packed_kernel<64><<<grid, KNN_THREADS, 0, st>>>(ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_packed_kernel<64>, grid, KNN_THREADS, 0, st, ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else {
         const size_t smem = (size_t)K * KNN_GEN_THREADS * 8;
         static bool attr_set = false;
@@ -206,8 +208,7 @@ extern "C" int pcfb_knn_packed(const float *ref_xyz, const int32_t *ref_off, con
             PCFB_CUDA(cudaFuncSetAttribute(knn_packed_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 255 * KNN_GEN_THREADS * 8));
             attr_set = true;
         }
-        knn_packed_generic_kernel<<<ceil_div(n_qry, KNN_GEN_THREADS), KNN_GEN_THREADS, smem, st>>>(
-            ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_packed_generic_kernel, ceil_div(n_qry, KNN_GEN_THREADS), KNN_GEN_THREADS, smem, st, ref_xyz, ref_off, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     }
     return check_launch("pcfb_knn_packed");
 }

@@ -38,6 +38,7 @@ __device__ __forceinline__ int g_find_seg(const int32_t *__restrict__ off, int n
 }
 
 __global__ void kg_init_kernel(int *__restrict__ mm, int n_seg) {
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_seg * 6) mm[i] = (i % 6 < 3) ? 0x7fffffff : (int)0x80000000;
 }
@@ -45,6 +46,7 @@ __global__ void kg_init_kernel(int *__restrict__ mm, int n_seg) {
 __global__ void kg_bounds_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ off, int n_seg, int n,
                                  int *__restrict__ mm)
 {
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int s = g_find_seg(off, n_seg, i);
 #pragma unroll
@@ -60,6 +62,7 @@ __global__ void kg_bounds_kernel(const float *__restrict__ xyz, const int32_t *_
 __global__ void kg_plan_kernel(const int *__restrict__ mm, const int32_t *__restrict__ off, int n_seg, float cell_hint,
                                GridPlan *__restrict__ plans)
 {
+    pdl_wait();
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     int cell_off = 0;
     for (int s = 0; s < n_seg; ++s) {
@@ -96,6 +99,7 @@ __device__ __forceinline__ int cell_coord(float x, float o, float h, int n) {
 __global__ void kg_cell_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ off, int n_seg, int n,
                                const GridPlan *__restrict__ plans, int64_t *__restrict__ cell)
 {
+    pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const GridPlan p = plans[g_find_seg(off, n_seg, i)];
         const int cx = cell_coord(xyz[3 * (size_t)i], p.ox, p.h, p.nx);
@@ -141,6 +145,7 @@ knn_grid_query_kernel(const float *__restrict__ ref, const GridPlan *__restrict_
                       const float *__restrict__ qry, const int32_t *__restrict__ qry_off, int n_seg, int n_qry, int K,
                       int64_t *__restrict__ out)
 {
+    pdl_wait();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_qry) return;
     const GridPlan p = plans[g_find_seg(qry_off, n_seg, q)];
@@ -252,16 +257,16 @@ extern "C" int pcfb_knn_grid_build(const float *ref_xyz, const int32_t *ref_off,
     if (workspace_bytes < w.bytes) { set_error("pcfb_knn_grid_build: workspace %zu < %zu", workspace_bytes, w.bytes); return PCFB_ERR_WORKSPACE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    kg_init_kernel<<<ceil_div(n_seg * 6, 256), 256, 0, st>>>(w.mm, n_seg);
+    launch_k(kg_init_kernel, ceil_div(n_seg * 6, 256), 256, 0, st, w.mm, n_seg);
     if ((rc = check_launch("kg_init_kernel"))) return rc;
     if (n_ref > 0) {
-        kg_bounds_kernel<<<kg_blocks(n_ref), 256, 0, st>>>(ref_xyz, ref_off, n_seg, n_ref, w.mm);
+        launch_k(kg_bounds_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, ref_off, n_seg, n_ref, w.mm);
         if ((rc = check_launch("kg_bounds_kernel"))) return rc;
     }
-    kg_plan_kernel<<<1, 32, 0, st>>>(w.mm, ref_off, n_seg, cell_hint, w.plans);
+    launch_k(kg_plan_kernel, 1, 32, 0, st, w.mm, ref_off, n_seg, cell_hint, w.plans);
     if ((rc = check_launch("kg_plan_kernel"))) return rc;
     if (n_ref > 0) {
-        kg_cell_kernel<<<kg_blocks(n_ref), 256, 0, st>>>(ref_xyz, ref_off, n_seg, n_ref, w.plans, w.cell);
+        launch_k(kg_cell_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, ref_off, n_seg, n_ref, w.plans, w.cell);
         if ((rc = check_launch("kg_cell_kernel"))) return rc;
     }
     return pcfb_knn_inverse(w.cell, n_ref, 1, w.max_cells, w.cell_pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream);
@@ -281,10 +286,10 @@ extern "C" int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, c
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = ceil_div(n_qry, 128);
     if (K <= 16)
-        knn_grid_query_kernel<16><<<grid, 128, 0, st>>>(ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_grid_query_kernel<16>, grid, 128, 0, st, ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else if (K <= 32)
-        knn_grid_query_kernel<32><<<grid, 128, 0, st>>>(ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_grid_query_kernel<32>, grid, 128, 0, st, ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else
-        knn_grid_query_kernel<64><<<grid, 128, 0, st>>>(ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_grid_query_kernel<64>, grid, 128, 0, st, ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     return check_launch("knn_grid_query_kernel");
 }

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(ML_THREADS)
 mlp_fwd_kernel(const float *__restrict__ x, int ldx, int64_t E, MlpLayer L, float *__restrict__ y, int ldy,
                float *__restrict__ stat_partial, int rows_per_thread)
 {
+    pdl_wait();
     __shared__ __align__(16) float W_s[COUT * CIN];
     __shared__ float b_s[COUT], s_s[CIN], t_s[CIN];
     __shared__ float red[ML_WARPS][2 * COUT];
@@ -151,6 +152,7 @@ __global__ void bn_act_kernel(const float *__restrict__ y, int64_t n, int C, con
                               const float *__restrict__ shift, int act, float *__restrict__ out,
                               const float *__restrict__ res, int res_after)
 {
+    pdl_wait();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i % C);
         float z = scale ? fmaf(y[i], scale[c], shift[c]) : y[i];
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(ML_THREADS)
 mlp_bwd_stats_kernel(const float *__restrict__ dA, int ldd, const float *__restrict__ y, int ldy, int64_t E, int C,
                      MlpBnCtx B, float *__restrict__ partial, int rows_per_thread)
 {
+    pdl_wait();
     __shared__ float red[ML_WARPS][2 * COUT];
     __shared__ BnConst<COUT> K;
     bn_const_fill<COUT>(K, B, C, 0.f);
@@ -275,6 +278,7 @@ mlp_bwd_stats_kernel(const float *__restrict__ dA, int ldd, const float *__restr
 // sums[2][C] = fixed-order (double) reduction of the block partials; also used for dgamma (= S2) / dbeta (= S1)
 __global__ void sum_partials_kernel(const float *__restrict__ partial, int nblocks, int n, float *__restrict__ out)
 {
+    pdl_wait();
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= n) return;
@@ -301,6 +305,7 @@ mlp_bwd_input_kernel(const float *__restrict__ dA, int ldd, const float *__restr
                      const float *__restrict__ y_prev, int ldyp, MlpBnCtx Bp, float *__restrict__ prev_partial,
                      int rows_per_thread)
 {
+    pdl_wait();
     __shared__ __align__(16) float Wt_s[CIN * COUT];          // transposed: [k][o]
     __shared__ float red[ML_WARPS][2 * CIN];
     __shared__ BnConst<COUT> K;                                 // this layer
@@ -386,6 +391,7 @@ mlp_bwd_weight_kernel(const float *__restrict__ dA, int ldd, const float *__rest
                       MlpBnCtx B, const float *__restrict__ x_prev, int ldx, const float *__restrict__ in_scale,
                       const float *__restrict__ in_shift, int in_act, float *__restrict__ partial)
 {
+    pdl_wait();
     constexpr int DS = COUT + 4, AS = CIN + 4;                  // padded row strides (floats), 16-byte aligned rows
     constexpr int NPB = (COUT / 4) * (CIN / 4);                 // 4x4 blocks of the gradient
     constexpr int NS = ML_THREADS / NPB;                        // row slices
@@ -509,6 +515,7 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
                      const float *__restrict__ x_prev, int ldx, MlpBnCtx Bp,
                      float *__restrict__ dA_prev, int ldp, float *__restrict__ prev_partial, float *__restrict__ w_partial)
 {
+    pdl_wait();
     constexpr int DS = COUT + 4, AS = CIN + 4;
     constexpr int NPB = (COUT / 4) * (CIN / 4);                 // 4x4 blocks of dW: 16 or 32
     constexpr int RH = 32 / NPB;                                // row halves per block (2 when NPB == 16, else 1)
@@ -738,6 +745,7 @@ mlp_bwd_fused_kernel(const float *__restrict__ dA, int ldd, const float *__restr
 __global__ void mlp_weight_finalize_kernel(const float *__restrict__ partial, int nblocks, int cout, int cin,
                                            float *__restrict__ dW, float *__restrict__ db)
 {
+    pdl_wait();
     const int n = cout * (cin + 1);
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -764,6 +772,7 @@ __global__ void mlp_fused_finalize_kernel(const float *__restrict__ w_partial, c
                                           int cout, int cin, float *__restrict__ dW, float *__restrict__ db,
                                           float *__restrict__ prev_sums)
 {
+    pdl_wait();
     const int n_w = cout * (cin + 1), n_p = p_partial ? 2 * cin : 0;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -867,10 +876,10 @@ extern "C" int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int ci, co;
     chain_dims(cin, cout, &ci, &co);
-    if (ci == 8 && co == 8) mlp_fwd_kernel<8, 8><<<blocks, ML_THREADS, 0, st>>>(x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E));
-    else if (ci == 8 && co == 16) mlp_fwd_kernel<8, 16><<<blocks, ML_THREADS, 0, st>>>(x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E));
-    else if (ci == 16 && co == 8) mlp_fwd_kernel<16, 8><<<blocks, ML_THREADS, 0, st>>>(x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E));
-    else ML_DISPATCH_IO(ci, co, (mlp_fwd_kernel<CI, CO><<<blocks, ML_THREADS, 0, st>>>(x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E))));
+    if (ci == 8 && co == 8) launch_k(mlp_fwd_kernel<8, 8>, blocks, ML_THREADS, 0, st, x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E));
+    else if (ci == 8 && co == 16) launch_k(mlp_fwd_kernel<8, 16>, blocks, ML_THREADS, 0, st, x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E));
+    else if (ci == 16 && co == 8) launch_k(mlp_fwd_kernel<16, 8>, blocks, ML_THREADS, 0, st, x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E));
+    else ML_DISPATCH_IO(ci, co, (launch_k(mlp_fwd_kernel<CI, CO>, blocks, ML_THREADS, 0, st, x, ldx, E, L, y, ldy, stat_partial, mlp_rpt(E))));
     return check_launch("mlp_fwd_kernel");
 }
 
@@ -887,11 +896,11 @@ extern "C" int pcfb_bn_act(const float *y, int64_t rows, int C, const float *sca
         const int c4 = C >> 2, ry = 256 / c4;
         int64_t b4 = (rows + ry - 1) / ry;
         if (b4 > (int64_t)kNumSMs * 8) b4 = (int64_t)kNumSMs * 8;
-        bn_act4_kernel<<<(int)b4, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, rows, C, scale, shift, act, out, c4, ry, residual,
+        launch_k(bn_act4_kernel, (int)b4, 256, 0, static_cast<cudaStream_t>(stream), y, rows, C, scale, shift, act, out, c4, ry, residual,
                                                                                residual_after_act);
         return check_launch("bn_act4_kernel");
     }
-    bn_act_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, n, C, scale, shift, act, out, residual, residual_after_act);
+    launch_k(bn_act_kernel, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), y, n, C, scale, shift, act, out, residual, residual_after_act);
     return check_launch("bn_act_kernel");
 }
 
@@ -910,14 +919,14 @@ extern "C" int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y,
     int rc;
     if (E > 0) {
         const int co = C <= 8 ? 8 : cmax_of(C);
-        if (co == 8) mlp_bwd_stats_kernel<8><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
-        else if (co == 16) mlp_bwd_stats_kernel<16><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
-        else if (co == 32) mlp_bwd_stats_kernel<32><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
-        else mlp_bwd_stats_kernel<64><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
+        if (co == 8) launch_k(mlp_bwd_stats_kernel<8>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
+        else if (co == 16) launch_k(mlp_bwd_stats_kernel<16>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
+        else if (co == 32) launch_k(mlp_bwd_stats_kernel<32>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
+        else launch_k(mlp_bwd_stats_kernel<64>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, C, B, partial, mlp_rpt(E));
         if ((rc = check_launch("mlp_bwd_stats_kernel"))) return rc;
     }
     if (!sums) return PCFB_OK;                                   // the caller reduces the partials itself (pcfb_bn_reduce_sums)
-    sum_partials_kernel<<<ceil_div(2 * C * 32, 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * C, sums);
+    launch_k(sum_partials_kernel, ceil_div(2 * C * 32, 128), 128, 0, st, partial, E > 0 ? blocks : 0, 2 * C, sums);
     return check_launch("sum_partials_kernel");
 }
 
@@ -957,10 +966,10 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
 #define ML_FUSED_CASE(CI_, CO_)                                                                                   \
         if (ci == CI_ && co == CO_) {                                                                             \
             if (act == ACT_SIGMOID)                                                                               \
-                mlp_bwd_fused_kernel<CI_, CO_, true><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, W, cin, cout, B, x_prev, ldx, Bp, \
+                launch_k(mlp_bwd_fused_kernel<CI_, CO_, true>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, W, cin, cout, B, x_prev, ldx, Bp, \
                                                                                     dA_prev, ldp, prev_sums ? p_part : nullptr, w_part); \
             else                                                                                                  \
-                mlp_bwd_fused_kernel<CI_, CO_, false><<<blocks, ML_THREADS, 0, st>>>(dA, ldd, y, ldy, E, W, cin, cout, B, x_prev, ldx, Bp, \
+                launch_k(mlp_bwd_fused_kernel<CI_, CO_, false>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, W, cin, cout, B, x_prev, ldx, Bp, \
                                                                                      dA_prev, ldp, prev_sums ? p_part : nullptr, w_part); \
         }
         ML_FUSED_CASE(8, 8) ML_FUSED_CASE(8, 16) ML_FUSED_CASE(16, 8) ML_FUSED_CASE(16, 16) ML_FUSED_CASE(16, 32)
@@ -968,19 +977,18 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
         ci = cmax_of(cin); co = cmax_of(cout);
         if ((rc = check_launch("mlp_bwd_fused_kernel"))) return rc;
         const int n_fin = cout * (cin + 1) + (prev_sums ? 2 * cin : 0);
-        mlp_fused_finalize_kernel<<<ceil_div(n_fin * 32, 256), 256, 0, st>>>(w_part, prev_sums ? p_part : nullptr, blocks, cout, cin,
+        launch_k(mlp_fused_finalize_kernel, ceil_div(n_fin * 32, 256), 256, 0, st, w_part, prev_sums ? p_part : nullptr, blocks, cout, cin,
                                                                             dW, db, prev_sums);
         return check_launch("mlp_fused_finalize_kernel");
     }
     if (dA_prev) {
         const int blocks = mlp_blocks(E);
         if (E > 0) {
-            ML_DISPATCH_IO(ci, co, (mlp_bwd_input_kernel<CI, CO, (CI <= 32)><<<blocks, ML_THREADS, 0, st>>>(
-                dA, ldd, y, ldy, E, W, cin, cout, B, dA_prev, ldp, x_prev, ldx, Bp, prev_sums ? partial : nullptr, mlp_rpt(E))));
+            ML_DISPATCH_IO(ci, co, (launch_k(mlp_bwd_input_kernel<CI, CO, (CI <= 32)>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, W, cin, cout, B, dA_prev, ldp, x_prev, ldx, Bp, prev_sums ? partial : nullptr, mlp_rpt(E))));
             if ((rc = check_launch("mlp_bwd_input_kernel"))) return rc;
         }
         if (prev_sums) {
-            sum_partials_kernel<<<ceil_div(2 * cin * 32, 128), 128, 0, st>>>(partial, E > 0 ? blocks : 0, 2 * cin, prev_sums);
+            launch_k(sum_partials_kernel, ceil_div(2 * cin * 32, 128), 128, 0, st, partial, E > 0 ? blocks : 0, 2 * cin, prev_sums);
             if ((rc = check_launch("sum_partials_kernel"))) return rc;
         }
     }
@@ -989,11 +997,10 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
         const int blocks = mlp_wblocks(E, &gpb);
         (void)gpb;
         if (E > 0) {
-            ML_DISPATCH_IO(ci, co, (mlp_bwd_weight_kernel<CI, CO><<<blocks, ML_THREADS, 0, st>>>(
-                dA, ldd, y, ldy, E, cin, cout, B, x_prev, ldx, in_scale, in_shift, in_act, partial)));
+            ML_DISPATCH_IO(ci, co, (launch_k(mlp_bwd_weight_kernel<CI, CO>, blocks, ML_THREADS, 0, st, dA, ldd, y, ldy, E, cin, cout, B, x_prev, ldx, in_scale, in_shift, in_act, partial)));
             if ((rc = check_launch("mlp_bwd_weight_kernel"))) return rc;
         }
-        mlp_weight_finalize_kernel<<<ceil_div(cout * (cin + 1) * 32, 256), 256, 0, st>>>(partial, E > 0 ? blocks : 0, cout, cin, dW, db);
+        launch_k(mlp_weight_finalize_kernel, ceil_div(cout * (cin + 1) * 32, 256), 256, 0, st, partial, E > 0 ? blocks : 0, cout, cin, dW, db);
         if ((rc = check_launch("mlp_weight_finalize_kernel"))) return rc;
     }
     return PCFB_OK;
@@ -1002,7 +1009,7 @@ extern "C" int pcfb_mlp_backward(const float *dA, int ldd, const float *y, int l
 extern "C" int pcfb_sum_partials(const float *partial, int nblocks, int n, float *out, void *stream)
 {
     PCFB_REQUIRE(partial && out && n >= 1, "pcfb_sum_partials: bad arguments");
-    sum_partials_kernel<<<ceil_div(n * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, nblocks, n, out);
+    launch_k(sum_partials_kernel, ceil_div(n * 32, 128), 128, 0, static_cast<cudaStream_t>(stream), partial, nblocks, n, out);
     return check_launch("sum_partials_kernel");
 }
 
@@ -1055,6 +1062,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 bn_stats_kernel(const float *__restrict__ x, int64_t rows, int C, const float *__restrict__ pivot, float *__restrict__ partial,
                 int c4, int ry, int rows_per_block)
 {
+    pdl_wait();
     extern __shared__ float4 ba_sm[];
     const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
     const bool active = ty < ry;
@@ -1080,6 +1088,7 @@ __global__ void __launch_bounds__(BA_THREADS)
 bn_act4_kernel(const float *__restrict__ y, int64_t rows, int C, const float *__restrict__ scale, const float *__restrict__ shift,
                int act, float *__restrict__ out, int c4, int ry, const float *__restrict__ res, int res_after)
 {
+    pdl_wait();
     const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
     if (ty >= ry) return;
     const float4 sc = scale ? __ldg(reinterpret_cast<const float4 *>(scale) + tx) : make_float4(1.f, 1.f, 1.f, 1.f);
@@ -1107,6 +1116,7 @@ bn_bwd_stats_kernel(const float *__restrict__ dA, const float *__restrict__ y, i
                     const float *__restrict__ shift, const float *__restrict__ mean, const float *__restrict__ invstd, int act,
                     float *__restrict__ partial, int c4, int ry, int rows_per_block, const float *__restrict__ res)
 {
+    pdl_wait();
     extern __shared__ float4 ba_sm[];
     const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
     const bool active = ty < ry;
@@ -1138,6 +1148,7 @@ bn_bwd_kernel(const float *__restrict__ dA, const float *__restrict__ y, int64_t
               const float *__restrict__ sums, int act, float inv_count, const double *__restrict__ d_count,
               float *__restrict__ dX, int c4, int ry, const float *__restrict__ res, float *__restrict__ dR)
 {
+    pdl_wait();
     const int tx = threadIdx.x % c4, ty = threadIdx.x / c4;
     if (ty >= ry) return;
     const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale) + tx), sh = __ldg(reinterpret_cast<const float4 *>(shift) + tx);
@@ -1194,8 +1205,7 @@ extern "C" int pcfb_bn_stats(const float *x, int64_t rows, int C, const float *p
     PCFB_REQUIRE(partial_bytes >= (size_t)g.blocks * 2 * C * sizeof(float), "pcfb_bn_stats: workspace too small");
     if (nblocks) *nblocks = g.blocks;
     if (g.blocks == 0) return PCFB_OK;
-    bn_stats_kernel<<<g.blocks, BA_THREADS, (size_t)2 * g.ry * g.c4 * sizeof(float4), static_cast<cudaStream_t>(stream)>>>(
-        x, rows, C, pivot, partial, g.c4, g.ry, g.rows_per_block);
+    launch_k(bn_stats_kernel, g.blocks, BA_THREADS, (size_t)2 * g.ry * g.c4 * sizeof(float4), static_cast<cudaStream_t>(stream), x, rows, C, pivot, partial, g.c4, g.ry, g.rows_per_block);
     return check_launch("bn_stats_kernel");
 }
 
@@ -1213,12 +1223,11 @@ extern "C" int pcfb_bn_backward_stats(const float *dA, const float *y, int64_t r
     float *partial = static_cast<float *>(workspace);
     int rc;
     if (g.blocks > 0) {
-        bn_bwd_stats_kernel<<<g.blocks, BA_THREADS, (size_t)2 * g.ry * g.c4 * sizeof(float4), st>>>(
-            dA, y, rows, C, scale, shift, mean, invstd, act, partial, g.c4, g.ry, g.rows_per_block, residual);
+        launch_k(bn_bwd_stats_kernel, g.blocks, BA_THREADS, (size_t)2 * g.ry * g.c4 * sizeof(float4), st, dA, y, rows, C, scale, shift, mean, invstd, act, partial, g.c4, g.ry, g.rows_per_block, residual);
         if ((rc = check_launch("bn_bwd_stats_kernel"))) return rc;
     }
     if (!sums) return PCFB_OK;                                   // the caller reduces the partials itself (pcfb_bn_reduce_sums)
-    sum_partials_kernel<<<ceil_div(2 * C * 32, 128), 128, 0, st>>>(partial, g.blocks, 2 * C, sums);
+    launch_k(sum_partials_kernel, ceil_div(2 * C * 32, 128), 128, 0, st, partial, g.blocks, 2 * C, sums);
     return check_launch("sum_partials_kernel");
 }
 
@@ -1232,7 +1241,6 @@ extern "C" int pcfb_bn_backward(const float *dA, const float *y, int64_t rows, i
                  ((uintptr_t)d_residual % 16 == 0), "pcfb_bn_backward: null or misaligned pointer");
     if (rows == 0) return PCFB_OK;
     const int c4 = C >> 2, ry = BA_THREADS / c4;
-    bn_bwd_kernel<<<ba_stream_blocks(rows, ry), BA_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        dA, y, rows, C, scale, shift, mean, invstd, sums, act, (float)(1.0 / (double)rows), d_count, dX, c4, ry, residual, d_residual);
+    launch_k(bn_bwd_kernel, ba_stream_blocks(rows, ry), BA_THREADS, 0, static_cast<cudaStream_t>(stream), dA, y, rows, C, scale, shift, mean, invstd, sums, act, (float)(1.0 / (double)rows), d_count, dX, c4, ry, residual, d_residual);
     return check_launch("bn_bwd_kernel");
 }

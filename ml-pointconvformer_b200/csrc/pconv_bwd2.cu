@@ -70,6 +70,7 @@ __device__ __forceinline__ void b2_wait() { asm volatile("cp.async.wait_group %0
 template <int CMID, bool GUIDE, int BT>
 __global__ void __launch_bounds__(4 * BT, 1) pconv_bwd2_kernel(Bwd2Args a)
 {
+    pdl_wait();
     constexpr int BNT = 4 * BT;                                 // thread = (point, quarter of the 16 neighbours)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const pcfb_pconv_shape &s = a.s;
@@ -290,14 +291,14 @@ static int launch_bwd2(const Bwd2Args &a, const Bwd2Plan &, cudaStream_t st) {
         const Bwd2Plan pl = b2_plan(a.s, BT_SMALL);
         PCFB_CUDA(cudaFuncSetAttribute(pconv_bwd2_kernel<CMID, GUIDE, BT_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         const int grid = max(1, min(ceil_div(a.s.n_out, BT_SMALL), kNumSMs * 6));
-        pconv_bwd2_kernel<CMID, GUIDE, BT_SMALL><<<grid, 4 * BT_SMALL, pl.total, st>>>(a);
+        launch_k(pconv_bwd2_kernel<CMID, GUIDE, BT_SMALL>, grid, 4 * BT_SMALL, pl.total, st, a);
         return check_launch("pconv_bwd2_kernel");
     }
     const Bwd2Plan pl = b2_plan(a.s, BT);
     PCFB_CUDA(cudaFuncSetAttribute(pconv_bwd2_kernel<CMID, GUIDE, BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int per_sm = (pl.total + 1024 <= 113 * 1024) ? 2 : 1;   // register use decides the real residency
     const int grid = max(1, min(ceil_div(a.s.n_out, BT), kNumSMs * per_sm));
-    pconv_bwd2_kernel<CMID, GUIDE, BT><<<grid, 4 * BT, pl.total, st>>>(a);
+    launch_k(pconv_bwd2_kernel<CMID, GUIDE, BT>, grid, 4 * BT, pl.total, st, a);
     return check_launch("pconv_bwd2_kernel");
 }
 

@@ -16,6 +16,7 @@ __global__ void mid1_fwd_kernel(const float *__restrict__ feats, const int64_t *
                                 const float *__restrict__ w, const float *__restrict__ add, int n_in, int n_out, int K,
                                 int C_in, int C_add, float *__restrict__ P)
 {
+    pdl_wait();
     const int C_cat = C_in + C_add, G4 = C_cat / 4, I4 = C_in / 4;
     const int64_t total = (int64_t)n_out * G4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -45,6 +46,7 @@ __global__ void mid1_bwd_point_kernel(const float *__restrict__ dP, const float 
                                       const float *__restrict__ add, int n_in, int n_out, int K, int C_in, int C_add,
                                       float *__restrict__ dw, float *__restrict__ dadd)
 {
+    pdl_wait();
     const int C_cat = C_in + C_add;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -78,6 +80,7 @@ __global__ void mid1_bwd_input_kernel(const float *__restrict__ dP, const float 
                                       const int32_t *__restrict__ inv_idx, int n_in, int K, int C_in, int C_cat,
                                       float *__restrict__ dx)
 {
+    pdl_wait();
     const int I4 = C_in / 4;
     const int64_t total = (int64_t)n_in * I4;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -111,7 +114,7 @@ int pconv_mid1_forward_p(const pcfb_pconv_shape *s, const float *feats, const in
                  "pcfb_pconv: C_mid=1 path needs 16-byte aligned feats/additional/P");
     if (s->n_out == 0) return PCFB_OK;
     const int64_t work = (int64_t)s->n_out * ((s->C_in + s->C_add) / 4);
-    mid1_fwd_kernel<<<m1_blocks(work, 256), 256, 0, st>>>(feats, nei, weights, additional, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
+    launch_k(mid1_fwd_kernel, m1_blocks(work, 256), 256, 0, st, feats, nei, weights, additional, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
     return check_launch("mid1_fwd_kernel");
 }
 
@@ -122,15 +125,13 @@ int pconv_mid1_backward(const pcfb_pconv_shape *s, const float *dP, const float 
 {
     int rc;
     if (s->n_out > 0 && (grad_weights || grad_additional)) {
-        mid1_bwd_point_kernel<<<m1_blocks((int64_t)s->n_out * 32, 256), 256, 0, st>>>(
-            dP, feats, nei, weights, additional, s->n_in, s->n_out, s->K, s->C_in, s->C_add, grad_weights, grad_additional);
+        launch_k(mid1_bwd_point_kernel, m1_blocks((int64_t)s->n_out * 32, 256), 256, 0, st, dP, feats, nei, weights, additional, s->n_in, s->n_out, s->K, s->C_in, s->C_add, grad_weights, grad_additional);
         if ((rc = check_launch("mid1_bwd_point_kernel"))) return rc;
     }
     if (grad_feats) {
         PCFB_REQUIRE(inv_n && inv_k && inv_idx, "pcfb_pconv_backward: grad_feats needs the inverse map");
         PCFB_REQUIRE(((uintptr_t)dP % 16 == 0) && ((uintptr_t)grad_feats % 16 == 0), "pcfb_pconv_backward: unaligned buffers");
-        mid1_bwd_input_kernel<<<m1_blocks((int64_t)s->n_in * (s->C_in / 4), 256), 256, 0, st>>>(
-            dP, weights, inv_n, inv_k, inv_idx, s->n_in, s->K, s->C_in, s->C_in + s->C_add, grad_feats);
+        launch_k(mid1_bwd_input_kernel, m1_blocks((int64_t)s->n_in * (s->C_in / 4), 256), 256, 0, st, dP, weights, inv_n, inv_k, inv_idx, s->n_in, s->K, s->C_in, s->C_in + s->C_add, grad_feats);
         if ((rc = check_launch("mid1_bwd_input_kernel"))) return rc;
     }
     return PCFB_OK;

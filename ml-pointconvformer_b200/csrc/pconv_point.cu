@@ -58,6 +58,7 @@ __device__ __forceinline__ void pp_stage(const PointArgs &a, int m, float *G_s, 
 __global__ void __launch_bounds__(PP_THREADS)
 pconv_point_fwd_p_kernel(PointArgs a)
 {
+    pdl_wait();
     __shared__ float G_s[PP_K * PP_CMAX], Gg_s[PP_K * PP_CMAX], w_s[PP_K * PP_MID], g_s[PP_K * 16];
     const int m = blockIdx.x, t = threadIdx.x;
     const int C_cat = a.s.C_in + a.s.C_add;
@@ -78,6 +79,7 @@ pconv_point_fwd_p_kernel(PointArgs a)
 __global__ void __launch_bounds__(PP_THREADS)
 pconv_point_bwd_kernel(PointArgs a)
 {
+    pdl_wait();
     __shared__ float G_s[PP_K * PP_CMAX], Gg_s[PP_K * PP_CMAX], w_s[PP_K * PP_MID], g_s[PP_K * 16];
     __shared__ float dP_s[PP_CMAX * PP_DPS];                     // rows padded to 17 floats: conflict-free column walks
     const int m = blockIdx.x, t = threadIdx.x;
@@ -157,7 +159,7 @@ int pconv_point_bwd(const pcfb_pconv_shape *s, const float *dP, const float *fea
     PointArgs a{};
     a.s = *s; a.dP = dP; a.feats = feats; a.nei = nei; a.weights = weights; a.additional = additional; a.guidance = guidance;
     a.grad_weights = grad_weights; a.grad_additional = grad_additional; a.grad_guidance = grad_guidance; a.grad_edge = grad_edge;
-    pconv_point_bwd_kernel<<<s->n_out, PP_THREADS, 0, st>>>(a);
+    launch_k(pconv_point_bwd_kernel, s->n_out, PP_THREADS, 0, st, a);
     return check_launch("pconv_point_bwd_kernel");
 }
 
@@ -168,7 +170,7 @@ int pconv_point_fwd_p(const pcfb_pconv_shape *s, const float *feats, const int64
     if (s->n_out == 0) return PCFB_OK;
     PointArgs a{};
     a.s = *s; a.feats = feats; a.nei = nei; a.weights = weights; a.additional = additional; a.guidance = guidance; a.P = P;
-    pconv_point_fwd_p_kernel<<<s->n_out, PP_THREADS, 0, st>>>(a);
+    launch_k(pconv_point_fwd_p_kernel, s->n_out, PP_THREADS, 0, st, a);
     return check_launch("pconv_point_fwd_p_kernel");
 }
 

@@ -140,6 +140,7 @@ __device__ __forceinline__ void stage_g(const PconvArgs &a, int m0, int c0, int 
 template <int CMP>
 __global__ void __launch_bounds__(NT, 1) pconv_fwd_simt_kernel(PconvArgs a)
 {
+    pdl_wait();
     extern __shared__ float smem[];
     const pcfb_pconv_shape &s = a.s;
     const SmemPlan pl = plan_smem(s, a.CC, false);
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(NT, 1) pconv_fwd_simt_kernel(PconvArgs a)
 template <int CMP, int KPT>
 __global__ void __launch_bounds__(NT, 1) pconv_bwd_simt_kernel(PconvArgs a)
 {
+    pdl_wait();
     extern __shared__ float smem[];
     const pcfb_pconv_shape &s = a.s;
     const SmemPlan pl = plan_smem(s, a.CC, true);
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(256)
 gradw_partial_kernel(const float *__restrict__ dY, const float *__restrict__ P, int M, int C_out, int KK,
                      int slice, float *__restrict__ partial)
 {
+    pdl_wait();
     __shared__ float A_s[GW_MB][GW_TO + 1];
     __shared__ __align__(16) float B_s[GW_MB][GW_TK];
     const int kk0 = blockIdx.x * GW_TK, o0 = blockIdx.y * GW_TO;
@@ -459,6 +462,7 @@ gradw_partial_kernel(const float *__restrict__ dY, const float *__restrict__ P, 
 __global__ void gradw_reduce_kernel(const float *__restrict__ partial, int S, int C_out, int KK,
                                     float *__restrict__ grad_w, float *__restrict__ grad_b)
 {
+    pdl_wait();
     const int ld = KK + 1;
     const int total = C_out * ld;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -496,7 +500,7 @@ static int launch_fwd_simt(const PconvArgs &a, cudaStream_t st) {
 #define LAUNCH_FWD(CMP)                                                                     \
     do {                                                                                    \
         if ((rc = set_smem(pconv_fwd_simt_kernel<CMP>, pl.total))) return rc;               \
-        pconv_fwd_simt_kernel<CMP><<<grid, NT, pl.total, st>>>(a);                          \
+        launch_k(pconv_fwd_simt_kernel<CMP>, grid, NT, pl.total, st, a);                          \
     } while (0)
     if (a.s.C_mid == 1) LAUNCH_FWD(1);
     else if (a.s.C_mid <= 4) LAUNCH_FWD(4);
@@ -514,7 +518,7 @@ static int launch_bwd_simt(const PconvArgs &a, cudaStream_t st) {
 #define LAUNCH_BWD(CMP, KPT)                                                                \
     do {                                                                                    \
         if ((rc = set_smem(pconv_bwd_simt_kernel<CMP, KPT>, pl.total))) return rc;          \
-        pconv_bwd_simt_kernel<CMP, KPT><<<grid, NT, pl.total, st>>>(a);                     \
+        launch_k(pconv_bwd_simt_kernel<CMP, KPT>, grid, NT, pl.total, st, a);                     \
     } while (0)
 #define LAUNCH_BWD_K(CMP)                                                                   \
     do {                                                                                    \
@@ -621,10 +625,10 @@ int pconv_backward_simt(const pcfb_pconv_shape *s, const float *grad_y, const fl
             P = w.p_recompute;
         }
         dim3 grid(ceil_div(KK + 1, GW_TK), ceil_div(s->C_out, GW_TO), w.S);
-        gradw_partial_kernel<<<grid, 256, 0, st>>>(grad_y, P, s->n_out, s->C_out, KK, w.slice, w.partial);
+        launch_k(gradw_partial_kernel, grid, 256, 0, st, grad_y, P, s->n_out, s->C_out, KK, w.slice, w.partial);
         if ((rc = check_launch("gradw_partial_kernel"))) return rc;
         const int total = s->C_out * (KK + 1);
-        gradw_reduce_kernel<<<min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st>>>(w.partial, w.S, s->C_out, KK, grad_lin_w, grad_lin_b);
+        launch_k(gradw_reduce_kernel, min(ceil_div(total, 256), kNumSMs * 8), 256, 0, st, w.partial, w.S, s->C_out, KK, grad_lin_w, grad_lin_b);
         if ((rc = check_launch("gradw_reduce_kernel"))) return rc;
     }
     return PCFB_OK;

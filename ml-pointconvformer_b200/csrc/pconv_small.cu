@@ -9,6 +9,7 @@ __global__ void pconv_p_small_kernel(pcfb_pconv_shape s, const float *__restrict
                                      const float *__restrict__ weights, const float *__restrict__ additional,
                                      const float *__restrict__ guidance, float *__restrict__ P)
 {
+    pdl_wait();
     const int C_cat = s.C_in + s.C_add, JQ = s.C_mid / 4;
     const int64_t total = (int64_t)s.n_out * C_cat * JQ;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -42,7 +43,7 @@ int pconv_p_small(const pcfb_pconv_shape *s, const float *feats, const int64_t *
     if (s->n_out == 0) return PCFB_OK;
     const int64_t total = (int64_t)s->n_out * (s->C_in + s->C_add) * (s->C_mid / 4);
     const int64_t blocks = (total + 255) / 256;
-    pconv_p_small_kernel<<<(int)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs), 256, 0, st>>>(*s, feats, nei, weights, additional, guidance, P);
+    launch_k(pconv_p_small_kernel, (int)(blocks < 8 * kNumSMs ? blocks : 8 * kNumSMs), 256, 0, st, *s, feats, nei, weights, additional, guidance, P);
     return check_launch("pconv_p_small_kernel");
 }
 

@@ -76,6 +76,7 @@ static int u_choose_kpt(const pcfb_pconv_shape &s) {
 template <int CMID, int KPT>
 __global__ void __launch_bounds__(UNT, 1) pconv_fwd_umma_kernel(UmmaArgs a)
 {
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const pcfb_pconv_shape &s = a.s;
     const UPlan pl = u_plan(s, KPT);
@@ -331,6 +332,7 @@ struct SelftestArgs {
 
 __global__ void __launch_bounds__(128, 1) umma_selftest_kernel(SelftestArgs t)
 {
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t a_bytes = 64 * 1024 / 2;      // generous fixed carve: A_hi, A_lo, B_hi, B_lo of 32 KB each
     unsigned char *Ah = smem_raw, *Al = smem_raw + a_bytes, *Bh = smem_raw + 2 * a_bytes, *Bl = smem_raw + 3 * a_bytes;
@@ -422,7 +424,7 @@ size_t pconv_forward_umma_workspace(const pcfb_pconv_shape *) { return 0; }
 template <int CMID, int KPT>
 static int launch_umma(const UmmaArgs &a, const UPlan &pl, int grid, cudaStream_t st) {
     PCFB_CUDA(cudaFuncSetAttribute(pconv_fwd_umma_kernel<CMID, KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U_SMEM_BUDGET));
-    pconv_fwd_umma_kernel<CMID, KPT><<<grid, UNT, pl.total, st>>>(a);
+    launch_k(pconv_fwd_umma_kernel<CMID, KPT>, grid, UNT, pl.total, st, a);
     return check_launch("pconv_fwd_umma_kernel");
 }
 
@@ -479,6 +481,6 @@ extern "C" int pcfb_selftest_umma(const float *A, const float *B, float *raw, in
     t.desc_or = desc_or; t.split = split; t.status = status;
     const size_t smem = 4 * 32 * 1024 + 64;
     PCFB_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    umma_selftest_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(t);
+    launch_k(umma_selftest_kernel, 1, 128, smem, static_cast<cudaStream_t>(stream), t);
     return check_launch("umma_selftest_kernel");
 }

@@ -101,6 +101,7 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float *p) {
 // W [C_out][KK] -> (hi, lo) tf32 pairs in UMMA K-major core-matrix order, one contiguous block per chunk
 __global__ void prep_w_kernel(const float *__restrict__ W, int C_out, int KK, int CK, int n_chunks, float *__restrict__ out)
 {
+    pdl_wait();
     const int units = CK / 4;
     const int64_t total = (int64_t)n_chunks * units * C_out;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -124,7 +125,7 @@ __global__ void prep_w_kernel(const float *__restrict__ W, int C_out, int KK, in
 void prep_w_launch(const float *lin_w, int C_out, int KK, int CK, int n_chunks, float *out, cudaStream_t st) {
     const int64_t total = (int64_t)n_chunks * (CK / 4) * C_out;
     const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-    prep_w_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(lin_w, C_out, KK, CK, n_chunks, out);
+    launch_k(prep_w_kernel, blocks < 1 ? 1 : blocks, 256, 0, st, lin_w, C_out, KK, CK, n_chunks, out);
 }
 
 // Tiling of one chunk (CK = 32 kk columns = CC channels x CMID weights) over the 4 thread groups of a point:
@@ -135,6 +136,7 @@ void prep_w_launch(const float *lin_w, int C_out, int KK, int CK, int n_chunks, 
 template <int CMID, bool GUIDE>
 __global__ void __launch_bounds__(VNT, 2) pconv_fwd_umma2_kernel(U2Args a)
 {
+    pdl_wait();
     constexpr int CK = VCK, KPT = VKPT, K = VK;
     constexpr int CC = CK / CMID;
     constexpr int TJ = CMID < 4 ? CMID : 4;
@@ -462,7 +464,7 @@ static int launch_v2(const U2Args &a, const V2Plan &pl, cudaStream_t st) {
     PCFB_CUDA(cudaFuncSetAttribute(pconv_fwd_umma2_kernel<CMID, GUIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V_SMEM_BUDGET));
     const int per_sm = (pl.total + 1024 <= 113 * 1024) ? 2 : 1;
     const int grid = max(1, min(ceil_div(a.s.n_out, VT), kNumSMs * per_sm));
-    pconv_fwd_umma2_kernel<CMID, GUIDE><<<grid, VNT, pl.total, st>>>(a);
+    launch_k(pconv_fwd_umma2_kernel<CMID, GUIDE>, grid, VNT, pl.total, st, a);
     return check_launch("pconv_fwd_umma2_kernel");
 }
 
@@ -496,7 +498,7 @@ int pconv_forward_umma2(const pcfb_pconv_shape *s, const float *feats, const int
     {
         const int64_t total = (int64_t)a.n_chunks * (VCK / 4) * s->C_out;
         const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
-        prep_w_kernel<<<blocks < 1 ? 1 : blocks, 256, 0, st>>>(lin_w, s->C_out, KK, VCK, a.n_chunks, static_cast<float *>(workspace));
+        launch_k(prep_w_kernel, blocks < 1 ? 1 : blocks, 256, 0, st, lin_w, s->C_out, KK, VCK, a.n_chunks, static_cast<float *>(workspace));
         if ((rc = check_launch("prep_w_kernel"))) return rc;
     }
     const bool guide = s->H > 0;

@@ -154,6 +154,7 @@ enum { WS_A_FULL = 0, WS_A_EMPTY = 4, WS_D_FULL = 8, WS_D_EMPTY = 10, WS_B_FULL 
 template <int STAGES, int GQ>
 __global__ void __launch_bounds__(WS_NT, 1) pconv_fwd_ws_kernel(WsArgs a)
 {
+    pdl_wait();
     constexpr int K = WS_K, S = STAGES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const pcfb_pconv_shape &s = a.s;
@@ -539,7 +540,7 @@ template <int STAGES, int GQ>
 static int launch_ws(const WsArgs &a, size_t smem, cudaStream_t st) {
     PCFB_CUDA(cudaFuncSetAttribute(pconv_fwd_ws_kernel<STAGES, GQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM_MAX));
     const int grid = max(1, min(a.n_tiles, kNumSMs));
-    pconv_fwd_ws_kernel<STAGES, GQ><<<grid, WS_NT, smem, st>>>(a);
+    launch_k(pconv_fwd_ws_kernel<STAGES, GQ>, grid, WS_NT, smem, st, a);
     return check_launch("pconv_fwd_ws_kernel");
 }
 

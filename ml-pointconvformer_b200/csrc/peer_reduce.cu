@@ -79,6 +79,7 @@ struct SbArgs {
 __global__ void __launch_bounds__(SB_THREADS)
 bn_reduce_kernel(SbArgs a)
 {
+    pdl_wait();
     __shared__ double part_s[16][17];             // [slice][column]
     __shared__ double msg_s[SB_MSG], glob_s[SB_MSG];
     __shared__ uint32_t ep_s;
@@ -227,7 +228,7 @@ extern "C" int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_
     a.pivot = pivot; a.gamma = gamma; a.beta = beta; a.eps = eps; a.momentum = momentum;
     a.running_mean = running_mean; a.running_var = running_var; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd;
     a.batches_tracked = reinterpret_cast<long long *>(batches_tracked); a.count_out = count_out;
-    bn_reduce_kernel<<<ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    launch_k(bn_reduce_kernel, ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_reduce_kernel<finalize>");
 }
 
@@ -242,6 +243,6 @@ extern "C" int pcfb_bn_reduce_sums(const float *partial, int nblocks, int C, flo
     a.bases = static_cast<const unsigned long long *>(peer_bases); a.rank = rank; a.world = peer_bases ? world : 1; a.channel = channel;
     a.timeout_ns = sb_timeout(timeout_s);
     a.sums_local = sums_local; a.sums_global = sums_global;
-    bn_reduce_kernel<<<ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    launch_k(bn_reduce_kernel, ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_reduce_kernel<sums>");
 }

@@ -14,6 +14,7 @@ static __global__ void __launch_bounds__(SCAN_THREADS)
 inv_scan_kernel(const int32_t *__restrict__ counts, int n, int32_t *__restrict__ out,
                 unsigned long long *__restrict__ state, unsigned int *__restrict__ ticket)
 {
+    pdl_wait();
     __shared__ int s_tile;
     __shared__ int s_warp[SCAN_THREADS / 32];
     __shared__ int s_prefix;

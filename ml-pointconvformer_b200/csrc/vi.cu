@@ -21,6 +21,7 @@ __global__ void edge_geometry_kernel(const float *__restrict__ xyz_in, const flo
                                      const int64_t *__restrict__ nei, int n_in, int64_t n_edges, int K,
                                      float *__restrict__ out_r, float *__restrict__ out_vi)
 {
+    pdl_wait();
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_edges;
          e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t m = e / K;
@@ -73,7 +74,6 @@ extern "C" int pcfb_edge_geometry(const float *xyz_in, const float *nrm_in, cons
     const int64_t E = (int64_t)n_out * K;
     int64_t blocks = (E + 255) / 256;
     if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
-    edge_geometry_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        xyz_in, nrm_in, xyz_out, nrm_out, nei, n_in, E, K, out_r, out_vi);
+    launch_k(edge_geometry_kernel, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), xyz_in, nrm_in, xyz_out, nrm_out, nei, n_in, E, K, out_r, out_vi);
     return check_launch("pcfb_edge_geometry");
 }

@@ -24,7 +24,9 @@ _POOL = {}
 # joined by join_leaves() (called by sharding.FlatParameters.gather_grads before the flat gradient is assembled), taking
 # ~120 small GEMM launches off the backward's critical path.  Opt-in: whoever reads .grad must call join_leaves() first.
 LEAF_ASYNC = False
+N_LEAF = 2                  # leaf streams, used round robin: the last (largest, level-0) products of the backward share the tail
 _LEAF = {}
+_LEAF_NEXT = [0]
 
 
 def _side_streams(device):
@@ -85,16 +87,18 @@ def join(branch):
 
 
 def fork_leaf(fn):
-    """Run fn() (a leaf of the backward graph: a weight gradient) on the leaf stream; NOT joined until join_leaves()."""
+    """Run fn() (a leaf of the backward graph: a weight gradient) on a leaf stream; NOT joined until join_leaves()."""
     if not (ENABLED and LEAF_ASYNC) or not torch.cuda.is_available():
         return fn()
     cur = torch.cuda.current_stream()
     key = (cur.device.type, cur.device.index)
-    leaf = _LEAF.get(key)
-    if leaf is None:
-        leaf = _LEAF[key] = torch.cuda.Stream(device=cur.device)
-    if leaf == cur:
+    pool = _LEAF.get(key)
+    if pool is None:
+        pool = _LEAF[key] = [torch.cuda.Stream(device=cur.device) for _ in range(N_LEAF)]
+    if cur in pool:
         return fn()
+    leaf = pool[_LEAF_NEXT[0] % N_LEAF]
+    _LEAF_NEXT[0] += 1
     leaf.wait_stream(cur)
     with torch.cuda.stream(leaf):
         return fn()
@@ -105,6 +109,7 @@ def join_leaves():
     if not torch.cuda.is_available():
         return
     cur = torch.cuda.current_stream()
-    leaf = _LEAF.get((cur.device.type, cur.device.index))
-    if leaf is not None and leaf != cur:
-        cur.wait_stream(leaf)
+    for leaf in _LEAF.get((cur.device.type, cur.device.index), []):
+        if leaf != cur:
+            cur.wait_stream(leaf)
+    _LEAF_NEXT[0] = 0
