@@ -175,6 +175,13 @@ int pcfb_pconv_backward(const pcfb_pconv_shape *s, const float *grad_y, const fl
  *                  1 <= N1 <= 256; reduction over M split across CTAs, partials summed in fixed order.
  * ------------------------------------------------------------------------------------------- */
 size_t pcfb_gemm_nt_workspace(int N, int K);
+/* pcfb_gemm_nt = pcfb_gemm_nt_prepare (weights -> split tf32 operands in tensor-core order, into the workspace; depends on
+ * the weights and on M only through the column-block width) + pcfb_gemm_nt_prepared (the product).  The two may run on
+ * different streams: a Linear's weights are ready long before its input. */
+int pcfb_gemm_nt_prepare(const float *W, int ldw, int w_is_kn, int M, int N, int K, void *workspace, size_t workspace_bytes,
+                         void *stream);
+int pcfb_gemm_nt_prepared(const float *A, int lda, const float *bias, float *C, int ldc, int M, int N, int K, int act,
+                          const void *workspace, size_t workspace_bytes, void *stream);
 int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,
                  int M, int N, int K, int act, void *workspace, size_t workspace_bytes, void *stream);
 size_t pcfb_gemm_tn_workspace(int M, int N1, int N2, int with_rowsum);

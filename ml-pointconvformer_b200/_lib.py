@@ -45,6 +45,8 @@ SIGNATURES = {
     "pcfb_pconv_backward": (c_int, [ctypes.POINTER(PconvShape)] + [_P] * 19 + [c_size_t, c_int, _P]),
     "pcfb_gemm_nt_workspace": (c_size_t, [c_int, c_int]),
     "pcfb_gemm_nt": (c_int, [_P, c_int, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "pcfb_gemm_nt_prepare": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
+    "pcfb_gemm_nt_prepared": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_size_t, _P]),
     "pcfb_gemm_tn_workspace": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pcfb_gemm_tn": (c_int, [_P, c_int, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, _P, c_size_t, _P]),
     "pcfb_mlp_supported": (c_int, [c_int, c_int]),

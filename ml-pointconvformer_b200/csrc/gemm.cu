@@ -620,13 +620,16 @@ extern "C" size_t pcfb_gemm_nt_workspace(int N, int K)
     return best;
 }
 
-extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,
-                            int M, int N, int K, int act, void *workspace, size_t workspace_bytes, void *stream)
+// phase bit 1: prepare B (weights -> hi / lo tf32 in UMMA order) into the workspace; bit 2: run the product from a prepared
+// workspace.  The weights of a Linear are known long before its input is: pcfb_gemm_nt_prepare lets the host run the
+// preparation on another stream, off the critical path of the step (~160 of them per training step).
+static int gemm_nt_phases(int phases, const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,
+                          int M, int N, int K, int act, void *workspace, size_t workspace_bytes, void *stream)
 {
     using namespace pcfb;
     PCFB_REQUIRE(M >= 0 && N >= 1 && K >= 1, "pcfb_gemm_nt: need N >= 1, K >= 1 (N=%d K=%d)", N, K);
-    PCFB_REQUIRE(A && W && C && workspace, "pcfb_gemm_nt: null pointer");
-    PCFB_REQUIRE(lda >= K && ldc >= N, "pcfb_gemm_nt: bad leading dimensions");
+    PCFB_REQUIRE(workspace && (!(phases & 1) || W) && (!(phases & 2) || (A && C)), "pcfb_gemm_nt: null pointer");
+    PCFB_REQUIRE(!(phases & 2) || (lda >= K && ldc >= N), "pcfb_gemm_nt: bad leading dimensions");
     NtSetup s = nt_setup(N, K, M);
     PCFB_REQUIRE(s.plan.total <= 225 * 1024, "pcfb_gemm_nt: tile does not fit in shared memory (N=%d K=%d)", N, K);
     PCFB_REQUIRE(s.n_blocks <= 65535, "pcfb_gemm_nt: too many column blocks");
@@ -634,13 +637,14 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     if (M == 0) return PCFB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc;
-    {
+    if (phases & 1) {
         const int64_t total = (int64_t)s.n_chunks * (GT_KC / 4) * s.Npad;
         const int blocks = (int)((total + 255) / 256 < 592 ? (total + 255) / 256 : 592);
         launch_k(gemm_prep_b_kernel, dim3(blocks < 1 ? 1 : blocks, s.n_blocks), 256, 0, st, W, ldw, w_is_kn, N, s.Nblk, s.Npad, K, s.n_chunks,
                                                                               s.block_bytes / sizeof(float), static_cast<float *>(workspace));
         if ((rc = check_launch("gemm_prep_b_kernel"))) return rc;
     }
+    if (!(phases & 2)) return PCFB_OK;
     GemmNtArgs a{};
     a.A = A; a.b_prep = static_cast<const float *>(workspace); a.bias = bias; a.C = C;
     a.M = M; a.N = N; a.Npad = s.Npad; a.K = K; a.lda = lda; a.ldc = ldc; a.n_chunks = s.n_chunks;
@@ -659,6 +663,25 @@ extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, in
     if (gx < 1) gx = 1;
     launch_k(gemm_nt_kernel, dim3(gx, s.n_blocks), G_NT, s.plan.total, st, a);
     return check_launch("gemm_nt_kernel");
+}
+
+extern "C" int pcfb_gemm_nt(const float *A, int lda, const float *W, int ldw, int w_is_kn, const float *bias, float *C, int ldc,
+                            int M, int N, int K, int act, void *workspace, size_t workspace_bytes, void *stream)
+{
+    PCFB_REQUIRE(A && W && C, "pcfb_gemm_nt: null pointer");
+    return gemm_nt_phases(3, A, lda, W, ldw, w_is_kn, bias, C, ldc, M, N, K, act, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pcfb_gemm_nt_prepare(const float *W, int ldw, int w_is_kn, int M, int N, int K, void *workspace, size_t workspace_bytes,
+                                    void *stream)
+{
+    return gemm_nt_phases(1, nullptr, 0, W, ldw, w_is_kn, nullptr, nullptr, 0, M, N, K, 0, workspace, workspace_bytes, stream);
+}
+
+extern "C" int pcfb_gemm_nt_prepared(const float *A, int lda, const float *bias, float *C, int ldc, int M, int N, int K, int act,
+                                     const void *workspace, size_t workspace_bytes, void *stream)
+{
+    return gemm_nt_phases(2, A, lda, nullptr, 0, 0, bias, C, ldc, M, N, K, act, const_cast<void *>(workspace), workspace_bytes, stream);
 }
 
 namespace pcfb {

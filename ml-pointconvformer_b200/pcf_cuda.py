@@ -286,9 +286,22 @@ def gemm_nt(x, w, bias=None, w_is_kn=False, act=0):
         raise RuntimeError("gemm_nt: inner dimensions do not match")
     out = torch.empty(M, N, device=x.device, dtype=F32)
     ws_bytes = lib().pcfb_gemm_nt_workspace(N, K)
-    ws = workspace(ws_bytes, x.device)
-    check(lib().pcfb_gemm_nt(ptr(x), x.stride(0), ptr(w), w.stride(0), 1 if w_is_kn else 0, ptr(bias), ptr(out), N, M, N, K, int(act),
-                             ptr(ws), ws_bytes, stream_ptr()), "gemm_nt")
+    prep = S.prep_stream(x.device)
+    if prep is None:
+        ws = workspace(ws_bytes, x.device)
+        check(lib().pcfb_gemm_nt(ptr(x), x.stride(0), ptr(w), w.stride(0), 1 if w_is_kn else 0, ptr(bias), ptr(out), N, M, N, K, int(act),
+                                 ptr(ws), ws_bytes, stream_ptr()), "gemm_nt")
+    else:
+        # the weight preparation only depends on the weights: it runs on the prep stream (ordered after the previous optimizer
+        # step, streams.prep_stream), off the critical path; the product waits for its event
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(prep):
+            ws = workspace(ws_bytes, x.device)
+            check(lib().pcfb_gemm_nt_prepare(ptr(w), w.stride(0), 1 if w_is_kn else 0, M, N, K, ptr(ws), ws_bytes, stream_ptr()), "gemm_nt_prepare")
+        cur.wait_stream(prep)
+        ws.record_stream(cur)
+        check(lib().pcfb_gemm_nt_prepared(ptr(x), x.stride(0), ptr(bias), ptr(out), N, M, N, K, int(act), ptr(ws), ws_bytes, stream_ptr()),
+              "gemm_nt_prepared")
     _lib.account(4.0 * (M * K + N * K + M * N), 2.0 * M * N * K)
     return out
 

@@ -47,6 +47,7 @@ class FlatParameters:
         if async_weight_grads:
             from . import streams
             streams.LEAF_ASYNC = True
+            streams.PREP_ASYNC = True
         self.params = [p for p in module.parameters() if p.requires_grad]
         if not self.params:
             raise ValueError("module has no trainable parameters")
@@ -123,4 +124,6 @@ class FlatAdamW:
                                          ptr(self.step_t), float(self.betas[0]), float(self.betas[1]), float(self.eps),
                                          float(self.weight_decay), float(self.max_norm), ptr(self.norm_t), ptr(self._ws),
                                          self._ws.numel(), stream_ptr()), "adamw_clip_step")
+        from . import streams
+        streams.weights_updated()                       # weight preparations of the next step wait for this update
         return self.norm_t

@@ -113,3 +113,42 @@ def join_leaves():
         if leaf != cur:
             cur.wait_stream(leaf)
     _LEAF_NEXT[0] = 0
+
+
+# ---- weight preparation stream ----------------------------------------------------------------------------------------
+# The operand preparation of a dense Linear (gemm.cu: weights -> split tf32 in tensor-core order) depends on the weights only.
+# With PREP_ASYNC (opt-in, like LEAF_ASYNC: sharding.FlatParameters(async_weight_grads=True) turns both on) it runs on its own
+# stream.  That stream must be ordered after the optimizer step that last wrote the weights: whoever updates the weights
+# calls weights_updated() (sharding.FlatAdamW.step does), and the first preparation after that waits for the updating stream.
+PREP_ASYNC = False
+_PREP = {}
+_PREP_DIRTY = {}
+
+
+def prep_stream(device):
+    """The preparation stream for `device`, or None when weight preparations run inline."""
+    if not (ENABLED and PREP_ASYNC) or device.type != "cuda":
+        return None
+    cur = torch.cuda.current_stream(device)
+    key = (device.type, device.index)
+    st = _PREP.get(key)
+    if st is None:
+        st = _PREP[key] = torch.cuda.Stream(device=device)
+        _PREP_DIRTY[key] = True
+    if st == cur:
+        return None
+    if _PREP_DIRTY.get(key, True):                       # first preparation since the weights changed
+        st.wait_stream(cur)
+        _PREP_DIRTY[key] = False
+    elif torch.cuda.is_current_stream_capturing():       # a capture that began after the last update: pull the stream in
+        with torch.cuda.stream(st):
+            inside = torch.cuda.is_current_stream_capturing()
+        if not inside:
+            st.wait_stream(cur)
+    return st
+
+
+def weights_updated():
+    """Call after the weights were written (optimizer step, load_state_dict): the next preparation waits for that work."""
+    for key in list(_PREP_DIRTY):
+        _PREP_DIRTY[key] = True
