@@ -10,6 +10,7 @@ def main():
     stacks = "stacks" in os.environ.get("PROFILE_STEP_FLAGS", "")
     sys.argv = ["bench.py", "--steps", "1", "--warmup", "2", "--no-cpu-baseline"] + sys.argv[1:]
     args = bench.parse()
+    args.points = args.points or 100000
     # reuse bench internals: run_ours builds everything; instead replicate the step here
     import pcf_b200
     from pcf_b200 import configs, model_architecture as MA, knn_post_dataloader_utils as KU, common_util as CU, pcf_cuda
