@@ -10,12 +10,14 @@
 //
 // Grid: one CTA per group of 8 channels (16 columns: sum and sum^2 / sum dz and sum dz*xhat of 8 channels).
 //   1. local reduction of the block partials, fixed order, double (thread = (column, slice of the blocks));
-//   2. world > 1: the CTA PUSHES its 16 sums + the local row count (17 doubles) into its slot of every rank's symmetric
-//      buffer (plain stores through the peer mapping), publishes an epoch flag (st.release.sys), waits for the peers' flags
-//      (ld.acquire.sys) and adds the slots in rank order: the same order on every rank => bit-identical, deterministic.
-//      CTA b of rank r talks only to CTA b of the other ranks.  No reset between calls: epochs only grow, the data slots are
-//      double buffered by epoch parity (a peer cannot reach use e+2 of a slot before this rank has published use e+1, i.e.
-//      finished reading use e).  `channel` selects an independent set of slots / flags / epochs: exchanges enqueued on
+//   2. world > 1: the CTA PUSHES its 16 sums + the local row count (17 doubles = 34 32-bit words) into its slot of every
+//      rank's symmetric buffer as 8-byte {word, epoch} stores through the peer mapping -- every 8-byte store carries its own
+//      validity tag (the NCCL "LL" idea), so there is no fence and no separate flag: the receiver polls each word until its
+//      tag equals the call's epoch, then adds the ranks' values in rank order: the same order on every rank => bit-identical,
+//      deterministic.  (Round-2 measurement: data + __threadfence_system + release flag + acquire spin cost ~10 us per
+//      exchange at 2 GPUs)  CTA b of rank r talks only to CTA b of the other ranks.  No reset between
+//      calls: epochs only grow, the slots are double buffered by epoch parity (a peer cannot reach use e+2 of a slot before
+//      this rank has pushed use e+1, i.e. finished reading use e).  `channel` selects an independent set of slots / flags / epochs: exchanges enqueued on
 //      different CUDA streams (streams.py: the branches of a layer run concurrently) use different channels, and every rank
 //      issues the same sequence of exchanges per channel;
 //   3. mode FINALIZE: mean / variance -> scale, shift, saved mean / invstd, running statistics (global count);
@@ -23,8 +25,8 @@
 // A peer that never arrives: after `timeout_s` (host-configurable; the NCCL scale of minutes by default) the CTA sets the
 // error word of its buffer, writes NaN results and RETURNS -- the context survives, the failure is loud.
 //
-// Symmetric buffer layout per rank (bytes): [0,4) error word | [1024, +NCH*MAXB*4) epochs | [4096, +NCH*MAXB*MAXW*4) flags |
-// [65536, ...) data[NCH][2][MAXB][world][17] doubles.
+// Symmetric buffer layout per rank (bytes): [0,4) error word | [1024, +NCH*MAXB*4) epochs |
+// [65536, ...) slots[NCH][2][MAXB][world][34] of {uint32 word, uint32 epoch}.
 #include "common.cuh"
 
 namespace pcfb {
@@ -32,23 +34,18 @@ namespace pcfb {
 constexpr int SB_NCH = 4;            // exchange channels (main stream + 3 side streams)
 constexpr int SB_MAXB = 128;         // CTAs per exchange = channel groups of 8 -> C <= 1024
 constexpr int SB_MAXW = 16;          // ranks
-constexpr int SB_MSG = 17;           // 16 column sums + the row count
+constexpr int SB_MSG = 17;           // 16 column sums + the row count (doubles)
+constexpr int SB_WORDS = 2 * SB_MSG; // 32-bit words per message, each sent as an 8-byte {word, epoch} store
 constexpr int SB_EPOCH_OFF = 1024;
-constexpr int SB_FLAG_OFF = 4096;
 constexpr int SB_DATA_OFF = 65536;
 constexpr int SB_THREADS = 256;
 
-__device__ __forceinline__ void sb_st_release(uint32_t *p, uint32_t v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;\n" :: "l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void sb_st_ll(unsigned long long *p, unsigned long long v) {   // one 8-byte store: single-copy atomic
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" :: "l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ uint32_t sb_ld_acquire(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double sb_ld_volatile(const double *p) {   // never from L1: the slot is written by the peers
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];\n" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long sb_ld_ll(const unsigned long long *p) {     // never from L1: written by the peers
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long sb_now_ns() {
@@ -87,6 +84,13 @@ bn_reduce_kernel(SbArgs a)
     const int t = threadIdx.x, col = t & 15, slice = t >> 4;
     const int c0 = blockIdx.x * 8;
     const int which = col >> 3, c = c0 + (col & 7);
+    const bool exchange = a.bases && a.world > 1;
+    if (exchange && t == 0) {                      // this use's epoch: read early, the load overlaps the local reduction
+        uint32_t *ctr = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(a.bases[a.rank]) + SB_EPOCH_OFF) +
+                        a.channel * SB_MAXB + blockIdx.x;
+        ep_s = *ctr + 1;
+        *ctr = ep_s;
+    }
     // 1. local reduction, fixed order: slice s adds blocks s, s+16, ... ; slices are then added 0..15
     double s = 0.0;
     if (c < a.C) {
@@ -113,43 +117,43 @@ bn_reduce_kernel(SbArgs a)
     if (t == 16) { msg_s[16] = a.count; glob_s[16] = a.d_count ? *a.d_count : a.count; }
     __syncthreads();
     // 2. exchange
-    if (a.bases && a.world > 1) {
+    if (exchange) {
+        __shared__ uint32_t recv_s[SB_MAXW][SB_WORDS];
         unsigned char *mine = reinterpret_cast<unsigned char *>(a.bases[a.rank]);
-        const int slot = a.channel * SB_MAXB + blockIdx.x;
-        if (t == 0) {
-            uint32_t *ctr = reinterpret_cast<uint32_t *>(mine + SB_EPOCH_OFF) + slot;
-            ep_s = *ctr + 1;
-            *ctr = ep_s;
+        const uint32_t ep = ep_s;                  // (written before the block barriers of step 1)
+        const size_t par_off = SB_DATA_OFF + ((((size_t)a.channel * 2 + (ep & 1u)) * SB_MAXB + blockIdx.x) * a.world) * SB_WORDS * sizeof(unsigned long long);
+        const uint32_t *msg_w = reinterpret_cast<const uint32_t *>(msg_s);
+        for (int j = t; j < SB_WORDS * a.world; j += SB_THREADS) {    // push: my words (+ the epoch tag) into my slot of every rank's buffer
+            const int q = j / SB_WORDS, i = j - q * SB_WORDS;
+            unsigned long long *dst = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(a.bases[q]) + par_off) +
+                                      (size_t)a.rank * SB_WORDS + i;
+            sb_st_ll(dst, ((unsigned long long)ep << 32) | msg_w[i]);
         }
-        __syncthreads();
-        const uint32_t ep = ep_s;
-        const size_t par_off = SB_DATA_OFF + ((((size_t)a.channel * 2 + (ep & 1u)) * SB_MAXB + blockIdx.x) * a.world) * SB_MSG * sizeof(double);
-        for (int j = t; j < SB_MSG * a.world; j += SB_THREADS) {      // push: my message into my slot of every rank's buffer
-            const int q = j / SB_MSG, i = j - q * SB_MSG;
-            double *dst = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(a.bases[q]) + par_off) + (size_t)a.rank * SB_MSG + i;
-            *dst = msg_s[i];
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (t < a.world) {
-            sb_st_release(reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(a.bases[t]) + SB_FLAG_OFF) + (size_t)slot * SB_MAXW + a.rank, ep);
-            const uint32_t *flag = reinterpret_cast<const uint32_t *>(mine + SB_FLAG_OFF) + (size_t)slot * SB_MAXW + t;
+        for (int j = t; j < SB_WORDS * a.world; j += SB_THREADS) {    // receive: poll every word of every rank until its tag is this epoch
+            const int q = j / SB_WORDS, i = j - q * SB_WORDS;
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(mine + par_off) + (size_t)q * SB_WORDS + i;
             const unsigned long long t0 = sb_now_ns();
-            while ((int32_t)(sb_ld_acquire(flag) - ep) < 0) {
+            unsigned long long v = sb_ld_ll(src);
+            while ((uint32_t)(v >> 32) != ep) {
                 if (a.timeout_ns && sb_now_ns() - t0 > a.timeout_ns) {
                     *reinterpret_cast<volatile uint32_t *>(mine) = 1u;            // error word: read by the host (fused_mlp.peer_error)
                     timed_out_s = 1;
-                    printf("pcfb SyncBatchNorm exchange: rank %d gave up waiting for rank %d (channel %d, cta %d, epoch %u)\n",
-                           a.rank, t, a.channel, (int)blockIdx.x, ep);
+                    if (i == 0)
+                        printf("pcfb SyncBatchNorm exchange: rank %d gave up waiting for rank %d (channel %d, cta %d, epoch %u)\n",
+                               a.rank, q, a.channel, (int)blockIdx.x, ep);
                     break;
                 }
+                v = sb_ld_ll(src);
             }
+            recv_s[q][i] = (uint32_t)v;
         }
         __syncthreads();
         if (t < SB_MSG) {
-            const double *data = reinterpret_cast<const double *>(mine + par_off);
             double v = 0.0;
-            for (int q = 0; q < a.world; ++q) v += sb_ld_volatile(data + (size_t)q * SB_MSG + t);   // rank order: identical everywhere
+            for (int q = 0; q < a.world; ++q) {                       // rank order: identical everywhere
+                const unsigned long long bits = ((unsigned long long)recv_s[q][2 * t + 1] << 32) | recv_s[q][2 * t];
+                v += __longlong_as_double((long long)bits);
+            }
             if (timed_out_s) v = __longlong_as_double(0x7ff8000000000000ll);
             if (t < 16 || !a.d_count) glob_s[t] = v;
         }
@@ -197,7 +201,7 @@ using namespace pcfb;
 extern "C" size_t pcfb_syncbn_buffer_bytes(int world)
 {
     if (world < 1 || world > SB_MAXW) return 0;
-    return SB_DATA_OFF + (size_t)SB_NCH * 2 * SB_MAXB * world * SB_MSG * sizeof(double);
+    return SB_DATA_OFF + (size_t)SB_NCH * 2 * SB_MAXB * world * SB_WORDS * sizeof(unsigned long long);
 }
 
 extern "C" int pcfb_syncbn_channels(void) { return SB_NCH; }
