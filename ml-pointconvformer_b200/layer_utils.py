@@ -312,7 +312,7 @@ class _LinearFunction(torch.autograd.Function):
             gx = pcf_cuda.gemm_nt(g2, weight, None, w_is_kn=True).reshape(*grad.shape[:-1], weight.shape[1])
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             # a leaf of the backward graph: off the critical path when streams.LEAF_ASYNC (joined by streams.join_leaves())
-            gw, gb = S.fork_leaf(lambda: pcf_cuda.gemm_tn(g2, x2, want_rowsum=ctx.has_bias))
+            gw, gb = S.fork_leaf(lambda: pcf_cuda.gemm_tn(g2, x2, want_rowsum=ctx.has_bias), inputs=(g2, x2))
         return gx, gw, gb
 
 

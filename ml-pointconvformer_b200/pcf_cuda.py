@@ -133,7 +133,7 @@ def _pconv_bwd(grad_y, grad_p, inp, inv, nei, weights, additional, guidance, lin
         _lib.account(M * (8.0 * K + 5.0 * K + 4.0 * C_out + 4.0 * KK + 8.0 * K * (C_mid + C_add + H)) + 8.0 * N_in * C_in + 4.0 * C_out * KK,
                      2.0 * M * (2.0 * K * (C_in + C_add) * C_mid + 2.0 * KK * C_out))
         if leaf:
-            g_lw, g_lb = S.fork_leaf(lambda: gemm_tn(grad_y[b], pconv_out[b], want_rowsum=True))
+            g_lw, g_lb = S.fork_leaf(lambda: gemm_tn(grad_y[b], pconv_out[b], want_rowsum=True), inputs=(grad_y, pconv_out))
         if n_lw:
             g_lw_acc = g_lw if g_lw_acc is None else g_lw_acc + g_lw
         if n_lb:

@@ -86,8 +86,11 @@ def join(branch):
     return branch.result
 
 
-def fork_leaf(fn):
-    """Run fn() (a leaf of the backward graph: a weight gradient) on a leaf stream; NOT joined until join_leaves()."""
+def fork_leaf(fn, inputs=()):
+    """Run fn() (a leaf of the backward graph: a weight gradient) on a leaf stream; NOT joined until join_leaves().
+    inputs: the tensors fn reads -- they are recorded on the leaf stream, so the caching allocator does not hand their
+    memory to a later allocation of the caller's stream while the leaf kernel may still be reading it (autograd frees the
+    incoming gradient as soon as the node returns)."""
     if not (ENABLED and LEAF_ASYNC) or not torch.cuda.is_available():
         return fn()
     cur = torch.cuda.current_stream()
@@ -100,6 +103,9 @@ def fork_leaf(fn):
     leaf = pool[_LEAF_NEXT[0] % N_LEAF]
     _LEAF_NEXT[0] += 1
     leaf.wait_stream(cur)
+    for t in inputs:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t.record_stream(leaf)
     with torch.cuda.stream(leaf):
         return fn()
 

@@ -134,7 +134,9 @@ def main():
         m = re.match(r"prof_(.+)_%s\.ncu-rep$" % re.escape(tag), fn)
         if m:
             ncu_report(os.path.join(OUT, fn), m.group(1), tag)
-    for fn in ("bench_%s.json" % tag, "bench_reference_%s.json" % tag, "step_kernels_%s.txt" % tag, "step_kernels_by_grid_%s.txt" % tag, "knn_sweep_%s.json" % tag):
+    for fn in ("bench_%s.json" % tag, "bench_reference_%s.json" % tag, "step_kernels_%s.txt" % tag, "step_kernels_by_grid_%s.txt" % tag,
+               "knn_sweep_%s.json" % tag, "step_timeline_%s.txt" % tag, "step_timeline_nopdl_%s.txt" % tag, "chain_times_%s.txt" % tag,
+               "bench_single_%s.json" % tag, "bench_tiny_%s.json" % tag, "bench_5cm_%s.json" % tag, "bench_ptf2_infer_%s.json" % tag):
         src = os.path.join(OUT, fn)
         if os.path.exists(src):
             with open(src) as f, open(os.path.join(PROF, fn), "w") as g:
