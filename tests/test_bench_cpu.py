@@ -24,6 +24,6 @@ def test_cpu_sample_follows_the_budget():
     sys.path.insert(0, ROOT)
     import bench
     import argparse
-    args = argparse.Namespace(cpu_points=0, cpu_budget=0.0, points=100000, scenes=1)
+    args = argparse.Namespace(cpu_points=0, cpu_budget=0.0, points=100000, scenes=1, config="10cm")
     assert bench.choose_cpu_points(args, n_steps=1, budget_s=1e-3) == 6000          # nothing fits: the smallest sample
     assert bench.choose_cpu_points(args, n_steps=1, budget_s=1e9) == 100000         # everything fits: the full scene
