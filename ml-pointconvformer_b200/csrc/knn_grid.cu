@@ -8,8 +8,13 @@
 // build : per scene bounding box -> cell edge h (caller hint, enlarged on the device until the dense grid
 //         fits the caller's cell budget; no host round trip) -> dense cell id per reference -> cell->refs CSR
 //         (the inverse-map kernels with K = 1).
-// query : one thread per query walks Chebyshev shells R = 0,1,2,... of cells around its own cell.  Every
-//         reference NOT yet visited after shell R differs from the query by more than R*h along some axis
+// query : one thread per query walks Chebyshev shells R = 0,1,2,... of cells around its own cell.  The references are
+//         kept as a CELL-SORTED float4 copy (x, y, z, index bits), and cells that are neighbours along x are neighbours
+//         in that copy, so a row of the shell is ONE contiguous range: one independent 16-byte load per candidate
+//         instead of the cell -> index -> coordinates chain of dependent loads.  Self queries (query cloud == reference
+//         cloud) are processed in cell-sorted order: the lanes of a warp then sit in the same or adjacent cells, walk
+//         the same ranges (no divergence in the trip counts, every load a broadcast) -- measured in profiles/README.md.
+//         Every reference NOT yet visited after shell R differs from the query by more than R*h along some axis
 //         (up to the fp32 rounding of the cell index, bounded explicitly in the kernel), so once the current
 //         K-th best squared distance is below ((R - margin)*h)^2 no unvisited reference can enter: exact.
 #include "common.cuh"
@@ -120,15 +125,18 @@ struct TopKLex {
     __device__ __forceinline__ bool accepts(float dist, int idx) const {
         return dist < d[KP - 1] || (dist == d[KP - 1] && idx < id[KP - 1]);
     }
+    // sorted insertion with INDEPENDENT comparisons (no bubble chain): position i takes its left neighbour if the new
+    // element sorts before that neighbour, the new element if it sorts before the old occupant, else keeps the occupant
     __device__ __forceinline__ void insert(float dist, int idx) {
-        d[KP - 1] = dist; id[KP - 1] = idx;
+        bool lt_i = true;                                          // accepts() held: the new element sorts before d[KP-1]
 #pragma unroll
         for (int i = KP - 1; i > 0; --i) {
-            const bool sw = d[i] < d[i - 1] || (d[i] == d[i - 1] && id[i] < id[i - 1]);
-            const float dl = sw ? d[i] : d[i - 1], dh = sw ? d[i - 1] : d[i];
-            const int il = sw ? id[i] : id[i - 1], ih = sw ? id[i - 1] : id[i];
-            d[i - 1] = dl; d[i] = dh; id[i - 1] = il; id[i] = ih;
+            const bool lt_l = dist < d[i - 1] || (dist == d[i - 1] && idx < id[i - 1]);
+            d[i] = lt_l ? d[i - 1] : (lt_i ? dist : d[i]);
+            id[i] = lt_l ? id[i - 1] : (lt_i ? idx : id[i]);
+            lt_i = lt_l;
         }
+        if (lt_i) { d[0] = dist; id[0] = idx; }
     }
     __device__ __forceinline__ float kth(int K) const {         // d[K-1] without dynamic register indexing
         float r = d[KP - 1];
@@ -138,16 +146,30 @@ struct TopKLex {
     }
 };
 
+// cell-sorted copy of the references: sorted[e] = (xyz of reference cell_pts[e], its index)
+__global__ void kg_pack_kernel(const float *__restrict__ ref, const int32_t *__restrict__ cell_pts, int n,
+                               float4 *__restrict__ sorted)
+{
+    pdl_wait();
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int idx = cell_pts[e];
+        sorted[e] = make_float4(ref[3 * (size_t)idx], ref[3 * (size_t)idx + 1], ref[3 * (size_t)idx + 2], __int_as_float(idx));
+    }
+}
+
+constexpr int KG_THREADS = 128;
+
 template <int KP>
-__global__ void __launch_bounds__(128)
-knn_grid_query_kernel(const float *__restrict__ ref, const GridPlan *__restrict__ plans,
-                      const int32_t *__restrict__ cell_ptr, const int32_t *__restrict__ cell_pts,
+__global__ void __launch_bounds__(KG_THREADS)
+knn_grid_query_kernel(const float4 *__restrict__ sorted, const GridPlan *__restrict__ plans,
+                      const int32_t *__restrict__ cell_ptr, const int32_t *__restrict__ order,
                       const float *__restrict__ qry, const int32_t *__restrict__ qry_off, int n_seg, int n_qry, int K,
                       int64_t *__restrict__ out)
 {
     pdl_wait();
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_qry) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_qry) return;
+    const int q = order ? order[i] : i;
     const GridPlan p = plans[g_find_seg(qry_off, n_seg, q)];
     const float qx = qry[3 * (size_t)q], qy = qry[3 * (size_t)q + 1], qz = qry[3 * (size_t)q + 2];
     TopKLex<KP> best;
@@ -155,25 +177,28 @@ knn_grid_query_kernel(const float *__restrict__ ref, const GridPlan *__restrict_
     const int n_ref = p.ref_hi - p.ref_lo;
     if (n_ref > 0) {
         const int cx = cell_coord(qx, p.ox, p.h, p.nx), cy = cell_coord(qy, p.oy, p.h, p.ny), cz = cell_coord(qz, p.oz, p.h, p.nz);
-        for (int R = 0;; ++R) {
+        for (int R = 1;; ++R) {
+            // R == 1: shells 0 and 1 together (the whole 3 x 3 x 3 cube -- shell 0 alone can never terminate the search)
             const int z0 = max(cz - R, 0), z1 = min(cz + R, p.nz - 1);
             const int y0 = max(cy - R, 0), y1 = min(cy + R, p.ny - 1);
             const int x0 = max(cx - R, 0), x1 = min(cx + R, p.nx - 1);
             for (int z = z0; z <= z1; ++z) {
-                const bool zface = (z == cz - R) || (z == cz + R);
+                const bool zface = (R == 1) || (z == cz - R) || (z == cz + R);
                 for (int y = y0; y <= y1; ++y) {
+                    const int c = p.cell_off + p.nx * (y + p.ny * z);
+                    // a row on a z / y face of the shell: the whole x range, one contiguous run of the cell-sorted copy;
+                    // an inner row: its two end cells
                     const bool full_row = zface || (y == cy - R) || (y == cy + R);
-                    // on the shell: whole x-row if the row lies on a z/y face, otherwise only its two end cells
-                    const int step = full_row ? 1 : max(2 * R, 1);
-                    for (int x = full_row ? x0 : cx - R; x <= (full_row ? x1 : cx + R); x += step) {
-                        if (x < 0 || x >= p.nx) continue;
-                        const int c = p.cell_off + x + p.nx * (y + p.ny * z);
-                        const int e1 = cell_ptr[c + 1];
-                        for (int e = cell_ptr[c]; e < e1; ++e) {
-                            const int idx = cell_pts[e];
-                            const float rx = ref[3 * (size_t)idx], ry = ref[3 * (size_t)idx + 1], rz = ref[3 * (size_t)idx + 2];
-                            const float dx = __fsub_rn(qx, rx), dy = __fsub_rn(qy, ry), dz = __fsub_rn(qz, rz);
+                    for (int seg = 0; seg < (full_row ? 1 : 2); ++seg) {
+                        const int xa = full_row ? x0 : (seg == 0 ? cx - R : cx + R);
+                        const int xb = full_row ? x1 : xa;
+                        if (xa < 0 || xb >= p.nx) continue;
+                        const int e1 = __ldg(cell_ptr + c + xb + 1);
+                        for (int e = __ldg(cell_ptr + c + xa); e < e1; ++e) {
+                            const float4 r = __ldg(sorted + e);
+                            const float dx = __fsub_rn(qx, r.x), dy = __fsub_rn(qy, r.y), dz = __fsub_rn(qz, r.z);
                             const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                            const int idx = __float_as_int(r.w);
                             if (best.accepts(dist, idx)) best.insert(dist, idx);
                         }
                     }
@@ -190,18 +215,18 @@ knn_grid_query_kernel(const float *__restrict__ ref, const GridPlan *__restrict_
     const int found = min(n_ref, K);
     int64_t *o = out + (size_t)q * K;
 #pragma unroll
-    for (int i = 0; i < KP; ++i) {
-        if (i < K) {
-            int v = best.id[i];
-            if (i >= found) {
+    for (int k = 0; k < KP; ++k) {
+        if (k < K) {
+            int v = best.id[k];
+            if (k >= found) {
                 v = -1;
                 if (found > 0) {
-                    const int src = i % found;
+                    const int src = k % found;
 #pragma unroll
                     for (int t = 0; t < KP; ++t) if (t == src) v = best.id[t];
                 }
             }
-            o[i] = (int64_t)v;
+            o[k] = (int64_t)v;
         }
     }
 }
@@ -211,6 +236,7 @@ struct KgWorkspace {
     GridPlan *plans;
     int64_t *cell;
     int32_t *cell_ptr, *cell_pts;
+    float4 *sorted;
     uint8_t *zero_k;
     void *inv_ws;
     size_t inv_ws_bytes, bytes;
@@ -227,6 +253,7 @@ static KgWorkspace carve_kg(void *ws, int n_seg, int n_ref) {
     w.cell_ptr = c.take<int32_t>((size_t)w.max_cells + 2);
     w.cell_pts = c.take<int32_t>((size_t)n_ref + 1);
     w.zero_k = c.take<uint8_t>((size_t)n_ref + 1);
+    w.sorted = c.take<float4>((size_t)n_ref + 1);
     w.inv_ws_bytes = pcfb_knn_inverse_workspace(n_ref, 1, w.max_cells);
     w.inv_ws = c.take<char>(w.inv_ws_bytes);
     w.bytes = align_up(c.off, 256);
@@ -269,7 +296,12 @@ extern "C" int pcfb_knn_grid_build(const float *ref_xyz, const int32_t *ref_off,
         launch_k(kg_cell_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, ref_off, n_seg, n_ref, w.plans, w.cell);
         if ((rc = check_launch("kg_cell_kernel"))) return rc;
     }
-    return pcfb_knn_inverse(w.cell, n_ref, 1, w.max_cells, w.cell_pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream);
+    if ((rc = pcfb_knn_inverse(w.cell, n_ref, 1, w.max_cells, w.cell_pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream))) return rc;
+    if (n_ref > 0) {
+        launch_k(kg_pack_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, (const int32_t *)w.cell_pts, n_ref, w.sorted);
+        if ((rc = check_launch("kg_pack_kernel"))) return rc;
+    }
+    return PCFB_OK;
 }
 
 extern "C" int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, const float *qry_xyz, const int32_t *qry_off,
@@ -284,12 +316,17 @@ extern "C" int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, c
     KgWorkspace w = carve_kg(const_cast<void *>(workspace), n_seg, n_ref);
     if (workspace_bytes < w.bytes) { set_error("pcfb_knn_grid_query: workspace %zu < %zu", workspace_bytes, w.bytes); return PCFB_ERR_WORKSPACE; }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = ceil_div(n_qry, 128);
+    const int grid = ceil_div(n_qry, KG_THREADS);
+    const float4 *sorted = w.sorted;
+    const int32_t *cell_ptr = w.cell_ptr;
+    const GridPlan *plans = w.plans;
+    // self queries (the query cloud IS the reference cloud): walk them in cell-sorted order
+    const int32_t *order = (qry_xyz == ref_xyz && n_qry == n_ref) ? w.cell_pts : nullptr;
     if (K <= 16)
-        launch_k(knn_grid_query_kernel<16>, grid, 128, 0, st, ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_grid_query_kernel<16>, grid, KG_THREADS, 0, st, sorted, plans, cell_ptr, order, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else if (K <= 32)
-        launch_k(knn_grid_query_kernel<32>, grid, 128, 0, st, ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_grid_query_kernel<32>, grid, KG_THREADS, 0, st, sorted, plans, cell_ptr, order, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else
-        launch_k(knn_grid_query_kernel<64>, grid, 128, 0, st, ref_xyz, w.plans, w.cell_ptr, w.cell_pts, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
+        launch_k(knn_grid_query_kernel<64>, grid, KG_THREADS, 0, st, sorted, plans, cell_ptr, order, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     return check_launch("knn_grid_query_kernel");
 }
