@@ -69,13 +69,19 @@ int pcfb_knn_packed(const float *ref_xyz, const int32_t *ref_off, const float *q
  * grid-accelerated kNN).  pcfb_knn_grid_build bins the references of every scene (cell edge = cell_hint,
  * enlarged on the device until each scene's dense grid has <= 2*n+64 cells; cell_hint <= 0 = automatic) into
  * the workspace; pcfb_knn_grid_query answers any number of query sets against it (1 <= K <= 64).  The grid
- * of one level serves its self-, forward- and propagate- edge sets. */
+ * of one level serves its self-, forward- and propagate- edge sets.
+ * qry_order (optional): a permutation of the queries in which neighbouring entries are neighbours in space -- the lanes
+ * of a warp then walk the same cells.  NULL = natural order, except self queries (qry_xyz == ref_xyz), which use the
+ * grid's own cell order.  pcfb_knn_grid_order returns that order of a built grid (a device pointer INTO its workspace,
+ * n_ref entries: the reference indices sorted by cell) so that the grid of level l can order level l's points when they
+ * are the queries against another level's grid.  The result does not depend on the order. */
 size_t pcfb_knn_grid_workspace(int n_seg, int n_ref);
 int pcfb_knn_grid_build(const float *ref_xyz, const int32_t *ref_off, int n_seg, int n_ref, float cell_hint,
                         void *workspace, size_t workspace_bytes, void *stream);
+const int32_t *pcfb_knn_grid_order(int n_seg, int n_ref, const void *workspace);
 int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, const float *qry_xyz, const int32_t *qry_off,
-                        int n_qry, int K, int64_t *out_idx, const void *workspace, size_t workspace_bytes,
-                        void *stream);
+                        int n_qry, int K, const int32_t *qry_order, int64_t *out_idx, const void *workspace,
+                        size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * kNN inverse map (CSR transpose).  Replaces pcf_cuda.compute_knn_inverse

@@ -30,7 +30,8 @@ SIGNATURES = {
     "pcfb_knn_packed": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "pcfb_knn_grid_workspace": (c_size_t, [c_int, c_int]),
     "pcfb_knn_grid_build": (c_int, [_P, _P, c_int, c_int, c_float, _P, c_size_t, _P]),
-    "pcfb_knn_grid_query": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P, c_size_t, _P]),
+    "pcfb_knn_grid_order": (_P, [c_int, c_int, _P]),
+    "pcfb_knn_grid_query": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P, _P, _P, c_size_t, _P]),
     "pcfb_knn_inverse_workspace": (c_size_t, [c_int, c_int, c_int]),
     "pcfb_knn_inverse": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
     "pcfb_gather": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),

@@ -6,8 +6,9 @@
 // lexicographic order, so the result does not depend on the order candidates are visited in.
 //
 // build : per scene bounding box -> cell edge h (caller hint, enlarged on the device until the dense grid
-//         fits the caller's cell budget; no host round trip) -> dense cell id per reference -> cell->refs CSR
-//         (the inverse-map kernels with K = 1).
+//         fits the caller's cell budget; no host round trip) -> dense cell id per reference + histogram -> exclusive scan
+//         (cell -> first slot) -> slot-claim fill of the cell-sorted index list and float4 copy.  The order of the
+//         references INSIDE a cell is whatever the atomics give: the query result does not depend on it.
 // query : one thread per query walks Chebyshev shells R = 0,1,2,... of cells around its own cell.  The references are
 //         kept as a CELL-SORTED float4 copy (x, y, z, index bits), and cells that are neighbours along x are neighbours
 //         in that copy, so a row of the shell is ONE contiguous range: one independent 16-byte load per candidate
@@ -18,6 +19,7 @@
 //         (up to the fp32 rounding of the cell index, bounded explicitly in the kernel), so once the current
 //         K-th best squared distance is below ((R - margin)*h)^2 no unvisited reference can enter: exact.
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace pcfb {
 
@@ -101,8 +103,9 @@ __device__ __forceinline__ int cell_coord(float x, float o, float h, int n) {
     return min(max(c, 0), n - 1);
 }
 
-__global__ void kg_cell_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ off, int n_seg, int n,
-                               const GridPlan *__restrict__ plans, int64_t *__restrict__ cell)
+__global__ void kg_cell_count_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ off, int n_seg, int n,
+                                     const GridPlan *__restrict__ plans, int32_t *__restrict__ cell,
+                                     int32_t *__restrict__ counts)
 {
     pdl_wait();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -110,54 +113,77 @@ __global__ void kg_cell_kernel(const float *__restrict__ xyz, const int32_t *__r
         const int cx = cell_coord(xyz[3 * (size_t)i], p.ox, p.h, p.nx);
         const int cy = cell_coord(xyz[3 * (size_t)i + 1], p.oy, p.h, p.ny);
         const int cz = cell_coord(xyz[3 * (size_t)i + 2], p.oz, p.h, p.nz);
-        cell[i] = (int64_t)p.cell_off + cx + (int64_t)p.nx * (cy + (int64_t)p.ny * cz);
+        const int c = p.cell_off + cx + p.nx * (cy + p.ny * cz);
+        cell[i] = c;
+        atomicAdd(&counts[c], 1);
     }
 }
 
+// slot claim: reference i takes one of its cell's slots (counts[] still holds the histogram and is counted down);
+// writes the cell-sorted index list and the cell-sorted float4 copy (x, y, z, index bits)
+__global__ void kg_fill_kernel(const float *__restrict__ xyz, const int32_t *__restrict__ cell, int n,
+                               const int32_t *__restrict__ cell_ptr, int32_t *__restrict__ counts,
+                               int32_t *__restrict__ cell_pts, float4 *__restrict__ sorted)
+{
+    pdl_wait();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int c = cell[i];
+        const int pos = cell_ptr[c] + atomicSub(&counts[c], 1) - 1;
+        cell_pts[pos] = i;
+        sorted[pos] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __int_as_float(i));
+    }
+}
+
+// K best (distance, index) pairs in ascending lexicographic order, in registers.  Distances are kept as their IEEE bit
+// patterns (a sum of squares is >= +0, so unsigned integer order == float order): (distance, index) then compares as ONE
+// 64-bit integer -- two ISETP instead of three float / integer compares plus predicate logic.
 template <int KP>
 struct TopKLex {
-    float d[KP];
+    unsigned d[KP];
     int id[KP];
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int i = 0; i < KP; ++i) { d[i] = __int_as_float(0x7f800000); id[i] = 0x7fffffff; }
+        for (int i = 0; i < KP; ++i) { d[i] = 0x7f800000u; id[i] = 0x7fffffff; }
     }
-    __device__ __forceinline__ bool accepts(float dist, int idx) const {
-        return dist < d[KP - 1] || (dist == d[KP - 1] && idx < id[KP - 1]);
+    static __device__ __forceinline__ unsigned long long key(unsigned dist, int idx) {
+        return ((unsigned long long)dist << 32) | (unsigned)idx;
     }
-    // sorted insertion with INDEPENDENT comparisons (no bubble chain): position i takes its left neighbour if the new
-    // element sorts before that neighbour, the new element if it sorts before the old occupant, else keeps the occupant
-    __device__ __forceinline__ void insert(float dist, int idx) {
+    __device__ __forceinline__ bool accepts(unsigned dist, int idx) const { return key(dist, idx) < key(d[KP - 1], id[KP - 1]); }
+    // sorted insertion, branch free, INDEPENDENT comparisons (no bubble chain): position i takes its left neighbour if the
+    // new element sorts before that neighbour, the new element if it sorts before the old occupant, else keeps the occupant
+    // (2 ISETP + 4 SEL per position; the first version of this, written with nested ?:, compiled to 292 instructions of
+    // branches per insertion -- profiles/ncu_knn_r02.txt)
+    __device__ __forceinline__ void insert(unsigned dist, int idx) {
+        const unsigned long long nk = key(dist, idx);
         bool lt_i = true;                                          // accepts() held: the new element sorts before d[KP-1]
 #pragma unroll
         for (int i = KP - 1; i > 0; --i) {
-            const bool lt_l = dist < d[i - 1] || (dist == d[i - 1] && idx < id[i - 1]);
-            d[i] = lt_l ? d[i - 1] : (lt_i ? dist : d[i]);
-            id[i] = lt_l ? id[i - 1] : (lt_i ? idx : id[i]);
+            const bool lt_l = nk < key(d[i - 1], id[i - 1]);
+            const unsigned td = lt_i ? dist : d[i];
+            const int ti = lt_i ? idx : id[i];
+            d[i] = lt_l ? d[i - 1] : td;
+            id[i] = lt_l ? id[i - 1] : ti;
             lt_i = lt_l;
         }
-        if (lt_i) { d[0] = dist; id[0] = idx; }
+        d[0] = lt_i ? dist : d[0];
+        id[0] = lt_i ? idx : id[0];
     }
     __device__ __forceinline__ float kth(int K) const {         // d[K-1] without dynamic register indexing
-        float r = d[KP - 1];
+        unsigned r = d[KP - 1];
 #pragma unroll
         for (int i = 0; i < KP; ++i) if (i == K - 1) r = d[i];
-        return r;
+        return __uint_as_float(r);
     }
 };
 
-// cell-sorted copy of the references: sorted[e] = (xyz of reference cell_pts[e], its index)
-__global__ void kg_pack_kernel(const float *__restrict__ ref, const int32_t *__restrict__ cell_pts, int n,
-                               float4 *__restrict__ sorted)
-{
-    pdl_wait();
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-        const int idx = cell_pts[e];
-        sorted[e] = make_float4(ref[3 * (size_t)idx], ref[3 * (size_t)idx + 1], ref[3 * (size_t)idx + 2], __int_as_float(idx));
-    }
-}
-
 constexpr int KG_THREADS = 128;
+// (dz, dy) of the nine rows of the 3 x 3 x 3 cube, nearest first, as 2-bit fields (value + 1)
+constexpr unsigned kg_pack9(int a0, int a1, int a2, int a3, int a4, int a5, int a6, int a7, int a8) {
+    return (unsigned)(a0 + 1) | (unsigned)(a1 + 1) << 2 | (unsigned)(a2 + 1) << 4 | (unsigned)(a3 + 1) << 6 | (unsigned)(a4 + 1) << 8 |
+           (unsigned)(a5 + 1) << 10 | (unsigned)(a6 + 1) << 12 | (unsigned)(a7 + 1) << 14 | (unsigned)(a8 + 1) << 16;
+}
+constexpr unsigned KG_CUBE_DZ = kg_pack9(0, 0, 0, -1, 1, -1, -1, 1, 1);
+constexpr unsigned KG_CUBE_DY = kg_pack9(0, -1, 1, 0, 0, -1, 1, -1, 1);
 
 template <int KP>
 __global__ void __launch_bounds__(KG_THREADS)
@@ -167,6 +193,7 @@ knn_grid_query_kernel(const float4 *__restrict__ sorted, const GridPlan *__restr
                       int64_t *__restrict__ out)
 {
     pdl_wait();
+    __shared__ int2 row_s[9][KG_THREADS];                         // the nine row ranges of every thread's cube
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_qry) return;
     const int q = order ? order[i] : i;
@@ -177,30 +204,51 @@ knn_grid_query_kernel(const float4 *__restrict__ sorted, const GridPlan *__restr
     const int n_ref = p.ref_hi - p.ref_lo;
     if (n_ref > 0) {
         const int cx = cell_coord(qx, p.ox, p.h, p.nx), cy = cell_coord(qy, p.oy, p.h, p.ny), cz = cell_coord(qz, p.oz, p.h, p.nz);
+        auto candidate = [&](const float4 rr) {
+            const float dx = __fsub_rn(qx, rr.x), dy2 = __fsub_rn(qy, rr.y), dz2 = __fsub_rn(qz, rr.z);
+            const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy2, dy2)), __fmul_rn(dz2, dz2));
+            const int idx = __float_as_int(rr.w);
+            if (best.accepts(__float_as_uint(dist), idx)) best.insert(__float_as_uint(dist), idx);
+        };
         for (int R = 1;; ++R) {
-            // R == 1: shells 0 and 1 together (the whole 3 x 3 x 3 cube -- shell 0 alone can never terminate the search)
-            const int z0 = max(cz - R, 0), z1 = min(cz + R, p.nz - 1);
-            const int y0 = max(cy - R, 0), y1 = min(cy + R, p.ny - 1);
             const int x0 = max(cx - R, 0), x1 = min(cx + R, p.nx - 1);
-            for (int z = z0; z <= z1; ++z) {
-                const bool zface = (R == 1) || (z == cz - R) || (z == cz + R);
-                for (int y = y0; y <= y1; ++y) {
+            if (R == 1) {
+                // Shells 0 and 1 together (the whole 3 x 3 x 3 cube -- shell 0 alone can never terminate the search): nine
+                // rows, each ONE contiguous range of the cell-sorted copy, nearest first (the query's own row, the four
+                // rows sharing a face with it, the four diagonal ones: the list fills with near candidates early and most of
+                // the later ones fail the K-th-distance test, which skips the insertion).  The ranges go to shared memory
+                // and the candidates of all nine are walked in ONE flat loop: a lane whose row is empty or short moves on
+                // to its next row instead of idling until the longest row of the warp is done.
+#pragma unroll
+                for (int r = 0; r < 9; ++r) {
+                    const int z = cz + (int)((KG_CUBE_DZ >> (2 * r)) & 3u) - 1, y = cy + (int)((KG_CUBE_DY >> (2 * r)) & 3u) - 1;
+                    const bool ok = z >= 0 && z < p.nz && y >= 0 && y < p.ny;
                     const int c = p.cell_off + p.nx * (y + p.ny * z);
-                    // a row on a z / y face of the shell: the whole x range, one contiguous run of the cell-sorted copy;
-                    // an inner row: its two end cells
-                    const bool full_row = zface || (y == cy - R) || (y == cy + R);
+                    row_s[r][threadIdx.x] = ok ? make_int2(__ldg(cell_ptr + c + x0), __ldg(cell_ptr + c + x1 + 1)) : make_int2(0, 0);
+                }
+                int r = 0;
+                int2 ee = row_s[0][threadIdx.x];
+                while (true) {
+                    while (ee.x >= ee.y && r < 8) ee = row_s[++r][threadIdx.x];
+                    if (ee.x >= ee.y) break;
+                    candidate(__ldg(sorted + ee.x));
+                    ++ee.x;
+                }
+            } else {
+                const int side = 2 * R + 1, n_rows = side * side;
+                for (int r = 0; r < n_rows; ++r) {
+                    const int dz = r / side - R, dy = r - (dz + R) * side - R;
+                    const int z = cz + dz, y = cy + dy;
+                    if (z < 0 || z >= p.nz || y < 0 || y >= p.ny) continue;
+                    const int c = p.cell_off + p.nx * (y + p.ny * z);
+                    // a row on a z / y face of the shell: the whole x range; an inner row: its two end cells
+                    const bool full_row = dz == -R || dz == R || dy == -R || dy == R;
                     for (int seg = 0; seg < (full_row ? 1 : 2); ++seg) {
                         const int xa = full_row ? x0 : (seg == 0 ? cx - R : cx + R);
                         const int xb = full_row ? x1 : xa;
                         if (xa < 0 || xb >= p.nx) continue;
                         const int e1 = __ldg(cell_ptr + c + xb + 1);
-                        for (int e = __ldg(cell_ptr + c + xa); e < e1; ++e) {
-                            const float4 r = __ldg(sorted + e);
-                            const float dx = __fsub_rn(qx, r.x), dy = __fsub_rn(qy, r.y), dz = __fsub_rn(qz, r.z);
-                            const float dist = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-                            const int idx = __float_as_int(r.w);
-                            if (best.accepts(dist, idx)) best.insert(dist, idx);
-                        }
+                        for (int e = __ldg(cell_ptr + c + xa); e < e1; ++e) candidate(__ldg(sorted + e));
                     }
                 }
             }
@@ -234,12 +282,12 @@ knn_grid_query_kernel(const float4 *__restrict__ sorted, const GridPlan *__restr
 struct KgWorkspace {
     int *mm;
     GridPlan *plans;
-    int64_t *cell;
-    int32_t *cell_ptr, *cell_pts;
+    int32_t *cell, *cell_ptr, *cell_pts;
     float4 *sorted;
-    uint8_t *zero_k;
-    void *inv_ws;
-    size_t inv_ws_bytes, bytes;
+    int32_t *counts;                 // zero-initialised region: counts, scan state, scan ticket (one memset)
+    unsigned long long *state;
+    unsigned int *ticket;
+    size_t zero_bytes, bytes;
     int max_cells;
 };
 
@@ -249,13 +297,14 @@ static KgWorkspace carve_kg(void *ws, int n_seg, int n_ref) {
     w.max_cells = 2 * n_ref + 64 * n_seg;
     w.mm = c.take<int>((size_t)n_seg * 6 + 1);
     w.plans = c.take<GridPlan>((size_t)n_seg);
-    w.cell = c.take<int64_t>((size_t)n_ref + 1);
+    w.cell = c.take<int32_t>((size_t)n_ref + 1);
     w.cell_ptr = c.take<int32_t>((size_t)w.max_cells + 2);
     w.cell_pts = c.take<int32_t>((size_t)n_ref + 1);
-    w.zero_k = c.take<uint8_t>((size_t)n_ref + 1);
     w.sorted = c.take<float4>((size_t)n_ref + 1);
-    w.inv_ws_bytes = pcfb_knn_inverse_workspace(n_ref, 1, w.max_cells);
-    w.inv_ws = c.take<char>(w.inv_ws_bytes);
+    w.counts = c.take<int32_t>((size_t)w.max_cells + 2);
+    w.state = c.take<unsigned long long>((size_t)ceil_div(w.max_cells + 1, SCAN_TILE) + 1);
+    w.ticket = c.take<unsigned int>(4);
+    w.zero_bytes = (size_t)((char *)(w.ticket + 4) - (char *)w.counts);
     w.bytes = align_up(c.off, 256);
     return w;
 }
@@ -292,21 +341,32 @@ extern "C" int pcfb_knn_grid_build(const float *ref_xyz, const int32_t *ref_off,
     }
     launch_k(kg_plan_kernel, 1, 32, 0, st, w.mm, ref_off, n_seg, cell_hint, w.plans);
     if ((rc = check_launch("kg_plan_kernel"))) return rc;
+    PCFB_CUDA(cudaMemsetAsync(w.counts, 0, w.zero_bytes, st));
     if (n_ref > 0) {
-        launch_k(kg_cell_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, ref_off, n_seg, n_ref, w.plans, w.cell);
-        if ((rc = check_launch("kg_cell_kernel"))) return rc;
+        launch_k(kg_cell_count_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, ref_off, n_seg, n_ref, (const GridPlan *)w.plans, w.cell, w.counts);
+        if ((rc = check_launch("kg_cell_count_kernel"))) return rc;
     }
-    if ((rc = pcfb_knn_inverse(w.cell, n_ref, 1, w.max_cells, w.cell_pts, w.zero_k, w.cell_ptr, w.inv_ws, w.inv_ws_bytes, stream))) return rc;
+    // exclusive scan over max_cells + 1 entries: cell_ptr[c] = first slot of cell c, cell_ptr[max_cells] = n_ref
+    launch_k(inv_scan_kernel, ceil_div(w.max_cells + 1, SCAN_TILE), SCAN_THREADS, 0, st, (const int32_t *)w.counts, w.max_cells, w.cell_ptr,
+             w.state, w.ticket);
+    if ((rc = check_launch("inv_scan_kernel"))) return rc;
     if (n_ref > 0) {
-        launch_k(kg_pack_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, (const int32_t *)w.cell_pts, n_ref, w.sorted);
-        if ((rc = check_launch("kg_pack_kernel"))) return rc;
+        launch_k(kg_fill_kernel, kg_blocks(n_ref), 256, 0, st, ref_xyz, (const int32_t *)w.cell, n_ref, (const int32_t *)w.cell_ptr, w.counts,
+                 w.cell_pts, w.sorted);
+        if ((rc = check_launch("kg_fill_kernel"))) return rc;
     }
     return PCFB_OK;
 }
 
+extern "C" const int32_t *pcfb_knn_grid_order(int n_seg, int n_ref, const void *workspace)
+{
+    if (!workspace || n_seg < 1 || n_ref < 0) return nullptr;
+    return pcfb::carve_kg(const_cast<void *>(workspace), n_seg, n_ref).cell_pts;
+}
+
 extern "C" int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, const float *qry_xyz, const int32_t *qry_off,
-                                   int n_qry, int K, int64_t *out_idx, const void *workspace, size_t workspace_bytes,
-                                   void *stream)
+                                   int n_qry, int K, const int32_t *qry_order, int64_t *out_idx, const void *workspace,
+                                   size_t workspace_bytes, void *stream)
 {
     using namespace pcfb;
     PCFB_REQUIRE(K >= 1 && K <= 64, "pcfb_knn_grid_query: K=%d outside [1,64] (use pcfb_knn_packed for larger K)", K);
@@ -320,8 +380,9 @@ extern "C" int pcfb_knn_grid_query(const float *ref_xyz, int n_seg, int n_ref, c
     const float4 *sorted = w.sorted;
     const int32_t *cell_ptr = w.cell_ptr;
     const GridPlan *plans = w.plans;
-    // self queries (the query cloud IS the reference cloud): walk them in cell-sorted order
-    const int32_t *order = (qry_xyz == ref_xyz && n_qry == n_ref) ? w.cell_pts : nullptr;
+    // spatially coherent order of the queries: the caller's permutation (e.g. another grid's cell order of the same
+    // cloud), or -- self queries, the query cloud IS the reference cloud -- this grid's own cell order
+    const int32_t *order = qry_order ? qry_order : ((qry_xyz == ref_xyz && n_qry == n_ref) ? w.cell_pts : nullptr);
     if (K <= 16)
         launch_k(knn_grid_query_kernel<16>, grid, KG_THREADS, 0, st, sorted, plans, cell_ptr, order, qry_xyz, qry_off, n_seg, n_qry, K, out_idx);
     else if (K <= 32)

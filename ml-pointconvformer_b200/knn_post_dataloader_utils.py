@@ -44,6 +44,7 @@ def compute_knn(ref_points, query_points, K, dilated_rate=1, method='keops'):
 # identical tables (tests/test_gpu_knn.py); brute force is O(N^2) per scene.
 KNN_METHOD = "grid"
 BRUTE_MAX_REFS = 256           # per-scene reference count below which brute force beats the grid search
+CELL_FACTOR = 1.75             # grid cell edge = CELL_FACTOR x the level's voxel size (scripts/time_knn_stage.py)
 
 
 def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagate, grid_size=None, method=None):
@@ -68,12 +69,13 @@ def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagat
     # search wins even when it is latency bound (measured per query set, grid vs brute force: 128 vs 232 us at 1 k
     # references, 185 vs 287 us at 5 k, 105 vs 84 us at 184) -- same table either way.
     small = [max(counts[j]) <= BRUTE_MAX_REFS for j in range(L)]
-    hint = lambda j: 2.5 * float(grid_size[j]) if grid_size is not None else 0.0
+    hint = lambda j: CELL_FACTOR * float(grid_size[j]) if grid_size is not None else 0.0
 
-    # Two fork / join stages over the side streams (streams.fork): the five grid builds, then the 13 queries -- the heaviest
-    # first, so that the two 100k-query sets (level-0 self, level-0 -> level-1 propagate) land on different streams.  The
-    # step's edge construction then costs one large query instead of the sum of all of them.
-    builds = [S.fork(lambda j=j: None if small[j] else pcf_cuda.KnnGrid(pcs[j], counts[j], hint(j)), j) for j in range(L)]
+    # Two fork / join stages (streams.fork, the wide pool: one stream per job): the five grid builds, then the 13 query
+    # sets.  The small sets go first: a 1 k .. 5 k-query set is a handful of CTAs that take ~100 us of pure latency, so they
+    # must be resident before the two 100k-query sets (level-0 self, level-0 -> level-1 propagate) fill every CTA slot --
+    # queued behind them they would run after the big ones and double the stage (scripts/time_knn_stage.py).
+    builds = [S.fork(lambda j=j: None if small[j] else pcf_cuda.KnnGrid(pcs[j], counts[j], hint(j)), j, wide=True) for j in range(L)]
     grids = [S.join(b) for b in builds]
     jobs = []                                                        # (kind, level index in the output list, jr, jq, K)
     for j in range(L):
@@ -81,13 +83,14 @@ def compute_knn_packed(pointclouds, points_stored, K_self, K_forward, K_propagat
         if j >= 1:
             jobs.append(("fwd", j - 1, j - 1, j, K_forward[j]))      # level j looks into level j-1
             jobs.append(("prop", j - 1, j, j - 1, K_propagate[j]))   # dense level j-1 looks into level j
-    jobs.sort(key=lambda t: -pcs[t[3]].shape[0])
+    jobs.sort(key=lambda t: pcs[t[3]].shape[0])
 
     def query(jr, jq, K):
         if grids[jr] is None:
             return pcf_cuda.knn_packed(pcs[jr], counts[jr], pcs[jq], counts[jq], K)
-        return grids[jr].query(pcs[jq], counts[jq], K)
-    running = [(job, S.fork(lambda job=job: query(job[2], job[3], job[4]), i)) for i, job in enumerate(jobs)]
+        # the query cloud's own grid (if it has one) supplies a spatially coherent order of the queries
+        return grids[jr].query(pcs[jq], counts[jq], K, order=grids[jq] if jq != jr else None)
+    running = [(job, S.fork(lambda job=job: query(job[2], job[3], job[4]), i, wide=True)) for i, job in enumerate(jobs)]
     out = {"self": [None] * L, "fwd": [None] * (L - 1), "prop": [None] * (L - 1)}
     for job, br in running:
         out[job[0]][job[1]] = S.join(br)

@@ -357,14 +357,22 @@ class KnnGrid:
         check(lib().pcfb_knn_grid_build(ptr(ref_xyz), ptr(self.ref_off), self.n_seg, ref_xyz.shape[0], float(cell_hint),
                                         ptr(self.ws), self.ws_bytes, stream_ptr()), "knn_grid_build")
 
-    def query(self, qry_xyz, qry_counts, K):
+    def order_ptr(self):
+        """Device pointer to the references' cell-sorted permutation (lives in this grid's workspace)."""
+        return lib().pcfb_knn_grid_order(self.n_seg, self.ref.shape[0], ptr(self.ws)) or 0
+
+    def query(self, qry_xyz, qry_counts, K, order=None):
+        """order: the KnnGrid built over qry_xyz itself (its cell order makes the warps spatially coherent), or None."""
         require(qry_xyz, F32, "qry_xyz")
+        if order is not None and (order.ref.data_ptr() != qry_xyz.data_ptr() or order.ref.shape[0] != qry_xyz.shape[0]):
+            raise RuntimeError("order: not the grid of this query cloud")
         if len(qry_counts) != self.n_seg or sum(map(int, qry_counts)) != qry_xyz.shape[0]:
             raise RuntimeError("query scene counts do not match")
         qo = _offsets(qry_counts, qry_xyz.device)
         out = torch.empty(qry_xyz.shape[0], K, device=qry_xyz.device, dtype=I64)
         check(lib().pcfb_knn_grid_query(ptr(self.ref), self.n_seg, self.ref.shape[0], ptr(qry_xyz), ptr(qo), qry_xyz.shape[0],
-                                        int(K), ptr(out), ptr(self.ws), self.ws_bytes, stream_ptr()), "knn_grid_query")
+                                        int(K), order.order_ptr() if order is not None else 0, ptr(out), ptr(self.ws),
+                                        self.ws_bytes, stream_ptr()), "knn_grid_query")
         _lib.account(12.0 * (self.ref.shape[0] + qry_xyz.shape[0]) + 8.0 * K * qry_xyz.shape[0])
         return out
 

@@ -18,7 +18,9 @@ import torch
 
 ENABLED = os.environ.get("PCFB_STREAMS", "1") != "0"
 N_SIDE = 4
+N_WIDE = 16                 # second pool for stages made of many independent jobs (the 13 kNN query sets of a batch)
 _POOL = {}
+_WIDE = {}
 # Weight-gradient products (dW = dY^T X of every Linear, dW of the fused contraction's Linear) are LEAVES of the backward
 # graph: nothing downstream waits for them except the optimizer.  With LEAF_ASYNC they run on their own stream and are only
 # joined by join_leaves() (called by sharding.FlatParameters.gather_grads before the flat gradient is assembled), taking
@@ -37,14 +39,25 @@ def _side_streams(device):
     return pool
 
 
+def _wide_streams(device):
+    key = (device.type, device.index)
+    pool = _WIDE.get(key)
+    if pool is None:
+        # the first half of the pool has high priority: whoever forks many jobs puts the SMALL ones there, so their few
+        # CTAs are placed as soon as a slot frees up instead of queueing behind a big kernel's remaining waves
+        pool = _WIDE[key] = [torch.cuda.Stream(device=device, priority=-1 if i < N_WIDE // 2 else 0) for i in range(N_WIDE)]
+    return pool
+
+
 def side_index(stream=None):
-    """0 for the caller's main stream, 1..N_SIDE for the side streams (used as the exchange channel of SyncBatchNorm)."""
+    """0 for the caller's main stream, 1..N_SIDE for the side streams, N_SIDE+1.. for the wide pool."""
     stream = stream or torch.cuda.current_stream()
-    pool = _POOL.get((stream.device.type, stream.device.index))
-    if pool:
-        for i, s in enumerate(pool):
-            if s == stream:
-                return i + 1
+    key = (stream.device.type, stream.device.index)
+    for base, pool in ((1, _POOL.get(key)), (N_SIDE + 1, _WIDE.get(key))):
+        if pool:
+            for i, s in enumerate(pool):
+                if s == stream:
+                    return base + i
     return 0
 
 
@@ -55,14 +68,15 @@ class Branch:
         self.result, self.stream, self.main = result, stream, main
 
 
-def fork(fn, slot, enabled=True):
-    """Run fn() on side stream `slot` (inline when disabled, on the CPU, or when already on a side stream)."""
+def fork(fn, slot, enabled=True, wide=False):
+    """Run fn() on side stream `slot` (inline when disabled, on the CPU, or when already on a side stream).
+    wide: take the stream from the N_WIDE pool -- for stages of many independent jobs without BatchNorm exchanges."""
     if not (ENABLED and enabled) or not torch.cuda.is_available():
         return Branch(fn())
     main = torch.cuda.current_stream()
     if side_index(main) != 0:                       # no nested forks
         return Branch(fn())
-    side = _side_streams(main.device)[slot % N_SIDE]
+    side = _wide_streams(main.device)[slot % N_WIDE] if wide else _side_streams(main.device)[slot % N_SIDE]
     side.wait_stream(main)
     with torch.cuda.stream(side):
         res = fn()

@@ -63,7 +63,7 @@ def main():
         elif what == "bwd":
             pcf_cuda.pconv_fused_backward(go, None, feats, inv, nei[None], w, add, gd, W, p, (True,) * 6)
         elif what == "knn":
-            pcf_cuda.KnnGrid(xyz, [n], 0.25).query(xyz, [n], K)
+            pcf_cuda.KnnGrid(xyz, [n], 0.175).query(xyz, [n], K)
         elif what == "knn_brute":
             pcf_cuda.knn_packed(xyz, [n], xyz, [n], K)
         elif what == "inv":

@@ -115,6 +115,27 @@ def _grid(ref, qry, ref_counts, qry_counts, K, hint=0.0):
     return _pc().KnnGrid(cuda(ref), ref_counts, hint).query(cuda(qry), qry_counts, K).cpu().numpy()
 
 
+def test_grid_knn_query_order_does_not_change_the_table():
+    """pcfb_knn_grid_query's optional query order (the cell order of the query cloud's own grid: coherent warps) is a
+    scheduling hint only: same table as the natural order and as the oracle, ragged packed scenes included."""
+    pc = _pc()
+    ref_counts, qry_counts = [900, 5, 1500, 129], [300, 9, 410, 33]
+    ref = np.concatenate([surface_cloud(n, 30 + i)[0] + i for i, n in enumerate(ref_counts)])
+    qry = np.concatenate([surface_cloud(n, 40 + i)[0] + i for i, n in enumerate(qry_counts)])
+    r, q = cuda(ref), cuda(qry)
+    g_ref, g_qry = pc.KnnGrid(r, ref_counts, 0.2), pc.KnnGrid(q, qry_counts, 0.1)
+    want = _knn_oracle_packed(ref, qry, ref_counts, qry_counts, 16)
+    for K in (3, 16, 33):
+        plain = g_ref.query(q, qry_counts, K).cpu().numpy()
+        ordered = g_ref.query(q, qry_counts, K, order=g_qry).cpu().numpy()
+        assert np.array_equal(plain, ordered)
+        if K == 16:
+            assert np.array_equal(ordered, want)
+    assert g_qry.order_ptr() != 0
+    with pytest.raises(RuntimeError):
+        g_ref.query(q, qry_counts, 16, order=g_ref)                      # not the grid of the query cloud
+
+
 @pytest.mark.parametrize("hint", [0.0, 0.05, 0.3, 5.0])
 def test_grid_knn_equals_brute_force_and_oracle(hint):
     """The grid search must return exactly the brute-force table whatever the cell size: random cloud,
