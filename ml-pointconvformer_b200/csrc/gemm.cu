@@ -14,6 +14,7 @@
 //             (deterministic).  Operands are transposed in registers while staging (4x4 blocks), so both are
 //             ordinary K-major descriptors.
 #include "common.cuh"
+#include <stdlib.h>
 #include "umma.cuh"
 
 namespace pcfb {
@@ -280,6 +281,223 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
         umma::fence_before_sync();
         if (!a.b_resident) g_cp_wait<0>();
         __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_d), "r"(a.tmem_cols) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// gemm_nt, pipelined variant for SMALL grids (every CTA owns one 128-row tile: the coarse levels of the pyramid).
+//
+// gemm_nt_kernel above walks the K chunks in lock step: wait for the chunk's global loads, split, st.shared, fence,
+// __syncthreads, one lane issues the MMAs -- ~2 300 cycles per 32-wide chunk when a CTA is alone on its SM (ncu,
+// profiles/ncu_gemm_small_r02.txt: 12 % of the samples wait for the A loads, 14 % at the block barrier, the rest is the
+// split arithmetic with 8 warps and nothing to overlap it with).  With 148+ tiles that latency hides behind other CTAs'
+// work; a 1 k-row product is 9 tiles and its 32 chunks are a 40 us chain on the critical path of the step.
+// Here the chain is cut into independent actors that only meet at mbarriers:
+//   * warps 0-7 (producers): A chunk -> registers (TWO chunks in flight per thread) -> hi / lo tf32 -> stage s of an
+//     S-deep ring; one mbarrier arrive per warp on full[s]; nobody waits for the other warps;
+//   * warp 8: waits full[s] and bfull[s], issues the chunk's 12 MMAs, tcgen05.commit -> empty[s];
+//   * the prepared weights of a chunk are ONE contiguous block: a single cp.async.bulk per chunk (issued by thread 0 as
+//     soon as empty[s] frees the stage) that completes on bfull[s].
+// Stage = [A hi 16 KB][A lo 16 KB][B hi][B lo]; S = 2..4 stages, whatever fits.
+// ------------------------------------------------------------------------------------------------------------
+namespace gp {
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wait_or_trap(uint64_t *bar, uint32_t parity) {
+    if (!umma::mbar_wait(bar, parity)) __trap();
+}
+}  // namespace gp
+
+constexpr int GP_THREADS = G_NT + 32;        // 8 producer warps + the MMA warp
+constexpr int GP_MAX_STAGES = 4;
+
+struct GemmPipePlan { uint32_t a_bytes, b_bytes, stage_bytes; int stages; size_t off_bar, total; };
+
+__host__ __device__ inline GemmPipePlan gemm_pipe_plan(int Npad, int n_chunks) {
+    GemmPipePlan pl;
+    pl.a_bytes = GT_M * GT_KC * 4;
+    pl.b_bytes = (uint32_t)Npad * GT_KC * 4;
+    pl.stage_bytes = 2 * pl.a_bytes + 2 * pl.b_bytes;
+    int S = (int)((220u * 1024u) / pl.stage_bytes);
+    if (S > GP_MAX_STAGES) S = GP_MAX_STAGES;
+    if (S > n_chunks) S = n_chunks;
+    pl.stages = S;
+    pl.off_bar = (size_t)(S > 0 ? S : 1) * pl.stage_bytes;
+    pl.total = pl.off_bar + 128;
+    return pl;
+}
+
+__global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs a)
+{
+    pdl_wait();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const GemmPipePlan pl = gemm_pipe_plan(a.Npad, a.n_chunks);
+    const int S = pl.stages;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + pl.off_bar);      // full[S] | empty[S] | bfull[S] | done
+    uint64_t *full = bars, *empty = bars + GP_MAX_STAGES, *bfull = bars + 2 * GP_MAX_STAGES, *done = bars + 3 * GP_MAX_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * GP_MAX_STAGES + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_col0 = blockIdx.y * a.Nblk;
+    const int M = a.M, N = min(a.Nblk, a.N - n_col0), Npad = a.Npad, K = a.K, n_chunks = a.n_chunks;
+    const int m0 = blockIdx.x * GT_M;
+    const unsigned char *b_src = reinterpret_cast<const unsigned char *>(a.b_prep + (size_t)blockIdx.y * a.b_block_floats);
+    a.C += n_col0;
+    if (a.bias) a.bias += n_col0;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                     :: "r"(umma::smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int s = 0; s < S; ++s) {
+            umma::mbar_init(&full[s], G_NT / 32);
+            umma::mbar_init(&empty[s], 1);
+            umma::mbar_init(&bfull[s], 1);
+        }
+        umma::mbar_init(done, 1);
+        umma::fence_mbar_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_d = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const uint32_t lbo_a = GT_M * 16, lbo_b = (uint32_t)Npad * 16, sbo = 128;
+    const uint32_t stage_u32 = umma::smem_u32(smem_raw);
+
+    if (warp_u == G_NT / 32) {
+        // ==================== MMA issuer ====================
+        const uint32_t idesc = umma::make_idesc_tf32(GT_M, Npad);
+        const uint64_t da0 = umma::make_smem_desc(0, lbo_a, sbo), db0 = umma::make_smem_desc(0, lbo_b, sbo);
+        int s = 0;
+        uint32_t use = 0;
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            gp::wait_or_trap(&bfull[s], use & 1);
+            gp::wait_or_trap(&full[s], use & 1);
+            umma::fence_after_sync();
+            const uint32_t base = stage_u32 + (uint32_t)s * pl.stage_bytes;
+            const uint64_t dah0 = da0 + (base >> 4), dal0 = da0 + ((base + pl.a_bytes) >> 4);
+            const uint64_t dbh0 = db0 + ((base + 2 * pl.a_bytes) >> 4), dbl0 = db0 + ((base + 2 * pl.a_bytes + pl.b_bytes) >> 4);
+            if (g_elect_one()) {
+#pragma unroll
+                for (int ks = 0; ks < GT_KC / 8; ++ks) {
+                    const uint32_t ao = (ks * 2 * lbo_a) >> 4, bo = (ks * 2 * lbo_b) >> 4;
+                    umma::mma_tf32_ss(tmem_d, dal0 + ao, dbh0 + bo, idesc, (chunk > 0 || ks > 0) ? 1u : 0u);
+                    umma::mma_tf32_ss(tmem_d, dah0 + ao, dbl0 + bo, idesc, 1u);
+                    umma::mma_tf32_ss(tmem_d, dah0 + ao, dbh0 + bo, idesc, 1u);
+                }
+                umma::commit(&empty[s]);
+                if (chunk == n_chunks - 1) umma::commit(done);
+            }
+            __syncwarp();
+            if (++s == S) { s = 0; ++use; }
+        }
+    } else {
+        // ==================== producers: A chunk -> hi / lo -> stage; epilogue ====================
+        auto load_a = [&](float4 (&r)[4], int chunk) {
+            const int k0 = chunk * GT_KC;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = tid + G_NT * i;
+                const int row = idx & (GT_M - 1), q = idx >> 7;
+                const int m = m0 + row, k = k0 + 4 * q;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < M && k < K) {
+                    const float *src = a.A + (size_t)m * a.lda + k;
+                    if (a.vec_a && k + 3 < K) {
+                        v = *reinterpret_cast<const float4 *>(src);
+                    } else {
+                        v.x = src[0];
+                        if (k + 1 < K) v.y = src[1];
+                        if (k + 2 < K) v.z = src[2];
+                        if (k + 3 < K) v.w = src[3];
+                    }
+                }
+                r[i] = v;
+            }
+        };
+        auto b_copy = [&](int chunk, int s) {                    // one thread: the chunk's prepared weights, one bulk copy
+            gp::mbar_expect_tx(&bfull[s], 2 * pl.b_bytes);
+            gp::bulk_g2s(stage_u32 + (uint32_t)s * pl.stage_bytes + 2 * pl.a_bytes, b_src + (size_t)chunk * 2 * pl.b_bytes, 2 * pl.b_bytes, &bfull[s]);
+        };
+        int s = 0;
+        uint32_t use = 0;
+        auto produce = [&](float4 (&r)[4], int chunk) {
+            if (use > 0) {                                        // stage free? (the MMAs that read it S chunks ago)
+                gp::wait_or_trap(&empty[s], (use - 1) & 1);
+                if (tid == 0) b_copy(chunk, s);
+            }
+            unsigned char *Ah = smem_raw + (size_t)s * pl.stage_bytes, *Al = Ah + pl.a_bytes;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int idx = tid + G_NT * i;
+                const int row = idx & (GT_M - 1), q = idx >> 7;
+                float4 hi, lo;
+                umma::split_tf32(r[i].x, hi.x, lo.x); umma::split_tf32(r[i].y, hi.y, lo.y);
+                umma::split_tf32(r[i].z, hi.z, lo.z); umma::split_tf32(r[i].w, hi.w, lo.w);
+                *reinterpret_cast<float4 *>(Ah + (size_t)q * lbo_a + row * 16) = hi;
+                *reinterpret_cast<float4 *>(Al + (size_t)q * lbo_a + row * 16) = lo;
+            }
+            if (chunk + 2 < n_chunks) load_a(r, chunk + 2);      // this register set is free again: two chunks in flight
+            umma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) gp::mbar_arrive(&full[s]);
+            if (++s == S) { s = 0; ++use; }
+        };
+        if (tid == 0)
+            for (int c = 0; c < S; ++c) b_copy(c, c);
+        float4 r0[4], r1[4];
+        load_a(r0, 0);
+        if (n_chunks > 1) load_a(r1, 1);
+        for (int chunk = 0; chunk < n_chunks; chunk += 2) {
+            produce(r0, chunk);
+            if (chunk + 1 < n_chunks) produce(r1, chunk + 1);
+        }
+        // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns split between w<4 and w>=4 ----
+        gp::wait_or_trap(done, 0);
+        umma::fence_after_sync();
+        const int row = (warp & 3) * 32 + lane;
+        const int m = m0 + row;
+        const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
+        const int half = Npad / 2 >= 8 ? ((Npad / 2 + 7) & ~7) : Npad;
+        const int c_begin = (warp < 4) ? 0 : half, c_end = (warp < 4) ? half : Npad;
+        for (int c0 = c_begin; c0 < c_end; c0 += 8) {
+            float v[8];
+            umma::tmem_ld8(taddr + c0, v);
+            if (m < M) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j;
+                    if (c < N) {
+                        float x = v[j] + (a.bias ? __ldg(a.bias + c) : 0.f);
+                        if (a.act == 1) x = fmaxf(x, 0.f);
+                        else if (a.act == 2) x = x > 0.f ? x : 0.1f * x;
+                        v[j] = x;
+                    }
+                }
+                float *dst = a.C + (size_t)m * a.ldc + c0;
+                if (c0 + 8 <= N && ((a.ldc & 3) == 0)) {
+                    reinterpret_cast<float4 *>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    reinterpret_cast<float4 *>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (c0 + j < N) dst[j] = v[j];
+                }
+            }
+        }
+        umma::fence_before_sync();
     }
     __syncthreads();
     if (warp == 0)
@@ -578,6 +796,11 @@ struct NtSetup { int Nblk, n_blocks, Npad, n_chunks, resident; size_t block_byte
 // 184 x 1536 x 192 product, profiles/step_kernels_by_grid_r01.txt); narrower column blocks spread the weight stream over
 // ~NT_TARGET_CTAS CTAs instead.
 constexpr int NT_TARGET_CTAS = 24;
+static bool nt_pipe_enabled() {                     // PCFB_GEMM_PIPE=0: A/B switch for the pipelined small-grid variant
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("PCFB_GEMM_PIPE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
 static NtSetup nt_setup(int N, int K, int M = 0) {
     NtSetup s;
     s.n_chunks = ceil_div(K, GT_KC);
@@ -657,6 +880,16 @@ static int gemm_nt_phases(int phases, const float *A, int lda, const float *W, i
     static bool attr = false;
     if (!attr) { PCFB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr = true; }
     const int tiles = ceil_div(M, GT_M);
+    if (nt_pipe_enabled() && (int64_t)tiles * s.n_blocks <= kNumSMs) {
+        // every CTA owns one row tile and is alone on its SM: the pipelined variant (see gemm_nt_pipe_kernel)
+        const GemmPipePlan pp = gemm_pipe_plan(s.Npad, s.n_chunks);
+        if (pp.stages >= 2 || s.n_chunks == 1) {
+            static bool attr_p = false;
+            if (!attr_p) { PCFB_CUDA(cudaFuncSetAttribute(gemm_nt_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); attr_p = true; }
+            launch_k(gemm_nt_pipe_kernel, dim3(tiles, s.n_blocks), GP_THREADS, pp.total, st, a);
+            return check_launch("gemm_nt_pipe_kernel");
+        }
+    }
     const int per_sm = (s.plan.total + 1024 <= 113 * 1024) ? 2 : 1;
     int gx = ceil_div(kNumSMs * per_sm, s.n_blocks);               // CTAs per column block: the whole grid is about one wave
     if (gx > tiles) gx = tiles;

@@ -107,12 +107,14 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
 // The tensor core reads only the upper 19 bits of an operand (it truncates): left as the exact fp32 remainder, lo would
 // lose up to 2^-10 of itself = 2^-21 |x|; rounded to nearest here the split carries 22 mantissa bits (unit round-off
 // 2^-22 |x|, fp32 itself: 2^-24) -- measured on the full-width model golden: logits error vs float64 1.5e-4 -> see DESIGN.md 4.
+// cvt.rna.tf32.f32 (round to nearest, ties away) is emulated on sm_100a as add-half-ulp, an Inf / NaN test, a mask and a
+// select (4 instructions); for finite values the test and the select are dead weight -- half an ulp added to the bit
+// pattern and the low 13 bits cleared is the same number (NaN stays NaN, Inf stays Inf): 5 instructions per split value
+// instead of 9, in kernels whose producers are bound by exactly this arithmetic (profiles/ncu_gemm_small_r02.txt).
+__device__ __forceinline__ float rna_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    uint32_t h, l;
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(l) : "f"(x - hi));
-    lo = __uint_as_float(l);
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
 }
 
 }  // namespace umma

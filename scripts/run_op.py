@@ -21,6 +21,14 @@ def main():
         torch.cuda.synchronize()
         print("ok", what)
         return
+    if what == "gemm_small":                    # Y = P W^T of a coarse level (latency-bound: few CTAs, long K chain)
+        M, C_out, KK = (int(a) for a in (sys.argv[3].split(",") if len(sys.argv) > 3 else (1026, 128, 1024)))
+        P = torch.randn(M, KK, device=dev); Wm = torch.randn(C_out, KK, device=dev)
+        for _ in range(reps):
+            pcf_cuda.gemm_nt(P, Wm)
+        torch.cuda.synchronize()
+        print("ok", what, M, C_out, KK)
+        return
     xyz, _, _ = synthetic.make_scene(1, 100000)
     xyz = torch.from_numpy(xyz).to(dev)
     n = xyz.shape[0]

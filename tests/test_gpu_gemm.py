@@ -16,7 +16,8 @@ def _pc():
 
 @pytest.mark.parametrize("M,K,N", [(1000, 64, 128), (100001, 12, 8), (5000, 3, 16), (777, 512, 32), (4096, 1536, 192),
                                     (300, 416, 256), (50000, 64, 64), (1, 8, 8), (129, 33, 20), (2000, 384, 300),
-                                    (23594, 64, 512), (1026, 128, 1024), (184, 192, 1536), (3001, 32, 1000)])
+                                    (23594, 64, 512), (1026, 128, 1024), (184, 192, 1536), (3001, 32, 1000),
+                                    (1026, 1024, 128), (184, 1536, 192), (5153, 768, 96), (130, 40, 24), (2050, 2100, 48)])
 @pytest.mark.parametrize("w_is_kn", [False, True])
 def test_gemm_nt(M, K, N, w_is_kn):
     g = torch.Generator().manual_seed(M + K + N)
