@@ -257,6 +257,26 @@ int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_t count, co
 int pcfb_bn_reduce_sums(const float *partial, int nblocks, int C, float *sums_local, float *sums_global,
                         const void *peer_bases, int rank, int world, int channel, double timeout_s, void *stream);
 
+/* BatchNorm (+ residual + activation) of a SMALL [rows, C] tensor (rows <= pcfb_bn_small_max_rows(), C % 4 == 0) as ONE
+ * kernel per direction: a CTA owns 8 channels for all rows, so statistics, the SyncBatchNorm exchange (same protocol and
+ * arguments as pcfb_bn_finalize / pcfb_bn_reduce_sums), the finalize and the apply pass need no second launch -- replaces
+ * pcfb_bn_stats -> pcfb_bn_finalize -> pcfb_bn_act and pcfb_bn_backward_stats -> pcfb_bn_reduce_sums -> pcfb_bn_backward
+ * on the coarse levels of the pyramid, where every launch is a bubble on the step's critical path.  Same formulas:
+ *   forward : out = act(x*scale + shift (+ residual)) (+ residual after the activation), scale / shift / mean / invstd /
+ *             running statistics / batches_tracked / count_out as pcfb_bn_finalize;
+ *   backward: dz = dA * act'(.), sums_local[2][C] = this rank's (sum dz | sum dz*xhat) = (dbeta | dgamma),
+ *             dX = scale * (dz - S1/E - xhat*S2/E) with the GLOBAL sums and count (d_count, NULL = rows), d_residual = dz. */
+int pcfb_bn_small_max_rows(void);
+int pcfb_bn_small_forward(const float *x, int64_t rows, int C, const float *pivot, const float *gamma, const float *beta,
+                          float eps, float momentum, float *running_mean, float *running_var, int64_t *batches_tracked,
+                          int act, const float *residual, int residual_after_act, float *out, float *scale, float *shift,
+                          float *mean, float *invstd, double *count_out, const void *peer_bases, int rank, int world,
+                          int channel, double timeout_s, void *stream);
+int pcfb_bn_small_backward(const float *dA, const float *x, int64_t rows, int C, const float *scale, const float *shift,
+                           const float *mean, const float *invstd, int act, const float *residual, const double *d_count,
+                           float *sums_local, float *dX, float *d_residual, const void *peer_bases, int rank, int world,
+                           int channel, double timeout_s, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * BatchNorm (+ activation) over a contiguous [rows, C] tensor, C % 4 == 0, C <= 1024: the BatchNorm + ReLU that
  * follows the fused contraction (layers.py:708-709, 721, 893-898, 1086-1092; `self.bn` / `linear.bn`) and the

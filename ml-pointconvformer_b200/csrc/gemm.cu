@@ -319,6 +319,11 @@ __device__ __forceinline__ void wait_or_trap(uint64_t *bar, uint32_t parity) {
 }
 }  // namespace gp
 
+// a thread's i-th (row, q) piece of an A chunk (q = 16-byte column group of the 32-wide chunk): a warp instruction covers
+// 8 consecutive rows x 4 consecutive q -- 64 contiguous bytes per row from global memory, and every 8-lane phase of the
+// st.shared.v4 into the canonical layout (q * 2048 + row * 16) hits 8 different 16-byte banks
+__device__ __forceinline__ int gp_row(int tid, int i) { return ((tid >> 5) * 8 + (tid & 7)) + 64 * (i & 1); }
+__device__ __forceinline__ int gp_q(int tid, int i) { return ((tid >> 3) & 3) + 4 * (i >> 1); }
 constexpr int GP_THREADS = G_NT + 32;        // 8 producer warps + the MMA warp
 constexpr int GP_MAX_STAGES = 4;
 
@@ -410,8 +415,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
             const int k0 = chunk * GT_KC;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int idx = tid + G_NT * i;
-                const int row = idx & (GT_M - 1), q = idx >> 7;
+                const int row = gp_row(tid, i), q = gp_q(tid, i);
                 const int m = m0 + row, k = k0 + 4 * q;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (m < M && k < K) {
@@ -442,15 +446,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
             unsigned char *Ah = smem_raw + (size_t)s * pl.stage_bytes, *Al = Ah + pl.a_bytes;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int idx = tid + G_NT * i;
-                const int row = idx & (GT_M - 1), q = idx >> 7;
+                const int row = gp_row(tid, i), q = gp_q(tid, i);
                 float4 hi, lo;
                 umma::split_tf32(r[i].x, hi.x, lo.x); umma::split_tf32(r[i].y, hi.y, lo.y);
                 umma::split_tf32(r[i].z, hi.z, lo.z); umma::split_tf32(r[i].w, hi.w, lo.w);
                 *reinterpret_cast<float4 *>(Ah + (size_t)q * lbo_a + row * 16) = hi;
                 *reinterpret_cast<float4 *>(Al + (size_t)q * lbo_a + row * 16) = lo;
             }
-            if (chunk + 2 < n_chunks) load_a(r, chunk + 2);      // this register set is free again: two chunks in flight
+            if (chunk + 3 < n_chunks) load_a(r, chunk + 3);      // this register set is free again: three chunks in flight
             umma::fence_proxy_async();
             __syncwarp();
             if (lane == 0) gp::mbar_arrive(&full[s]);
@@ -458,12 +461,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
         };
         if (tid == 0)
             for (int c = 0; c < S; ++c) b_copy(c, c);
-        float4 r0[4], r1[4];
+        float4 r0[4], r1[4], r2[4];
         load_a(r0, 0);
         if (n_chunks > 1) load_a(r1, 1);
-        for (int chunk = 0; chunk < n_chunks; chunk += 2) {
+        if (n_chunks > 2) load_a(r2, 2);
+        for (int chunk = 0; chunk < n_chunks; chunk += 3) {
             produce(r0, chunk);
             if (chunk + 1 < n_chunks) produce(r1, chunk + 1);
+            if (chunk + 2 < n_chunks) produce(r2, chunk + 2);
         }
         // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns split between w<4 and w>=4 ----
         gp::wait_or_trap(done, 0);

@@ -13,27 +13,13 @@
 // the weight / bias gradient (warps own output channels, rows live in lanes, fixed-order reductions, no atomics).
 // One thread owns one row; weights sit in shared memory, zero padded to the template maxima.
 #include "common.cuh"
+#include "act.cuh"
 
 namespace pcfb {
 
 constexpr int ML_THREADS = 256;
 constexpr int ML_WARPS = ML_THREADS / 32;
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_SIGMOID = 3 };
-
-__device__ __forceinline__ float act_fwd(float z, int act) {
-    if (act == ACT_RELU) return fmaxf(z, 0.f);
-    if (act == ACT_LEAKY) return z > 0.f ? z : 0.1f * z;
-    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-z));
-    return z;
-}
-// derivative given pre-activation z and activation value a
-__device__ __forceinline__ float act_bwd(float z, float a, int act) {
-    if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
-    if (act == ACT_LEAKY) return z > 0.f ? 1.f : 0.1f;
-    if (act == ACT_SIGMOID) return a * (1.f - a);
-    return 1.f;
-}
 
 template <int CMAX>
 __device__ __forceinline__ void load_row(const float *__restrict__ base, int ld, int64_t row, int c, bool vec, float *out) {

@@ -338,6 +338,28 @@ def bn_supported(C):
     return bool(lib().pcfb_bn_supported(int(C)))
 
 
+SMALL_BN = os.environ.get("PCFB_BN_SMALL", "1") != "0"      # one-kernel BatchNorm for small tensors (csrc/peer_reduce.cu)
+_SMALL_ROWS = []
+
+
+def _small_bn_rows():
+    if not _SMALL_ROWS:
+        _SMALL_ROWS.append(int(os.environ.get("PCFB_BN_SMALL_ROWS", lib().pcfb_bn_small_max_rows())))
+    return _SMALL_ROWS[0]
+
+
+def _exchange_args(sync, dev):
+    """(run, bases, rank, world, timeout) for a kernel that contains a SyncBatchNorm exchange: `run(launch)` executes the
+    launch on the exchange stream when there is an exchange.  None if the peer path is unavailable (torch.distributed fallback)."""
+    world = dist.get_world_size() if sync else 1
+    if world == 1:
+        return (lambda launch: launch()), 0, 0, 1, 0.0
+    st = _peer(dev)
+    if not st:
+        return None
+    return (lambda launch: _on_exchange_stream(launch, dev)), ptr(st["bases"]), st["rank"], st["world"], st["timeout"]
+
+
 class _BnActFunction(torch.autograd.Function):
     """out = act(BatchNorm(x2)) for contiguous x2 [rows, C]; cfg = dict(act, training, eps, momentum, sync, nbt)."""
 
@@ -347,6 +369,31 @@ class _BnActFunction(torch.autograd.Function):
         dev = x2.device
         act, training = cfg["act"], cfg["training"]
         d_count = None
+        xa = _exchange_args(cfg["sync"], dev) if (training and SMALL_BN and 1 <= rows <= _small_bn_rows()) else None
+        ctx.small = xa is not None
+        if ctx.small:
+            # small tensor: statistics + (exchange) + finalize + apply in ONE launch
+            run, bases, rank, world, timeout = xa
+            scale = torch.empty(C, device=dev, dtype=F32); shift = torch.empty_like(scale)
+            mean = torch.empty_like(scale); invstd = torch.empty_like(scale)
+            momentum, nbt = cfg["momentum"], cfg["nbt"]
+            if momentum is None:                                   # cumulative moving average: 1 / num_batches_tracked
+                if nbt is not None:
+                    nbt.add_(1)
+                momentum = -1.0
+            d_count = torch.empty(1, device=dev, dtype=torch.float64) if world > 1 else None
+            out = torch.empty_like(x2)
+            after = 1 if cfg.get("res_after") else 0
+            run(lambda: check(lib().pcfb_bn_small_forward(
+                ptr(x2), rows, C, ptr(pivot), ptr(gamma), ptr(beta), float(cfg["eps"]), float(momentum), ptr(running_mean), ptr(running_var),
+                ptr(nbt), act, ptr(residual), after, ptr(out), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(d_count),
+                bases, rank, world, 0, timeout, stream_ptr()), "bn_small_forward"))
+            _lib.account((12.0 if residual is None else 16.0) * rows * C)
+            ctx.cfg, ctx.d_count = cfg, d_count
+            ctx.has_affine = gamma is not None
+            ctx.pre_res = residual is not None and not after
+            ctx.save_for_backward(x2, scale, shift, mean, invstd, residual if ctx.pre_res else None)
+            return out
         if training:
             ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
             nblk = ctypes.c_int(0)
@@ -382,6 +429,21 @@ class _BnActFunction(torch.autograd.Function):
         need_res = ctx.needs_input_grad[7]
         need_affine = ctx.has_affine and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
         sums = local = None
+        xa = _exchange_args(cfg["sync"], dev) if ctx.small else None
+        if xa is not None:
+            # small tensor (training mode): sums + (exchange) + dX / d_residual in ONE launch
+            run, bases, rank, world, timeout = xa
+            want_dres = need_res and ctx.pre_res
+            local = torch.empty(2 * C, device=dev, dtype=F32)
+            dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+            d_res = torch.empty_like(x2) if want_dres else None
+            run(lambda: check(lib().pcfb_bn_small_backward(
+                ptr(dA), ptr(x2), rows, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), cfg["act"], ptr(res), ptr(ctx.d_count),
+                ptr(local), ptr(dx), ptr(d_res), bases, rank, world, 0, timeout, stream_ptr()), "bn_small_backward"))
+            _lib.account((20.0 + (8.0 if res is not None else 0.0) + (4.0 if want_dres else 0.0)) * rows * C)
+            if need_res and not ctx.pre_res:
+                d_res = dA
+            return (dx, local[C:] if need_affine else None, local[:C] if need_affine else None, None, None, None, None, d_res)
         if cfg["training"] or need_affine:
             ws = workspace(lib().pcfb_bn_workspace(rows, C), dev)
             nblk = ctypes.c_int(0)

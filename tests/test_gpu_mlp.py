@@ -128,11 +128,16 @@ def test_chain_strided_input_and_determinism():
 
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("act", [0, 1, 2])
-@pytest.mark.parametrize("rows,C", [(102095, 32), (5153, 96), (1026, 128), (184, 384), (7, 64), (40000, 20)])
-def test_bn_act_matches_float64(rows, C, act, training):
+@pytest.mark.parametrize("small", [True, False])
+@pytest.mark.parametrize("rows,C", [(102095, 32), (5153, 96), (1026, 128), (184, 384), (7, 64), (40000, 20), (300, 20), (2048, 12), (1500, 64)])
+def test_bn_act_matches_float64(rows, C, act, training, small, monkeypatch):
     """pcfb_bn_* (the BatchNorm + activation behind the fused contraction and the wide per-point blocks) vs
-    torch BatchNorm1d + activation in float64: output, input gradient, dgamma / dbeta, running statistics."""
+    torch BatchNorm1d + activation in float64: output, input gradient, dgamma / dbeta, running statistics.
+    small: the one-kernel path for tensors of <= pcfb_bn_small_max_rows() rows (pcfb_bn_small_*) on / off."""
     from pcf_b200 import fused_mlp
+    if small and (rows > fused_mlp._small_bn_rows() or not training):
+        pytest.skip("the one-kernel path only takes small training-mode tensors")
+    monkeypatch.setattr(fused_mlp, "SMALL_BN", small)
     assert fused_mlp.bn_supported(C)
     torch.manual_seed(rows + C)
     bn = nn.BatchNorm1d(C, momentum=0.1)
@@ -172,14 +177,16 @@ def test_bn_act_deterministic_and_rejects_cpu():
         fused_mlp.bn_act(x.cpu(), bn, 1)
 
 
+@pytest.mark.parametrize("small", [True, False])
 @pytest.mark.parametrize("after", [False, True])
-def test_bn_act_with_fused_residual_matches_float64(after):
+def test_bn_act_with_fused_residual_matches_float64(after, small, monkeypatch):
     """act(bn(x) + r) (the tail of a PointConvFormer block, /root/reference/layers.py:413-415) and act(bn(x)) + r (the
     decoder's skip connection, layers.py:1096-1097) in the BatchNorm apply pass, forward and backward, against float64."""
     import copy
     from pcf_b200 import fused_mlp
+    monkeypatch.setattr(fused_mlp, "SMALL_BN", small)
     g = torch.Generator().manual_seed(9)
-    rows, C = 3001, 96
+    rows, C = (1001 if small else 3001), 96
     x = torch.randn(1, rows, C, generator=g) * 1.5 + 0.2
     r = torch.randn(1, rows, C, generator=g)
     go = torch.randn(1, rows, C, generator=g)
