@@ -229,7 +229,7 @@ bn_reduce_kernel(SbArgs a)
 // path of the step: profiles/step_timeline_r02.txt).  The second pass re-reads the CTA's 32-byte column slice of every
 // row from L1 / L2.  Thread = (row lane 0..127, half 0..1): a float4 of each row it visits.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SBS_MAXT = 1024;                    // threads per CTA: 256 up to 1 k rows, 1024 above (row lanes = threads / 2)
+constexpr int SBS_MAXT = 1024;                    // threads per CTA: 256, or 1024 above 4 k rows (row lanes = threads / 2)
 
 // 8 column sums (float4 s1 | float4 s2 of this thread's half) over the block's 128 row lanes -> msg_s[0..15] in double,
 // fixed order: xor-shuffles inside the warp, then the 8 warps added 0..7
@@ -533,8 +533,9 @@ extern "C" int pcfb_bn_small_forward(const float *x, int64_t rows, int C, const 
     a.f.running_mean = running_mean; a.f.running_var = running_var; a.f.scale = scale; a.f.shift = shift; a.f.mean = mean; a.f.invstd = invstd;
     a.f.batches_tracked = reinterpret_cast<long long *>(batches_tracked); a.count_out = count_out;
     a.xc = sb_xchg(peer_bases, rank, world, channel, timeout_s);
-    // 256 threads (128 row lanes, 8 rows per load batch) up to 1 k rows; above, 1024 threads (64 registers: batches of 4)
-    if (rows > 1024) launch_k(bn_small_fwd_kernel<SBS_MAXT, 4>, ceil_div(C, 8), SBS_MAXT, 0, static_cast<cudaStream_t>(stream), a);
+    // 256 threads (128 row lanes, 8 rows per load batch); 1024 threads (64 registers: batches of 4) only for callers that
+    // force the one-kernel path on larger tensors (PCFB_BN_SMALL_ROWS): at 1 k rows the big CTA costs 9 us against 5
+    if (rows > 4096) launch_k(bn_small_fwd_kernel<SBS_MAXT, 4>, ceil_div(C, 8), SBS_MAXT, 0, static_cast<cudaStream_t>(stream), a);
     else launch_k(bn_small_fwd_kernel<SB_THREADS, 8>, ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_small_fwd_kernel");
 }
@@ -555,7 +556,7 @@ extern "C" int pcfb_bn_small_backward(const float *dA, const float *x, int64_t r
     a.dA = dA; a.x = x; a.res = residual; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.d_count = d_count;
     a.sums_local = sums_local; a.dX = dX; a.dR = d_residual; a.rows = rows; a.C = C; a.act = act;
     a.xc = sb_xchg(peer_bases, rank, world, channel, timeout_s);
-    if (rows > 1024) launch_k(bn_small_bwd_kernel<SBS_MAXT, 2>, ceil_div(C, 8), SBS_MAXT, 0, static_cast<cudaStream_t>(stream), a);
+    if (rows > 4096) launch_k(bn_small_bwd_kernel<SBS_MAXT, 2>, ceil_div(C, 8), SBS_MAXT, 0, static_cast<cudaStream_t>(stream), a);
     else launch_k(bn_small_bwd_kernel<SB_THREADS, 4>, ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_small_bwd_kernel");
 }

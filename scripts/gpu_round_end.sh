@@ -22,6 +22,14 @@ for op in fwdp bwd; do
   ncu --set full --clock-control none --import-source on -k regex:"pconv_fwd_ws|pconv_fwd_umma2|pconv_bwd2" -s 1 -c 1 -o gpurun_out/prof_${op}_$R -f python scripts/run_op.py $op 3 > gpurun_out/ncu_$op.log 2>&1
   echo "ncu $op exit $?" >> gpurun_out/summary.log
 done
+python scripts/run_op.py knn 3 > gpurun_out/run_op.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:knn_grid_query -s 1 -c 1 -o gpurun_out/prof_knn_$R -f python scripts/run_op.py knn 3 > gpurun_out/ncu_knn.log 2>&1
+echo "ncu knn exit $?" >> gpurun_out/summary.log
+python scripts/run_op.py gemm_small 3 > gpurun_out/run_op.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:gemm_nt_pipe -s 2 -c 1 -o gpurun_out/prof_gemmpipe_$R -f python scripts/run_op.py gemm_small 3 > gpurun_out/ncu_gemmpipe.log 2>&1
+echo "ncu gemm pipe exit $?" >> gpurun_out/summary.log
+timeout 300 python scripts/time_knn_stage.py 1.75 2.5 > gpurun_out/knn_stage_$R.txt 2>&1; echo "knn stage exit $?" >> gpurun_out/summary.log
+timeout 300 python scripts/time_gemm.py > gpurun_out/gemm_times_$R.txt 2>&1; echo "gemm times exit $?" >> gpurun_out/summary.log
 python scripts/time_chain.py > gpurun_out/chain_times_$R.txt 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"mlp_bwd_fused_kernel|mlp_fwd_kernel|mlp_bwd_stats" -c 7 -o gpurun_out/prof_chain_$R -f python scripts/time_chain.py > gpurun_out/ncu_chain.log 2>&1
 echo "ncu chain exit $?" >> gpurun_out/summary.log
