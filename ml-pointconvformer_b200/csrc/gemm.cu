@@ -296,9 +296,9 @@ __global__ void __launch_bounds__(G_NT, 1) gemm_nt_kernel(GemmNtArgs a)
 // split arithmetic with 8 warps and nothing to overlap it with).  With 148+ tiles that latency hides behind other CTAs'
 // work; a 1 k-row product is 9 tiles and its 32 chunks are a 40 us chain on the critical path of the step.
 // Here the chain is cut into independent actors that only meet at mbarriers:
-//   * warps 0-7 (producers): A chunk -> registers (TWO chunks in flight per thread) -> hi / lo tf32 -> stage s of an
+//   * warps 0-15 (producers): A chunk -> registers (three chunks in flight per thread) -> hi / lo tf32 -> stage s of an
 //     S-deep ring; one mbarrier arrive per warp on full[s]; nobody waits for the other warps;
-//   * warp 8: waits full[s] and bfull[s], issues the chunk's 12 MMAs, tcgen05.commit -> empty[s];
+//   * warp 16: waits full[s] and bfull[s], issues the chunk's 12 MMAs, tcgen05.commit -> empty[s];
 //   * the prepared weights of a chunk are ONE contiguous block: a single cp.async.bulk per chunk (issued by thread 0 as
 //     soon as empty[s] frees the stage) that completes on bfull[s].
 // Stage = [A hi 16 KB][A lo 16 KB][B hi][B lo]; S = 2..4 stages, whatever fits.
@@ -321,10 +321,14 @@ __device__ __forceinline__ void wait_or_trap(uint64_t *bar, uint32_t parity) {
 
 // a thread's i-th (row, q) piece of an A chunk (q = 16-byte column group of the 32-wide chunk): a warp instruction covers
 // 8 consecutive rows x 4 consecutive q -- 64 contiguous bytes per row from global memory, and every 8-lane phase of the
-// st.shared.v4 into the canonical layout (q * 2048 + row * 16) hits 8 different 16-byte banks
-__device__ __forceinline__ int gp_row(int tid, int i) { return ((tid >> 5) * 8 + (tid & 7)) + 64 * (i & 1); }
-__device__ __forceinline__ int gp_q(int tid, int i) { return ((tid >> 3) & 3) + 4 * (i >> 1); }
-constexpr int GP_THREADS = G_NT + 32;        // 8 producer warps + the MMA warp
+// st.shared.v4 into the canonical layout (q * 2048 + row * 16) hits 8 different 16-byte banks.  16 producer warps: the
+// chunk is paced by the producers' instruction stream (split + addresses), so twice the warps per scheduler of the
+// 8-warp version (profiles/ncu_gemmpipe_r02.txt: 28 % issue utilisation with two warps per scheduler).
+constexpr int GP_PROD = 512;                 // producer threads
+constexpr int GP_NP = GT_M * (GT_KC / 4) / GP_PROD;   // float4 pieces per thread and chunk (2)
+__device__ __forceinline__ int gp_row(int tid, int i) { return (tid >> 5) * 8 + (tid & 7); }
+__device__ __forceinline__ int gp_q(int tid, int i) { return ((tid >> 3) & 3) + 4 * i; }
+constexpr int GP_THREADS = GP_PROD + 32;     // 16 producer warps + the MMA warp
 constexpr int GP_MAX_STAGES = 4;
 
 struct GemmPipePlan { uint32_t a_bytes, b_bytes, stage_bytes; int stages; size_t off_bar, total; };
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
     }
     if (tid == 32) {
         for (int s = 0; s < S; ++s) {
-            umma::mbar_init(&full[s], G_NT / 32);
+            umma::mbar_init(&full[s], GP_PROD / 32);
             umma::mbar_init(&empty[s], 1);
             umma::mbar_init(&bfull[s], 1);
         }
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
     const uint32_t lbo_a = GT_M * 16, lbo_b = (uint32_t)Npad * 16, sbo = 128;
     const uint32_t stage_u32 = umma::smem_u32(smem_raw);
 
-    if (warp_u == G_NT / 32) {
+    if (warp_u == GP_PROD / 32) {
         // ==================== MMA issuer ====================
         const uint32_t idesc = umma::make_idesc_tf32(GT_M, Npad);
         const uint64_t da0 = umma::make_smem_desc(0, lbo_a, sbo), db0 = umma::make_smem_desc(0, lbo_b, sbo);
@@ -411,19 +415,28 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
         }
     } else {
         // ==================== producers: A chunk -> hi / lo -> stage; epilogue ====================
-        auto load_a = [&](float4 (&r)[4], int chunk) {
+        // this thread's GP_NP pieces: row pointers and validity once per tile, a pointer bump per chunk
+        const float *src0[GP_NP];
+        bool row_ok[GP_NP];
+#pragma unroll
+        for (int i = 0; i < GP_NP; ++i) {
+            const int m = m0 + gp_row(tid, i);
+            row_ok[i] = m < M;
+            src0[i] = a.A + (size_t)(row_ok[i] ? m : 0) * a.lda + 4 * gp_q(tid, i);
+        }
+        const int n_fast = a.vec_a ? K / GT_KC : 0;             // chunks that need no column checks
+        auto load_a = [&](float4 (&r)[GP_NP], int chunk) {
             const int k0 = chunk * GT_KC;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int row = gp_row(tid, i), q = gp_q(tid, i);
-                const int m = m0 + row, k = k0 + 4 * q;
+            for (int i = 0; i < GP_NP; ++i) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < M && k < K) {
-                    const float *src = a.A + (size_t)m * a.lda + k;
-                    if (a.vec_a && k + 3 < K) {
+                if (row_ok[i]) {
+                    const float *src = src0[i] + k0;
+                    if (chunk < n_fast) {
                         v = *reinterpret_cast<const float4 *>(src);
                     } else {
-                        v.x = src[0];
+                        const int k = k0 + 4 * gp_q(tid, i);
+                        if (k < K) v.x = src[0];
                         if (k + 1 < K) v.y = src[1];
                         if (k + 2 < K) v.z = src[2];
                         if (k + 3 < K) v.w = src[3];
@@ -438,14 +451,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
         };
         int s = 0;
         uint32_t use = 0;
-        auto produce = [&](float4 (&r)[4], int chunk) {
+        auto produce = [&](float4 (&r)[GP_NP], int chunk) {
             if (use > 0) {                                        // stage free? (the MMAs that read it S chunks ago)
                 gp::wait_or_trap(&empty[s], (use - 1) & 1);
                 if (tid == 0) b_copy(chunk, s);
             }
             unsigned char *Ah = smem_raw + (size_t)s * pl.stage_bytes, *Al = Ah + pl.a_bytes;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < GP_NP; ++i) {
                 const int row = gp_row(tid, i), q = gp_q(tid, i);
                 float4 hi, lo;
                 umma::split_tf32(r[i].x, hi.x, lo.x); umma::split_tf32(r[i].y, hi.y, lo.y);
@@ -461,7 +474,7 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
         };
         if (tid == 0)
             for (int c = 0; c < S; ++c) b_copy(c, c);
-        float4 r0[4], r1[4], r2[4];
+        float4 r0[GP_NP], r1[GP_NP], r2[GP_NP];
         load_a(r0, 0);
         if (n_chunks > 1) load_a(r1, 1);
         if (n_chunks > 2) load_a(r2, 2);
@@ -470,14 +483,14 @@ __global__ void __launch_bounds__(GP_THREADS, 1) gemm_nt_pipe_kernel(GemmNtArgs 
             if (chunk + 1 < n_chunks) produce(r1, chunk + 1);
             if (chunk + 2 < n_chunks) produce(r2, chunk + 2);
         }
-        // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., columns split between w<4 and w>=4 ----
+        // ---- epilogue: warp w reads TMEM lanes 32*(w%4).., the columns split over the four warps of a lane quarter ----
         gp::wait_or_trap(done, 0);
         umma::fence_after_sync();
         const int row = (warp & 3) * 32 + lane;
         const int m = m0 + row;
         const uint32_t taddr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
-        const int half = Npad / 2 >= 8 ? ((Npad / 2 + 7) & ~7) : Npad;
-        const int c_begin = (warp < 4) ? 0 : half, c_end = (warp < 4) ? half : Npad;
+        const int cq = ((Npad + 3) / 4 + 7) & ~7;                // columns per warp of the quarter (multiple of 8)
+        const int c_begin = min((warp >> 2) * cq, Npad), c_end = min(c_begin + cq, Npad);
         for (int c0 = c_begin; c0 < c_end; c0 += 8) {
             float v[8];
             umma::tmem_ld8(taddr + c0, v);
