@@ -832,7 +832,7 @@ def _gpu_time(fn, reps, warm=3):
         a.record(); fn(); b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    return float(np.mean(ts))
+    return float(np.median(ts))            # eager launches: one host hiccup in ten repetitions must not move the figure
 
 
 def _oracle_cfg(cfgd):

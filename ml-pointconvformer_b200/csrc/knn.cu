@@ -41,23 +41,16 @@ struct TopK {
 #pragma unroll
         for (int i = 0; i < KP; ++i) { d[i] = __int_as_float(0x7f800000); id[i] = -1; }
     }
-    // precondition: dist < d[KP-1].  Sorted insertion with independent comparisons (1 FSETP + 4 SEL per position, no
-    // bubble chain): position i takes its left neighbour if the new distance is smaller than that neighbour's (strict:
-    // equal distance keeps the earlier index first -- candidates arrive in ascending index order), the new element if
-    // it is smaller than the old occupant's, else keeps the occupant.
+    // precondition: dist < d[KP-1]
     __device__ __forceinline__ void insert(float dist, int idx) {
-        bool lt_i = true;
+        d[KP - 1] = dist; id[KP - 1] = idx;
 #pragma unroll
         for (int i = KP - 1; i > 0; --i) {
-            const bool lt_l = dist < d[i - 1];
-            const float td = lt_i ? dist : d[i];
-            const int ti = lt_i ? idx : id[i];
-            d[i] = lt_l ? d[i - 1] : td;
-            id[i] = lt_l ? id[i - 1] : ti;
-            lt_i = lt_l;
+            const bool sw = d[i] < d[i - 1];          // strict: equal distance keeps the earlier index first
+            const float dl = sw ? d[i] : d[i - 1], dh = sw ? d[i - 1] : d[i];
+            const int il = sw ? id[i] : id[i - 1], ih = sw ? id[i - 1] : id[i];
+            d[i - 1] = dl; d[i] = dh; id[i - 1] = il; id[i] = ih;
         }
-        d[0] = lt_i ? dist : d[0];
-        id[0] = lt_i ? idx : id[0];
     }
 };
 

@@ -126,7 +126,10 @@ def bn_finalize(part, nb, C, rows, pivot, gamma, beta, eps, momentum, rm, rv, nb
                                      float(momentum), ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(nbt),
                                      ptr(d_count) if d_count_in is None else 0, bases, rank, wld, 0, timeout, stream_ptr()), "bn_finalize")
     if world == 1:
-        launch(part, nb, None, 0, 0, 1, 0.0)
+        if FORCE_XSTREAM:
+            _on_exchange_stream(lambda: launch(part, nb, None, 0, 0, 1, 0.0), dev)
+        else:
+            launch(part, nb, None, 0, 0, 1, 0.0)
         return scale, shift, mean, invstd, None
     st = _peer(dev)
     if st:
@@ -149,7 +152,8 @@ def bn_reduce_sums(part, nb, C, sync, dev):
     local = torch.empty(2 * C, device=dev, dtype=F32)
     world = dist.get_world_size() if sync else 1
     if world == 1:
-        check(lib().pcfb_bn_reduce_sums(ptr(part), nb, C, ptr(local), 0, 0, 0, 1, 0, 0.0, stream_ptr()), "bn_reduce_sums")
+        run = (lambda f: _on_exchange_stream(f, dev)) if FORCE_XSTREAM else (lambda f: f())
+        run(lambda: check(lib().pcfb_bn_reduce_sums(ptr(part), nb, C, ptr(local), 0, 0, 0, 1, 0, 0.0, stream_ptr()), "bn_reduce_sums"))
         return local, local
     st = _peer(dev)
     if st:
@@ -338,6 +342,7 @@ def bn_supported(C):
     return bool(lib().pcfb_bn_supported(int(C)))
 
 
+FORCE_XSTREAM = os.environ.get("PCFB_FORCE_XSTREAM", "0") == "1"   # diagnostic: pay the exchange-stream hop at world size 1
 SMALL_BN = os.environ.get("PCFB_BN_SMALL", "1") != "0"      # one-kernel BatchNorm for small tensors (csrc/peer_reduce.cu)
 _SMALL_ROWS = []
 
@@ -353,7 +358,7 @@ def _exchange_args(sync, dev):
     launch on the exchange stream when there is an exchange.  None if the peer path is unavailable (torch.distributed fallback)."""
     world = dist.get_world_size() if sync else 1
     if world == 1:
-        return (lambda launch: launch()), 0, 0, 1, 0.0
+        return ((lambda launch: _on_exchange_stream(launch, dev)) if FORCE_XSTREAM else (lambda launch: launch())), 0, 0, 1, 0.0
     st = _peer(dev)
     if not st:
         return None
