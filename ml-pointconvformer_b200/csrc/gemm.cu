@@ -823,7 +823,10 @@ static NtSetup nt_setup(int N, int K, int M = 0) {
     NtSetup s;
     s.n_chunks = ceil_div(K, GT_KC);
     const int tiles = M > 0 ? ceil_div(M, GT_M) : (1 << 20);
-    const int widths[] = {N, 128, 64, 32, 16};
+    // N > 256: equal blocks of <= 128 columns rounded up to 16 (288 = 3 x 96: three blocks of 128 would leave the last one
+    // three-quarters empty and still read A three times)
+    const int even = N > 256 ? round_up(ceil_div(N, ceil_div(N, 128)), 16) : 128;
+    const int widths[] = {N, even, 64, 32, 16};
     for (int wi = 0; wi < 5; ++wi) {
         const int nb = widths[wi];
         if (wi > 0 && nb >= N) continue;
@@ -850,7 +853,8 @@ extern "C" size_t pcfb_gemm_nt_workspace(int N, int K)
     using namespace pcfb;
     size_t best = nt_setup(N, K).prep_bytes;
     const int n_chunks = ceil_div(K, GT_KC);
-    const int widths[] = {N, 128, 64, 32, 16};
+    const int even = N > 256 ? round_up(ceil_div(N, ceil_div(N, 128)), 16) : 128;
+    const int widths[] = {N, even, 64, 32, 16};
     for (int wi = 0; wi < 5; ++wi) {
         const int nb = widths[wi];
         if ((wi > 0 && nb >= N) || nb > 256) continue;
