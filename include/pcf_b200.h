@@ -213,6 +213,14 @@ size_t pcfb_mlp_workspace(int64_t E, int cin, int cout);
 int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int cout, const float *W, const float *b,
                      const float *in_scale, const float *in_shift, int in_act, float *y, int ldy,
                      float *stat_partial, int *h_nblocks, void *stream);
+/* Inference-mode chain of three Linear (+ BatchNorm with running statistics, given as per-channel scale / shift; NULL =
+ * folded or absent) + activation layers as ONE kernel: the WeightNet of a PointConv / PointConvFormer layer
+ * (layers.py:127-171) under model.eval().  W, b, scale, shift: arrays of three device pointers (W[l] row-major
+ * [c_{l+1}][c_l]); act: three activation codes.  Supported: c0 in {1..4, 12}, c1 = c2 = 8, c3 = 16. */
+int pcfb_mlp_chain_eval_supported(int c0, int c1, int c2, int c3);
+int pcfb_mlp_chain_eval(const float *x, int ldx, int64_t E, int c0, int c1, int c2, int c3,
+                        const float *const *W, const float *const *b, const float *const *scale,
+                        const float *const *shift, const int *act, float *out, int ldo, void *stream);
 int pcfb_bn_act(const float *y, int64_t rows, int C, const float *scale, const float *shift, int act, float *out,
                 const float *residual /* optional [rows, C] */, int residual_after_act, void *stream);
 int pcfb_mlp_backward_stats(const float *dA, int ldd, const float *y, int ldy, int64_t E, int C, const float *scale,

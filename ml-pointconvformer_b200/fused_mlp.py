@@ -167,6 +167,41 @@ def bn_reduce_sums(part, nb, C, sync, dev):
     return glob, local
 
 
+CHAIN_EVAL = os.environ.get("PCFB_CHAIN_EVAL", "1") != "0"      # one-kernel inference chain (csrc/mlp_eval.cu)
+
+
+def _chain_eval(x2, spec, buffers, params):
+    """The whole three-layer chain in one kernel when no BatchNorm uses batch statistics and no gradient is recorded
+    (pcfb_mlp_chain_eval); None if the sizes have no fused kernel."""
+    Ws = [params[4 * l] for l in range(3)]
+    dims = [Ws[0].shape[1]] + [w.shape[0] for w in Ws]
+    if any(Ws[l].shape[1] != dims[l] for l in range(3)) or not lib().pcfb_mlp_chain_eval_supported(*dims):
+        return None
+    keep, scales, shifts = [], [], []
+    for l, s in enumerate(spec):
+        gamma, beta = params[4 * l + 2], params[4 * l + 3]
+        if s["has_bn"]:                                       # eval-mode BatchNorm: a fixed affine map
+            rm, rv, _ = buffers[l]
+            invstd = torch.rsqrt(rv + s["eps"])
+            scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
+            shift = ((beta if beta is not None else 0.) - rm * scale).contiguous()
+            keep += [scale, shift]
+            scales.append(ptr(scale)); shifts.append(ptr(shift))
+        else:
+            scales.append(0); shifts.append(0)
+    arr = lambda vals: (ctypes.c_void_p * 3)(*[v or None for v in vals])
+    Wc = [w if w.is_contiguous() else w.contiguous() for w in Ws]
+    w_arr, b_arr = arr([ptr(w) for w in Wc]), arr([ptr(params[4 * l + 1]) for l in range(3)])
+    sc_arr, sh_arr = arr(scales), arr(shifts)
+    acts = (ctypes.c_int * 3)(*[int(s["act"]) for s in spec])
+    E = x2.shape[0]
+    out = torch.empty(E, dims[3], device=x2.device, dtype=F32)
+    check(lib().pcfb_mlp_chain_eval(ptr(x2), x2.stride(0), E, dims[0], dims[1], dims[2], dims[3], w_arr, b_arr, sc_arr, sh_arr,
+                                    acts, ptr(out), dims[3], stream_ptr()), "mlp_chain_eval")
+    _lib.account(4.0 * E * (dims[0] + dims[3]), 2.0 * E * (dims[0] * dims[1] + dims[1] * dims[2] + dims[2] * dims[3]))
+    return out
+
+
 class _ChainFunction(torch.autograd.Function):
     """args: x2 [E, cin] (rows contiguous), spec (python: list of dict(act, has_bn, train, eps, momentum, sync)), then per
     layer (W, b, gamma, beta) tensors (gamma/beta None without BN); running stats are passed through `buffers`."""
@@ -176,6 +211,11 @@ class _ChainFunction(torch.autograd.Function):
         E = x2.shape[0]
         dev = x2.device
         L = len(spec)
+        # (grad mode is always off inside Function.forward: whether a backward can follow is decided by mlp_chain())
+        if CHAIN_EVAL and L == 3 and spec[0].get("no_grad") and not any(s["train"] for s in spec):
+            fused = _chain_eval(x2, spec, buffers, params)
+            if fused is not None:
+                return fused
         cur, ld = x2, x2.stride(0)
         in_scale = in_shift = None
         in_act = ACT_NONE
@@ -333,6 +373,7 @@ def mlp_chain(x, layers, training=None):
         # num_batches_tracked is incremented by the finalize kernel (one tiny torch add_ per BatchNorm was 273 launches a step)
         tracked = has_bn and bn.track_running_stats
         buffers.append((bn.running_mean, bn.running_var, bn.num_batches_tracked) if tracked else (None, None, None))
+    spec[0]["no_grad"] = not torch.is_grad_enabled()           # inference: the one-kernel chain may be used (no backward follows)
     out = _ChainFunction.apply(x2, spec, buffers, *params)
     return out.reshape(*lead, out.shape[-1])
 

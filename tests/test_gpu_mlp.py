@@ -204,3 +204,47 @@ def test_bn_act_with_fused_residual_matches_float64(after, small, monkeypatch):
     assert max_err_scaled(y, yr) < 1e-5
     assert max_err_scaled(xc.grad, xr.grad) < 1e-4 and max_err_scaled(rc.grad, rr.grad) < 1e-5
     assert max_err_scaled(bn.weight.grad, ref.weight.grad) < 1e-4 and max_err_scaled(bn.bias.grad, ref.bias.grad) < 1e-4
+
+
+@pytest.mark.parametrize("c0", [12, 3])
+@pytest.mark.parametrize("bn", [True, False])
+def test_inference_chain_in_one_kernel(c0, bn, monkeypatch):
+    """model.eval() + torch.no_grad(): the WeightNet chain c0 -> 8 -> 8 -> 16 runs as ONE kernel (pcfb_mlp_chain_eval): same
+    result as the layer-by-layer kernels to rounding, and as Linear -> BatchNorm(running statistics) -> ReLU in float64;
+    with BatchNorm modules and with them folded away (replace_batchnorm leaves bare Linears); strided input rows; and the
+    one-kernel path must NOT be taken when a gradient is recorded."""
+    import copy
+    from pcf_b200 import fused_mlp
+    dims, acts = [c0, 8, 8, 16], [1, 1, 1]
+    assert fused_mlp.lib().pcfb_mlp_chain_eval_supported(*dims)
+    mods = build(dims, bn, 11 + c0)
+    ref = copy.deepcopy(mods)
+    rows = 40003
+    g = torch.Generator().manual_seed(3)
+    wide = torch.randn(rows, c0 + 5, generator=g) * 0.7 + 0.1
+    h = wide[:, :c0].double()
+    for (lin, norm), a in zip(ref, acts):
+        h = lin.double()(h)
+        if norm is not None:
+            h = norm.double().eval()(h)
+        h = act_ref(h, a)
+    spec = []
+    for (lin, norm), a in zip(mods, acts):
+        lin.cuda()
+        if norm is not None:
+            norm.cuda().eval()
+        spec.append((lin, norm, a))
+    xc = wide.cuda()[:, :c0]                                             # row stride c0 + 5: not contiguous
+    with torch.no_grad():
+        monkeypatch.setattr(fused_mlp, "CHAIN_EVAL", True)
+        one = fused_mlp.mlp_chain(xc, spec)
+        monkeypatch.setattr(fused_mlp, "CHAIN_EVAL", False)
+        many = fused_mlp.mlp_chain(xc, spec)
+    assert one.shape == (rows, 16)
+    assert max_err_scaled(one, h) < 1e-5, max_err_scaled(one, h)
+    assert max_err_scaled(one, many.double()) < 2e-6                      # same maths, accumulation order may differ
+    monkeypatch.setattr(fused_mlp, "CHAIN_EVAL", True)
+    xg = wide.cuda()[:, :c0].clone().requires_grad_(True)
+    out = fused_mlp.mlp_chain(xg, spec)                                   # gradient recorded: the per-layer path with a backward
+    out.sum().backward()
+    assert xg.grad is not None and torch.isfinite(xg.grad).all()
