@@ -107,13 +107,19 @@ def test_forward_matches_oracle(name, variant):
     assert rel_err(y, Y) < 2e-5
 
 
-def test_forward_mid3_falls_back_to_simt():
-    """configPCF_2cm_PTF2 uses mid_dim_back = 3, which the tcgen05 variant does not cover: auto must still work."""
-    d = make_case(3, 500, 900, 16, 64, 16, 3, 32, 0)
+@pytest.mark.parametrize("n_in,n_out,C_mid", [(500, 900, 3), (6000, 20000, 3), (6000, 17001, 2), (6000, 18000, 4)])
+def test_forward_small_mid_dim(n_in, n_out, C_mid):
+    """configPCF_2cm_PTF2 uses mid_dim_back = 3, which the tcgen05 contraction kernels do not cover: auto composes the
+    streaming weighted-sum kernel (midn_fwd_kernel, levels of > 16 k points) or the small-level P kernel with the
+    tensor-core Linear; P and Y against the oracle."""
+    d = make_case(3, n_in, n_out, 16, 64, 16, C_mid, 32, 0)
     P, Y, _ = oracle_eval(d)
     dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
     y, p = _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], None, dc["W"], dc["b"], want_p=True, variant=0)
     torch.testing.assert_close(y.cpu().double(), Y, **TOL)
+    torch.testing.assert_close(p.cpu().double().reshape(P.shape), P, **TOL)
+    if C_mid != 3:
+        return
     with pytest.raises(RuntimeError):
         _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], None, dc["W"], dc["b"], want_p=True, variant=2)
 
