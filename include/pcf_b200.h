@@ -217,6 +217,10 @@ int pcfb_mlp_forward(const float *x, int ldx, int64_t E, int cin, int cout, cons
  * folded or absent) + activation layers as ONE kernel: the WeightNet of a PointConv / PointConvFormer layer
  * (layers.py:127-171) under model.eval().  W, b, scale, shift: arrays of three device pointers (W[l] row-major
  * [c_{l+1}][c_l]); act: three activation codes.  Supported: c0 in {1..4, 12}, c1 = c2 = 8, c3 = 16. */
+/* eval-mode BatchNorm as an affine map: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale
+ * (gamma / beta / invstd optional); one launch instead of torch's five per BatchNorm and forward. */
+int pcfb_bn_eval_affine(const float *gamma, const float *beta, const float *running_mean, const float *running_var,
+                        float eps, int C, float *scale, float *shift, float *invstd, void *stream);
 int pcfb_mlp_chain_eval_supported(int c0, int c1, int c2, int c3);
 int pcfb_mlp_chain_eval(const float *x, int ldx, int64_t E, int c0, int c1, int c2, int c3,
                         const float *const *W, const float *const *b, const float *const *scale,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pcfb_bn_finalize": (c_int, [_P, c_int, c_int, c_int64, _P, _P, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, _P, _P, _P,
                                  _P, c_int, c_int, c_int, ctypes.c_double, _P]),
     "pcfb_bn_reduce_sums": (c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, c_int, ctypes.c_double, _P]),
+    "pcfb_bn_eval_affine": (c_int, [_P, _P, _P, _P, c_float, c_int, _P, _P, _P, _P]),
     "pcfb_mlp_chain_eval_supported": (c_int, [c_int, c_int, c_int, c_int]),
     "pcfb_mlp_chain_eval": (c_int, [_P, c_int, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "pcfb_bn_small_max_rows": (c_int, []),

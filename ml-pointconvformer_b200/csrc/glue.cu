@@ -253,6 +253,22 @@ __global__ void ce_finalize_kernel(const double *__restrict__ partial, int nbloc
     if (threadIdx.x == 0) { *loss = (float)(a / b); *den = (float)b; }
 }
 
+// eval-mode BatchNorm as a per-channel affine map: scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale
+// (torch: rsqrt, two multiplies, a subtraction and a contiguous copy -- five launches per BatchNorm and forward)
+__global__ void bn_eval_affine_kernel(const float *__restrict__ gamma, const float *__restrict__ beta, const float *__restrict__ rm,
+                                      const float *__restrict__ rv, float eps, int C, float *__restrict__ scale,
+                                      float *__restrict__ shift, float *__restrict__ invstd)
+{
+    pdl_wait();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float is = rsqrtf(rv[c] + eps);
+    const float sc = gamma ? gamma[c] * is : is;
+    scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.f) - rm[c] * sc;
+    if (invstd) invstd[c] = is;
+}
+
 }  // namespace pcfb
 
 using namespace pcfb;
@@ -344,4 +360,13 @@ extern "C" int pcfb_ce_backward(const float *logits, const int64_t *labels, cons
     launch_k(ce_kernel<true>, ce_blocks(N), CE_THREADS, 0, static_cast<cudaStream_t>(stream), logits, labels, weight, N, C, ignore_index, smoothing,
                                                                                        nullptr, den, grad_scale, dlogits);
     return check_launch("ce_kernel<bwd>");
+}
+
+extern "C" int pcfb_bn_eval_affine(const float *gamma, const float *beta, const float *running_mean, const float *running_var,
+                                   float eps, int C, float *scale, float *shift, float *invstd, void *stream)
+{
+    PCFB_REQUIRE(running_mean && running_var && scale && shift && C >= 1, "pcfb_bn_eval_affine: null pointer");
+    launch_k(bn_eval_affine_kernel, ceil_div(C, 128), 128, 0, static_cast<cudaStream_t>(stream), gamma, beta, running_mean, running_var, eps, C,
+             scale, shift, invstd);
+    return check_launch("bn_eval_affine_kernel");
 }

@@ -44,14 +44,12 @@ __global__ void gs_bounds_kernel(const float *__restrict__ xyz, const int32_t *_
                                  int n_pts, int *__restrict__ mm)
 {
     pdl_wait();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
-        const int s = find_seg(seg_off, n_seg, i);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int o = float_to_ordered(xyz[3 * (size_t)i + d]);
-            atomicMin(&mm[s * 6 + d], o);
-            atomicMax(&mm[s * 6 + 3 + d], o);
-        }
+    for (int base = blockIdx.x * blockDim.x; base < n_pts; base += gridDim.x * blockDim.x) {     // warp-uniform trip count
+        const int i = base + threadIdx.x;
+        const bool in = i < n_pts;
+        const size_t j = in ? (size_t)i : 0;
+        warp_scene_minmax(in, in ? find_seg(seg_off, n_seg, i) : 0, float_to_ordered(xyz[3 * j]), float_to_ordered(xyz[3 * j + 1]),
+                          float_to_ordered(xyz[3 * j + 2]), mm);
     }
 }
 
@@ -141,14 +139,12 @@ __global__ void gs_bounds_dev_kernel(const float *__restrict__ xyz, const int32_
 {
     pdl_wait();
     const int n_pts = min(seg_off[n_seg], n_pts_max);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pts; i += gridDim.x * blockDim.x) {
-        const int s = find_seg(seg_off, n_seg, i);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int o = float_to_ordered(xyz[3 * (size_t)i + d]);
-            atomicMin(&mm[s * 6 + d], o);
-            atomicMax(&mm[s * 6 + 3 + d], o);
-        }
+    for (int base = blockIdx.x * blockDim.x; base < n_pts; base += gridDim.x * blockDim.x) {     // warp-uniform trip count
+        const int i = base + threadIdx.x;
+        const bool in = i < n_pts;
+        const size_t j = in ? (size_t)i : 0;
+        warp_scene_minmax(in, in ? find_seg(seg_off, n_seg, i) : 0, float_to_ordered(xyz[3 * j]), float_to_ordered(xyz[3 * j + 1]),
+                          float_to_ordered(xyz[3 * j + 2]), mm);
     }
 }
 

@@ -54,14 +54,12 @@ __global__ void kg_bounds_kernel(const float *__restrict__ xyz, const int32_t *_
                                  int *__restrict__ mm)
 {
     pdl_wait();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int s = g_find_seg(off, n_seg, i);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int o = g_float_to_ordered(xyz[3 * (size_t)i + d]);
-            atomicMin(&mm[s * 6 + d], o);
-            atomicMax(&mm[s * 6 + 3 + d], o);
-        }
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {         // warp-uniform trip count
+        const int i = base + threadIdx.x;
+        const bool in = i < n;
+        const size_t j = in ? (size_t)i : 0;
+        warp_scene_minmax(in, in ? g_find_seg(off, n_seg, i) : 0, g_float_to_ordered(xyz[3 * j]), g_float_to_ordered(xyz[3 * j + 1]),
+                          g_float_to_ordered(xyz[3 * j + 2]), mm);
     }
 }
 

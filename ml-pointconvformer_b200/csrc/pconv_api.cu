@@ -39,7 +39,7 @@ int pconv_p_small(const pcfb_pconv_shape *s, const float *feats, const int64_t *
 bool pconv_mid1_supported(const pcfb_pconv_shape *s);
 bool pconv_midn_supported(const pcfb_pconv_shape *s);
 int pconv_midn_forward_p(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
-                         const float *additional, float *P, cudaStream_t st);
+                         const float *additional, const float *guidance, float *P, cudaStream_t st);
 int pconv_mid1_forward_p(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
                          const float *additional, float *P, cudaStream_t st);
 int pconv_mid1_backward(const pcfb_pconv_shape *s, const float *dP, const float *feats, const int64_t *nei,
@@ -172,12 +172,16 @@ extern "C" int pcfb_pconv_forward(const pcfb_pconv_shape *s, const float *feats,
         else if (s->n_out <= 16384 && pconv_p_small_supported(s, weights, P)) rc = pconv_p_small(s, feats, nei, weights, additional, guidance, P, st);
         else if (pconv_midn_supported(s) && ((uintptr_t)feats % 16 == 0) && ((uintptr_t)P % 16 == 0) &&
                  (s->C_add == 0 || (uintptr_t)additional % 16 == 0))
-            rc = pconv_midn_forward_p(s, feats, nei, weights, additional, P, st);      // C_mid 2..4: streaming weighted sums
+            rc = pconv_midn_forward_p(s, feats, nei, weights, additional, guidance, P, st);      // C_mid 2..4: streaming weighted sums
         else rc = pconv_forward_simt(s, feats, nei, weights, additional, guidance, nullptr, nullptr, nullptr, P, st);
         if (rc) return rc;
         return pcfb_gemm_nt(P, KK, lin_w, KK, 0, lin_b, out_y, s->C_out, s->n_out, s->C_out, KK, 0,
                             static_cast<char *>(workspace) + p_bytes, nt_bytes, stream);
     }
+    // contraction only (the unfused layers, PCONV_OPT: False), C_mid 2..4, more points than the small-level kernel takes
+    if (variant == 0 && !lin_w && out_p && s->n_out > 16384 && pconv_midn_supported(s) && ((uintptr_t)feats % 16 == 0) &&
+        ((uintptr_t)out_p % 16 == 0) && (s->C_add == 0 || (uintptr_t)additional % 16 == 0))
+        return pconv_midn_forward_p(s, feats, nei, weights, additional, guidance, out_p, st);
     const bool u1_ok = lin_w && pconv_forward_umma_supported(s, true);
     const bool u2_ok = lin_w && variant != 3 && pconv_forward_umma2_supported(s, true);
     if ((variant == 2 || variant == 3) && !u1_ok && !u2_ok) {

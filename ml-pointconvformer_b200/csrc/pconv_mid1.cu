@@ -103,15 +103,16 @@ static inline int m1_blocks(int64_t work, int threads) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-// C_mid in {2, 3, 4} (mid_dim_back = 3: every PointConvTransposePE of configPCF_2cm_PTF2): the same streaming structure with
+// C_mid in {2, 3, 4} (mid_dim_back = 3: every PointConvTransposePE of configPCF_2cm_PTF2; mid_dim = 4 with guidance: the
+// unfused PointConvFormer layers of configPCF_10cm_lite): the same streaming structure with
 // CM accumulators per channel -- P[m, c*CM + j] = sum_k G[m,k,c] * w[m,k,j]; thread <-> (point, 4 channels), its 4 x CM
 // results are 16 x CM contiguous bytes of P.  The generic CUDA-core contraction kernel these layers used before spends
 // 6 ms on the 250 k-point level of that config (59 % of an inference pass, scripts/profile_infer.py); this one is bound by
 // the L2 gather like mid1_fwd_kernel.
 template <int CM>
 __global__ void midn_fwd_kernel(const float *__restrict__ feats, const int64_t *__restrict__ nei,
-                                const float *__restrict__ w, const float *__restrict__ add, int n_in, int n_out, int K,
-                                int C_in, int C_add, float *__restrict__ P)
+                                const float *__restrict__ w, const float *__restrict__ add, const float *__restrict__ gd, int H,
+                                int n_in, int n_out, int K, int C_in, int C_add, float *__restrict__ P)
 {
     pdl_wait();
     const int C_cat = C_in + C_add, G4 = C_cat / 4, I4 = C_in / 4;
@@ -131,6 +132,11 @@ __global__ void midn_fwd_kernel(const float *__restrict__ feats, const int64_t *
             if (c4 < I4) {
                 const int64_t q = nm[k];
                 if (q >= 0 && q < n_in) v = __ldg(reinterpret_cast<const float4 *>(feats + (size_t)q * C_in) + c4);
+                if (gd) {                                          // guidance: channel c of the gathered row times head c % H
+                    const float *gk = gd + ((size_t)m * K + k) * H;
+                    const int c = c4 * 4;
+                    v.x *= __ldg(gk + c % H); v.y *= __ldg(gk + (c + 1) % H); v.z *= __ldg(gk + (c + 2) % H); v.w *= __ldg(gk + (c + 3) % H);
+                }
             } else {
                 v = __ldg(reinterpret_cast<const float4 *>(add + ((size_t)m * K + k) * C_add) + (c4 - I4));
             }
@@ -154,21 +160,24 @@ __global__ void midn_fwd_kernel(const float *__restrict__ feats, const int64_t *
 }
 
 bool pconv_midn_supported(const pcfb_pconv_shape *s) {
-    return s->C_mid >= 2 && s->C_mid <= 4 && s->H == 0 && s->C_in >= 4 && s->C_in % 4 == 0 && s->C_add % 4 == 0;
+    return s->C_mid >= 2 && s->C_mid <= 4 && s->H >= 0 && s->C_in >= 4 && s->C_in % 4 == 0 && s->C_add % 4 == 0;
 }
 
 int pconv_midn_forward_p(const pcfb_pconv_shape *s, const float *feats, const int64_t *nei, const float *weights,
-                         const float *additional, float *P, cudaStream_t st)
+                         const float *additional, const float *guidance, float *P, cudaStream_t st)
 {
+    PCFB_REQUIRE((s->H > 0) == (guidance != nullptr), "pconv_midn_forward_p: H and guidance disagree");
+    const float *gd = guidance;
+    const int H = s->H;
     PCFB_REQUIRE(pconv_midn_supported(s), "pconv_midn_forward_p: unsupported shape");
     PCFB_REQUIRE(((uintptr_t)feats % 16 == 0) && ((uintptr_t)P % 16 == 0) && (s->C_add == 0 || (uintptr_t)additional % 16 == 0),
                  "pcfb_pconv: the small-C_mid path needs 16-byte aligned feats/additional/P");
     if (s->n_out == 0) return PCFB_OK;
     const int64_t work = (int64_t)s->n_out * ((s->C_in + s->C_add) / 4);
     const int blocks = m1_blocks(work, 256);
-    if (s->C_mid == 2) launch_k(midn_fwd_kernel<2>, blocks, 256, 0, st, feats, nei, weights, additional, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
-    else if (s->C_mid == 3) launch_k(midn_fwd_kernel<3>, blocks, 256, 0, st, feats, nei, weights, additional, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
-    else launch_k(midn_fwd_kernel<4>, blocks, 256, 0, st, feats, nei, weights, additional, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
+    if (s->C_mid == 2) launch_k(midn_fwd_kernel<2>, blocks, 256, 0, st, feats, nei, weights, additional, gd, H, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
+    else if (s->C_mid == 3) launch_k(midn_fwd_kernel<3>, blocks, 256, 0, st, feats, nei, weights, additional, gd, H, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
+    else launch_k(midn_fwd_kernel<4>, blocks, 256, 0, st, feats, nei, weights, additional, gd, H, s->n_in, s->n_out, s->K, s->C_in, s->C_add, P);
     return check_launch("midn_fwd_kernel");
 }
 

@@ -167,6 +167,25 @@ def bn_reduce_sums(part, nb, C, sync, dev):
     return glob, local
 
 
+def eval_affine(gamma, beta, rm, rv, eps):
+    """(scale, shift, invstd) of a BatchNorm that uses its running statistics: scale = gamma / sqrt(rv + eps), shift = beta -
+    rm * scale, in ONE launch (pcfb_bn_eval_affine): torch's rsqrt / mul / mul / sub / contiguous were 1 065 of the 1 764
+    launches of an eval-mode forward of configPCF_10cm_lite (scripts/profile_infer.py).  Not cached: the running statistics
+    are updated by kernels (and graph replays) that no version counter sees."""
+    C = rv.shape[0]
+    scale = torch.empty(C, device=rv.device, dtype=F32); shift = torch.empty_like(scale); invstd = torch.empty_like(scale)
+    ok = all(t is None or (t.dtype == F32 and t.is_contiguous()) for t in (gamma, beta, rm, rv))
+    if not ok:
+        with torch.no_grad():
+            invstd = torch.rsqrt(rv + eps)
+            scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
+            shift = ((beta if beta is not None else 0.) - rm * scale).contiguous()
+        return scale, shift, invstd
+    check(lib().pcfb_bn_eval_affine(ptr(gamma), ptr(beta), ptr(rm), ptr(rv), float(eps), C, ptr(scale), ptr(shift), ptr(invstd),
+                                    stream_ptr()), "bn_eval_affine")
+    return scale, shift, invstd
+
+
 CHAIN_EVAL = os.environ.get("PCFB_CHAIN_EVAL", "1") != "0"      # one-kernel inference chain (csrc/mlp_eval.cu)
 
 
@@ -182,9 +201,7 @@ def _chain_eval(x2, spec, buffers, params):
         gamma, beta = params[4 * l + 2], params[4 * l + 3]
         if s["has_bn"]:                                       # eval-mode BatchNorm: a fixed affine map
             rm, rv, _ = buffers[l]
-            invstd = torch.rsqrt(rv + s["eps"])
-            scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
-            shift = ((beta if beta is not None else 0.) - rm * scale).contiguous()
+            scale, shift, _ = eval_affine(gamma, beta, rm, rv, s["eps"])
             keep += [scale, shift]
             scales.append(ptr(scale)); shifts.append(ptr(shift))
         else:
@@ -237,9 +254,7 @@ class _ChainFunction(torch.autograd.Function):
                     scale, shift, mean, invstd, d_count = bn_finalize(ws, nblk.value, cout, E, b, gamma, beta, s["eps"], s["momentum"],
                                                                       rm, rv, nbt, s["sync"], dev)
                 else:                                        # eval-mode BatchNorm: a fixed affine map
-                    invstd = torch.rsqrt(rv + s["eps"])
-                    scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
-                    shift = ((beta if beta is not None else 0.) - rm * scale).contiguous()
+                    scale, shift, invstd = eval_affine(gamma, beta, rm, rv, s["eps"])
                     mean = rm
             ys.append(y)
             ctxs.append((scale, shift, mean, invstd))
@@ -448,9 +463,7 @@ class _BnActFunction(torch.autograd.Function):
             scale, shift, mean, invstd, d_count = bn_finalize(ws, nblk.value, C, rows, pivot, gamma, beta, cfg["eps"], cfg["momentum"],
                                                               running_mean, running_var, cfg["nbt"], cfg["sync"], dev)
         else:
-            invstd = torch.rsqrt(running_var + cfg["eps"])
-            scale = (gamma * invstd).contiguous() if gamma is not None else invstd.contiguous()
-            shift = ((beta if beta is not None else 0.) - running_mean * scale).contiguous()
+            scale, shift, invstd = eval_affine(gamma, beta, running_mean, running_var, cfg["eps"])
             mean = running_mean
         out = torch.empty_like(x2)
         after = 1 if cfg.get("res_after") else 0

@@ -146,6 +146,18 @@ def test_backward_matches_autograd(name):
     assert max_err_scaled(g2[4], G["W"]) < 1e-4 and max_err_scaled(g2[5], G["b"]) < 1e-4
 
 
+@pytest.mark.parametrize("C_mid,H,C_add", [(4, 8, 0), (4, 4, 16), (3, 2, 0), (2, 0, 8)])
+def test_contraction_only_small_mid_dim_large_level(C_mid, H, C_add):
+    """The unfused layers (PCONV_OPT: False; configPCF_10cm_lite: mid_dim 4 with 8 heads) call the contraction alone: above
+    16 k output points it runs as the streaming weighted-sum kernel with the guidance factor folded into the gathered row
+    (midn_fwd_kernel); P against the oracle, -1 neighbours included."""
+    d = make_case(31 + C_mid + H, 7000, 17500, 16, 32, C_add, C_mid, 0, H, pad=True)
+    P, _, _ = oracle_eval(d)
+    dc = {k: (cuda(v).contiguous() if v is not None else None) for k, v in d.items()}
+    _, p = _pc().pconv_fused_forward(dc["x"], dc["nei"], dc["w"], dc["add"], dc["gd"], None, None, want_p=True, variant=0)
+    torch.testing.assert_close(p.cpu().double().reshape(P.shape), P, **TOL)
+
+
 def test_backward_without_linear():
     """pconv_backward / pcf_backward contracts (pcf.h:60-66,106-112): incoming gradient is dP."""
     for name in ("level1_pcf", "lite_mid4"):
