@@ -835,6 +835,21 @@ def _gpu_time(fn, reps, warm=3):
     return float(np.median(ts))            # eager launches: one host hiccup in ten repetitions must not move the figure
 
 
+def _graph_time(fn, reps):
+    """fn() captured once as a CUDA graph (after a warm-up on a side stream) and replayed: the GPU-side time of a forward whose
+    eager timing is dominated by the host issuing its launches."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    return _gpu_time(graph.replay, reps)
+
+
 def _oracle_cfg(cfgd):
     return dict(USE_VI=True, USE_PE=cfgd.get("USE_PE", False), USE_XYZ=True, use_level_1=cfgd.get("use_level_1", True),
                 num_level=cfgd["num_level"], guided_level=cfgd.get("guided_level", 0), resblocks=cfgd["resblocks"],
@@ -876,9 +891,12 @@ def run_extra_config(args):
                 ms_knn = _gpu_time(lambda: KU.compute_knn(xyz_d[0], xyz_d[0], 16), args.steps)
                 ms_pc = _gpu_time(lambda: layer(xyz_d, feats_d, nei), args.steps)
                 ms_pcf = _gpu_time(lambda: pcf(xyz_d, f64_d, nei, nrm_d), args.steps)
+                ms_pc_graph = _graph_time(lambda: layer(xyz_d, feats_d, nei), args.steps)
+                ms_pcf_graph = _graph_time(lambda: pcf(xyz_d, f64_d, nei, nrm_d), args.steps)
                 y, _ = layer(xyz_d, feats_d, nei)
                 z, _ = pcf(xyz_d, f64_d, nei, nrm_d)
             row = {"N": n, "knn_ms": ms_knn, "pointconv_fwd_ms": ms_pc, "pcf_layer_fwd_ms": ms_pcf,
+                   "pointconv_fwd_graph_ms": ms_pc_graph, "pcf_layer_fwd_graph_ms": ms_pcf_graph,
                    "pointconv_Mpts_per_s": n / ms_pc / 1e3, "pcf_layer_Mpts_per_s": n / ms_pcf / 1e3}
             if n <= 8192:                                            # parity + CPU baseline at the CPU-runnable size
                 P = {"." + k: v.detach().cpu() for k, v in layer.state_dict().items()}
