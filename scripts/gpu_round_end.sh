@@ -16,6 +16,8 @@ for c in single tiny 5cm ptf2_infer; do
 done
 timeout 600 python scripts/profile_step.py > gpurun_out/profile_step.log 2>&1 && cp gpurun_out/prof_table.txt gpurun_out/step_kernels_$R.txt && cp gpurun_out/prof_kernels_by_grid.txt gpurun_out/step_kernels_by_grid_$R.txt && cp gpurun_out/prof_timeline.txt gpurun_out/step_timeline_$R.txt
 PCFB_PDL=0 timeout 600 python scripts/profile_step.py > gpurun_out/profile_step_nopdl.log 2>&1 && cp gpurun_out/prof_timeline.txt gpurun_out/step_timeline_nopdl_$R.txt
+timeout 300 python scripts/profile_infer.py 250000 ptf2 > gpurun_out/infer_kernels_ptf2_$R.txt 2>&1; echo "profile infer ptf2 exit $?" >> gpurun_out/summary.log
+timeout 300 python scripts/profile_infer.py 19000 lite > gpurun_out/infer_kernels_lite_$R.txt 2>&1; echo "profile infer lite exit $?" >> gpurun_out/summary.log
 timeout 300 python bench.py --knn-sweep > gpurun_out/knn_sweep_$R.json 2> gpurun_out/knn_sweep.err; echo "knn sweep exit $?" >> gpurun_out/summary.log
 for op in fwdp bwd; do
   python scripts/run_op.py $op 3 > gpurun_out/run_op.log 2>&1 &&

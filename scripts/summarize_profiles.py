@@ -136,7 +136,7 @@ def main():
             ncu_report(os.path.join(OUT, fn), m.group(1), tag)
     for fn in ("bench_%s.json" % tag, "bench_reference_%s.json" % tag, "step_kernels_%s.txt" % tag, "step_kernels_by_grid_%s.txt" % tag,
                "knn_sweep_%s.json" % tag, "step_timeline_%s.txt" % tag, "step_timeline_nopdl_%s.txt" % tag, "chain_times_%s.txt" % tag,
-               "knn_stage_%s.txt" % tag, "gemm_times_%s.txt" % tag,
+               "knn_stage_%s.txt" % tag, "gemm_times_%s.txt" % tag, "infer_kernels_ptf2_%s.txt" % tag, "infer_kernels_lite_%s.txt" % tag,
                "bench_single_%s.json" % tag, "bench_tiny_%s.json" % tag, "bench_5cm_%s.json" % tag, "bench_ptf2_infer_%s.json" % tag):
         src = os.path.join(OUT, fn)
         if os.path.exists(src):
