@@ -11,6 +11,8 @@ meaning: cfg.USE_CUDA_KERNEL selects the fused contraction, cfg.PCONV_OPT additi
 Linear and changes the parameter spelling.  With USE_CUDA_KERNEL False the contraction is the
 reference's unfused formulation (gather kernel + batched matmul).  CUDA tensors only.
 """
+import os
+
 import torch
 from torch import nn
 import torch.nn.functional as F
@@ -64,10 +66,22 @@ def _inv_tuple(nei_inds, n_in, inv_neighbors, inv_k, inv_idx, needed):
     return resolve_inverse(nei_inds, n_in, inv_neighbors, inv_k, inv_idx)
 
 
+PAD_C_IN = os.environ.get("PCFB_PAD_CIN", "1") != "0"     # pad C_in to a multiple of 4 in front of the fused contraction
+
+
 def _contract(cfg, feats, nei_inds, inv, weights, additional, guidance, lin_w, lin_b):
     """gather -> (x guidance) -> concat additional -> sum_k (.) w -> (Linear).  Fused kernel when
     cfg.USE_CUDA_KERNEL, else the reference's unfused torch formulation on our gather."""
     if cfg.USE_CUDA_KERNEL:
+        C_in, pad = feats.shape[-1], (-feats.shape[-1]) % 4
+        if PAD_C_IN and pad and lin_w is not None and guidance is None and feats.is_cuda:
+            # The first layer of the encoder sees colour + xyz = 6 channels; the warp-specialised forward and the vector path
+            # of the contraction backward need C_in % 4 == 0.  Two zero channels (and the matching zero columns of the Linear)
+            # change nothing in the result and move the 100 k-point level-0 layer from the 64-point-tile fallback kernel
+            # (276 us) to the kernels every other layer uses; autograd slices the gradients back (pad / cat backward).
+            M = weights.shape[-1]
+            feats = F.pad(feats, (0, pad))
+            lin_w = torch.cat([lin_w[:, :C_in * M], lin_w.new_zeros(lin_w.shape[0], pad * M), lin_w[:, C_in * M:]], dim=1)
         return FusedPConvFunction.apply(feats.contiguous(), nei_inds, inv, weights.contiguous(),
                                         None if additional is None else additional.contiguous(),
                                         None if guidance is None else guidance.contiguous(), lin_w, lin_b)
