@@ -40,6 +40,7 @@ constexpr int SB_WORDS = 2 * SB_MSG; // 32-bit words per message, each sent as a
 constexpr int SB_EPOCH_OFF = 1024;
 constexpr int SB_DATA_OFF = 65536;
 constexpr int SB_THREADS = 256;
+constexpr int SB_MAXT = 1024;        // bn_reduce_kernel with many block partials
 
 __device__ __forceinline__ void sb_st_ll(unsigned long long *p, unsigned long long v) {   // one 8-byte store: single-copy atomic
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;\n" :: "l"(p), "l"(v) : "memory");
@@ -159,40 +160,41 @@ struct SbArgs {
     float *sums_local, *sums_global; // [2][C] (mode 1)
 };
 
-__global__ void __launch_bounds__(SB_THREADS)
+// blockDim.x = 256 (16 slices of the block partials per column) or 1024 (64 slices: level-0 tensors leave ~800 partials per
+// column, and a 50-deep chain of dependent L2 loads per thread was most of this kernel's 5.6 us)
+__global__ void __launch_bounds__(SB_MAXT)
 bn_reduce_kernel(SbArgs a)
 {
     pdl_wait();
-    __shared__ double part_s[16][17];             // [slice][column]
+    __shared__ double part_s[SB_MAXT / 16][17];   // [slice][column]
     __shared__ double msg_s[SB_MSG], glob_s[SB_MSG];
     __shared__ uint32_t recv_s[SB_MAXW][SB_WORDS];
     __shared__ uint32_t ep_s;
     __shared__ int timed_out_s;
-    const int t = threadIdx.x, col = t & 15, slice = t >> 4;
+    const int t = threadIdx.x, col = t & 15, slice = t >> 4, n_slices = (int)blockDim.x >> 4;
     const int c0 = blockIdx.x * 8;
     const int which = col >> 3, c = c0 + (col & 7);
     const bool exchange = a.x.on();
     if (exchange && t == 0) ep_s = sb_epoch_begin(a.x, blockIdx.x);
-    // 1. local reduction, fixed order: slice s adds blocks s, s+16, ... ; slices are then added 0..15
+    // 1. local reduction, fixed order: slice s adds blocks s, s + n_slices, ... ; slices are then added 0 .. n_slices-1
     double s = 0.0;
     if (c < a.C) {
         const float *src = a.partial + (size_t)which * a.C + c;
         const size_t stride = (size_t)2 * a.C;
         int b = slice;
-        for (; b + 48 < a.nblocks; b += 64) {      // four independent loads in flight
-            const float v0 = src[(size_t)b * stride], v1 = src[(size_t)(b + 16) * stride];
-            const float v2 = src[(size_t)(b + 32) * stride], v3 = src[(size_t)(b + 48) * stride];
+        for (; b + 3 * n_slices < a.nblocks; b += 4 * n_slices) {      // four independent loads in flight
+            const float v0 = src[(size_t)b * stride], v1 = src[(size_t)(b + n_slices) * stride];
+            const float v2 = src[(size_t)(b + 2 * n_slices) * stride], v3 = src[(size_t)(b + 3 * n_slices) * stride];
             s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
         }
-        for (; b < a.nblocks; b += 16) s += (double)src[(size_t)b * stride];
+        for (; b < a.nblocks; b += n_slices) s += (double)src[(size_t)b * stride];
     }
     part_s[slice][col] = s;
     if (t == 0) timed_out_s = 0;
     __syncthreads();
     if (t < 16) {
         double v = 0.0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v += part_s[k][t];
+        for (int k = 0; k < n_slices; ++k) v += part_s[k][t];
         msg_s[t] = v;
         glob_s[t] = v;
     }
@@ -492,7 +494,7 @@ extern "C" int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_
     a.f.pivot = pivot; a.f.gamma = gamma; a.f.beta = beta; a.f.eps = eps; a.f.momentum = momentum;
     a.f.running_mean = running_mean; a.f.running_var = running_var; a.f.scale = scale; a.f.shift = shift; a.f.mean = mean; a.f.invstd = invstd;
     a.f.batches_tracked = reinterpret_cast<long long *>(batches_tracked); a.count_out = count_out;
-    launch_k(bn_reduce_kernel, ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
+    launch_k(bn_reduce_kernel, ceil_div(C, 8), nblocks > 128 ? SB_MAXT : SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_reduce_kernel<finalize>");
 }
 
@@ -506,7 +508,7 @@ extern "C" int pcfb_bn_reduce_sums(const float *partial, int nblocks, int C, flo
     a.partial = partial; a.nblocks = nblocks; a.C = C; a.mode = 1; a.count = 0.0;
     a.x = sb_xchg(peer_bases, rank, world, channel, timeout_s);
     a.sums_local = sums_local; a.sums_global = sums_global;
-    launch_k(bn_reduce_kernel, ceil_div(C, 8), SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
+    launch_k(bn_reduce_kernel, ceil_div(C, 8), nblocks > 128 ? SB_MAXT : SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_reduce_kernel<sums>");
 }
 
