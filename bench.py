@@ -950,6 +950,16 @@ def run_extra_config(args):
             ms_edges = _gpu_time(edges, max(args.steps // 2, 2))
             ms_lite = _gpu_time(lambda: model(col, pcs, es, ef, ep, nrms), args.steps)
             ms_tiny = _gpu_time(lambda: tiny(col, pcs, es, ef, nrms), args.steps)
+
+            _, _, stored0, info0 = GS.build_pyramid(p0, n0, h["stored0"], cfgd["grid_size"])
+
+            def whole():                                         # edges + forward, as one replayable unit (no host reads)
+                pts, nrm, _, _ = GS.build_pyramid(p0, n0, h["stored0"], cfgd["grid_size"], expect=stored0, boxes=info0["boxes"])
+                a_pcs = [p[None] for p in pts]
+                a_es, a_ef, a_ep = KU.prepare(*KU.compute_knn_packed(a_pcs, stored0, cfgd["K_self"], cfgd["K_forward"], cfgd["K_propagate"],
+                                                                     grid_size=cfgd["grid_size"]))
+                return model(col, a_pcs, a_es, a_ef, a_ep, [x[None] for x in nrm])
+            ms_graph = _graph_time(whole, args.steps)
         n_total = int(p0.shape[0])
         # parity + CPU baseline on a 2-room batch through the oracle port
         h2, q0, m0, col2 = batch(2, 5)
@@ -972,6 +982,7 @@ def run_extra_config(args):
                     config={"workload": "configPCF_10cm_lite segmentation model, eval forward incl. post_knn edge construction (pyramid + 13 kNN sets), "
                                         "16 packed synthetic rooms", "points": n_total, "levels": [int(p.shape[1]) for p in pcs]},
                     parts={"edges_ms": ms_edges, "lite_forward_ms": ms_lite, "pcf_tiny_backbone_forward_ms": ms_tiny},
+                    graph_replay_ms=ms_graph, graph_replay_points_per_s=n_total / ms_graph * 1e3,
                     parity={"max_abs_logit_err_vs_oracle_2_rooms": err},
                     cpu_baseline={"value": int(q0.shape[0]) / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                                   "sample": "oracle forward (no edges) on a 2-room batch of %d points" % int(q0.shape[0])})
