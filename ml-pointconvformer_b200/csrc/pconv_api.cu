@@ -1,5 +1,6 @@
 // C-ABI entry points of the fused PointConv / PointConvFormer contraction: variant dispatch.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace pcfb {
 // pconv_simt.cu
@@ -81,8 +82,16 @@ static bool mid1_path(const pcfb_pconv_shape *s, int variant) {
 // auto only: shapes that neither pipelined tcgen05 kernel holds (wide C_out at the deep levels, a few hundred points):
 // P by the CUDA-core contraction kernel, Y = P W^T + b as a column-block tensor-core GEMM.  The simple tcgen05 kernel
 // these shapes used before keeps 2-3 CTAs busy for ~0.4 ms.
+static bool midn_compose() {                        // PCFB_MIDN_COMPOSE=0: A/B switch
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("PCFB_MIDN_COMPOSE"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
 static bool compose_path(const pcfb_pconv_shape *s) {
     if (s->C_out > 0 && s->C_mid > 1 && point_path(s) && s->n_out <= pcfb::pconv_point_max_points() / 2) return true;
+    // C_mid 2..4 on a large level: the streaming weighted-sum kernel + the tensor-core Linear beat the 64-point-tile fused
+    // kernel (configPCF_10cm_lite, 305 k points: 580 us per layer, 10 % of the HBM roofline)
+    if (midn_compose() && s->C_out > 0 && s->n_out > 16384 && pcfb::pconv_midn_supported(s)) return true;
     return s->C_out > 0 && s->C_mid > 1 && !pcfb::pconv_forward_ws_supported(s, true) && !pcfb::pconv_forward_umma2_supported(s, true);
 }
 
