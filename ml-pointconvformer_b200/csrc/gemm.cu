@@ -813,7 +813,12 @@ struct NtSetup { int Nblk, n_blocks, Npad, n_chunks, resident; size_t block_byte
 // 184- and 1 k-point levels gave 2 .. 8 row tiles, i.e. 2 .. 8 CTAs each streaming the whole weight matrix (31 us for a
 // 184 x 1536 x 192 product, profiles/step_kernels_by_grid_r01.txt); narrower column blocks spread the weight stream over
 // ~NT_TARGET_CTAS CTAs instead.
-constexpr int NT_TARGET_CTAS = 24;
+constexpr int NT_TARGET_CTAS = 48;          // measured on the replayed step: 8 -> 20.56, 24 -> 20.39, 48 -> 20.26, 96 -> 20.26 ms (scripts/ab_step.sh)
+static int nt_target_ctas() {                       // PCFB_NT_TARGET: A/B override of NT_TARGET_CTAS
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PCFB_NT_TARGET"); v = e ? atoi(e) : NT_TARGET_CTAS; if (v < 1) v = 1; }
+    return v;
+}
 static bool nt_pipe_enabled() {                     // PCFB_GEMM_PIPE=0: A/B switch for the pipelined small-grid variant
     static int on = -1;
     if (on < 0) { const char *e = getenv("PCFB_GEMM_PIPE"); on = (e && e[0] == '0') ? 0 : 1; }
@@ -831,7 +836,7 @@ static NtSetup nt_setup(int N, int K, int M = 0) {
         const int nb = widths[wi];
         if (wi > 0 && nb >= N) continue;
         if (nb > 256) continue;
-        if (wi < 4 && nb > 16 && tiles * ceil_div(N, nb) < NT_TARGET_CTAS && N > 16) continue;   // too few CTAs: try narrower blocks
+        if (wi < 4 && nb > 16 && tiles * ceil_div(N, nb) < nt_target_ctas() && N > 16) continue;   // too few CTAs: try narrower blocks
         s.Nblk = nb;
         s.n_blocks = ceil_div(N, nb);
         s.Npad = round_up(nb < 16 ? 16 : nb, 16);
