@@ -350,7 +350,7 @@ int pcfb_gridsub_emit(const float *xyz, const float *feats, int n_seg, int n_pts
                       size_t workspace_bytes, void *stream);
 
 /* Output-point count up to which pcfb_pconv_forward / pcfb_pconv_backward use the per-point CTA kernels of the coarse
- * pyramid levels (csrc/pconv_point.cu; K = 16, C_mid = 16) instead of the tiled ones; default 12000 (env
+ * pyramid levels (csrc/pconv_point.cu; K = 16, C_mid = 16) instead of the tiled ones; default 4000 (env
  * PCFB_POINT_KERNEL_MAX).  Returns the previous value.  Same results either way (exact fp32 contraction). */
 int pcfb_set_point_kernel_max(int n_points);
 

@@ -144,7 +144,7 @@ static int g_point_max = -1;
 int pconv_point_max_points() {
     if (g_point_max < 0) {
         const char *e = getenv("PCFB_POINT_KERNEL_MAX");
-        g_point_max = e ? atoi(e) : 12000;
+        g_point_max = e ? atoi(e) : 4000;            // 10 cm pyramid: 3 000 -> 20.22, 12 000 -> 20.28, 30 000 -> 20.39 ms/step
     }
     return g_point_max;
 }
