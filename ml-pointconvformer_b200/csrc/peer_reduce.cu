@@ -28,6 +28,7 @@
 // Symmetric buffer layout per rank (bytes): [0,4) error word | [1024, +NCH*MAXB*4) epochs |
 // [65536, ...) slots[NCH][2][MAXB][world][34] of {uint32 word, uint32 epoch}.
 #include "common.cuh"
+#include <stdlib.h>
 #include "act.cuh"
 
 namespace pcfb {
@@ -469,6 +470,11 @@ static int sb_check(int C, const void *peer_bases, int rank, int world, int chan
     return PCFB_OK;
 }
 
+static int sb_wide_min() {                           // block partials above which bn_reduce runs with 64 slices (PCFB_BNR_WIDE_MIN)
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("PCFB_BNR_WIDE_MIN"); v = e ? atoi(e) : 128; }
+    return v;
+}
 static unsigned long long sb_timeout(double timeout_s) { return timeout_s > 0.0 ? (unsigned long long)(timeout_s * 1e9) : 0ull; }
 
 static SbXchg sb_xchg(const void *peer_bases, int rank, int world, int channel, double timeout_s)
@@ -494,7 +500,7 @@ extern "C" int pcfb_bn_finalize(const float *partial, int nblocks, int C, int64_
     a.f.pivot = pivot; a.f.gamma = gamma; a.f.beta = beta; a.f.eps = eps; a.f.momentum = momentum;
     a.f.running_mean = running_mean; a.f.running_var = running_var; a.f.scale = scale; a.f.shift = shift; a.f.mean = mean; a.f.invstd = invstd;
     a.f.batches_tracked = reinterpret_cast<long long *>(batches_tracked); a.count_out = count_out;
-    launch_k(bn_reduce_kernel, ceil_div(C, 8), nblocks > 128 ? SB_MAXT : SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
+    launch_k(bn_reduce_kernel, ceil_div(C, 8), nblocks > sb_wide_min() ? SB_MAXT : SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_reduce_kernel<finalize>");
 }
 
@@ -508,7 +514,7 @@ extern "C" int pcfb_bn_reduce_sums(const float *partial, int nblocks, int C, flo
     a.partial = partial; a.nblocks = nblocks; a.C = C; a.mode = 1; a.count = 0.0;
     a.x = sb_xchg(peer_bases, rank, world, channel, timeout_s);
     a.sums_local = sums_local; a.sums_global = sums_global;
-    launch_k(bn_reduce_kernel, ceil_div(C, 8), nblocks > 128 ? SB_MAXT : SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
+    launch_k(bn_reduce_kernel, ceil_div(C, 8), nblocks > sb_wide_min() ? SB_MAXT : SB_THREADS, 0, static_cast<cudaStream_t>(stream), a);
     return check_launch("bn_reduce_kernel<sums>");
 }
 

@@ -26,7 +26,7 @@ _WIDE = {}
 # joined by join_leaves() (called by sharding.FlatParameters.gather_grads before the flat gradient is assembled), taking
 # ~120 small GEMM launches off the backward's critical path.  Opt-in: whoever reads .grad must call join_leaves() first.
 LEAF_ASYNC = False
-N_LEAF = 2                  # leaf streams, used round robin: the last (largest, level-0) products of the backward share the tail
+N_LEAF = int(os.environ.get("PCFB_N_LEAF", "2"))                  # leaf streams, used round robin: the last (largest, level-0) products of the backward share the tail
 _LEAF = {}
 _LEAF_NEXT = [0]
 
