@@ -343,7 +343,7 @@ def _offsets(counts, dev):
 
 class KnnGrid:
     """Uniform grid over a packed reference cloud (pcfb_knn_grid_build); query() returns exactly what
-    knn_packed() returns.  cell_hint: cell edge (about 2.5x the point spacing works best; <= 0 = automatic)."""
+    knn_packed() returns.  cell_hint: cell edge (about 1.75x the point spacing works best; <= 0 = automatic)."""
 
     def __init__(self, ref_xyz, ref_counts, cell_hint=0.0):
         require(ref_xyz, F32, "ref_xyz")
